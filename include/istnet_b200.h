@@ -1,0 +1,83 @@
+/*
+ * istnet_b200 — C ABI of the B200 (sm_100a) implementation of IST-Net's per-instance hot path.
+ *
+ * Every entry point takes raw DEVICE pointers, plain sizes and a CUDA stream (as void*, i.e. cudaStream_t),
+ * launches asynchronously on that stream and returns 0 on success or a non-zero cudaError_t / negative
+ * argument-error code.  The library keeps no global device state, never allocates device memory, never
+ * synchronises and never exits the process (the reference's CUDA_CHECK_ERRORS exit(-1)s:
+ * model/pointnet2/_ext_src/include/cuda_utils.h:35-44).  All tensors are contiguous; float = FP32,
+ * indices = int32, exactly as the reference's CHECK_* macros demand (include/utils.h:10-30).
+ *
+ * Section 1 mirrors, one for one, the nine functions of the reference pybind module `pointnet2._ext`
+ * (model/pointnet2/_ext_src/src/bindings.cpp:11-24).  The reference-side binding a maintainer would add is
+ * shown in INTEGRATION.md.  Sections 2+ are the fused entry points used by the istnet_b200 modules.
+ */
+#ifndef ISTNET_B200_H
+#define ISTNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISTNET_OK 0
+#define ISTNET_ERR_BAD_ARG (-1)
+#define ISTNET_ERR_UNSUPPORTED (-2)
+
+/* Library / build information: returns the compiled arch (100 for sm_100a). */
+int istnet_version(void);
+/* Human readable text for a status returned by any function below. */
+const char *istnet_strerror(int status);
+
+/* ------------------------------------------------------------------------------------------------------
+ * 1. The nine `pointnet2._ext` operators
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* bindings.cpp:13 furthest_point_sampling  (sampling.cpp:70-91, sampling_gpu.cu:74-234)
+ * xyz[b,n,3] -> idx[b,m].  Bit-exact with the reference, including its block-reduction tie-break
+ * (bit-reversed thread id, then lowest k).  No scratch buffer is needed (the reference's `temp` lives in
+ * registers here). */
+int istnet_furthest_point_sampling(int b, int n, int m, const float *xyz, int32_t *idx, void *stream);
+
+/* bindings.cpp:11 gather_points  (sampling.cpp:20-43, sampling_gpu.cu:13-35): out[b,c,m] = points[b,c,idx[b,m]] */
+int istnet_gather_points(int b, int c, int n, int m, const float *points, const int32_t *idx, float *out, void *stream);
+
+/* bindings.cpp:12 gather_points_grad (sampling.cpp:45-69, sampling_gpu.cu:39-62). grad_points[b,c,n] must be zeroed by the caller. */
+int istnet_gather_points_grad(int b, int c, int n, int m, const float *grad_out, const int32_t *idx, float *grad_points, void *stream);
+
+/* bindings.cpp:19 ball_query (ball_query.cpp:13-37, ball_query_gpu.cu:14-59).  Centroids first, as in the
+ * reference.  idx[b,m,nsample] is fully written (rows without any hit are zero, like the reference's zeros-init). */
+int istnet_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz, int32_t *idx, void *stream);
+
+/* bindings.cpp:21 group_points (group_points.cpp:17-40, group_points_gpu.cu:13-44): out[b,c,m,ns] = points[b,c,idx[b,m,ns]] */
+int istnet_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int32_t *idx, float *out, void *stream);
+
+/* bindings.cpp:22 group_points_grad (group_points.cpp:42-65, group_points_gpu.cu:48-80). grad_points[b,c,n] must be zeroed by the caller. */
+int istnet_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int32_t *idx, float *grad_points, void *stream);
+
+/* bindings.cpp:15 three_nn (interpolate.cpp:19-45, interpolate_gpu.cu:14-73): dist2[b,n,3] ascending, idx[b,n,3] */
+int istnet_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int32_t *idx, void *stream);
+
+/* bindings.cpp:16 three_interpolate (interpolate.cpp:47-75, interpolate_gpu.cu:77-117) points[b,c,m] -> out[b,c,n] */
+int istnet_three_interpolate(int b, int c, int m, int n, const float *points, const int32_t *idx, const float *weight, float *out, void *stream);
+
+/* bindings.cpp:17 three_interpolate_grad (interpolate.cpp:76-104, interpolate_gpu.cu:121-159). grad_points[b,c,m] must be zeroed by the caller. */
+int istnet_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int32_t *idx, const float *weight, float *grad_points, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * 2. Fused point-cloud entry points (PointNet2MSG, model/modules.py:244-327)
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* FPS + gather for ALL set-abstraction levels of one extractor in ONE launch
+ * (pointnet2_modules.py:47-58 executed for SA_modules[0..nlevels-1], modules.py:249-299).
+ * xyz[b,n,3]; level l samples npoint[l] points out of the previous level's output.
+ * idx_out[l]  -> int32 [b,npoint[l]]   (indices into level l's input cloud)
+ * xyz_out[l]  -> float [b,npoint[l],3] (the gathered centroids, == gather_points on the transposed cloud)
+ * nlevels <= 4. */
+int istnet_fps_chain(int b, int n, int nlevels, const int *npoint, const float *xyz, int32_t *const *idx_out, float *const *xyz_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISTNET_B200_H */

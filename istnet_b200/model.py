@@ -1,0 +1,282 @@
+"""IST-Net top-level modules on the B200 kernels, behind the reference's module surface.
+
+Same class names, constructor signatures, forward dict keys, train/eval behaviour and `state_dict` keys as
+`model/ist_net.py` and `model/posenet_gt.py` of the reference, so `train.py` / `test.py` run unchanged when
+`compat/` is on sys.path.  Differences from the reference are deliberate and documented:
+no hard-coded `.cuda()` (everything follows the input's device), no weight download.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .image import ModifiedResnet
+from .pointnet2 import PointNet2MSG
+
+CAM_RADII = [[0.01, 0.02], [0.02, 0.04], [0.04, 0.08], [0.08, 0.16]]  # ist_net.py:16, posenet_gt.py:18
+WORLD_RADII = [[0.05, 0.10], [0.10, 0.20], [0.20, 0.30], [0.30, 0.40]]  # ist_net.py:189, posenet_gt.py:19
+
+
+# --------------------------------------------------------------------------------------------- small pieces
+def ortho6d_to_mat(x_raw, y_raw):
+    """Ortho6d2Mat (utils/rotation_utils.py:4-28): y=norm(y_raw); z=norm(x_raw x y); x=y x z; columns [x,y,z]."""
+
+    def nrm(v):
+        mag = torch.sqrt(v.pow(2).sum(dim=1, keepdim=True))
+        return v / torch.clamp(mag, min=1e-8)
+
+    def cross(u, v):
+        return torch.stack(
+            (u[:, 1] * v[:, 2] - u[:, 2] * v[:, 1], u[:, 2] * v[:, 0] - u[:, 0] * v[:, 2], u[:, 0] * v[:, 1] - u[:, 1] * v[:, 0]), 1
+        )
+
+    y = nrm(y_raw)
+    z = nrm(cross(x_raw, y))
+    x = cross(y, z)
+    return torch.stack((x, y, z), 2)
+
+
+def _pt_mlp(*widths, last_relu=True):
+    """[Conv1d(k=1)+bias, ReLU]* as an nn.Sequential with the reference's child indices (0,2,4,...)."""
+    layers = []
+    for i in range(len(widths) - 1):
+        layers.append(nn.Conv1d(widths[i], widths[i + 1], 1))
+        if last_relu or i + 2 < len(widths):
+            layers.append(nn.ReLU())
+    return nn.Sequential(*layers)
+
+
+def _head(out):
+    return nn.Sequential(nn.Linear(512, 512), nn.ReLU(), nn.Linear(512, 256), nn.ReLU(), nn.Linear(256, out))
+
+
+def gather_pixels(rgb_map, choose):
+    """ist_net.py:42-45: (B,d,H,W), choose (B,N) int64 -> (B,d,N)"""
+    b, d = rgb_map.shape[:2]
+    return torch.gather(rgb_map.view(b, d, -1), 2, choose.unsqueeze(1).expand(-1, d, -1)).contiguous()
+
+
+class _PoseHeads(nn.Module):
+    """pose_mlp1 -> global mean concat -> pose_mlp2 -> avg pool -> rotation / translation / size heads."""
+
+    def _tail(self, feat):
+        feat = self.pose_mlp1(feat)
+        glob = torch.mean(feat, 2, keepdim=True)
+        feat = torch.cat([feat, glob.expand_as(feat)], 1)
+        feat = self.pose_mlp2(feat).squeeze(2)
+        r6 = self.rotation_estimator(feat)
+        r = ortho6d_to_mat(r6[:, :3].contiguous(), r6[:, 3:].contiguous()).view(-1, 3, 3)
+        return r, self.translation_estimator(feat), self.size_estimator(feat)
+
+
+class LightEstimator(_PoseHeads):
+    """ist_net.py:202-264"""
+
+    def __init__(self):
+        super().__init__()
+        self.pts_mlp = _pt_mlp(3, 32, 64)
+        self.pose_mlp1 = _pt_mlp(128 + 64 + 128, 256, 256)
+        self.pose_mlp2 = nn.Sequential(nn.Conv1d(512, 512, 1), nn.ReLU(), nn.Conv1d(512, 512, 1), nn.ReLU(), nn.AdaptiveAvgPool1d(1))
+        self.rotation_estimator, self.translation_estimator, self.size_estimator = _head(6), _head(3), _head(3)
+
+    def forward(self, pts, rgb_local, pts_local):
+        e = self.pts_mlp(pts.transpose(1, 2))
+        return self._tail(torch.cat([rgb_local, e, pts_local], dim=1))
+
+
+class HeavyEstimator(_PoseHeads):
+    """ist_net.py:267-332 (identical copy at posenet_gt.py:71-136)"""
+
+    def __init__(self):
+        super().__init__()
+        self.pts_mlp1 = _pt_mlp(3, 32, 64)
+        self.pts_mlp2 = _pt_mlp(3, 32, 64)
+        self.pose_mlp1 = _pt_mlp(64 + 64 + 384, 256, 256)
+        self.pose_mlp2 = nn.Sequential(nn.Conv1d(512, 512, 1), nn.ReLU(), nn.Conv1d(512, 512, 1), nn.ReLU(), nn.AdaptiveAvgPool1d(1))
+        self.rotation_estimator, self.translation_estimator, self.size_estimator = _head(6), _head(3), _head(3)
+
+    def forward(self, pts, pts_w, rgb_local, pts_local, pts_w_local):
+        e1 = self.pts_mlp1(pts.transpose(1, 2))
+        e2 = self.pts_mlp2(pts_w.transpose(1, 2))
+        return self._tail(torch.cat([rgb_local, e1, pts_local, e2, pts_w_local], dim=1))
+
+
+class FeatureDeformer(nn.Module):
+    """Implicit space transformation (ist_net.py:125-183)."""
+
+    def __init__(self, nclass=6):
+        super().__init__()
+        self.nclass = nclass
+        self.pts_mlp1 = _pt_mlp(3, 32, 64)
+        self.deform_mlp1 = _pt_mlp(64 + 256, 384, 256)
+        self.deform_mlp2 = _pt_mlp(512, 384, 256, 128)
+        self.pred_nocs = _pt_mlp(128, 256, 128, nclass * 3, last_relu=False)
+
+    def forward(self, pts, rgb_local, pts_local, index):
+        npoint = pts_local.size(2)
+        e = self.pts_mlp1(pts.transpose(1, 2))
+        x = self.deform_mlp1(torch.cat([e, pts_local, rgb_local], dim=1))
+        glob = torch.mean(x, 2, keepdim=True)
+        x = self.deform_mlp2(torch.cat([x, glob.expand_as(x)], 1))
+        q = self.pred_nocs(x).view(-1, 3, npoint).contiguous()
+        q = torch.index_select(q, 0, index).permute(0, 2, 1).contiguous()
+        return x, q
+
+
+class ImplicitTransformation(nn.Module):
+    """ist_net.py:114-122"""
+
+    def __init__(self, nclass=6):
+        super().__init__()
+        self.nclass = nclass
+        self.feature_refine = FeatureDeformer(nclass)
+
+    def forward(self, rgb_local, pts_local, pts, center, index):
+        pts_local_w, pts_w = self.feature_refine(pts, rgb_local, pts_local, index)
+        return pts_w, pts_local_w
+
+
+class WorldSpaceEnhancer(nn.Module):
+    """ist_net.py:185-200"""
+
+    def __init__(self, freeze=False):
+        super().__init__()
+        self.freeze = freeze
+        self.extractor = PointNet2MSG(radii_list=WORLD_RADII)
+        if not freeze:
+            self.pose_estimator = HeavyEstimator()
+
+    def forward(self, pts, pts_w_gt, rgb_local, pts_local):
+        pts_w_local_gt = self.extractor(pts_w_gt)
+        if self.freeze:
+            return None, None, None, pts_w_local_gt
+        r, t, s = self.pose_estimator(pts, pts_w_gt, rgb_local.detach(), pts_local.detach(), pts_w_local_gt)
+        return r, t, s, pts_w_local_gt
+
+
+# --------------------------------------------------------------------------------------------- top modules
+class IST_Net(nn.Module):
+    """ist_net.py:10-76"""
+
+    def __init__(self, nclass=6, freeze_world_enhancer=False):
+        super().__init__()
+        self.nclass = nclass
+        self.freeze_world_enhancer = freeze_world_enhancer
+        self.rgb_cam_extractor = ModifiedResnet()
+        self.pts_cam_extractor = PointNet2MSG(radii_list=CAM_RADII)
+        self.implicit_transform = ImplicitTransformation(nclass)
+        self.main_estimator = HeavyEstimator()
+        self.cam_enhancer = LightEstimator()
+        self.world_enhancer = WorldSpaceEnhancer(freeze=freeze_world_enhancer)
+
+    def forward(self, inputs):
+        end_points = {}
+        rgb, pts, choose = inputs["rgb"], inputs["pts"], inputs["choose"]
+        cls = inputs["category_label"].reshape(-1)
+        c = torch.mean(pts, 1, keepdim=True)
+        pts = pts - c
+        b = pts.size(0)
+        index = cls + torch.arange(b, dtype=torch.long, device=pts.device) * self.nclass
+
+        rgb_local = gather_pixels(self.rgb_cam_extractor(rgb), choose)
+        pts_local = self.pts_cam_extractor(pts)
+        if self.training:
+            r_c, t_c, s_c = self.cam_enhancer(pts, rgb_local, pts_local)
+        pts_w, pts_w_local = self.implicit_transform(rgb_local, pts_local, pts, c, index)
+        r, t, s = self.main_estimator(pts, pts_w, rgb_local, pts_local, pts_w_local)
+        end_points["pred_qo"] = pts_w
+        if self.training:
+            r_w, t_w, s_w, pts_w_local_gt = self.world_enhancer(pts, inputs["qo"], rgb_local, pts_local)
+            end_points["pts_w_local"] = pts_w_local
+            end_points["pts_w_local_gt"] = pts_w_local_gt
+        end_points["pred_rotation"] = r
+        end_points["pred_translation"] = t + c.squeeze(1)
+        end_points["pred_size"] = s
+        if self.training:
+            end_points["pred_rotation_aux_cam"] = r_c
+            end_points["pred_translation_aux_cam"] = t_c + c.squeeze(1)
+            end_points["pred_size_aux_cam"] = s_c
+            if not self.freeze_world_enhancer:
+                end_points["pred_rotation_aux_world"] = r_w
+                end_points["pred_translation_aux_world"] = t_w + c.squeeze(1)
+                end_points["pred_size_aux_world"] = s_w
+        return end_points
+
+
+class PoseNetGT(nn.Module):
+    """posenet_gt.py:11-51 (phase-1 "world enhancer" training): only pts_gt_extractor and the estimator
+    receive gradients; the rgb / camera-space extractors still run (BN running stats, dropout draws)."""
+
+    def __init__(self, nclass=6, nprior=1024):
+        super().__init__()
+        self.nclass, self.nprior = nclass, nprior
+        self.rgb_extractor = ModifiedResnet()
+        self.pts_extractor = PointNet2MSG(radii_list=CAM_RADII)
+        self.pts_gt_extractor = PointNet2MSG(radii_list=WORLD_RADII)
+        self.pose_estimator_aux = HeavyEstimator()
+
+    def forward(self, inputs):
+        rgb, pts, choose, pts_w_gt = inputs["rgb"], inputs["pts"], inputs["choose"], inputs["qo"]
+        c = torch.mean(pts, 1, keepdim=True)
+        pts = pts - c
+        with torch.no_grad():  # outputs are detached in the reference (posenet_gt.py:43); same values, no graph
+            rgb_local = gather_pixels(self.rgb_extractor(rgb), choose)
+            pts_local = self.pts_extractor(pts)
+        gt_local = self.pts_gt_extractor(pts_w_gt)
+        r, t, s = self.pose_estimator_aux(pts, pts_w_gt, rgb_local, pts_local, gt_local)
+        return {"pts_local_w_gt": gt_local, "pred_rotation": r, "pred_translation": t + c.squeeze(1), "pred_size": s}
+
+
+# --------------------------------------------------------------------------------------------- losses
+def SmoothL1Dis(p1, p2, threshold=0.1):
+    """losses.py:3-22"""
+    diff = torch.abs(p1 - p2)
+    dis = torch.where(diff > threshold, diff - threshold / 2.0, torch.pow(diff, 2) / (2.0 * threshold))
+    return torch.mean(torch.sum(dis, dim=2 if p1.dim() == 3 else 1))
+
+
+def PoseDis(r1, t1, s1, r2, t2, s2):
+    """losses.py:37-49"""
+    return torch.mean(torch.norm(r1 - r2, dim=1)) + torch.mean(torch.norm(t1 - t2, dim=1)) + torch.mean(torch.norm(s1 - s2, dim=1))
+
+
+class SupervisedLoss(nn.Module):
+    """ist_net.py:78-111.  `cfg` needs `.loss.gamma1`, `.loss.gamma2`, `.freeze_world_enhancer`."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg.loss
+        self.freeze_world_enhancer = cfg.freeze_world_enhancer
+
+    def forward(self, ep):
+        R, T, S = ep["rotation_label"], ep["translation_label"], ep["size_label"]
+        loss_feat = F.mse_loss(ep["pts_w_local"], ep["pts_w_local_gt"])
+        loss_qo = SmoothL1Dis(ep["pred_qo"], ep["qo"])
+        loss = PoseDis(ep["pred_rotation"], ep["pred_translation"], ep["pred_size"], R, T, S)
+        loss = loss + PoseDis(ep["pred_rotation_aux_cam"], ep["pred_translation_aux_cam"], ep["pred_size_aux_cam"], R, T, S)
+        loss = loss + self.cfg.gamma1 * loss_qo + self.cfg.gamma2 * loss_feat
+        if not self.freeze_world_enhancer:
+            loss = loss + PoseDis(ep["pred_rotation_aux_world"], ep["pred_translation_aux_world"], ep["pred_size_aux_world"], R, T, S)
+        return loss
+
+
+class PoseNetGTLoss(nn.Module):
+    """posenet_gt.py:53-67"""
+
+    def __init__(self, cfg=None):
+        super().__init__()
+        self.cfg = getattr(cfg, "loss", None)
+
+    def forward(self, ep):
+        return PoseDis(ep["pred_rotation"], ep["pred_translation"], ep["pred_size"], ep["rotation_label"], ep["translation_label"], ep["size_label"])
+
+
+class LossCfg:
+    """Minimal stand-in for the gorilla Config object (`cfg.loss.gamma1`, config/ist_net_default.yaml:25-30)."""
+
+    class _L:
+        def __init__(self, g1, g2):
+            self.gamma1, self.gamma2 = g1, g2
+
+    def __init__(self, gamma1=1.0, gamma2=10.0, freeze_world_enhancer=False):
+        self.loss = LossCfg._L(gamma1, gamma2)
+        self.freeze_world_enhancer = freeze_world_enhancer

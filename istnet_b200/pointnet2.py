@@ -1,0 +1,148 @@
+"""PointNet++ MSG encoder of IST-Net on the B200 kernels.
+
+Module / parameter names mirror the reference so `state_dict`s interchange
+(model/modules.py:244-327 `PointNet2MSG`, model/pointnet2/pointnet2_modules.py:21-209,
+model/pointnet2/pytorch_utils.py:25-206 `SharedMLP`): e.g. `SA_modules.0.mlps.0.layer0.conv.weight`,
+`SA_modules.0.mlps.0.layer0.normlayer.bn.running_var`, `FP_modules.3.mlp.layer1.conv.weight`.
+BN layers are real `nn.BatchNorm2d` instances so the reference BNMomentumScheduler (utils/scheduler.py:277-303)
+finds them; momentum / eps / training are read at call time.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ext
+from . import functional as PF
+
+
+class _NormLayer(nn.Sequential):
+    def __init__(self, c):
+        super().__init__()
+        self.add_module("bn", nn.BatchNorm2d(c))
+        nn.init.constant_(self.bn.weight, 1.0)
+        nn.init.constant_(self.bn.bias, 0.0)
+
+
+class _ConvBnRelu(nn.Sequential):
+    """pytorch_utils.Conv2d with bn=True: 1x1 conv without bias, BN2d, ReLU (pytorch_utils.py:80-134,173-206)."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.add_module("conv", nn.Conv2d(cin, cout, kernel_size=(1, 1), bias=False))
+        nn.init.kaiming_normal_(self.conv.weight)
+        self.add_module("normlayer", _NormLayer(cout))
+        self.add_module("activation", nn.ReLU(inplace=True))
+
+
+class SharedMLP(nn.Sequential):
+    def __init__(self, spec, bn=True):
+        super().__init__()
+        assert bn, "the IST-Net hot path only uses bn=True"
+        for i in range(len(spec) - 1):
+            self.add_module(f"layer{i}", _ConvBnRelu(spec[i], spec[i + 1]))
+
+
+class QueryAndGroup(nn.Module):
+    """pointnet2_utils.py:294-377 (use_xyz=True, no normalize_xyz / sample_uniformly on this path)."""
+
+    def __init__(self, radius, nsample, use_xyz=True):
+        super().__init__()
+        self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
+
+    def forward(self, xyz, new_xyz, features=None, xyz_t=None):
+        idx = PF.ball_query(self.radius, self.nsample, xyz, new_xyz)
+        if xyz_t is None:
+            xyz_t = xyz.transpose(1, 2).contiguous()
+        with torch.no_grad():
+            grouped_xyz = ext.group_points(xyz_t, idx)
+            grouped_xyz -= new_xyz.transpose(1, 2).unsqueeze(-1)
+        if features is None:
+            return grouped_xyz
+        grouped = PF.group_points(features, idx)
+        return torch.cat([grouped_xyz, grouped], dim=1) if self.use_xyz else grouped
+
+
+class PointnetSAModuleMSG(nn.Module):
+    """pointnet2_modules.py:21-114"""
+
+    def __init__(self, npoint, radii, nsamples, mlps, bn=True, use_xyz=True):
+        super().__init__()
+        assert len(radii) == len(nsamples) == len(mlps)
+        self.npoint = npoint
+        self.groupers = nn.ModuleList()
+        self.mlps = nn.ModuleList()
+        for r, ns, spec in zip(radii, nsamples, mlps):
+            self.groupers.append(QueryAndGroup(r, ns, use_xyz=use_xyz))
+            spec = list(spec)
+            if use_xyz:
+                spec[0] += 3
+            self.mlps.append(SharedMLP(spec, bn=bn))
+
+    def forward(self, xyz, features=None, new_xyz=None):
+        """xyz (B,N,3), features (B,C,N) -> new_xyz (B,npoint,3), new_features (B,sum mlp[-1],npoint).
+        `new_xyz` may be supplied by a caller that already ran the fused FPS chain."""
+        xyz = xyz.contiguous()
+        xyz_t = xyz.transpose(1, 2).contiguous()
+        if new_xyz is None:
+            fidx = PF.furthest_point_sample(xyz, self.npoint)
+            new_xyz = ext.gather_points(xyz_t, fidx).transpose(1, 2).contiguous()
+        outs = []
+        for grouper, mlp in zip(self.groupers, self.mlps):
+            g = grouper(xyz, new_xyz, features, xyz_t)
+            g = mlp(g)
+            outs.append(F.max_pool2d(g, kernel_size=[1, g.size(3)]).squeeze(-1))
+        return new_xyz, torch.cat(outs, dim=1)
+
+
+class PointnetFPModule(nn.Module):
+    """pointnet2_modules.py:153-209"""
+
+    def __init__(self, mlp, bn=True):
+        super().__init__()
+        self.mlp = SharedMLP(mlp, bn=bn)
+
+    def forward(self, unknown, known, unknow_feats, known_feats):
+        idx, weight = PF.three_nn_weights(unknown, known)
+        x = PF.three_interpolate(known_feats, idx, weight)
+        if unknow_feats is not None:
+            x = torch.cat([x, unknow_feats], dim=1)
+        return self.mlp(x.unsqueeze(-1)).squeeze(-1)
+
+
+class PointNet2MSG(nn.Module):
+    """modules.py:244-327: 4 SA-MSG levels (512/256/128/64 centroids, 16|32 neighbours) + 4 FP levels."""
+
+    NPOINT = (512, 256, 128, 64)
+
+    def __init__(self, radii_list, use_xyz=True):
+        super().__init__()
+        self.SA_modules = nn.ModuleList()
+        c_in, widths = 0, ((16, 16, 32), (32, 32, 64), (64, 64, 128), (128, 128, 256))
+        outs = []
+        for lvl in range(4):
+            w = widths[lvl]
+            self.SA_modules.append(
+                PointnetSAModuleMSG(self.NPOINT[lvl], radii_list[lvl], [16, 32], [[c_in, *w], [c_in, *w]], use_xyz=use_xyz, bn=True)
+            )
+            c_in = 2 * w[-1]
+            outs.append(c_in)
+        self.FP_modules = nn.ModuleList()
+        self.FP_modules.append(PointnetFPModule(mlp=[256, 128, 128]))
+        self.FP_modules.append(PointnetFPModule(mlp=[256 + outs[0], 256, 256]))
+        self.FP_modules.append(PointnetFPModule(mlp=[512 + outs[1], 256, 256]))
+        self.FP_modules.append(PointnetFPModule(mlp=[outs[3] + outs[2], 512, 512]))
+
+    def forward(self, pointcloud):
+        xyz = pointcloud[..., 0:3].contiguous()
+        features = pointcloud[..., 3:].transpose(1, 2).contiguous() if pointcloud.size(-1) > 3 else None
+        # all four FPS levels + centroid gathers in ONE launch (the reference runs 4 FPS + 4 gather kernels)
+        with torch.no_grad():
+            _, centroids = ext.fps_chain(xyz, self.NPOINT)
+        l_xyz, l_feats = [xyz], [features]
+        for i, sa in enumerate(self.SA_modules):
+            nx, nf = sa(l_xyz[i], l_feats[i], new_xyz=centroids[i])
+            l_xyz.append(nx)
+            l_feats.append(nf)
+        for i in range(-1, -(len(self.FP_modules) + 1), -1):
+            l_feats[i - 1] = self.FP_modules[i](l_xyz[i - 1], l_xyz[i], l_feats[i - 1], l_feats[i])
+        return l_feats[0]

@@ -24,7 +24,7 @@ def _random_rotations(b, g):
     ).view(b, 3, 3)
 
 
-def make_batch(batch, npts=1024, img=192, seed=1, duplicates=False, nclass=6):
+def make_batch(batch, npts=1024, img=192, seed=1, duplicates=False, nclass=6, quantize=False):
     """Returns the dict the reference data pipeline hands to the model (provider/dataset.py:204-263)."""
     g = torch.Generator().manual_seed(int(seed))
     R = _random_rotations(batch, g)
@@ -47,6 +47,10 @@ def make_batch(batch, npts=1024, img=192, seed=1, duplicates=False, nclass=6):
     else:
         cam = cam + torch.clamp(0.001 * torch.randn(batch, npts, 3, generator=g), -0.005, 0.005)
     pts = (cam + t[:, None, :]).contiguous()
+    if quantize:
+        # 2^-12 m grid: every partial sum of <= 4096 coordinates is exact in FP32, so `pts - mean(pts)`
+        # (ist_net.py:34-35) is bit-identical on every device / reduction order.
+        pts = torch.round(pts * 4096.0) / 4096.0
     size = 2 * axes
     diag = size.norm(dim=1)
     qo = ((pts - t[:, None, :]) / diag[:, None, None]) @ R  # dataset.py:249

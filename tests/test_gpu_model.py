@@ -1,0 +1,123 @@
+"""GPU parity of the full hot path (IST_Net / PoseNetGT forward, SupervisedLoss, backward) against the golden
+vectors produced by the reference itself and against the oracle port run live on the CPU.
+Tolerance: 1e-4 relative (max|a-b| / max|b|) for float tensors — BASELINE.json north_star."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import fixed_dropout_noise, golden_inputs, load_golden, rel_err, sd_checksum
+from istnet_b200 import model as M
+from istnet_b200.synth import make_batch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+LABELS = ("qo", "rotation_label", "translation_label", "size_label")
+
+
+def cuda_inputs(inp):
+    return {k: v.cuda() for k, v in inp.items()}
+
+
+def test_cfg0_eval_forward_matches_reference_golden():
+    z = load_golden("cfg0_eval.npz")
+    torch.manual_seed(1)
+    m = M.IST_Net(6, False)
+    assert abs(sd_checksum(m.state_dict()) - float(z["sd_checksum"])) < 1e-6 * float(z["sd_checksum"])
+    m = m.cuda().eval()
+    with torch.no_grad():
+        ep = m(cuda_inputs(golden_inputs(z)))
+    assert set(ep) == {"pred_qo", "pred_rotation", "pred_translation", "pred_size"}
+    for k, v in ep.items():
+        assert rel_err(v, z["out_" + k]) < TOL, (k, rel_err(v, z["out_" + k]))
+
+
+def _train_step(m, inp, loss_mod, noise_seed, momentum=None):
+    psp = (m.rgb_cam_extractor if hasattr(m, "rgb_cam_extractor") else m.rgb_extractor).model
+    psp.dropout_noise_fn = fixed_dropout_noise(noise_seed)
+    if momentum is not None:
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.momentum = momentum
+    m.train()
+    ep = m(cuda_inputs(inp))
+    ep.update({k: inp[k].cuda() for k in LABELS})
+    loss = loss_mod(ep)
+    loss.backward()
+    return ep, loss
+
+
+def test_train_step_matches_reference_golden():
+    z = load_golden("train_b4.npz")
+    torch.manual_seed(1)
+    m = M.IST_Net(6, False).cuda()
+    ep, loss = _train_step(m, golden_inputs(z), M.SupervisedLoss(M.LossCfg(1.0, 10.0, False)), 77, momentum=0.9)
+    for k in z:
+        if k.startswith("out_"):
+            assert rel_err(ep[k[4:]], z[k]) < TOL, (k, rel_err(ep[k[4:]], z[k]))
+    assert abs(loss.item() - float(z["loss"])) < TOL * abs(float(z["loss"]))
+    params = dict(m.named_parameters())
+    sd = m.state_dict()
+    worst = 0.0
+    for k in z:
+        if k.startswith("grad_"):
+            e = rel_err(params[k[5:]].grad, z[k])
+            worst = max(worst, e)
+            assert e < 5 * TOL, (k, e)  # individual small gradient tensors (BN-amplified rounding)
+        elif k.startswith("gradnorm_"):
+            g = params[k[9:]].grad
+            assert abs(g.double().norm().item() - float(z[k])) <= 5 * TOL * float(z[k]) + 1e-10, k
+        elif k.startswith("stat_"):
+            assert rel_err(sd[k[5:]], z[k]) < TOL, k
+    for n in z["nograd"]:
+        assert params[str(n)].grad is None, n
+    print("worst small-gradient rel err", worst)
+
+
+def test_posenet_gt_matches_reference_golden():
+    z = load_golden("posenet_gt_b2.npz")
+    torch.manual_seed(1)
+    m = M.PoseNetGT(6).cuda()
+    ep, loss = _train_step(m, golden_inputs(z), M.PoseNetGTLoss(), 78)
+    for k in z:
+        if k.startswith("out_"):
+            assert rel_err(ep[k[4:]], z[k]) < TOL, (k, rel_err(ep[k[4:]], z[k]))
+    assert abs(loss.item() - float(z["loss"])) < TOL * abs(float(z["loss"]))
+    params = dict(m.named_parameters())
+    for n in z["nograd"]:
+        assert params[str(n)].grad is None, n
+    for k in z:
+        if k.startswith("gradnorm_"):
+            assert abs(params[k[9:]].grad.double().norm().item() - float(z[k])) <= 5 * TOL * float(z[k]) + 1e-10, k
+
+
+def test_full_resolution_train_step_matches_oracle_port():
+    """B=2 at the bench resolution (1024 pts, 192x192): oracle port on the host CPU vs the CUDA path."""
+    from oracle import istnet_port as port
+
+    torch.manual_seed(1)
+    m = M.IST_Net(6, False)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+    inp = make_batch(2, 1024, 192, seed=21, quantize=True)
+    noise = fixed_dropout_noise(5)
+    masks = [noise(2, 1024, 0.3), noise(2, 256, 0.15), noise(2, 64, 0.15)]
+    ep_o = port.ist_net_forward(sd, inp, training=True, dropout_noise=masks)
+    loss_o = port.ist_net_loss(ep_o, inp)
+    loss_o.backward()
+    m = m.cuda()
+    ep, loss = _train_step(m, inp, M.SupervisedLoss(M.LossCfg()), 5)
+    for k in ep_o:
+        assert rel_err(ep[k], ep_o[k]) < TOL, (k, rel_err(ep[k], ep_o[k]))
+    assert abs(loss.item() - loss_o.item()) < TOL * abs(loss_o.item())
+    bad = []
+    for n, p in m.named_parameters():
+        go = sd[n].grad
+        if go is None:
+            assert p.grad is None, n
+            continue
+        e = rel_err(p.grad, go)
+        if e > 10 * TOL:
+            bad.append((n, e))
+    assert not bad, bad[:10]

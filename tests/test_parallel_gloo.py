@@ -1,0 +1,75 @@
+"""world_size-2 gloo test of the gradient all-reduce plumbing (istnet_b200/parallel.py) on CPU."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+
+class Toy(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = nn.Linear(8, 16)
+        self.b = nn.Linear(16, 4)
+        self.unused = nn.Linear(4, 4)  # never receives a gradient (like feats.fc)
+        self.frozen = nn.Linear(4, 4)
+        for p in self.frozen.parameters():
+            p.requires_grad_(False)
+
+    def forward(self, x):
+        return self.b(torch.relu(self.a(x)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from istnet_b200.parallel import GradAllReducer, broadcast_module
+
+    torch.manual_seed(100 + rank)  # different init per rank: broadcast must fix it
+    m = Toy()
+    broadcast_module(m)
+    red = GradAllReducer(m, bucket_mb=0.0002)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(3, 8, 8, generator=g)  # 3 steps, global batch 8
+    out = []
+    for step in range(3):
+        red.zero_grad()
+        xs = x[step, rank * 4 : (rank + 1) * 4]
+        m(xs).pow(2).mean().backward()
+        red.finish()
+        out.append([p.grad.clone() if p.grad is not None else None for p in m.parameters()])
+    if rank == 0:
+        ret["grads"] = out
+        ret["state"] = {k: v.clone() for k, v in m.state_dict().items()}
+        ret["nb"] = red.num_buckets()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_matches_full_batch_gradient():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    ref = Toy()
+    ref.load_state_dict(ret["state"])
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(3, 8, 8, generator=g)
+    assert ret["nb"] >= 2
+    for step in range(3):
+        ref.zero_grad(set_to_none=True)
+        ref(x[step]).pow(2).mean().backward()
+        for p, got in zip(ref.parameters(), ret["grads"][step]):
+            if p.grad is None:
+                assert got is None
+            else:
+                assert torch.allclose(p.grad, got, atol=1e-6), step
