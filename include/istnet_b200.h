@@ -77,6 +77,23 @@ int istnet_three_interpolate_grad(int b, int c, int n, int m, const float *grad_
  * nlevels <= 4. */
 int istnet_fps_chain(int b, int n, int nlevels, const int *npoint, const float *xyz, int32_t *const *idx_out, float *const *xyz_out, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * 3. Dense contractions on tcgen05 tensor cores (image branch model/resnet.py + model/modules.py:10-81,
+ *    per-point MLPs model/ist_net.py:125-332, SharedMLP 1x1 convolutions pytorch_utils.py:25-206)
+ *
+ * FP32 tensors are carried as bf16 (hi, lo) pairs, x ~= hi + lo; products are evaluated as
+ * hi*hi + hi*lo + lo*hi with FP32 accumulation in tensor memory (error ~1e-5 relative).
+ * Activations are channels-last: act[b][h][w][c] with a channel stride `*_cs` (elements, multiple of 8).
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* Stride-1 "same" convolution / GEMM:  out[b,h,w,n] = bias[n] + sum_{r,s,c} act[b,h+r-kh/2,w+s-kw/2,c] * wgt[r*kw+s][n][c]
+ * (replaces nn.Conv2d / nn.Conv1d(k=1) / nn.Linear call sites: resnet.py:34-35, modules.py:17-25,41-44,64-66,
+ * ist_net.py:130-160).  wgt_{hi,lo}: bf16 [kh*kw][Cout][wgt_cs].  Any of out_f32 / (out_hi,out_lo) may be null.
+ * (box_w, box_h): pixel tile; box_w*box_h must divide 128 (images: 8x8 -> 2 images per tile; row matrices: 128x1). */
+int istnet_conv_gemm(const void *act_hi, const void *act_lo, int B, int H, int W, int Cin, int act_cs, const void *wgt_hi,
+                     const void *wgt_lo, int Cout, int wgt_cs, int kh, int kw, const float *bias, int relu, float *out_f32,
+                     int out_cs, void *out_hi, void *out_lo, int split_cs, int box_w, int box_h, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=8) as ex:
         list(ex.map(cc, jobs))
     if force or jobs or _newer(LIB, objs):
-        r = subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-lcuda"] + ["-L/usr/local/cuda/lib64/stubs"], capture_output=True, text=True)
+        r = subprocess.run([NVCC, "-shared", "-o", LIB] + objs + [], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return LIB
