@@ -94,6 +94,16 @@ int istnet_conv_gemm(const void *act_hi, const void *act_lo, int B, int H, int W
                      const void *wgt_lo, int Cout, int wgt_cs, int kh, int kw, const float *bias, int relu, float *out_f32,
                      int out_cs, void *out_hi, void *out_lo, int split_cs, int box_w, int box_h, void *stream);
 
+/* Weight gradient of the layer above (cuDNN wgrad in the reference):
+ *   grad_w[co][ci][r][s] = sum_{b,h,w} dy[b,h,w,co] * x[b,h+r-kh/2,w+s-kw/2,ci]       (PyTorch weight layout, FP32)
+ * The pixel sum is split over `ksplit` CTAs per tile (istnet_wgrad_ksplit gives the recommended value);
+ * partial_ws must hold ksplit*kh*kw*Cout*Cin floats.  Deterministic (fixed-order reduction of the partials).
+ * (box_w, box_h): pixel tile with box_w*box_h dividing 64 (images: 8x8; row matrices: 64x1). */
+int istnet_wgrad_ksplit(int B, int H, int W, int Cout, int Cin, int kh, int kw);
+int istnet_conv_wgrad(const void *dy_hi, const void *dy_lo, int dy_cs, const void *x_hi, const void *x_lo, int x_cs, int B, int H,
+                      int W, int Cout, int Cin, int kh, int kw, float *partial_ws, int ksplit, float *grad_w, int box_w, int box_h,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

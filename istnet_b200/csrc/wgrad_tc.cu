@@ -1,0 +1,253 @@
+// Weight gradient of the stride-1 "same" convolutions / 1x1 layers on tcgen05 tensor cores, FP32-accurate.
+//
+//   dW[tap][co][ci] = sum_{pixels p} dY[p][co] * X[p + shift(tap)][ci]
+//
+// GEMM view: M = output channels (128 per CTA), N = input channels (BN <= 256 per CTA), K = pixels.  Both operands
+// are channels-last activations, i.e. "MN-major" for the tensor core: a TMA box of 64 pixels x 64 channels
+// (SWIZZLE_128B, 8 KB) is exactly one canonical MN-major swizzle slab (8-pixel groups 1024 B apart), and
+// consecutive 64-channel slabs sit 8 KB apart (the descriptor's leading-byte-offset).  The tap shift and the
+// zero padding are the TMA coordinates / out-of-bounds fill, exactly as in the forward kernel.
+// Split-bf16 arithmetic as in conv_gemm_tc.cu (dY_lo*X_hi + dY_hi*X_lo + dY_hi*X_hi).
+// K (pixels) is split across CTAs; each CTA writes its FP32 partial tile and a second tiny kernel reduces the
+// partials in a fixed order into the PyTorch weight layout [Cout][Cin][kh][kw] — deterministic, unlike the
+// atomics of the reference's custom grads (SURVEY.md §7 hard part 5).
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kPixTile = 64;                     // pixels per pipeline stage (K of the GEMM)
+constexpr int kSlabBytes = kPixTile * 64 * 2;    // 64 pixels x 64 channels bf16 = 8 KB
+constexpr int kTileM = 128;
+constexpr int kThreads = 192;
+
+struct WgradParams {
+    int B, H, W;
+    int box_w, box_h, box_b;  // box_w*box_h*box_b == 64
+    int tiles_w, tiles_h, tiles_b, num_pix_tiles;
+    int kh, kw;
+    int Cout, Cin, BN;        // BN multiple of 64
+    int n_ci_tiles;
+    int ksplit, stages;
+    float *partial;           // [ksplit][taps][Cout][Cin]
+    uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_constant__ CUtensorMap tm_dy_lo,
+                const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo, const WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int n_slabs_b = p.BN / 64;
+    const int a_bytes = 2 * kSlabBytes;          // 128 output channels = 2 slabs (per hi / lo)
+    const int b_bytes = n_slabs_b * kSlabBytes;
+    const int stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t *empty_bar = full_bar + p.stages;
+    uint64_t *tmem_full_bar = empty_bar + p.stages;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x;
+    const int co0 = (blockIdx.y / p.n_ci_tiles) * kTileM;
+    const int ci0 = (blockIdx.y % p.n_ci_tiles) * p.BN;
+    const int tap = blockIdx.z;
+    const int r = tap / p.kw, s = tap % p.kw;
+    const int per = (p.num_pix_tiles + p.ksplit - 1) / p.ksplit;
+    const int t_begin = split * per;
+    const int t_end = min(p.num_pix_tiles, t_begin + per);
+    const int num_k = max(0, t_end - t_begin);
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tm_dy_hi); tc::prefetch_tmap(&tm_dy_lo); tc::prefetch_tmap(&tm_x_hi); tc::prefetch_tmap(&tm_x_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+        tc::mbar_init(tmem_full_bar, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc(tmem_holder, p.tmem_cols);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int pad_h = p.kh / 2, pad_w = p.kw / 2;
+            for (int it = 0; it < num_k; ++it) {
+                int t = t_begin + it;
+                const int tw = t % p.tiles_w; t /= p.tiles_w;
+                const int th = t % p.tiles_h; t /= p.tiles_h;
+                const int w0 = tw * p.box_w, h0 = th * p.box_h, b0 = t * p.box_b;
+                const int st = it % p.stages;
+                const uint32_t ph = (it / p.stages) & 1;
+                tc::mbar_wait(&empty_bar[st], ph ^ 1);
+                uint8_t *sa = smem + (size_t)st * stage_bytes;
+                tc::mbar_arrive_expect_tx(&full_bar[st], stage_bytes);
+                for (int c = 0; c < 2; ++c) {
+                    tc::tma_load_4d(sa + c * kSlabBytes, &tm_dy_hi, &full_bar[st], co0 + c * 64, w0, h0, b0);
+                    tc::tma_load_4d(sa + a_bytes + c * kSlabBytes, &tm_dy_lo, &full_bar[st], co0 + c * 64, w0, h0, b0);
+                }
+                uint8_t *sb = sa + 2 * a_bytes;
+                for (int c = 0; c < n_slabs_b; ++c) {
+                    tc::tma_load_4d(sb + c * kSlabBytes, &tm_x_hi, &full_bar[st], ci0 + c * 64, w0 + s - pad_w, h0 + r - pad_h, b0);
+                    tc::tma_load_4d(sb + b_bytes + c * kSlabBytes, &tm_x_lo, &full_bar[st], ci0 + c * 64, w0 + s - pad_w, h0 + r - pad_h, b0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(kTileM, p.BN, 1, 1);  // both operands MN-major
+            for (int it = 0; it < num_k; ++it) {
+                const int st = it % p.stages;
+                const uint32_t ph = (it / p.stages) & 1;
+                tc::mbar_wait(&full_bar[st], ph);
+                tc::tc_fence_after();
+                const uint32_t a_hi = tc::smem_u32(smem + (size_t)st * stage_bytes);
+                const uint32_t a_lo = a_hi + a_bytes;
+                const uint32_t b_hi = a_hi + 2 * a_bytes;
+                const uint32_t b_lo = b_hi + b_bytes;
+#pragma unroll
+                for (int j = 0; j < kPixTile / 16; ++j) {  // 16 pixels (k) per MMA = 2 groups of 8 rows x 128 B
+                    const uint32_t off = j * 2048;
+                    const uint64_t dah = tc::make_desc_sw128(a_hi + off, kSlabBytes, 1024);
+                    const uint64_t dal = tc::make_desc_sw128(a_lo + off, kSlabBytes, 1024);
+                    const uint64_t dbh = tc::make_desc_sw128(b_hi + off, kSlabBytes, 1024);
+                    const uint64_t dbl = tc::make_desc_sw128(b_lo + off, kSlabBytes, 1024);
+                    tc::umma_bf16(tmem_base, dal, dbh, idesc, (it | j) != 0);
+                    tc::umma_bf16(tmem_base, dah, dbl, idesc, 1);
+                    tc::umma_bf16(tmem_base, dah, dbh, idesc, 1);
+                }
+                tc::umma_commit(&empty_bar[st]);
+            }
+            tc::umma_commit(tmem_full_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        const int co = co0 + q * 32 + lane;
+        float *dst = p.partial + (((size_t)split * (p.kh * p.kw) + tap) * p.Cout + co) * p.Cin;
+        if (num_k > 0) {
+            tc::mbar_wait(tmem_full_bar, 0);
+            tc::tc_fence_after();
+        }
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            uint32_t v[32];
+            if (num_k > 0) {
+                tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                tc::tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0u;
+            }
+            if (co >= p.Cout) continue;
+            const int ci = ci0 + c0;
+            if (ci >= p.Cin) continue;
+            const int valid = min(32, p.Cin - ci);
+            float *o = dst + ci;
+            if (valid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4 *>(o + i) =
+                        make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            } else {
+                for (int i = 0; i < valid; ++i) o[i] = __uint_as_float(v[i]);
+            }
+        }
+        tc::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// grad_w[co][ci][tap] = sum_split partial[split][tap][co][ci]   (fixed summation order)
+__global__ void wgrad_reduce_kernel(int ksplit, int taps, int Cout, int Cin, const float *__restrict__ partial, float *__restrict__ grad_w) {
+    const long long total = (long long)taps * Cout * Cin;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Cin);
+        const long long rest = i / Cin;
+        const int co = (int)(rest % Cout);
+        const int tap = (int)(rest / Cout);
+        float acc = 0.f;
+        for (int sp = 0; sp < ksplit; ++sp) acc += partial[(size_t)sp * total + i];
+        grad_w[((size_t)co * Cin + ci) * taps + tap] = acc;
+    }
+}
+
+}  // namespace
+
+static int wgrad_pick_bn(int cin) {
+    int bn = (cin + 63) / 64 * 64;
+    return bn > 256 ? 256 : bn;
+}
+
+extern "C" int istnet_wgrad_ksplit(int B, int H, int W, int Cout, int Cin, int kh, int kw) {
+    // enough CTAs to fill the chip ~2x, at least 4 pixel tiles per CTA
+    const int bn = wgrad_pick_bn(Cin);
+    const int base = ceil_div(Cout, kTileM) * ceil_div(Cin, bn) * kh * kw;
+    const long long pix_tiles = ((long long)B * H * W + kPixTile - 1) / kPixTile;
+    int ks = ceil_div(2 * kNumSMs, base);
+    if (ks > pix_tiles / 4) ks = (int)(pix_tiles / 4);
+    if (ks < 1) ks = 1;
+    if (ks > 64) ks = 64;
+    return ks;
+}
+
+extern "C" int istnet_conv_wgrad(const void *dy_hi, const void *dy_lo, int dy_cs, const void *x_hi, const void *x_lo, int x_cs, int B,
+                                 int H, int W, int Cout, int Cin, int kh, int kw, float *partial_ws, int ksplit, float *grad_w,
+                                 int box_w, int box_h, void *stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || ksplit <= 0) return ISTNET_ERR_BAD_ARG;
+    if ((dy_cs & 7) || (x_cs & 7) || dy_cs < Cout || x_cs < Cin) return ISTNET_ERR_BAD_ARG;
+    if (box_w <= 0 || box_h <= 0 || (kPixTile % (box_w * box_h)) != 0) return ISTNET_ERR_BAD_ARG;
+    if ((kh & 1) == 0 || (kw & 1) == 0) return ISTNET_ERR_UNSUPPORTED;
+    WgradParams p{};
+    p.B = B; p.H = H; p.W = W;
+    p.box_w = box_w; p.box_h = box_h; p.box_b = kPixTile / (box_w * box_h);
+    p.tiles_w = ceil_div(W, box_w); p.tiles_h = ceil_div(H, box_h); p.tiles_b = ceil_div(B, p.box_b);
+    p.num_pix_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+    p.kh = kh; p.kw = kw; p.Cout = Cout; p.Cin = Cin;
+    p.BN = wgrad_pick_bn(Cin);
+    p.n_ci_tiles = ceil_div(Cin, p.BN);
+    p.ksplit = ksplit;
+    p.partial = partial_ws;
+    p.tmem_cols = 32;
+    while ((int)p.tmem_cols < p.BN) p.tmem_cols *= 2;
+    const int stage_bytes = 2 * 2 * kSlabBytes + 2 * (p.BN / 64) * kSlabBytes;
+    int max_stages = (225 * 1024 - 1024 - 256) / stage_bytes;
+    if (max_stages > 6) max_stages = 6;
+    const int per = ceil_div(p.num_pix_tiles, ksplit);
+    p.stages = per < max_stages ? per : max_stages;
+    if (p.stages < 1) p.stages = 1;
+    size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+
+    CUtensorMap t_dy_hi, t_dy_lo, t_x_hi, t_x_lo;
+    uint32_t box[4] = {64u, (uint32_t)box_w, (uint32_t)box_h, (uint32_t)p.box_b};
+    {
+        uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        uint64_t str[3] = {(uint64_t)dy_cs * 2, (uint64_t)W * dy_cs * 2, (uint64_t)H * W * dy_cs * 2};
+        int e = istnet_make_tmap_bf16(&t_dy_hi, dy_hi, 4, dims, str, box);
+        if (e) return e;
+        e = istnet_make_tmap_bf16(&t_dy_lo, dy_lo, 4, dims, str, box);
+        if (e) return e;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        uint64_t str[3] = {(uint64_t)x_cs * 2, (uint64_t)W * x_cs * 2, (uint64_t)H * W * x_cs * 2};
+        int e = istnet_make_tmap_bf16(&t_x_hi, x_hi, 4, dims, str, box);
+        if (e) return e;
+        e = istnet_make_tmap_bf16(&t_x_lo, x_lo, 4, dims, str, box);
+        if (e) return e;
+    }
+    ISTNET_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    dim3 grid(ksplit, ceil_div(Cout, kTileM) * p.n_ci_tiles, kh * kw);
+    wgrad_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(t_dy_hi, t_dy_lo, t_x_hi, t_x_lo, p);
+    ISTNET_LAUNCH_CHECK();
+    const long long total = (long long)kh * kw * Cout * Cin;
+    int rgrid = (int)((total + 255) / 256);
+    if (rgrid > kNumSMs * 8) rgrid = kNumSMs * 8;
+    wgrad_reduce_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(ksplit, kh * kw, Cout, Cin, partial_ws, grad_w);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}

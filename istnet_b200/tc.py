@@ -60,3 +60,19 @@ def conv_gemm(act_hi, act_lo, cin, wgt_hi, wgt_lo, cout, kh, kw, bias=None, relu
         ptr(ol) if ol is not None else NULL, c_int(split_cs or 0), c_int(bw), c_int(bh),
     )
     return out, ((oh, ol) if out_split else None)
+
+
+def conv_wgrad(dy_hi, dy_lo, cout, x_hi, x_lo, cin, kh, kw):
+    """dy_{hi,lo}: bf16 [B,H,W,cs_dy]; x_{hi,lo}: bf16 [B,H,W,cs_x] -> grad_w fp32 [cout, cin, kh, kw]"""
+    B, H, W, cs_dy = dy_hi.shape
+    cs_x = x_hi.shape[-1]
+    dev = dy_hi.device
+    ks = _C.lib().istnet_wgrad_ksplit(B, H, W, cout, cin, kh, kw)
+    ws = torch.empty(ks * kh * kw * cout * cin, dtype=torch.float32, device=dev)
+    gw = torch.empty(cout, cin, kh, kw, dtype=torch.float32, device=dev)
+    bw, bh = (64, 1) if H == 1 else (8, 8)
+    _C.call(
+        "conv_wgrad", ptr(dy_hi), ptr(dy_lo), c_int(cs_dy), ptr(x_hi), ptr(x_lo), c_int(cs_x), c_int(B), c_int(H), c_int(W),
+        c_int(cout), c_int(cin), c_int(kh), c_int(kw), ptr(ws), c_int(ks), ptr(gw), c_int(bw), c_int(bh),
+    )
+    return gw
