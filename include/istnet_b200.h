@@ -104,6 +104,60 @@ int istnet_conv_wgrad(const void *dy_hi, const void *dy_lo, int dy_cs, const voi
                       int W, int Cout, int Cin, int kh, int kw, float *partial_ws, int ksplit, float *grad_w, int box_w, int box_h,
                       void *stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * 4. HBM-bound passes between contractions (channels-last FP32 [P pixels][C channels], C % 4 == 0)
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* nn.BatchNorm2d training statistics (resnet.py:129, modules.py:43,65, pytorch_utils.py:53-71): per-channel mean and
+ * 1/sqrt(biased var + eps) over P rows; running stats updated in place with `momentum` (unbiased variance) when the
+ * pointers are non-null.  ws: 2*C doubles of scratch. */
+int istnet_bn_stats(const float *y, long long P, int C, double *ws, float eps, float momentum, float *running_mean,
+                    float *running_var, float *mean, float *invstd, void *stream);
+
+/* z = noise[b,c] * act( bn(y) + bn_res(res) )  written as FP32 and/or as a bf16 (hi,lo) pair (channel stride cs, offset ch_off).
+ * mean==NULL: no BN.  res==NULL: no residual; res_mean==NULL: raw residual.  act: 0 none, 1 ReLU, 2 PReLU(*prelu_a).
+ * noise: Dropout2d scale [B][C] or NULL, b = pixel / HW.  (BasicBlock resnet.py:50-66, PSPUpsample modules.py:37-48) */
+int istnet_bn_act_split(const float *y, long long P, int C, long long HW, const float *mean, const float *invstd, const float *gamma,
+                        const float *beta, const float *res, const float *res_mean, const float *res_invstd, const float *res_gamma,
+                        const float *res_beta, int act, const float *prelu_a, const float *noise, float *out_f32, void *out_hi,
+                        void *out_lo, int cs, int ch_off, void *stream);
+
+/* Backward of the unit above: g = (dz + dz2) * noise * act'(u);  ws[0:C] = sum g, ws[C:2C] = sum g*xhat, ws[2C:3C] = PReLU
+ * slope partials;  dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))  (or g without BN) written as bf16 pair and/or FP32;
+ * g_out (optional) receives g (the residual branch's gradient).  ReLU masks come from the saved forward output z_hi. */
+int istnet_bn_act_bwd(const float *dz, const float *dz2, const float *y, long long P, int C, long long HW, const float *mean,
+                      const float *invstd, const float *gamma, const float *beta, int act, const float *prelu_a, const void *z_hi,
+                      int cs_z, const float *noise, double *ws, void *dy_hi, void *dy_lo, int cs_dy, float *dy_f32, float *g_out,
+                      void *stream);
+
+/* FP32 [P][C] (or NCHW with HW pixels per image when nchw != 0) -> bf16 pair [P][cs] at channel offset ch_off */
+int istnet_split(const float *x, long long P, int C, long long HW, int nchw, void *hi, void *lo, int cs, int ch_off, void *stream);
+/* ws[c] = sum_p x[p][c] (double; bias gradients) */
+int istnet_colsum(const float *x, long long P, int C, double *ws, void *stream);
+
+/* nn.Upsample(scale_factor=2, bilinear, align_corners=True) (modules.py:41) fused with the operand split; and its adjoint */
+int istnet_upsample2x_split(const float *x, int B, int H, int W, int C, void *hi, void *lo, int cs, float *out_f32, void *stream);
+int istnet_upsample2x_bwd(const float *dout, int B, int H, int W, int C, float *dx, void *stream);
+
+/* im2col for the strided convolutions (conv1 7x7/2 resnet.py:127, layer2.0 3x3/2 + 1x1/2 resnet.py:153-180) and its adjoint */
+int istnet_im2col_split(const float *x, int nchw, int B, int H, int W, int C, int kh, int kw, int stride, int pad, void *hi, void *lo,
+                        int cs, void *stream);
+int istnet_col2im(const float *dcol, int B, int H, int W, int C, int kh, int kw, int stride, int pad, float *dx, int accumulate,
+                  void *stream);
+
+/* stem: BN + ReLU + MaxPool2d(3,2,1) in one pass (resnet.py:183-186) and the matching backward to the conv1 output */
+int istnet_bn_relu_maxpool(const float *y, int B, int H, int W, int C, const float *mean, const float *invstd, const float *gamma,
+                           const float *beta, float *out_f32, void *hi, void *lo, int cs, uint8_t *argmax, void *stream);
+int istnet_maxpool_relu_bwd(const float *y, int B, int H, int W, int C, const float *mean, const float *invstd, const float *gamma,
+                            const float *beta, const float *dz, const float *dz2, const uint8_t *argmax, float *g, void *stream);
+
+/* head: BN + PReLU evaluated only at the `choose`d pixels, output in the reference layout (B,C,N) (ist_net.py:42-45) */
+int istnet_gather_bn_prelu(const float *y, int B, long long HW, int C, int N, const long long *choose, const float *mean,
+                           const float *invstd, const float *gamma, const float *beta, const float *prelu_a, float *out, void *stream);
+int istnet_gather_bn_prelu_bwd(const float *y, int B, long long HW, int C, int N, const long long *choose, const float *mean,
+                               const float *invstd, const float *gamma, const float *beta, const float *prelu_a, const float *dout,
+                               float *g_dense, double *slope_ws, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,3 +27,13 @@ __device__ __forceinline__ float sqdist_ref(float dx, float dy, float dz) {
 }
 
 constexpr int kNumSMs = 148;
+
+// FP32 -> bf16 operand pair: hi = bf16(x), lo = bf16(x - hi); x - (hi + lo) <= 2^-18 |x|.
+// (A bf16-hi / fp16-lo pair would leave a 2^-21 residual, but tcgen05.mma kind::f16 rejects mixed A/B formats on
+// sm_100a — measured: "illegal instruction" — so both halves stay bf16.)
+#include <cuda_bf16.h>
+__device__ __forceinline__ void split_hi_lo(float v, unsigned short &hi, unsigned short &lo) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+}

@@ -7,8 +7,8 @@
 //
 // Precision: the 1e-4 relative target rules out single-pass TF32/BF16.  Each FP32 operand x is carried as a
 // bf16 pair (hi = bf16(x), lo = bf16(x - hi), residual <= 2^-18 |x|) and each product is evaluated as
-// hi*hi + hi*lo + lo*hi with FP32 accumulation in TMEM (3 tcgen05.mma per k-step, error ~1e-5 per product
-// before averaging over K) — 3 BF16 passes cost half of what 3xTF32 would.
+// lo*hi + hi*lo + hi*hi with FP32 accumulation in TMEM (3 tcgen05.mma kind::f16 per k-step, error ~3e-6 RMS per
+// product before averaging over K) — 3 BF16 passes cost half of what 3xTF32 would.
 //
 // Structure (one 128 x BN output tile per CTA, 192 threads):
 //   warp 0 : TMA producer  — per (tap, 64-channel block): 2 activation boxes (hi/lo; 4-D map over C,W,H,B with
@@ -101,7 +101,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc_bf16(kTileM, p.BN, 0, 0);
+            const uint32_t id_hh = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 0, 0), id_hl = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 0, 0);
+            const uint32_t id_lh = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 0, 0), id_ll = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 0, 0);
             for (int it = 0; it < num_k; ++it) {
                 const int st = it % p.stages;
                 const uint32_t ph = (it / p.stages) & 1;
@@ -117,9 +118,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                     const uint64_t dal = tc::make_desc_sw128(a_lo + j * 32, 16, 1024);
                     const uint64_t dbh = tc::make_desc_sw128(b_hi + j * 32, 16, 1024);
                     const uint64_t dbl = tc::make_desc_sw128(b_lo + j * 32, 16, 1024);
-                    tc::umma_bf16(tmem_base, dal, dbh, idesc, (it | j) != 0);  // small terms first
-                    tc::umma_bf16(tmem_base, dah, dbl, idesc, 1);
-                    tc::umma_bf16(tmem_base, dah, dbh, idesc, 1);
+                    tc::umma_bf16(tmem_base, dal, dbh, id_lh, (it | j) != 0);  // small terms first
+                    tc::umma_bf16(tmem_base, dah, dbl, id_hl, 1);
+                    tc::umma_bf16(tmem_base, dah, dbh, id_hh, 1);
                 }
                 tc::umma_commit(&empty_bar[st]);  // frees the smem stage once these MMAs retire
             }
@@ -171,20 +172,21 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                         uint32_t hh[4], ll[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            __nv_bfloat16 h0_ = __float2bfloat16_rn(f[i + 2 * k]), h1_ = __float2bfloat16_rn(f[i + 2 * k + 1]);
-                            __nv_bfloat16 l0_ = __float2bfloat16_rn(f[i + 2 * k] - __bfloat162float(h0_));
-                            __nv_bfloat16 l1_ = __float2bfloat16_rn(f[i + 2 * k + 1] - __bfloat162float(h1_));
-                            hh[k] = (uint32_t)__bfloat16_as_ushort(h0_) | ((uint32_t)__bfloat16_as_ushort(h1_) << 16);
-                            ll[k] = (uint32_t)__bfloat16_as_ushort(l0_) | ((uint32_t)__bfloat16_as_ushort(l1_) << 16);
+                            unsigned short h0_, h1_, l0_, l1_;
+                            split_hi_lo(f[i + 2 * k], h0_, l0_);
+                            split_hi_lo(f[i + 2 * k + 1], h1_, l1_);
+                            hh[k] = (uint32_t)h0_ | ((uint32_t)h1_ << 16);
+                            ll[k] = (uint32_t)l0_ | ((uint32_t)l1_ << 16);
                         }
                         *reinterpret_cast<uint4 *>(oh + i) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
                         *reinterpret_cast<uint4 *>(ol + i) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
                     }
                 } else {
                     for (int i = 0; i < valid; ++i) {
-                        __nv_bfloat16 hv = __float2bfloat16_rn(f[i]);
-                        oh[i] = hv;
-                        ol[i] = __float2bfloat16_rn(f[i] - __bfloat162float(hv));
+                        unsigned short hv, lv;
+                        split_hi_lo(f[i], hv, lv);
+                        oh[i] = __ushort_as_bfloat16(hv);
+                        ol[i] = __ushort_as_bfloat16(lv);
                     }
                 }
             }

@@ -1,0 +1,632 @@
+// HBM-bound companions of the tensor-core kernels: everything between two contractions of the image branch /
+// per-point MLPs is fused into ONE pass per tensor — BatchNorm statistics, BN-apply + residual + ReLU/PReLU +
+// Dropout2d scale + split into the bf16 (hi, lo) operand pair, bilinear x2 up-sampling straight into the operand
+// pair, BN backward (reduce + apply + split), im2col for the few strided convolutions, the stem max-pool.
+// All tensors are channels-last [P pixels][C channels] FP32 (C % 4 == 0, float4 accesses, a warp reads 512
+// contiguous bytes); bf16 pairs have a channel stride `cs` (multiple of 8) and a channel offset.
+//
+// Reference call sites replaced: nn.BatchNorm2d (resnet.py:40-46,129; modules.py:43,65), ReLU/PReLU, Dropout2d
+// (modules.py:56,62), nn.Upsample x2 align_corners=True (modules.py:41), MaxPool2d(3,2,1) (resnet.py:131),
+// torch.gather of pixel features (ist_net.py:42-45) and their autograd backward formulas.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kEwThreads = 256;
+
+__device__ __forceinline__ void split_store4(__nv_bfloat16 *hi, __nv_bfloat16 *lo, float4 v) {
+    unsigned short h0, h1, h2, h3, l0, l1, l2, l3;
+    split_hi_lo(v.x, h0, l0); split_hi_lo(v.y, h1, l1); split_hi_lo(v.z, h2, l2); split_hi_lo(v.w, h3, l3);
+    uint2 ph, pl;
+    ph.x = (uint32_t)h0 | ((uint32_t)h1 << 16);
+    ph.y = (uint32_t)h2 | ((uint32_t)h3 << 16);
+    pl.x = (uint32_t)l0 | ((uint32_t)l1 << 16);
+    pl.y = (uint32_t)l2 | ((uint32_t)l3 << 16);
+    *reinterpret_cast<uint2 *>(hi) = ph;
+    *reinterpret_cast<uint2 *>(lo) = pl;
+}
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ float4 bf4_to_f4(const __nv_bfloat16 *p) {
+    uint2 r = *reinterpret_cast<const uint2 *>(p);
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                       __uint_as_float(r.y & 0xffff0000u));
+}
+
+struct BnP {           // per-channel BatchNorm parameters (null mean => identity)
+    const float *mean, *invstd, *gamma, *beta;
+};
+__device__ __forceinline__ float4 bn4(float4 y, const BnP &b, int c) {
+    if (!b.mean) return y;
+    float4 m = ld4(b.mean + c), s = ld4(b.invstd + c), g = ld4(b.gamma + c), be = ld4(b.beta + c);
+    // same operation order as ATen's batch_norm transform: (x - mean) * invstd * weight + bias
+    return make_float4((y.x - m.x) * s.x * g.x + be.x, (y.y - m.y) * s.y * g.y + be.y, (y.z - m.z) * s.z * g.z + be.z,
+                       (y.w - m.w) * s.w * g.w + be.w);
+}
+
+// ------------------------------------------------------------------ per-channel reductions
+// Each thread owns 4 channels (float4) of rows r = row0 + i*rows_per_iter; partial sums are combined through shared
+// memory and flushed with double atomics (one per channel per CTA).
+template <int NACC, typename F>
+__device__ void column_reduce(long long P, int C, double *ws, F row_fn) {
+    const int lanes = C >> 2;  // float4 lanes per row
+    __shared__ float red[kEwThreads * 4];
+    float acc[NACC][4];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
+    if (lanes <= kEwThreads) {
+        const int rows_per_iter = kEwThreads / lanes;
+        const int cv = threadIdx.x % lanes, rr = threadIdx.x / lanes;
+        if (rr < rows_per_iter) {
+            for (long long r = (long long)blockIdx.x * rows_per_iter + rr; r < P; r += (long long)gridDim.x * rows_per_iter) row_fn(r, cv * 4, acc);
+        }
+        for (int a = 0; a < NACC; ++a) {
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) red[threadIdx.x * 4 + k] = (rr < rows_per_iter) ? acc[a][k] : 0.f;
+            __syncthreads();
+            if (threadIdx.x < lanes) {
+                for (int k = 0; k < 4; ++k) {
+                    float s = 0.f;
+                    for (int q = 0; q < rows_per_iter; ++q) s += red[(q * lanes + threadIdx.x) * 4 + k];
+                    atomicAdd(ws + (size_t)a * C + threadIdx.x * 4 + k, (double)s);
+                }
+            }
+        }
+    } else {
+        for (int cv = threadIdx.x; cv < lanes; cv += kEwThreads) {
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
+            for (long long r = blockIdx.x; r < P; r += gridDim.x) row_fn(r, cv * 4, acc);
+            for (int a = 0; a < NACC; ++a)
+                for (int k = 0; k < 4; ++k) atomicAdd(ws + (size_t)a * C + cv * 4 + k, (double)acc[a][k]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const float *__restrict__ y, long long P, int C, double *ws) {
+    column_reduce<2>(P, C, ws, [&](long long r, int c, float (*acc)[4]) {
+        float4 v = ld4(y + r * C + c);
+        acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
+        acc[1][0] += v.x * v.x; acc[1][1] += v.y * v.y; acc[1][2] += v.z * v.z; acc[1][3] += v.w * v.w;
+    });
+}
+
+__global__ void bn_finalize_kernel(const double *__restrict__ ws, long long P, int C, float eps, float momentum, float *running_mean,
+                                   float *running_var, float *mean, float *invstd) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double m = ws[c] / (double)P;
+    double var = ws[C + c] / (double)P - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        double unbiased = P > 1 ? var * (double)P / (double)(P - 1) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+    }
+}
+
+// ------------------------------------------------------------------ forward: BN + residual + act + noise + split
+struct ActFwdP {
+    const float *y;         // [P,C]
+    BnP bn;
+    const float *res;       // optional residual [P,C] (raw, or pre-BN if res_bn.mean != null)
+    BnP res_bn;
+    int act;                // 0 none, 1 relu, 2 prelu
+    const float *prelu_a;   // scalar
+    const float *noise;     // optional [B,C] Dropout2d scale
+    long long HW;
+    float *out_f32;         // optional [P,C]
+    __nv_bfloat16 *out_hi, *out_lo;  // optional [P,cs] (+ch_off)
+    int cs, ch_off;
+};
+__device__ __forceinline__ float4 act_fwd4(float4 u, int act, float a) {
+    if (act == 1) return make_float4(fmaxf(u.x, 0.f), fmaxf(u.y, 0.f), fmaxf(u.z, 0.f), fmaxf(u.w, 0.f));
+    if (act == 2) return make_float4(u.x > 0.f ? u.x : a * u.x, u.y > 0.f ? u.y : a * u.y, u.z > 0.f ? u.z : a * u.z, u.w > 0.f ? u.w : a * u.w);
+    return u;
+}
+__global__ void __launch_bounds__(kEwThreads) bn_act_split_kernel(long long P, int C, ActFwdP p) {
+    const int lanes = C >> 2;
+    const long long total = P * lanes;
+    const float a = (p.act == 2) ? *p.prelu_a : 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / lanes;
+        const int c = (int)(i % lanes) * 4;
+        float4 u = bn4(ld4(p.y + r * C + c), p.bn, c);
+        if (p.res) {
+            float4 rv = bn4(ld4(p.res + r * C + c), p.res_bn, c);
+            u.x += rv.x; u.y += rv.y; u.z += rv.z; u.w += rv.w;
+        }
+        float4 z = act_fwd4(u, p.act, a);
+        if (p.noise) {
+            float4 nz = ld4(p.noise + (r / p.HW) * C + c);
+            z.x *= nz.x; z.y *= nz.y; z.z *= nz.z; z.w *= nz.w;
+        }
+        if (p.out_f32) *reinterpret_cast<float4 *>(p.out_f32 + r * C + c) = z;
+        if (p.out_hi) split_store4(p.out_hi + r * p.cs + p.ch_off + c, p.out_lo + r * p.cs + p.ch_off + c, z);
+    }
+}
+
+// ------------------------------------------------------------------ backward: g = (dz1+dz2)*noise*act'(u); BN backward
+struct ActBwdP {
+    const float *dz, *dz2;  // [P,C] (+ optional second gradient stream)
+    const float *y;         // conv output (pre-BN) [P,C]; needed for BN / PReLU
+    BnP bn;
+    int act;
+    const float *prelu_a;
+    const __nv_bfloat16 *z_hi;  // ReLU mask source (saved forward output), [P,cs_z]
+    int cs_z;
+    const float *noise;
+    long long HW;
+};
+// returns g (gradient w.r.t. u = bn(y) [+res]) and xhat; extra = dz*noise*u*[u<=0] (PReLU slope gradient)
+__device__ __forceinline__ void act_bwd4(const ActBwdP &p, long long r, int c, int C, float a, float4 &g, float4 &xh, float4 &extra) {
+    float4 d = ld4(p.dz + r * C + c);
+    if (p.dz2) {
+        float4 d2 = ld4(p.dz2 + r * C + c);
+        d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
+    }
+    if (p.noise) {
+        float4 nz = ld4(p.noise + (r / p.HW) * C + c);
+        d.x *= nz.x; d.y *= nz.y; d.z *= nz.z; d.w *= nz.w;
+    }
+    xh = make_float4(0.f, 0.f, 0.f, 0.f);
+    extra = xh;
+    float4 u = xh;
+    if (p.bn.mean) {
+        float4 yv = ld4(p.y + r * C + c), m = ld4(p.bn.mean + c), s = ld4(p.bn.invstd + c);
+        xh = make_float4((yv.x - m.x) * s.x, (yv.y - m.y) * s.y, (yv.z - m.z) * s.z, (yv.w - m.w) * s.w);
+        if (p.act == 2) {
+            float4 ga = ld4(p.bn.gamma + c), be = ld4(p.bn.beta + c);
+            u = make_float4(xh.x * ga.x + be.x, xh.y * ga.y + be.y, xh.z * ga.z + be.z, xh.w * ga.w + be.w);
+        }
+    } else if (p.act == 2) {
+        u = ld4(p.y + r * C + c);
+    }
+    if (p.act == 1) {
+        float4 z = bf4_to_f4(p.z_hi + r * p.cs_z + c);
+        g = make_float4(z.x > 0.f ? d.x : 0.f, z.y > 0.f ? d.y : 0.f, z.z > 0.f ? d.z : 0.f, z.w > 0.f ? d.w : 0.f);
+    } else if (p.act == 2) {
+        g = make_float4(u.x > 0.f ? d.x : a * d.x, u.y > 0.f ? d.y : a * d.y, u.z > 0.f ? d.z : a * d.z, u.w > 0.f ? d.w : a * d.w);
+        extra = make_float4(u.x > 0.f ? 0.f : d.x * u.x, u.y > 0.f ? 0.f : d.y * u.y, u.z > 0.f ? 0.f : d.z * u.z, u.w > 0.f ? 0.f : d.w * u.w);
+    } else {
+        g = d;
+    }
+}
+// ws[0:C] = sum g, ws[C:2C] = sum g*xhat, ws[2C:3C] = PReLU slope partial
+__global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(long long P, int C, ActBwdP p, double *ws) {
+    const float a = (p.act == 2) ? *p.prelu_a : 0.f;
+    column_reduce<3>(P, C, ws, [&](long long r, int c, float (*acc)[4]) {
+        float4 g, xh, ex;
+        act_bwd4(p, r, c, C, a, g, xh, ex);
+        acc[0][0] += g.x; acc[0][1] += g.y; acc[0][2] += g.z; acc[0][3] += g.w;
+        acc[1][0] += g.x * xh.x; acc[1][1] += g.y * xh.y; acc[1][2] += g.z * xh.z; acc[1][3] += g.w * xh.w;
+        acc[2][0] += ex.x; acc[2][1] += ex.y; acc[2][2] += ex.z; acc[2][3] += ex.w;
+    });
+}
+// dy = gamma*invstd*(g - sum_g/P - xhat*sum_gx/P)  (BN)   or   dy = g   (no BN);  dy -> bf16 pair (+ optional FP32 copies)
+__global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(long long P, int C, ActBwdP p, const double *__restrict__ ws,
+                                                                  __nv_bfloat16 *dy_hi, __nv_bfloat16 *dy_lo, int cs_dy, float *dy_f32,
+                                                                  float *g_out) {
+    const int lanes = C >> 2;
+    const long long total = P * lanes;
+    const float a = (p.act == 2) ? *p.prelu_a : 0.f;
+    const double invP = 1.0 / (double)P;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / lanes;
+        const int c = (int)(i % lanes) * 4;
+        float4 g, xh, ex;
+        act_bwd4(p, r, c, C, a, g, xh, ex);
+        if (g_out) *reinterpret_cast<float4 *>(g_out + r * C + c) = g;
+        float4 dy = g;
+        if (p.bn.mean) {
+            float4 s = ld4(p.bn.invstd + c), ga = ld4(p.bn.gamma + c);
+            float mg[4], mgx[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { mg[k] = (float)(ws[c + k] * invP); mgx[k] = (float)(ws[C + c + k] * invP); }
+            dy.x = ga.x * s.x * (g.x - mg[0] - xh.x * mgx[0]);
+            dy.y = ga.y * s.y * (g.y - mg[1] - xh.y * mgx[1]);
+            dy.z = ga.z * s.z * (g.z - mg[2] - xh.z * mgx[2]);
+            dy.w = ga.w * s.w * (g.w - mg[3] - xh.w * mgx[3]);
+        }
+        if (dy_hi) split_store4(dy_hi + r * cs_dy + c, dy_lo + r * cs_dy + c, dy);
+        if (dy_f32) *reinterpret_cast<float4 *>(dy_f32 + r * C + c) = dy;
+    }
+}
+
+// ------------------------------------------------------------------ generic FP32 -> bf16 pair (optionally NCHW -> NHWC), column sums
+__global__ void __launch_bounds__(kEwThreads) split_kernel(long long P, int C, const float *__restrict__ x, long long HW, int nchw,
+                                                           __nv_bfloat16 *hi, __nv_bfloat16 *lo, int cs, int ch_off) {
+    const long long total = P * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / C;
+        const int c = (int)(i % C);
+        float v = nchw ? x[((r / HW) * C + c) * HW + (r % HW)] : x[i];
+        unsigned short hv, lv;
+        split_hi_lo(v, hv, lv);
+        hi[r * cs + ch_off + c] = __ushort_as_bfloat16(hv);
+        lo[r * cs + ch_off + c] = __ushort_as_bfloat16(lv);
+    }
+}
+__global__ void __launch_bounds__(kEwThreads) colsum_kernel(const float *__restrict__ x, long long P, int C, double *ws) {
+    column_reduce<1>(P, C, ws, [&](long long r, int c, float (*acc)[4]) {
+        float4 v = ld4(x + r * C + c);
+        acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
+    });
+}
+
+// ------------------------------------------------------------------ bilinear x2, align_corners=True (modules.py:41)
+__device__ __forceinline__ void up_src(int o, int in, int out, int &i0, int &i1, float &l0, float &l1) {
+    // ATen area_pixel_compute_source_index(align_corners=True): src = scale*dst, scale = (in-1)/(out-1)
+    const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    const float s = scale * (float)o;
+    i0 = (int)s;
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    l1 = s - (float)i0;
+    l0 = 1.f - l1;
+}
+__global__ void __launch_bounds__(kEwThreads) upsample2x_split_kernel(int B, int H, int W, int C, const float *__restrict__ x,
+                                                                       __nv_bfloat16 *hi, __nv_bfloat16 *lo, int cs, float *out_f32) {
+    const int lanes = C >> 2, Ho = 2 * H, Wo = 2 * W;
+    const long long total = (long long)B * Ho * Wo * lanes;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % lanes) * 4;
+        long long r = i / lanes;
+        const int wo = (int)(r % Wo); r /= Wo;
+        const int ho = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        int h0, h1, w0, w1;
+        float hl0, hl1, wl0, wl1;
+        up_src(ho, H, Ho, h0, h1, hl0, hl1);
+        up_src(wo, W, Wo, w0, w1, wl0, wl1);
+        const float *base = x + (size_t)b * H * W * C + c;
+        float4 a = ld4(base + ((size_t)h0 * W + w0) * C), bq = ld4(base + ((size_t)h0 * W + w1) * C);
+        float4 cq = ld4(base + ((size_t)h1 * W + w0) * C), d = ld4(base + ((size_t)h1 * W + w1) * C);
+        float4 o;
+        o.x = hl0 * (wl0 * a.x + wl1 * bq.x) + hl1 * (wl0 * cq.x + wl1 * d.x);
+        o.y = hl0 * (wl0 * a.y + wl1 * bq.y) + hl1 * (wl0 * cq.y + wl1 * d.y);
+        o.z = hl0 * (wl0 * a.z + wl1 * bq.z) + hl1 * (wl0 * cq.z + wl1 * d.z);
+        o.w = hl0 * (wl0 * a.w + wl1 * bq.w) + hl1 * (wl0 * cq.w + wl1 * d.w);
+        const size_t op = ((size_t)b * Ho + ho) * Wo + wo;
+        if (hi) split_store4(hi + op * cs + c, lo + op * cs + c, o);
+        if (out_f32) *reinterpret_cast<float4 *>(out_f32 + op * C + c) = o;
+    }
+}
+// gather form of the adjoint: dx[b,h,w,:] = sum over the output pixels that read (h,w)
+__global__ void __launch_bounds__(kEwThreads) upsample2x_bwd_kernel(int B, int H, int W, int C, const float *__restrict__ dout, float *dx) {
+    const int lanes = C >> 2, Ho = 2 * H, Wo = 2 * W;
+    const long long total = (long long)B * H * W * lanes;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % lanes) * 4;
+        long long r = i / lanes;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int b = (int)(r / H);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // candidate outputs: src in (h-1, h+1)  =>  o in ((h-1)*(Ho-1)/(H-1), (h+1)*(Ho-1)/(H-1)); scan a safe window
+        const int ho_lo = max(0, 2 * h - 3), ho_hi = min(Ho - 1, 2 * h + 3);
+        const int wo_lo = max(0, 2 * w - 3), wo_hi = min(Wo - 1, 2 * w + 3);
+        for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+            int h0, h1; float hl0, hl1;
+            up_src(ho, H, Ho, h0, h1, hl0, hl1);
+            float wh = (h0 == h ? hl0 : 0.f) + (h1 == h ? hl1 : 0.f);
+            if (wh == 0.f) continue;
+            for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+                int w0, w1; float wl0, wl1;
+                up_src(wo, W, Wo, w0, w1, wl0, wl1);
+                float ww = (w0 == w ? wl0 : 0.f) + (w1 == w ? wl1 : 0.f);
+                if (ww == 0.f) continue;
+                float4 d = ld4(dout + (((size_t)b * Ho + ho) * Wo + wo) * C + c);
+                const float k = wh * ww;
+                acc.x += k * d.x; acc.y += k * d.y; acc.z += k * d.z; acc.w += k * d.w;
+            }
+        }
+        *reinterpret_cast<float4 *>(dx + i * 4) = acc;
+    }
+}
+
+// ------------------------------------------------------------------ im2col (strided convs) and its adjoint
+// out[b,ho,wo,(r*kw+s)*C + c] = x[b, ho*stride+r-pad, wo*stride+s-pad, c]   (zero outside); x NHWC or NCHW
+__global__ void __launch_bounds__(kEwThreads) im2col_split_kernel(int B, int H, int W, int C, int kh, int kw, int stride, int pad, int Ho,
+                                                                   int Wo, const float *__restrict__ x, int nchw, __nv_bfloat16 *hi,
+                                                                   __nv_bfloat16 *lo, int cs) {
+    const int K = kh * kw * C;
+    const long long total = (long long)B * Ho * Wo * K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % K);
+        long long r = i / K;
+        const int wo = (int)(r % Wo); r /= Wo;
+        const int ho = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        const int c = k % C, tap = k / C;
+        const int h = ho * stride + tap / kw - pad, w = wo * stride + tap % kw - pad;
+        float v = 0.f;
+        if (h >= 0 && h < H && w >= 0 && w < W) v = nchw ? x[(((size_t)b * C + c) * H + h) * W + w] : x[(((size_t)b * H + h) * W + w) * C + c];
+        const size_t o = (((size_t)b * Ho + ho) * Wo + wo) * cs + k;
+        unsigned short hv, lv;
+        split_hi_lo(v, hv, lv);
+        hi[o] = __ushort_as_bfloat16(hv);
+        lo[o] = __ushort_as_bfloat16(lv);
+    }
+}
+// dx[b,h,w,c] (+)= sum over (r,s) with (h+pad-r) % stride == 0 ... of dcol[b,ho,wo,(r*kw+s)*C+c]
+__global__ void __launch_bounds__(kEwThreads) col2im_kernel(int B, int H, int W, int C, int kh, int kw, int stride, int pad, int Ho, int Wo,
+                                                            const float *__restrict__ dcol, float *dx, int accumulate) {
+    const int K = kh * kw * C;
+    const long long total = (long long)B * H * W * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long r = i / C;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int b = (int)(r / H);
+        float acc = 0.f;
+        for (int rr = 0; rr < kh; ++rr) {
+            const int hn = h + pad - rr;
+            if (hn < 0 || hn % stride) continue;
+            const int ho = hn / stride;
+            if (ho >= Ho) continue;
+            for (int ss = 0; ss < kw; ++ss) {
+                const int wn = w + pad - ss;
+                if (wn < 0 || wn % stride) continue;
+                const int wo = wn / stride;
+                if (wo >= Wo) continue;
+                acc += dcol[(((size_t)b * Ho + ho) * Wo + wo) * K + (rr * kw + ss) * C + c];
+            }
+        }
+        dx[i] = accumulate ? dx[i] + acc : acc;
+    }
+}
+
+// ------------------------------------------------------------------ stem: BN + ReLU + MaxPool(3,2,1) fused
+__global__ void __launch_bounds__(kEwThreads) bn_relu_maxpool_kernel(int B, int H, int W, int C, const float *__restrict__ y, BnP bn,
+                                                                      float *out_f32, __nv_bfloat16 *hi, __nv_bfloat16 *lo, int cs,
+                                                                      uint8_t *argmax) {
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1, lanes = C >> 2;
+    const long long total = (long long)B * Ho * Wo * lanes;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % lanes) * 4;
+        long long r = i / lanes;
+        const int wo = (int)(r % Wo); r /= Wo;
+        const int ho = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int bi[4] = {0, 0, 0, 0};
+        for (int rr = 0; rr < 3; ++rr) {
+            const int h = 2 * ho - 1 + rr;
+            if (h < 0 || h >= H) continue;
+            for (int ss = 0; ss < 3; ++ss) {
+                const int w = 2 * wo - 1 + ss;
+                if (w < 0 || w >= W) continue;
+                float4 u = bn4(ld4(y + (((size_t)b * H + h) * W + w) * C + c), bn, c);
+                float v[4] = {fmaxf(u.x, 0.f), fmaxf(u.y, 0.f), fmaxf(u.z, 0.f), fmaxf(u.w, 0.f)};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (v[k] > best[k]) { best[k] = v[k]; bi[k] = rr * 3 + ss; }
+            }
+        }
+        const size_t op = ((size_t)b * Ho + ho) * Wo + wo;
+        float4 z = make_float4(best[0], best[1], best[2], best[3]);
+        if (out_f32) *reinterpret_cast<float4 *>(out_f32 + op * C + c) = z;
+        if (hi) split_store4(hi + op * cs + c, lo + op * cs + c, z);
+        *reinterpret_cast<uchar4 *>(argmax + op * C + c) = make_uchar4((uint8_t)bi[0], (uint8_t)bi[1], (uint8_t)bi[2], (uint8_t)bi[3]);
+    }
+}
+// g[b,h,w,c] = relu'(bn(y)) * sum over pooled windows whose argmax is (h,w) of (dz1+dz2)
+__global__ void __launch_bounds__(kEwThreads) maxpool_relu_bwd_kernel(int B, int H, int W, int C, const float *__restrict__ y, BnP bn,
+                                                                       const float *__restrict__ dz, const float *__restrict__ dz2,
+                                                                       const uint8_t *__restrict__ argmax, float *g) {
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long long total = (long long)B * H * W * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long r = i / C;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int b = (int)(r / H);
+        float acc = 0.f;
+        for (int ho = max(0, (h - 1 + 1) / 2); ho <= min(Ho - 1, (h + 1) / 2); ++ho) {
+            const int rr = h - (2 * ho - 1);
+            if (rr < 0 || rr > 2) continue;
+            for (int wo = max(0, w / 2); wo <= min(Wo - 1, (w + 1) / 2); ++wo) {
+                const int ss = w - (2 * wo - 1);
+                if (ss < 0 || ss > 2) continue;
+                const size_t op = (((size_t)b * Ho + ho) * Wo + wo) * C + c;
+                if (argmax[op] == rr * 3 + ss) acc += dz[op] + (dz2 ? dz2[op] : 0.f);
+            }
+        }
+        float yv = y[i];
+        float u = bn.mean ? (yv - bn.mean[c]) * bn.invstd[c] * bn.gamma[c] + bn.beta[c] : yv;
+        g[i] = u > 0.f ? acc : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------ final head: BN + PReLU only at the chosen pixels
+// out[b,c,n] = prelu(bn(y[b, choose[b,n], c]))   (ist_net.py:42-45 gather after modules.py:64-66)
+__global__ void __launch_bounds__(kEwThreads) gather_bn_prelu_kernel(int B, long long HW, int C, int N, const float *__restrict__ y,
+                                                                      const long long *__restrict__ choose, BnP bn, const float *prelu_a,
+                                                                      float *out) {
+    const float a = prelu_a ? *prelu_a : 1.f;
+    const long long total = (long long)B * N * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long long bn_ = i / C;
+        const int n = (int)(bn_ % N);
+        const int b = (int)(bn_ / N);
+        const long long px = choose[(long long)b * N + n];
+        float yv = y[((long long)b * HW + px) * C + c];
+        float u = bn.mean ? (yv - bn.mean[c]) * bn.invstd[c] * bn.gamma[c] + bn.beta[c] : yv;
+        out[((long long)b * C + c) * N + n] = u > 0.f ? u : a * u;
+    }
+}
+// g_dense[b, choose[b,n], c] += dout[b,c,n] * prelu'(u);  slope_ws[c] += dout*u*[u<=0]   (g_dense pre-zeroed)
+__global__ void __launch_bounds__(kEwThreads) gather_bn_prelu_bwd_kernel(int B, long long HW, int C, int N, const float *__restrict__ y,
+                                                                          const long long *__restrict__ choose, BnP bn, const float *prelu_a,
+                                                                          const float *__restrict__ dout, float *g_dense, double *slope_ws) {
+    const float a = prelu_a ? *prelu_a : 1.f;
+    const long long total = (long long)B * N * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long long bn_ = i / C;
+        const int n = (int)(bn_ % N);
+        const int b = (int)(bn_ / N);
+        const long long px = choose[(long long)b * N + n];
+        const long long src = ((long long)b * HW + px) * C + c;
+        float yv = y[src];
+        float u = bn.mean ? (yv - bn.mean[c]) * bn.invstd[c] * bn.gamma[c] + bn.beta[c] : yv;
+        float d = dout[((long long)b * C + c) * N + n];
+        atomicAdd(g_dense + src, u > 0.f ? d : a * d);
+        if (!(u > 0.f) && slope_ws) atomicAdd(slope_ws + c, (double)(d * u));
+    }
+}
+
+inline int ew_grid(long long total) {
+    long long g = (total + kEwThreads - 1) / kEwThreads;
+    long long cap = (long long)kNumSMs * 8;
+    return (int)(g < 1 ? 1 : (g < cap ? g : cap));
+}
+inline int red_grid(long long P, int C) {
+    int lanes = C / 4;
+    int rows_per_iter = lanes <= kEwThreads ? kEwThreads / lanes : 1;
+    long long g = (P + rows_per_iter - 1) / rows_per_iter;
+    long long cap = (long long)kNumSMs * 4;
+    return (int)(g < 1 ? 1 : (g < cap ? g : cap));
+}
+inline BnP make_bn(const float *mean, const float *invstd, const float *gamma, const float *beta) { return BnP{mean, invstd, gamma, beta}; }
+
+}  // namespace
+
+#define ST ((cudaStream_t)stream)
+
+extern "C" int istnet_bn_stats(const float *y, long long P, int C, double *ws, float eps, float momentum, float *running_mean,
+                               float *running_var, float *mean, float *invstd, void *stream) {
+    if (P <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
+    ISTNET_CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, ST));
+    bn_stats_kernel<<<red_grid(P, C), kEwThreads, 0, ST>>>(y, P, C, ws);
+    ISTNET_LAUNCH_CHECK();
+    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, ST>>>(ws, P, C, eps, momentum, running_mean, running_var, mean, invstd);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+
+extern "C" int istnet_bn_act_split(const float *y, long long P, int C, long long HW, const float *mean, const float *invstd,
+                                   const float *gamma, const float *beta, const float *res, const float *res_mean,
+                                   const float *res_invstd, const float *res_gamma, const float *res_beta, int act, const float *prelu_a,
+                                   const float *noise, float *out_f32, void *out_hi, void *out_lo, int cs, int ch_off, void *stream) {
+    if (P <= 0 || C <= 0 || (C & 3) || (out_hi && ((cs & 3) || (ch_off & 3)))) return ISTNET_ERR_BAD_ARG;
+    ActFwdP p{};
+    p.y = y; p.bn = make_bn(mean, invstd, gamma, beta);
+    p.res = res; p.res_bn = make_bn(res_mean, res_invstd, res_gamma, res_beta);
+    p.act = act; p.prelu_a = prelu_a; p.noise = noise; p.HW = HW > 0 ? HW : 1;
+    p.out_f32 = out_f32; p.out_hi = (__nv_bfloat16 *)out_hi; p.out_lo = (__nv_bfloat16 *)out_lo; p.cs = cs; p.ch_off = ch_off;
+    bn_act_split_kernel<<<ew_grid(P * (C / 4)), kEwThreads, 0, ST>>>(P, C, p);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+
+extern "C" int istnet_bn_act_bwd(const float *dz, const float *dz2, const float *y, long long P, int C, long long HW, const float *mean,
+                                 const float *invstd, const float *gamma, const float *beta, int act, const float *prelu_a,
+                                 const void *z_hi, int cs_z, const float *noise, double *ws /*3C*/, void *dy_hi, void *dy_lo, int cs_dy,
+                                 float *dy_f32, float *g_out, void *stream) {
+    if (P <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
+    if (act == 1 && !z_hi) return ISTNET_ERR_BAD_ARG;
+    ActBwdP p{};
+    p.dz = dz; p.dz2 = dz2; p.y = y; p.bn = make_bn(mean, invstd, gamma, beta);
+    p.act = act; p.prelu_a = prelu_a; p.z_hi = (const __nv_bfloat16 *)z_hi; p.cs_z = cs_z; p.noise = noise; p.HW = HW > 0 ? HW : 1;
+    ISTNET_CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(double) * 3 * C, ST));
+    bn_bwd_reduce_kernel<<<red_grid(P, C), kEwThreads, 0, ST>>>(P, C, p, ws);
+    ISTNET_LAUNCH_CHECK();
+    bn_bwd_apply_kernel<<<ew_grid(P * (C / 4)), kEwThreads, 0, ST>>>(P, C, p, ws, (__nv_bfloat16 *)dy_hi, (__nv_bfloat16 *)dy_lo, cs_dy,
+                                                                     dy_f32, g_out);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+
+extern "C" int istnet_split(const float *x, long long P, int C, long long HW, int nchw, void *hi, void *lo, int cs, int ch_off, void *stream) {
+    if (P <= 0 || C <= 0) return ISTNET_ERR_BAD_ARG;
+    split_kernel<<<ew_grid(P * C), kEwThreads, 0, ST>>>(P, C, x, HW > 0 ? HW : 1, nchw, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, cs, ch_off);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+
+extern "C" int istnet_colsum(const float *x, long long P, int C, double *ws, void *stream) {
+    if (P <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
+    ISTNET_CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(double) * C, ST));
+    colsum_kernel<<<red_grid(P, C), kEwThreads, 0, ST>>>(x, P, C, ws);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+
+extern "C" int istnet_upsample2x_split(const float *x, int B, int H, int W, int C, void *hi, void *lo, int cs, float *out_f32, void *stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
+    upsample2x_split_kernel<<<ew_grid((long long)B * 4 * H * W * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, x, (__nv_bfloat16 *)hi,
+                                                                                               (__nv_bfloat16 *)lo, cs, out_f32);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+extern "C" int istnet_upsample2x_bwd(const float *dout, int B, int H, int W, int C, float *dx, void *stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
+    upsample2x_bwd_kernel<<<ew_grid((long long)B * H * W * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, dout, dx);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+
+extern "C" int istnet_im2col_split(const float *x, int nchw, int B, int H, int W, int C, int kh, int kw, int stride, int pad, void *hi,
+                                   void *lo, int cs, void *stream) {
+    const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+    if (B <= 0 || Ho <= 0 || Wo <= 0 || cs < kh * kw * C) return ISTNET_ERR_BAD_ARG;
+    im2col_split_kernel<<<ew_grid((long long)B * Ho * Wo * kh * kw * C), kEwThreads, 0, ST>>>(B, H, W, C, kh, kw, stride, pad, Ho, Wo, x, nchw,
+                                                                                             (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, cs);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+extern "C" int istnet_col2im(const float *dcol, int B, int H, int W, int C, int kh, int kw, int stride, int pad, float *dx, int accumulate,
+                             void *stream) {
+    const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+    if (B <= 0 || Ho <= 0 || Wo <= 0) return ISTNET_ERR_BAD_ARG;
+    col2im_kernel<<<ew_grid((long long)B * H * W * C), kEwThreads, 0, ST>>>(B, H, W, C, kh, kw, stride, pad, Ho, Wo, dcol, dx, accumulate);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+
+extern "C" int istnet_bn_relu_maxpool(const float *y, int B, int H, int W, int C, const float *mean, const float *invstd, const float *gamma,
+                                      const float *beta, float *out_f32, void *hi, void *lo, int cs, uint8_t *argmax, void *stream) {
+    if (B <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    bn_relu_maxpool_kernel<<<ew_grid((long long)B * Ho * Wo * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, y, make_bn(mean, invstd, gamma, beta),
+                                                                                            out_f32, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, cs, argmax);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+extern "C" int istnet_maxpool_relu_bwd(const float *y, int B, int H, int W, int C, const float *mean, const float *invstd, const float *gamma,
+                                       const float *beta, const float *dz, const float *dz2, const uint8_t *argmax, float *g, void *stream) {
+    if (B <= 0) return ISTNET_ERR_BAD_ARG;
+    maxpool_relu_bwd_kernel<<<ew_grid((long long)B * H * W * C), kEwThreads, 0, ST>>>(B, H, W, C, y, make_bn(mean, invstd, gamma, beta), dz, dz2,
+                                                                                     argmax, g);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+
+extern "C" int istnet_gather_bn_prelu(const float *y, int B, long long HW, int C, int N, const long long *choose, const float *mean,
+                                      const float *invstd, const float *gamma, const float *beta, const float *prelu_a, float *out,
+                                      void *stream) {
+    if (B <= 0 || N <= 0) return ISTNET_ERR_BAD_ARG;
+    gather_bn_prelu_kernel<<<ew_grid((long long)B * N * C), kEwThreads, 0, ST>>>(B, HW, C, N, y, choose, make_bn(mean, invstd, gamma, beta),
+                                                                                prelu_a, out);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+extern "C" int istnet_gather_bn_prelu_bwd(const float *y, int B, long long HW, int C, int N, const long long *choose, const float *mean,
+                                          const float *invstd, const float *gamma, const float *beta, const float *prelu_a,
+                                          const float *dout, float *g_dense, double *slope_ws, void *stream) {
+    if (B <= 0 || N <= 0) return ISTNET_ERR_BAD_ARG;
+    ISTNET_CUDA_TRY(cudaMemsetAsync(g_dense, 0, sizeof(float) * (size_t)B * HW * C, ST));
+    if (slope_ws) ISTNET_CUDA_TRY(cudaMemsetAsync(slope_ws, 0, sizeof(double) * C, ST));
+    gather_bn_prelu_bwd_kernel<<<ew_grid((long long)B * N * C), kEwThreads, 0, ST>>>(B, HW, C, N, y, choose, make_bn(mean, invstd, gamma, beta),
+                                                                                    prelu_a, dout, g_dense, slope_ws);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}

@@ -109,12 +109,13 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t
     d |= (uint64_t)2 << 61;  // layout_type = SWIZZLE_128B
     return d;
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16 with BF16 inputs, FP32 accumulate.
-__host__ __device__ inline uint32_t make_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16, FP32 accumulate.
+// a_bf16 / b_bf16: 1 = BF16 operand, 0 = FP16 operand (the formats may differ between A and B).
+__host__ __device__ inline uint32_t make_idesc_f16(int m, int n, int a_bf16, int b_bf16, int a_mn_major, int b_mn_major) {
     uint32_t d = 0;
     d |= 1u << 4;                          // c_format = F32
-    d |= 1u << 7;                          // a_format = BF16
-    d |= 1u << 10;                         // b_format = BF16
+    d |= (uint32_t)(a_bf16 & 1) << 7;      // a_format: 0 = F16, 1 = BF16
+    d |= (uint32_t)(b_bf16 & 1) << 10;     // b_format
     d |= (uint32_t)(a_mn_major & 1) << 15;  // a_major
     d |= (uint32_t)(b_mn_major & 1) << 16;  // b_major
     d |= (uint32_t)(n >> 3) << 17;         // n_dim

@@ -7,7 +7,7 @@
 // (SWIZZLE_128B, 8 KB) is exactly one canonical MN-major swizzle slab (8-pixel groups 1024 B apart), and
 // consecutive 64-channel slabs sit 8 KB apart (the descriptor's leading-byte-offset).  The tap shift and the
 // zero padding are the TMA coordinates / out-of-bounds fill, exactly as in the forward kernel.
-// Split-bf16 arithmetic as in conv_gemm_tc.cu (dY_lo*X_hi + dY_hi*X_lo + dY_hi*X_hi).
+// Split-bf16 arithmetic as in conv_gemm_tc.cu: lo*hi + hi*lo + hi*hi.
 // K (pixels) is split across CTAs; each CTA writes its FP32 partial tile and a second tiny kernel reduces the
 // partials in a fixed order into the PyTorch weight layout [Cout][Cin][kh][kw] — deterministic, unlike the
 // atomics of the reference's custom grads (SURVEY.md §7 hard part 5).
@@ -97,7 +97,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_const
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc_bf16(kTileM, p.BN, 1, 1);  // both operands MN-major
+            // both operands MN-major
+            const uint32_t id_hh = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 1, 1), id_hl = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 1, 1);
+            const uint32_t id_lh = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 1, 1), id_ll = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 1, 1);
             for (int it = 0; it < num_k; ++it) {
                 const int st = it % p.stages;
                 const uint32_t ph = (it / p.stages) & 1;
@@ -114,9 +116,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_const
                     const uint64_t dal = tc::make_desc_sw128(a_lo + off, kSlabBytes, 1024);
                     const uint64_t dbh = tc::make_desc_sw128(b_hi + off, kSlabBytes, 1024);
                     const uint64_t dbl = tc::make_desc_sw128(b_lo + off, kSlabBytes, 1024);
-                    tc::umma_bf16(tmem_base, dal, dbh, idesc, (it | j) != 0);
-                    tc::umma_bf16(tmem_base, dah, dbl, idesc, 1);
-                    tc::umma_bf16(tmem_base, dah, dbh, idesc, 1);
+                    tc::umma_bf16(tmem_base, dal, dbh, id_lh, (it | j) != 0);
+                    tc::umma_bf16(tmem_base, dah, dbl, id_hl, 1);
+                    tc::umma_bf16(tmem_base, dah, dbh, id_hh, 1);
                 }
                 tc::umma_commit(&empty_bar[st]);
             }

@@ -151,4 +151,15 @@ class ModifiedResnet(nn.Module):
         self.model = Modified_PSPNet()
 
     def forward(self, x):
+        """Dense (B,128,H,W) feature map through PyTorch library ops — API compatibility only; the hot path is gather()."""
         return self.model(x)
+
+    def gather(self, rgb, choose):
+        """rgb (B,3,H,W), choose (B,N) int64 -> per-point pixel features (B,128,N) == `torch.gather(self(rgb).view(b,d,-1), 2, choose)`
+        (ist_net.py:41-45), computed channels-last on the B200 kernels (tcgen05 convolutions, fused BN / activation
+        passes, the head evaluated only at the chosen pixels).  There is no CPU path."""
+        if not rgb.is_cuda:
+            raise RuntimeError("istnet_b200: the image branch runs on CUDA only (no CPU fallback)")
+        from .image_engine import image_branch
+
+        return image_branch(self.model, rgb, choose)

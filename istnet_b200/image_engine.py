@@ -1,0 +1,221 @@
+"""The image branch (ResNet-18/8 + PSP + 3 up-sampling stages + head, model/modules.py:51-81, model/resnet.py:182-202)
+executed channels-last on the B200 kernels with an explicit tape and a hand-written backward.
+
+Forward dataflow (train): rgb -> im2col -> conv1 GEMM -> [BN+ReLU+MaxPool fused] -> 8 BasicBlocks (each conv is an
+implicit-GEMM tcgen05 kernel; BN statistics, BN-apply + residual + ReLU + operand split are one pass each) -> PSP priors
+(tiny pooled maps, torch) + concat -> bottleneck GEMM -> [ReLU + Dropout2d scale] -> 3 x [bilinear x2 fused with the
+operand split -> conv3x3 GEMM -> BN + PReLU (+Dropout2d scale)] -> final 1x1 GEMM -> BN + PReLU evaluated only at the
+`choose`d pixels, directly in the reference's (B,128,N) layout (ist_net.py:41-45).
+"""
+import torch
+import torch.nn.functional as F
+
+from . import _C
+from . import nhwc as K
+from ._C import c_int, c_ll, ptr
+from .nhwc import ACT_NONE, ACT_PRELU, ACT_RELU, Act, ConvUnit
+
+
+def _units(net):
+    """ConvUnit objects for every conv of Modified_PSPNet, keyed like the state dict (built once per module)."""
+    u = getattr(net, "_b200_units", None)
+    if u is not None:
+        return u
+    f = net.feats
+    u = {"conv1": ConvUnit(f.conv1.weight, None, f.bn1, ACT_RELU, k=7, stride=2, pad=3)}
+    for li in (1, 2, 3, 4):
+        for bi, blk in enumerate(getattr(f, f"layer{li}")):
+            pre = f"layer{li}.{bi}"
+            u[pre + ".conv1"] = ConvUnit(blk.conv1.weight, None, blk.bn1, ACT_RELU, k=3, stride=blk.stride)
+            u[pre + ".conv2"] = ConvUnit(blk.conv2.weight, None, blk.bn2, ACT_RELU, k=3)
+            if blk.downsample is not None:
+                u[pre + ".down"] = ConvUnit(blk.downsample[0].weight, None, blk.downsample[1], ACT_NONE, k=1, stride=blk.stride, pad=0)
+    u["bottleneck"] = ConvUnit(net.psp.bottleneck.weight, net.psp.bottleneck.bias, None, ACT_RELU, k=1)
+    for name in ("up_1", "up_2", "up_3"):
+        seq = getattr(net, name).conv
+        u[name] = ConvUnit(seq[1].weight, seq[1].bias, seq[2], ACT_PRELU, prelu=seq[3].weight, k=3)
+    u["final"] = ConvUnit(net.final[0].weight, net.final[0].bias, net.final[1], ACT_PRELU, prelu=net.final[2].weight, k=1)
+    net._b200_units = u
+    return u
+
+
+def _basic_block_fwd(u, pre, x, training, record, tape):
+    """resnet.py:50-66.  x: Act with f32 + pair."""
+    c1, c2, dn = u[pre + ".conv1"], u[pre + ".conv2"], u.get(pre + ".down")
+    z1, r1 = c1.forward(x, training, record, want_f32=False, want_pair=True)
+    if dn is not None:
+        yd, rd = dn.forward(x, training, record, defer_act=True)
+        out, r2 = c2.forward(z1, training, record, res=yd.f32, res_bn=rd["bn"], want_f32=True)
+    else:
+        rd = None
+        out, r2 = c2.forward(z1, training, record, res=x.f32, want_f32=True)
+    if record:
+        tape.append(("block", pre, r1, r2, rd))
+    return out
+
+
+def forward(net, rgb, choose, training, record):
+    """rgb (B,3,H,W) FP32 NCHW, choose (B,N) int64 -> rgb_local (B,128,N) FP32; tape (list) when record."""
+    u = _units(net)
+    dev = rgb.device
+    B, _, H, W = rgb.shape
+    tape = []
+    rgb = rgb.contiguous()
+    # ---- stem: conv1 7x7/2 (im2col GEMM) + BN + ReLU + MaxPool(3,2,1)
+    x0 = Act(B, H, W, 3)
+    y0, r0 = u["conv1"].forward(x0, training, True, x_f32_nchw=rgb, defer_act=True)
+    st0 = r0["bn"]
+    Hp, Wp = (y0.H - 1) // 2 + 1, (y0.W - 1) // 2 + 1
+    z = Act(B, Hp, Wp, 64, torch.empty(B, Hp, Wp, 64, dtype=torch.float32, device=dev))
+    z.hi, z.lo = K.empty_pair(B, Hp, Wp, 64, dev)
+    argmax = torch.empty(B, Hp, Wp, 64, dtype=torch.uint8, device=dev)
+    _C.call("bn_relu_maxpool", ptr(y0.f32), c_int(B), c_int(y0.H), c_int(y0.W), c_int(64), ptr(st0.mean), ptr(st0.invstd), ptr(st0.gamma),
+            ptr(st0.beta), ptr(z.f32), ptr(z.hi), ptr(z.lo), c_int(z.cs), ptr(argmax))
+    if record:
+        tape.append(("stem", r0, argmax, (y0.H, y0.W)))
+    # ---- layer1..4
+    for li in (1, 2, 3, 4):
+        for bi in (0, 1):
+            z = _basic_block_fwd(u, f"layer{li}.{bi}", z, training, record, tape)
+    # ---- PSP: priors on tiny pooled maps stay in torch (autograd sub-graph), concat buffer feeds the bottleneck GEMM
+    Hf, Wf = z.H, z.W
+    feats_nchw = z.f32.permute(0, 3, 1, 2)  # free view of the channels-last tensor
+    with torch.enable_grad():
+        leaf = feats_nchw.detach().requires_grad_(record)
+        priors = [F.interpolate(stage(leaf), size=(Hf, Wf), mode="bilinear", align_corners=False) for stage in net.psp.stages]
+        pri = torch.cat(priors, 1).permute(0, 2, 3, 1).contiguous()  # [B,Hf,Wf,2048] channels-last
+    cat = Act(B, Hf, Wf, 2560)
+    cat.hi, cat.lo = K.empty_pair(B, Hf, Wf, 2560, dev)
+    K.split(pri.detach(), B * Hf * Wf, 2048, cat.hi, cat.lo, ch_off=0)
+    cat.hi[..., 2048:] = z.hi
+    cat.lo[..., 2048:] = z.lo
+    noise = _draw_noise(net, B, training, dev)
+    p, rb = u["bottleneck"].forward(cat, training, record, noise=noise[0], want_f32=True, want_pair=False)
+    if record:
+        tape.append(("psp", rb, leaf, pri))
+    # ---- up_1..3: bilinear x2 (align_corners=True) fused with the operand split, conv3x3, BN, PReLU, Dropout2d scale
+    for i, name in enumerate(("up_1", "up_2", "up_3")):
+        cin = p.C
+        xu = Act(B, 2 * p.H, 2 * p.W, cin)
+        xu.hi, xu.lo = K.empty_pair(B, xu.H, xu.W, cin, dev)
+        K.upsample2x(p.f32, B, p.H, p.W, cin, (xu.hi, xu.lo))
+        last = name == "up_3"
+        p, ru = u[name].forward(xu, training, record, noise=None if last else noise[i + 1], want_f32=not last, want_pair=last)
+        if record:
+            tape.append(("up", name, ru))
+    # ---- head: final 1x1 conv, BN statistics over every pixel, BN + PReLU only at the chosen pixels
+    yf, rf = u["final"].forward(p, training, True, defer_act=True)
+    stf = rf["bn"]
+    N = choose.shape[1]
+    out = torch.empty(B, 128, N, dtype=torch.float32, device=dev)
+    choose = choose.contiguous()
+    _C.call("gather_bn_prelu", ptr(yf.f32), c_int(B), c_ll(yf.H * yf.W), c_int(128), c_int(N), ptr(choose), ptr(stf.mean), ptr(stf.invstd),
+            ptr(stf.gamma), ptr(stf.beta), ptr(u["final"].prelu), ptr(out))
+    if record:
+        tape.append(("final", rf, choose, N))
+    return out, (tape if record else None)
+
+
+def _draw_noise(net, B, training, dev):
+    """Dropout2d masks (modules.py:56,62,72-78): bernoulli(1-p)/(1-p) per (b,c); tests may inject fixed masks."""
+    if not training:
+        return [None, None, None]
+    out = []
+    for c, p in ((1024, net.drop_1.p), (256, net.drop_2.p), (64, net.drop_2.p)):
+        if p == 0.0:
+            out.append(None)
+        elif net.dropout_noise_fn is not None:
+            out.append(net.dropout_noise_fn(B, c, p).to(dev).reshape(B, c).float().contiguous())
+        else:
+            out.append(torch.empty(B, c, device=dev, dtype=torch.float32).bernoulli_(1 - p).div_(1 - p))
+    return out
+
+
+def backward(net, tape, d_out):
+    """d_out (B,128,N) -> {parameter: gradient} for every parameter of the branch that receives one."""
+    u = _units(net)
+    grads = {}
+    dev = d_out.device
+    d_out = d_out.contiguous()
+    dz, dz2 = None, None
+    for entry in reversed(tape):
+        kind = entry[0]
+        if kind == "final":
+            _, rf, choose, N = entry
+            unit = u["final"]
+            xin, st = rf["xin"], rf["bn"]
+            B, HW = xin.B, xin.H * xin.W
+            g = torch.empty(B, xin.H, xin.W, 128, dtype=torch.float32, device=dev)
+            slope = torch.empty(128, dtype=torch.float64, device=dev)
+            _C.call("gather_bn_prelu_bwd", ptr(rf["y"]), c_int(B), c_ll(HW), c_int(128), c_int(N), ptr(choose), ptr(st.mean), ptr(st.invstd),
+                    ptr(st.gamma), ptr(st.beta), ptr(unit.prelu), ptr(d_out), ptr(g), ptr(slope))
+            dy = K.empty_pair(B, xin.H, xin.W, 128, dev)
+            ws = K.bn_act_bwd(g, None, rf["y"], rf["P"], 128, HW, st, ACT_NONE, None, None, None, dy_pair=dy)
+            wsf = ws.float()
+            grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = wsf[128:256], wsf[0:128]
+            grads[id(unit.b)] = torch.zeros_like(unit.b)
+            grads[id(unit.prelu)] = slope.sum().float().reshape(1)
+            dz = unit.data_grads(rf, dy, True, grads)
+            dz2 = None
+        elif kind == "up":
+            _, name, ru = entry
+            dxu, _ = u[name].backward(ru, dz, dz2, need_dx=True, grads=grads)
+            xin = ru["xin"]
+            dz = K.upsample2x_bwd(dxu, xin.B, xin.H // 2, xin.W // 2, xin.C)
+            dz2 = None
+        elif kind == "psp":
+            _, rb, leaf, pri = entry
+            dcat, _ = u["bottleneck"].backward(rb, dz, dz2, need_dx=True, grads=grads)
+            stage_w = [s[1].weight for s in net.psp.stages]
+            gs = torch.autograd.grad(pri, [leaf] + stage_w, dcat[..., :2048])
+            for w_, g_ in zip(stage_w, gs[1:]):
+                grads[id(w_)] = g_
+            dz = dcat[..., 2048:].contiguous()
+            dz2 = gs[0].permute(0, 2, 3, 1).contiguous()
+        elif kind == "block":
+            _, pre, r1, r2, rd = entry
+            c1, c2, dn = u[pre + ".conv1"], u[pre + ".conv2"], u.get(pre + ".down")
+            dmid, g = c2.backward(r2, dz, dz2, need_dx=True, g_out=True, grads=grads)
+            dx1, _ = c1.backward(r1, dmid, None, need_dx=True, grads=grads)
+            if dn is not None:
+                dxd, _ = dn.backward(rd, g, None, need_dx=True, grads=grads)
+                dz, dz2 = dx1, dxd
+            else:
+                dz, dz2 = dx1, g
+        elif kind == "stem":
+            _, r0, argmax, (H0, W0) = entry
+            unit = u["conv1"]
+            st = r0["bn"]
+            B = r0["xin"].B
+            g0 = torch.empty(B, H0, W0, 64, dtype=torch.float32, device=dev)
+            _C.call("maxpool_relu_bwd", ptr(r0["y"]), c_int(B), c_int(H0), c_int(W0), c_int(64), ptr(st.mean), ptr(st.invstd), ptr(st.gamma),
+                    ptr(st.beta), ptr(dz), K._p(dz2), ptr(argmax), ptr(g0))
+            dy = K.empty_pair(B, H0, W0, 64, dev)
+            ws = K.bn_act_bwd(g0, None, r0["y"], r0["P"], 64, H0 * W0, st, ACT_NONE, None, None, None, dy_pair=dy)
+            wsf = ws.float()
+            grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = wsf[64:128], wsf[0:64]
+            unit.data_grads(r0, dy, False, grads)
+    return grads
+
+
+class _ImageBranchFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net, rgb, choose, *params):
+        out, tape = forward(net, rgb, choose, net.training, True)
+        ctx.net, ctx.tape, ctx.params = net, tape, params
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        grads = backward(ctx.net, ctx.tape, d_out)
+        ctx.tape = None
+        return (None, None, None) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
+
+
+def image_branch(net, rgb, choose):
+    """Modified_PSPNet forward + pixel gather on the B200 kernels; differentiable w.r.t. the module's parameters."""
+    params = tuple(p for n, p in net.named_parameters() if not n.startswith("feats.fc."))
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        return _ImageBranchFn.apply(net, rgb, choose, *params)
+    out, _ = forward(net, rgb, choose, net.training, False)
+    return out

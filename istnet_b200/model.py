@@ -177,7 +177,7 @@ class IST_Net(nn.Module):
         b = pts.size(0)
         index = cls + torch.arange(b, dtype=torch.long, device=pts.device) * self.nclass
 
-        rgb_local = gather_pixels(self.rgb_cam_extractor(rgb), choose)
+        rgb_local = self.rgb_cam_extractor.gather(rgb, choose)
         pts_local = self.pts_cam_extractor(pts)
         if self.training:
             r_c, t_c, s_c = self.cam_enhancer(pts, rgb_local, pts_local)
@@ -219,7 +219,7 @@ class PoseNetGT(nn.Module):
         c = torch.mean(pts, 1, keepdim=True)
         pts = pts - c
         with torch.no_grad():  # outputs are detached in the reference (posenet_gt.py:43); same values, no graph
-            rgb_local = gather_pixels(self.rgb_extractor(rgb), choose)
+            rgb_local = self.rgb_extractor.gather(rgb, choose)
             pts_local = self.pts_extractor(pts)
         gt_local = self.pts_gt_extractor(pts_w_gt)
         r, t, s = self.pose_estimator_aux(pts, pts_w_gt, rgb_local, pts_local, gt_local)

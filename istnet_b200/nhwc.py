@@ -1,0 +1,282 @@
+"""Channels-last building blocks on the B200 kernels: the "conv -> BatchNorm -> activation" unit with a hand-written
+backward (tcgen05 GEMMs for forward / dgrad / wgrad, fused HBM passes in between).
+
+Everything here works on FP32 tensors [B,H,W,C] (or [1,1,rows,C] for point sets) and on their bf16 (hi, lo) operand
+pairs; see include/istnet_b200.h §3-§4 for the kernels.  The classes mirror what PyTorch autograd records for the
+reference modules (cuDNN conv fwd/dgrad/wgrad, BN fwd/bwd, ReLU/PReLU, Dropout2d), but as an explicit tape.
+"""
+import ctypes
+
+import torch
+
+from . import _C
+from ._C import c_float, c_int, c_ll, c_void_p, ptr
+
+NULL = c_void_p(0)
+
+
+def _p(t):
+    return ptr(t) if t is not None else NULL
+
+
+def pad8(c):
+    return (c + 7) // 8 * 8
+
+
+class Act:
+    """An activation tensor in channels-last layout: optional FP32 copy + optional bf16 (hi, lo) operand pair."""
+
+    __slots__ = ("f32", "hi", "lo", "B", "H", "W", "C")
+
+    def __init__(self, B, H, W, C, f32=None, hi=None, lo=None):
+        self.B, self.H, self.W, self.C, self.f32, self.hi, self.lo = B, H, W, C, f32, hi, lo
+
+    @property
+    def P(self):
+        return self.B * self.H * self.W
+
+    @property
+    def cs(self):
+        return self.hi.shape[-1]
+
+
+def empty_pair(B, H, W, C, dev, cs=None):
+    cs = cs or pad8(C)
+    return (torch.empty(B, H, W, cs, dtype=torch.bfloat16, device=dev), torch.empty(B, H, W, cs, dtype=torch.bfloat16, device=dev))
+
+
+# ----------------------------------------------------------------------------------------- thin kernel wrappers
+def split(x_f32, P, C, hi, lo, ch_off=0, HW=1, nchw=False):
+    _C.call("split", ptr(x_f32), c_ll(P), c_int(C), c_ll(HW), c_int(1 if nchw else 0), ptr(hi), ptr(lo), c_int(hi.shape[-1]), c_int(ch_off))
+
+
+def prep_weight(w, transpose=False):
+    """Conv / linear weight [co, ci, kh, kw] (or [co, ci]) -> bf16 pair [taps, rows, pad8(cols)].
+    transpose=False: forward operand  [tap][co][ci];  transpose=True: data-gradient operand [flipped tap][ci][co]."""
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    elif w.dim() == 3:
+        w = w[:, :, :, None]
+    co, ci, kh, kw = w.shape
+    if transpose:
+        m = w.flip(2, 3).permute(2, 3, 1, 0).reshape(kh * kw, ci, co).contiguous()
+    else:
+        m = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
+    taps, rows, cols = m.shape
+    cs = pad8(cols)
+    hi = torch.empty(taps, rows, cs, dtype=torch.bfloat16, device=w.device)
+    lo = torch.empty(taps, rows, cs, dtype=torch.bfloat16, device=w.device)
+    split(m, taps * rows, cols, hi, lo)
+    return hi, lo
+
+
+def pick_box(H, W):
+    if H == 1:
+        return 128, 1
+    if W % 16 == 0 and H % 8 == 0:
+        return 16, 8
+    return 8, 8
+
+
+def conv_gemm(x, w_pair, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pair=None):
+    """x: Act with (hi, lo); returns nothing — writes out_f32 [B,H,W,cout] and/or out_pair."""
+    bw, bh = pick_box(x.H, x.W)
+    oh, ol = out_pair if out_pair is not None else (None, None)
+    _C.call(
+        "conv_gemm", ptr(x.hi), ptr(x.lo), c_int(x.B), c_int(x.H), c_int(x.W), c_int(x.C), c_int(x.cs), ptr(w_pair[0]), ptr(w_pair[1]),
+        c_int(cout), c_int(w_pair[0].shape[-1]), c_int(kh), c_int(kw), _p(bias), c_int(1 if relu else 0), _p(out_f32),
+        c_int(out_f32.shape[-1] if out_f32 is not None else 0), _p(oh), _p(ol), c_int(oh.shape[-1] if oh is not None else 0), c_int(bw), c_int(bh),
+    )
+
+
+def conv_wgrad(dy_pair, cout, x, kh, kw):
+    """grad_w [cout, cin, kh, kw] from dy (hi, lo) [B,H,W,cs] and x: Act (hi, lo)."""
+    dev = x.hi.device
+    ks = _C.lib().istnet_wgrad_ksplit(x.B, x.H, x.W, cout, x.C, kh, kw)
+    ws = torch.empty(ks * kh * kw * cout * x.C, dtype=torch.float32, device=dev)
+    gw = torch.empty(cout, x.C, kh, kw, dtype=torch.float32, device=dev)
+    bw, bh = (64, 1) if x.H == 1 else (8, 8)
+    _C.call(
+        "conv_wgrad", ptr(dy_pair[0]), ptr(dy_pair[1]), c_int(dy_pair[0].shape[-1]), ptr(x.hi), ptr(x.lo), c_int(x.cs), c_int(x.B), c_int(x.H),
+        c_int(x.W), c_int(cout), c_int(x.C), c_int(kh), c_int(kw), ptr(ws), c_int(ks), ptr(gw), c_int(bw), c_int(bh),
+    )
+    return gw
+
+
+class BnState:
+    """Per-call BatchNorm quantities: batch (train) or running (eval) mean / invstd + affine parameters."""
+
+    __slots__ = ("mean", "invstd", "gamma", "beta")
+
+    def __init__(self, mean, invstd, gamma, beta):
+        self.mean, self.invstd, self.gamma, self.beta = mean, invstd, gamma, beta
+
+
+def bn_state(bn, y, P, C, training):
+    """Reads momentum / eps / running stats from the nn.BatchNorm2d at call time (BNMomentumScheduler, scheduler.py:277-303)."""
+    dev = y.device
+    if training:
+        mean = torch.empty(C, dtype=torch.float32, device=dev)
+        invstd = torch.empty(C, dtype=torch.float32, device=dev)
+        ws = torch.empty(2 * C, dtype=torch.float64, device=dev)
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        track = bn.track_running_stats and bn.running_mean is not None
+        _C.call("bn_stats", ptr(y), c_ll(P), c_int(C), ptr(ws), c_float(bn.eps), c_float(mom), _p(bn.running_mean if track else None),
+                _p(bn.running_var if track else None), ptr(mean), ptr(invstd))
+        if track:
+            bn.num_batches_tracked += 1
+    else:
+        mean = bn.running_mean
+        invstd = torch.rsqrt(bn.running_var + bn.eps)
+    return BnState(mean, invstd, bn.weight, bn.bias)
+
+
+def bn_act_split(y, P, C, HW, bn=None, res=None, res_bn=None, act=0, prelu=None, noise=None, out_f32=None, out_pair=None, ch_off=0):
+    oh, ol = out_pair if out_pair is not None else (None, None)
+    _C.call(
+        "bn_act_split", ptr(y), c_ll(P), c_int(C), c_ll(HW), _p(bn.mean if bn else None), _p(bn.invstd if bn else None),
+        _p(bn.gamma if bn else None), _p(bn.beta if bn else None), _p(res), _p(res_bn.mean if res_bn else None),
+        _p(res_bn.invstd if res_bn else None), _p(res_bn.gamma if res_bn else None), _p(res_bn.beta if res_bn else None), c_int(act),
+        _p(prelu), _p(noise), _p(out_f32), _p(oh), _p(ol), c_int(oh.shape[-1] if oh is not None else 0), c_int(ch_off),
+    )
+
+
+def bn_act_bwd(dz, dz2, y, P, C, HW, bn, act, prelu, z_hi, noise, dy_pair=None, dy_f32=None, g_out=None):
+    """Returns ws (3*C doubles): [sum g | sum g*xhat | PReLU slope partials]."""
+    ws = torch.empty(3 * C, dtype=torch.float64, device=dz.device)
+    dh, dl = dy_pair if dy_pair is not None else (None, None)
+    _C.call(
+        "bn_act_bwd", ptr(dz), _p(dz2), _p(y), c_ll(P), c_int(C), c_ll(HW), _p(bn.mean if bn else None), _p(bn.invstd if bn else None),
+        _p(bn.gamma if bn else None), _p(bn.beta if bn else None), c_int(act), _p(prelu), _p(z_hi), c_int(z_hi.shape[-1] if z_hi is not None else 0),
+        _p(noise), ptr(ws), _p(dh), _p(dl), c_int(dh.shape[-1] if dh is not None else 0), _p(dy_f32), _p(g_out),
+    )
+    return ws
+
+
+def upsample2x(x_f32, B, H, W, C, out_pair):
+    _C.call("upsample2x_split", ptr(x_f32), c_int(B), c_int(H), c_int(W), c_int(C), ptr(out_pair[0]), ptr(out_pair[1]), c_int(out_pair[0].shape[-1]), NULL)
+
+
+def upsample2x_bwd(dout, B, H, W, C):
+    dx = torch.empty(B, H, W, C, dtype=torch.float32, device=dout.device)
+    _C.call("upsample2x_bwd", ptr(dout), c_int(B), c_int(H), c_int(W), c_int(C), ptr(dx))
+    return dx
+
+
+def im2col(x_f32, nchw, B, H, W, C, k, stride, pad):
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    K = k * k * C
+    hi, lo = empty_pair(B, Ho, Wo, K, x_f32.device)
+    _C.call("im2col_split", ptr(x_f32), c_int(1 if nchw else 0), c_int(B), c_int(H), c_int(W), c_int(C), c_int(k), c_int(k), c_int(stride),
+            c_int(pad), ptr(hi), ptr(lo), c_int(hi.shape[-1]))
+    return Act(B, Ho, Wo, K, None, hi, lo)
+
+
+def col2im(dcol, B, H, W, C, k, stride, pad, dx=None):
+    acc = dx is not None
+    if dx is None:
+        dx = torch.empty(B, H, W, C, dtype=torch.float32, device=dcol.device)
+    _C.call("col2im", ptr(dcol), c_int(B), c_int(H), c_int(W), c_int(C), c_int(k), c_int(k), c_int(stride), c_int(pad), ptr(dx), c_int(1 if acc else 0))
+    return dx
+
+
+# ----------------------------------------------------------------------------------------- the conv+BN+act unit
+ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
+
+
+class ConvUnit:
+    """One `conv (+bias) -> [BatchNorm] -> [residual add] -> activation -> [Dropout2d scale]` step with its tape.
+
+    stride-1 "same" convolutions run as implicit GEMM on the activation pair; strided ones (conv1, layer2.0) go through
+    im2col (the patch matrix is then the GEMM's A operand and the wgrad's B operand)."""
+
+    def __init__(self, conv_w, conv_b, bn, act, prelu=None, k=1, stride=1, pad=None):
+        self.w, self.b, self.bn, self.act, self.prelu = conv_w, conv_b, bn, act, prelu
+        self.k, self.stride = k, stride
+        self.pad = k // 2 if pad is None else pad
+        self.cout = conv_w.shape[0]
+
+    # ---- forward
+    def forward(self, x, training, record, noise=None, res=None, res_bn=None, want_f32=False, want_pair=True, x_f32_nchw=None, defer_act=False):
+        """x: Act (pair required unless strided with x.f32 / x_f32_nchw).  res: FP32 residual (raw) or, with res_bn, the
+        pre-BN output of the downsample unit.  Returns (out Act, tape record).  defer_act=True stops after conv + BN stats
+        (used by the stem and the head, which fuse their own epilogues)."""
+        dev = self.w.device
+        if self.stride != 1 or x_f32_nchw is not None:
+            src = x_f32_nchw if x_f32_nchw is not None else x.f32
+            xin = im2col(src, x_f32_nchw is not None, x.B, x.H, x.W, x.C, self.k, self.stride, self.pad)
+            wp = prep_weight(self.w.permute(0, 2, 3, 1).reshape(self.cout, -1))  # [co, (r,s,c)] = the im2col K order
+            kk = 1
+        else:
+            xin, kk = x, self.k
+            wp = prep_weight(self.w)
+        B, H, W = xin.B, xin.H, xin.W
+        P, C = B * H * W, self.cout
+        y = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
+        conv_gemm(xin, wp, C, kk, kk, bias=self.b, out_f32=y)
+        st = bn_state(self.bn, y, P, C, training) if self.bn is not None else None
+        rec = {"bn": st}
+        if record:
+            rec.update({"xin": xin, "y": y, "noise": noise, "kk": kk, "P": P, "HW": H * W, "in_shape": (x.B, x.H, x.W, x.C)})
+        if defer_act:
+            return Act(B, H, W, C, y), rec
+        out = Act(B, H, W, C)
+        if want_f32:
+            out.f32 = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
+        if want_pair or (record and self.act == ACT_RELU):
+            out.hi, out.lo = empty_pair(B, H, W, C, dev)
+        bn_act_split(y, P, C, H * W, bn=st, res=res, res_bn=res_bn, act=self.act, prelu=self.prelu, noise=noise, out_f32=out.f32,
+                     out_pair=(out.hi, out.lo) if out.hi is not None else None)
+        if record:
+            rec["z_hi"] = out.hi
+            if self.bn is None and self.act != ACT_PRELU:
+                rec["y"] = None  # not needed by the backward of a BN-free ReLU/identity unit
+        return out, rec
+
+    # ---- backward
+    def backward(self, rec, dz, dz2=None, need_dx=True, g_out=False, grads=None):
+        """dz (+dz2): FP32 gradient w.r.t. the unit output.  Fills grads[param] and returns (dx FP32 or None, g or None)."""
+        dev = dz.device
+        xin, P, C = rec["xin"], rec["P"], self.cout
+        B, H, W = xin.B, xin.H, xin.W
+        dy = empty_pair(B, H, W, C, dev)
+        g = torch.empty(B, H, W, C, dtype=torch.float32, device=dev) if g_out else None
+        ws = bn_act_bwd(dz, dz2, rec["y"], P, C, rec["HW"], rec["bn"], self.act, self.prelu, rec.get("z_hi"), rec["noise"], dy_pair=dy, g_out=g)
+        self.param_grads(rec, ws, grads)
+        dx = self.data_grads(rec, dy, need_dx, grads)
+        return dx, g
+
+    def param_grads(self, rec, ws, grads):
+        C = self.cout
+        wsf = ws.float()
+        if self.bn is not None:
+            grads[id(self.bn.weight)] = wsf[C : 2 * C]
+            grads[id(self.bn.bias)] = wsf[0:C]
+            if self.b is not None:  # a bias feeding a train-mode BatchNorm has an identically zero gradient
+                grads[id(self.b)] = torch.zeros_like(self.b)
+        elif self.b is not None:
+            grads[id(self.b)] = wsf[0:C]
+        if self.act == ACT_PRELU:
+            grads[id(self.prelu)] = ws[2 * C : 3 * C].sum().float().reshape(1)
+
+    def data_grads(self, rec, dy, need_dx, grads):
+        xin, kk, C = rec["xin"], rec["kk"], self.cout
+        gw = conv_wgrad(dy, C, xin, kk, kk)
+        if kk != self.k or self.stride != 1:  # im2col path: [co, (r,s,c)] -> [co, c, r, s]
+            cin = self.w.shape[1]
+            gw = gw.reshape(C, self.k, self.k, cin).permute(0, 3, 1, 2).contiguous()
+        grads[id(self.w)] = gw.reshape(self.w.shape)
+        if not need_dx:
+            return None
+        dyA = Act(xin.B, xin.H, xin.W, C, None, dy[0], dy[1])
+        if kk != self.k or self.stride != 1:
+            wm = self.w.permute(0, 2, 3, 1).reshape(C, -1)
+            wd = prep_weight(wm, transpose=True)
+            dcol = torch.empty(xin.B, xin.H, xin.W, xin.C, dtype=torch.float32, device=dy[0].device)
+            conv_gemm(dyA, wd, xin.C, 1, 1, out_f32=dcol)
+            b, h, w, c = rec["in_shape"]
+            return col2im(dcol, b, h, w, c, self.k, self.stride, self.pad)
+        wd = prep_weight(self.w, transpose=True)
+        dx = torch.empty(xin.B, xin.H, xin.W, xin.C, dtype=torch.float32, device=dy[0].device)
+        conv_gemm(dyA, wd, xin.C, kk, kk, out_f32=dx)
+        return dx
