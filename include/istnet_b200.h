@@ -81,28 +81,31 @@ int istnet_fps_chain(int b, int n, int nlevels, const int *npoint, const float *
  * 3. Dense contractions on tcgen05 tensor cores (image branch model/resnet.py + model/modules.py:10-81,
  *    per-point MLPs model/ist_net.py:125-332, SharedMLP 1x1 convolutions pytorch_utils.py:25-206)
  *
- * FP32 tensors are carried as bf16 (hi, lo) pairs, x ~= hi + lo; products are evaluated as
- * hi*hi + hi*lo + lo*hi with FP32 accumulation in tensor memory (error ~1e-5 relative).
+ * An FP32 tensor x is carried as `nsplit` bf16 "operand planes" stored plane-major (planes[i] is a whole bf16
+ * tensor, `plane_stride` ELEMENTS after planes[i-1]): p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1).
+ * A product is evaluated as the sum of all plane products a_i*b_j with i + j < nsplit, FP32-accumulated in tensor
+ * memory: nsplit = 2 -> 3 MMAs (~3e-6 per product), nsplit = 3 -> 6 MMAs (~1e-8, below FP32 rounding; default).
  * Activations are channels-last: act[b][h][w][c] with a channel stride `*_cs` (elements, multiple of 8).
  * ---------------------------------------------------------------------------------------------------- */
 
 /* Stride-1 "same" convolution / GEMM:  out[b,h,w,n] = bias[n] + sum_{r,s,c} act[b,h+r-kh/2,w+s-kw/2,c] * wgt[r*kw+s][n][c]
  * (replaces nn.Conv2d / nn.Conv1d(k=1) / nn.Linear call sites: resnet.py:34-35, modules.py:17-25,41-44,64-66,
- * ist_net.py:130-160).  wgt_{hi,lo}: bf16 [kh*kw][Cout][wgt_cs].  Any of out_f32 / (out_hi,out_lo) may be null.
+ * ist_net.py:130-160).  wgt planes: bf16 [nsplit][kh*kw][Cout][wgt_cs].  Any of out_f32 / out_planes may be null.
  * (box_w, box_h): pixel tile; box_w*box_h must divide 128 (images: 8x8 -> 2 images per tile; row matrices: 128x1). */
-int istnet_conv_gemm(const void *act_hi, const void *act_lo, int B, int H, int W, int Cin, int act_cs, const void *wgt_hi,
-                     const void *wgt_lo, int Cout, int wgt_cs, int kh, int kw, const float *bias, int relu, float *out_f32,
-                     int out_cs, void *out_hi, void *out_lo, int split_cs, int box_w, int box_h, void *stream);
+int istnet_conv_gemm(const void *act_planes, long long act_plane_stride, int B, int H, int W, int Cin, int act_cs,
+                     const void *wgt_planes, long long wgt_plane_stride, int Cout, int wgt_cs, int kh, int kw, int nsplit,
+                     const float *bias, int relu, float *out_f32, int out_cs, void *out_planes, long long out_plane_stride,
+                     int nsplit_out, int split_cs, int box_w, int box_h, void *stream);
 
 /* Weight gradient of the layer above (cuDNN wgrad in the reference):
  *   grad_w[co][ci][r][s] = sum_{b,h,w} dy[b,h,w,co] * x[b,h+r-kh/2,w+s-kw/2,ci]       (PyTorch weight layout, FP32)
  * The pixel sum is split over `ksplit` CTAs per tile (istnet_wgrad_ksplit gives the recommended value);
  * partial_ws must hold ksplit*kh*kw*Cout*Cin floats.  Deterministic (fixed-order reduction of the partials).
  * (box_w, box_h): pixel tile with box_w*box_h dividing 64 (images: 8x8; row matrices: 64x1). */
-int istnet_wgrad_ksplit(int B, int H, int W, int Cout, int Cin, int kh, int kw);
-int istnet_conv_wgrad(const void *dy_hi, const void *dy_lo, int dy_cs, const void *x_hi, const void *x_lo, int x_cs, int B, int H,
-                      int W, int Cout, int Cin, int kh, int kw, float *partial_ws, int ksplit, float *grad_w, int box_w, int box_h,
-                      void *stream);
+int istnet_wgrad_ksplit(int B, int H, int W, int Cout, int Cin, int kh, int kw, int nsplit);
+int istnet_conv_wgrad(const void *dy_planes, long long dy_plane_stride, int dy_cs, const void *x_planes, long long x_plane_stride,
+                      int x_cs, int nsplit, int B, int H, int W, int Cout, int Cin, int kh, int kw, float *partial_ws, int ksplit,
+                      float *grad_w, int box_w, int box_h, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * 4. HBM-bound passes between contractions (channels-last FP32 [P pixels][C channels], C % 4 == 0)
@@ -114,49 +117,73 @@ int istnet_conv_wgrad(const void *dy_hi, const void *dy_lo, int dy_cs, const voi
 int istnet_bn_stats(const float *y, long long P, int C, double *ws, float eps, float momentum, float *running_mean,
                     float *running_var, float *mean, float *invstd, void *stream);
 
-/* z = noise[b,c] * act( bn(y) + bn_res(res) )  written as FP32 and/or as a bf16 (hi,lo) pair (channel stride cs, offset ch_off).
+/* z = noise[b,c] * act( bn(y) + bn_res(res) )  written as FP32 and/or as bf16 operand planes (channel stride cs, offset ch_off).
  * mean==NULL: no BN.  res==NULL: no residual; res_mean==NULL: raw residual.  act: 0 none, 1 ReLU, 2 PReLU(*prelu_a).
  * noise: Dropout2d scale [B][C] or NULL, b = pixel / HW.  (BasicBlock resnet.py:50-66, PSPUpsample modules.py:37-48) */
 int istnet_bn_act_split(const float *y, long long P, int C, long long HW, const float *mean, const float *invstd, const float *gamma,
                         const float *beta, const float *res, const float *res_mean, const float *res_invstd, const float *res_gamma,
-                        const float *res_beta, int act, const float *prelu_a, const float *noise, float *out_f32, void *out_hi,
-                        void *out_lo, int cs, int ch_off, void *stream);
+                        const float *res_beta, int act, const float *prelu_a, const float *noise, float *out_f32, void *out_planes,
+                        long long plane_stride, int nsplit, int cs, int ch_off, void *stream);
 
 /* Backward of the unit above: g = (dz + dz2) * noise * act'(u);  ws[0:C] = sum g, ws[C:2C] = sum g*xhat, ws[2C:3C] = PReLU
- * slope partials;  dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))  (or g without BN) written as bf16 pair and/or FP32;
- * g_out (optional) receives g (the residual branch's gradient).  ReLU masks come from the saved forward output z_hi. */
+ * slope partials;  dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))  (or g without BN) written as bf16 operand planes and/or FP32;
+ * g_out (optional) receives g (the residual branch's gradient).  ReLU masks come from plane 0 (z_hi) of the saved forward output. */
 int istnet_bn_act_bwd(const float *dz, const float *dz2, const float *y, long long P, int C, long long HW, const float *mean,
                       const float *invstd, const float *gamma, const float *beta, int act, const float *prelu_a, const void *z_hi,
-                      int cs_z, const float *noise, double *ws, void *dy_hi, void *dy_lo, int cs_dy, float *dy_f32, float *g_out,
-                      void *stream);
+                      int cs_z, const float *noise, double *ws, void *dy_planes, long long plane_stride, int nsplit, int cs_dy,
+                      float *dy_f32, float *g_out, void *stream);
 
-/* FP32 [P][C] (or NCHW with HW pixels per image when nchw != 0) -> bf16 pair [P][cs] at channel offset ch_off */
-int istnet_split(const float *x, long long P, int C, long long HW, int nchw, void *hi, void *lo, int cs, int ch_off, void *stream);
+/* FP32 [P][C] (or NCHW with HW pixels per image when nchw != 0) -> bf16 operand planes [nsplit][P][cs] at channel offset ch_off */
+int istnet_split(const float *x, long long P, int C, long long HW, int nchw, void *planes, long long plane_stride, int nsplit, int cs,
+                 int ch_off, void *stream);
 /* ws[c] = sum_p x[p][c] (double; bias gradients) */
 int istnet_colsum(const float *x, long long P, int C, double *ws, void *stream);
 
 /* nn.Upsample(scale_factor=2, bilinear, align_corners=True) (modules.py:41) fused with the operand split; and its adjoint */
-int istnet_upsample2x_split(const float *x, int B, int H, int W, int C, void *hi, void *lo, int cs, float *out_f32, void *stream);
+int istnet_upsample2x_split(const float *x, int B, int H, int W, int C, void *planes, long long plane_stride, int nsplit, int cs,
+                            float *out_f32, void *stream);
 int istnet_upsample2x_bwd(const float *dout, int B, int H, int W, int C, float *dx, void *stream);
 
 /* im2col for the strided convolutions (conv1 7x7/2 resnet.py:127, layer2.0 3x3/2 + 1x1/2 resnet.py:153-180) and its adjoint */
-int istnet_im2col_split(const float *x, int nchw, int B, int H, int W, int C, int kh, int kw, int stride, int pad, void *hi, void *lo,
-                        int cs, void *stream);
+int istnet_im2col_split(const float *x, int nchw, int B, int H, int W, int C, int kh, int kw, int stride, int pad, void *planes,
+                        long long plane_stride, int nsplit, int cs, void *stream);
 int istnet_col2im(const float *dcol, int B, int H, int W, int C, int kh, int kw, int stride, int pad, float *dx, int accumulate,
                   void *stream);
 
 /* stem: BN + ReLU + MaxPool2d(3,2,1) in one pass (resnet.py:183-186) and the matching backward to the conv1 output */
 int istnet_bn_relu_maxpool(const float *y, int B, int H, int W, int C, const float *mean, const float *invstd, const float *gamma,
-                           const float *beta, float *out_f32, void *hi, void *lo, int cs, uint8_t *argmax, void *stream);
+                           const float *beta, float *out_f32, void *planes, long long plane_stride, int nsplit, int cs, uint8_t *argmax,
+                           void *stream);
 int istnet_maxpool_relu_bwd(const float *y, int B, int H, int W, int C, const float *mean, const float *invstd, const float *gamma,
                             const float *beta, const float *dz, const float *dz2, const uint8_t *argmax, float *g, void *stream);
 
-/* head: BN + PReLU evaluated only at the `choose`d pixels, output in the reference layout (B,C,N) (ist_net.py:42-45) */
+/* head: BN + PReLU evaluated only at the `choose`d pixels (ist_net.py:42-45), output as rows out[b][n][c] */
 int istnet_gather_bn_prelu(const float *y, int B, long long HW, int C, int N, const long long *choose, const float *mean,
                            const float *invstd, const float *gamma, const float *beta, const float *prelu_a, float *out, void *stream);
 int istnet_gather_bn_prelu_bwd(const float *y, int B, long long HW, int C, int N, const long long *choose, const float *mean,
                                const float *invstd, const float *gamma, const float *beta, const float *prelu_a, const float *dout,
                                float *g_dense, double *slope_ws, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * 5. Channels-last PointNet++ companions (rows = points, features[b][point][channel])
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* QueryAndGroup (pointnet2_utils.py:317-377) straight into the operand planes of the first shared-MLP GEMM:
+ * row (b,j,l) = [xyz[b,idx[b,j,l]] - new_xyz[b,j] (3 channels first) | feats[b,idx[b,j,l],0:C]];  feats may be NULL when C == 0. */
+int istnet_group_rows_split(int B, int N, int M, int ns, int C, const float *xyz, const float *new_xyz, const float *feats,
+                            const int32_t *idx, void *planes, long long plane_stride, int nsplit, int cs, void *stream);
+/* adjoint w.r.t. feats: d_feats[b,idx,c] += d_grouped[row, 3+c]  (d_feats is zeroed here) */
+int istnet_group_rows_bwd(int B, int N, int M, int ns, int C, const float *d_grouped, const int32_t *idx, float *d_feats, void *stream);
+/* last BN + ReLU of a SharedMLP fused with F.max_pool2d over nsample (pointnet2_modules.py:65-69): y [G*ns][C] -> out[g][out_off+c] */
+int istnet_bn_relu_maxrows(const float *y, long long G, int ns, int C, const float *mean, const float *invstd, const float *gamma,
+                           const float *beta, float *out, int out_ld, int out_off, uint8_t *argmax, void *stream);
+int istnet_maxrows_bwd(const float *y, long long G, int ns, int C, const float *mean, const float *invstd, const float *gamma,
+                       const float *beta, const float *dz, int dz_ld, int dz_off, const uint8_t *argmax, float *gsel, void *stream);
+/* three_interpolate (interpolate_gpu.cu:77-159) on rows: feats [B][m][C] -> out [B][n][out_ld] at channel out_off; and its adjoint */
+int istnet_interp_rows(int B, int m, int n, int C, const float *feats, const int32_t *idx, const float *weight, float *out, int out_ld,
+                       int out_off, void *stream);
+int istnet_interp_rows_bwd(int B, int m, int n, int C, const float *dout, int d_ld, int d_off, const int32_t *idx, const float *weight,
+                           float *d_feats, void *stream);
 
 #ifdef __cplusplus
 }

@@ -28,12 +28,42 @@ __device__ __forceinline__ float sqdist_ref(float dx, float dy, float dz) {
 
 constexpr int kNumSMs = 148;
 
-// FP32 -> bf16 operand pair: hi = bf16(x), lo = bf16(x - hi); x - (hi + lo) <= 2^-18 |x|.
-// (A bf16-hi / fp16-lo pair would leave a 2^-21 residual, but tcgen05.mma kind::f16 rejects mixed A/B formats on
-// sm_100a — measured: "illegal instruction" — so both halves stay bf16.)
+// FP32 -> bf16 operand planes: p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1) ...; the residual after n
+// planes is <= 2^(-9n) |x|.  Operand tensors are stored plane-major: planes[i] is a complete bf16 tensor,
+// `plane_stride` elements after planes[i-1].  nsplit = 2 -> 3 tensor-core products (error ~3e-6 per product),
+// nsplit = 3 -> 6 products (error ~1e-8, below FP32 accumulation noise).
+// (A bf16-hi / fp16-lo pair would reach 2^-21 with 4 products, but tcgen05.mma kind::f16 rejects mixed A/B formats on
+// sm_100a — measured: "illegal instruction" — and fp16 alone underflows on gradient-sized tensors.)
 #include <cuda_bf16.h>
-__device__ __forceinline__ void split_hi_lo(float v, unsigned short &hi, unsigned short &lo) {
-    __nv_bfloat16 h = __float2bfloat16_rn(v);
-    hi = __bfloat16_as_ushort(h);
-    lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+constexpr int kMaxPlanes = 3;
+__device__ __forceinline__ void split_planes(float v, unsigned short (&out)[kMaxPlanes], int n) {
+    float r = v;
+#pragma unroll
+    for (int i = 0; i < kMaxPlanes; ++i) {
+        if (i < n) {
+            __nv_bfloat16 h = __float2bfloat16_rn(r);
+            out[i] = __bfloat16_as_ushort(h);
+            r -= __bfloat162float(h);
+        }
+    }
+}
+// scalar / 4-wide stores of one value group into every plane
+__device__ __forceinline__ void store_planes1(__nv_bfloat16 *base, long long plane_stride, int n, float v) {
+    unsigned short o[kMaxPlanes];
+    split_planes(v, o, n);
+#pragma unroll
+    for (int i = 0; i < kMaxPlanes; ++i)
+        if (i < n) base[i * plane_stride] = __ushort_as_bfloat16(o[i]);
+}
+__device__ __forceinline__ void store_planes4(__nv_bfloat16 *base, long long plane_stride, int n, float4 v) {
+    unsigned short a[kMaxPlanes], b[kMaxPlanes], c[kMaxPlanes], d[kMaxPlanes];
+    split_planes(v.x, a, n); split_planes(v.y, b, n); split_planes(v.z, c, n); split_planes(v.w, d, n);
+#pragma unroll
+    for (int i = 0; i < kMaxPlanes; ++i)
+        if (i < n) {
+            uint2 p;
+            p.x = (uint32_t)a[i] | ((uint32_t)b[i] << 16);
+            p.y = (uint32_t)c[i] | ((uint32_t)d[i] << 16);
+            *reinterpret_cast<uint2 *>(base + i * plane_stride) = p;
+        }
 }

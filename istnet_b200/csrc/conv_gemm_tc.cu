@@ -5,17 +5,17 @@
 // covers every stride-1 convolution of the image branch (modules.py / resnet.py), its data
 // gradient (same kernel, flipped+transposed weights), and all 1x1 convolutions / per-point MLP layers (taps = 1).
 //
-// Precision: the 1e-4 relative target rules out single-pass TF32/BF16.  Each FP32 operand x is carried as a
-// bf16 pair (hi = bf16(x), lo = bf16(x - hi), residual <= 2^-18 |x|) and each product is evaluated as
-// lo*hi + hi*lo + hi*hi with FP32 accumulation in TMEM (3 tcgen05.mma kind::f16 per k-step, error ~3e-6 RMS per
-// product before averaging over K) — 3 BF16 passes cost half of what 3xTF32 would.
+// Precision: the 1e-4 relative target rules out single-pass TF32/BF16.  Each FP32 operand x is carried as `nsplit`
+// bf16 planes (p0 = bf16(x), p1 = bf16(x - p0), p2 = ...; residual <= 2^(-9 nsplit) |x|) and a product is evaluated as
+// the sum of all plane products a_i*b_j with i + j < nsplit, smallest first, FP32-accumulated in TMEM:
+//   nsplit = 2: 3 tcgen05.mma per k-step, ~3e-6 RMS per product;  nsplit = 3: 6 per k-step, ~1e-8 (below FP32 noise).
 //
 // Structure (one 128 x BN output tile per CTA, 192 threads):
-//   warp 0 : TMA producer  — per (tap, 64-channel block): 2 activation boxes (hi/lo; 4-D map over C,W,H,B with
-//            box 64 x bw x bh x bb = 128 pixels, coordinates shifted by the tap, out-of-bounds = zero padding)
-//            and 2 weight boxes (hi/lo; 64 x BN) into a SWIZZLE_128B ring, completion on mbarriers
-//   warp 1 : MMA issuer    — one elected thread, 4 k-steps x 3 products per stage, tcgen05.commit frees the stage
-//   warps 2-5 : epilogue   — tcgen05.ld 32x32b, + bias, ReLU, FP32 and/or split-bf16 stores (NHWC rows)
+//   warp 0 : TMA producer  — per (tap, 64-channel block): nsplit activation boxes (5-D map over C,W,H,B,plane with
+//            box 64 x bw x bh x bb x 1 = 128 pixels, coordinates shifted by the tap, out-of-bounds = zero padding)
+//            and nsplit weight boxes (64 x BN) into a SWIZZLE_128B ring, completion on mbarriers
+//   warp 1 : MMA issuer    — one elected thread, 4 k-steps x 3|6 products per stage, tcgen05.commit frees the stage
+//   warps 2-5 : epilogue   — tcgen05.ld 32x32b, + bias, ReLU, FP32 and/or bf16-plane stores (NHWC rows)
 #include "tc_common.cuh"
 
 namespace {
@@ -37,18 +37,19 @@ struct ConvGemmParams {
     int relu;
     float *out_f32;           // [B,H,W,out_cs] or null
     int out_cs;
-    __nv_bfloat16 *out_hi, *out_lo;  // [B,H,W,split_cs] or null
-    int split_cs;
+    __nv_bfloat16 *out_pl;    // operand planes [nsplit_out][B,H,W,split_cs] or null
+    long long out_pl_stride;
+    int split_cs, nsplit_out;
+    int nsplit;               // planes of the input operands
     uint32_t tmem_cols;
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const ConvGemmParams p) {
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const ConvGemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_tile_bytes = p.BN * kBlockK * 2;
-    const int stage_bytes = 2 * kATileBytes + 2 * b_tile_bytes;
+    const int stage_bytes = p.nsplit * (kATileBytes + b_tile_bytes);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
     uint64_t *empty_bar = full_bar + p.stages;
     uint64_t *tmem_full_bar = empty_bar + p.stages;
@@ -65,7 +66,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     const int num_k = p.kh * p.kw * p.cin_blocks;
 
     if (warp == 0 && lane == 0) {
-        tc::prefetch_tmap(&tm_a_hi); tc::prefetch_tmap(&tm_a_lo); tc::prefetch_tmap(&tm_b_hi); tc::prefetch_tmap(&tm_b_lo);
+        tc::prefetch_tmap(&tm_a); tc::prefetch_tmap(&tm_b);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
@@ -91,36 +92,38 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                     tc::mbar_wait(&empty_bar[st], ph ^ 1);
                     uint8_t *sa = smem + (size_t)st * stage_bytes;
                     tc::mbar_arrive_expect_tx(&full_bar[st], stage_bytes);
-                    tc::tma_load_4d(sa, &tm_a_hi, &full_bar[st], kb * kBlockK, w0 + s - pad_w, h0 + r - pad_h, b0);
-                    tc::tma_load_4d(sa + kATileBytes, &tm_a_lo, &full_bar[st], kb * kBlockK, w0 + s - pad_w, h0 + r - pad_h, b0);
-                    tc::tma_load_3d(sa + 2 * kATileBytes, &tm_b_hi, &full_bar[st], kb * kBlockK, n0, tap);
-                    tc::tma_load_3d(sa + 2 * kATileBytes + b_tile_bytes, &tm_b_lo, &full_bar[st], kb * kBlockK, n0, tap);
+                    uint8_t *sb = sa + p.nsplit * kATileBytes;
+                    for (int pl = 0; pl < p.nsplit; ++pl) {
+                        tc::tma_load_5d(sa + pl * kATileBytes, &tm_a, &full_bar[st], kb * kBlockK, w0 + s - pad_w, h0 + r - pad_h, b0, pl);
+                        tc::tma_load_4d(sb + pl * b_tile_bytes, &tm_b, &full_bar[st], kb * kBlockK, n0, tap, pl);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t id_hh = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 0, 0), id_hl = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 0, 0);
-            const uint32_t id_lh = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 0, 0), id_ll = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 0, 0);
+            const uint32_t idesc = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 0, 0);
             for (int it = 0; it < num_k; ++it) {
                 const int st = it % p.stages;
                 const uint32_t ph = (it / p.stages) & 1;
                 tc::mbar_wait(&full_bar[st], ph);
                 tc::tc_fence_after();
-                const uint32_t a_hi = tc::smem_u32(smem + (size_t)st * stage_bytes);
-                const uint32_t a_lo = a_hi + kATileBytes;
-                const uint32_t b_hi = a_hi + 2 * kATileBytes;
-                const uint32_t b_lo = b_hi + b_tile_bytes;
+                const uint32_t a0 = tc::smem_u32(smem + (size_t)st * stage_bytes);
+                const uint32_t b0 = a0 + p.nsplit * kATileBytes;
 #pragma unroll
                 for (int j = 0; j < kBlockK / 16; ++j) {
-                    const uint64_t dah = tc::make_desc_sw128(a_hi + j * 32, 16, 1024);
-                    const uint64_t dal = tc::make_desc_sw128(a_lo + j * 32, 16, 1024);
-                    const uint64_t dbh = tc::make_desc_sw128(b_hi + j * 32, 16, 1024);
-                    const uint64_t dbl = tc::make_desc_sw128(b_lo + j * 32, 16, 1024);
-                    tc::umma_bf16(tmem_base, dal, dbh, id_lh, (it | j) != 0);  // small terms first
-                    tc::umma_bf16(tmem_base, dah, dbl, id_hl, 1);
-                    tc::umma_bf16(tmem_base, dah, dbh, id_hh, 1);
+                    uint32_t acc = (it | j) != 0;
+                    // all plane products a_i * b_j with i + j < nsplit, smallest magnitude first
+                    for (int sum = p.nsplit - 1; sum >= 0; --sum) {
+                        for (int ia = sum; ia >= 0; --ia) {
+                            const int ib = sum - ia;
+                            const uint64_t da = tc::make_desc_sw128(a0 + ia * kATileBytes + j * 32, 16, 1024);
+                            const uint64_t db = tc::make_desc_sw128(b0 + ib * b_tile_bytes + j * 32, 16, 1024);
+                            tc::umma_bf16(tmem_base, da, db, idesc, acc);
+                            acc = 1;
+                        }
+                    }
                 }
                 tc::umma_commit(&empty_bar[st]);  // frees the smem stage once these MMAs retire
             }
@@ -163,31 +166,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                     for (int i = 0; i < valid; ++i) o[i] = f[i];
                 }
             }
-            if (p.out_hi) {
-                __nv_bfloat16 *oh = p.out_hi + pix * p.split_cs + n;
-                __nv_bfloat16 *ol = p.out_lo + pix * p.split_cs + n;
-                if (valid == 32 && ((reinterpret_cast<uintptr_t>(oh) & 15) == 0)) {
+            if (p.out_pl) {
+                __nv_bfloat16 *o = p.out_pl + pix * p.split_cs + n;
+                if (valid == 32 && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 8) {
-                        uint32_t hh[4], ll[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            unsigned short h0_, h1_, l0_, l1_;
-                            split_hi_lo(f[i + 2 * k], h0_, l0_);
-                            split_hi_lo(f[i + 2 * k + 1], h1_, l1_);
-                            hh[k] = (uint32_t)h0_ | ((uint32_t)h1_ << 16);
-                            ll[k] = (uint32_t)l0_ | ((uint32_t)l1_ << 16);
-                        }
-                        *reinterpret_cast<uint4 *>(oh + i) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-                        *reinterpret_cast<uint4 *>(ol + i) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-                    }
+                    for (int i = 0; i < 32; i += 4) store_planes4(o + i, p.out_pl_stride, p.nsplit_out, make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]));
                 } else {
-                    for (int i = 0; i < valid; ++i) {
-                        unsigned short hv, lv;
-                        split_hi_lo(f[i], hv, lv);
-                        oh[i] = __ushort_as_bfloat16(hv);
-                        ol[i] = __ushort_as_bfloat16(lv);
-                    }
+                    for (int i = 0; i < valid; ++i) store_planes1(o + i, p.out_pl_stride, p.nsplit_out, f[i]);
                 }
             }
         }
@@ -228,62 +213,62 @@ int istnet_make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const ui
     return r == CUDA_SUCCESS ? ISTNET_OK : ISTNET_ERR_BAD_ARG;
 }
 
-static int pick_bn(int cout) {
-    if (cout >= 256) return 256;
+static int pick_bn(int cout, int nsplit) {
+    const int cap = nsplit >= 3 ? 128 : 256;  // keep >= 2 pipeline stages in 227 KB of shared memory
+    if (cout >= cap) return cap;
     int bn = (cout + 15) / 16 * 16;
     return bn < 16 ? 16 : bn;
 }
 
-extern "C" int istnet_conv_gemm(const void *act_hi, const void *act_lo, int B, int H, int W, int Cin, int act_cs, const void *wgt_hi,
-                                const void *wgt_lo, int Cout, int wgt_cs, int kh, int kw, const float *bias, int relu, float *out_f32,
-                                int out_cs, void *out_hi, void *out_lo, int split_cs, int box_w, int box_h, void *stream) {
+extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stride, int B, int H, int W, int Cin, int act_cs,
+                                const void *wgt_planes, long long wgt_plane_stride, int Cout, int wgt_cs, int kh, int kw, int nsplit,
+                                const float *bias, int relu, float *out_f32, int out_cs, void *out_planes, long long out_plane_stride,
+                                int nsplit_out, int split_cs, int box_w, int box_h, void *stream) {
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return ISTNET_ERR_BAD_ARG;
+    if (nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
     if ((act_cs & 7) || (wgt_cs & 7) || act_cs < Cin || wgt_cs < Cin) return ISTNET_ERR_BAD_ARG;
     if (box_w <= 0 || box_h <= 0 || (kTileM % (box_w * box_h)) != 0 || box_w > 256 || box_h > 256) return ISTNET_ERR_BAD_ARG;
     if ((kh & 1) == 0 || (kw & 1) == 0) return ISTNET_ERR_UNSUPPORTED;
-    if (out_hi && ((split_cs & 7) || !out_lo)) return ISTNET_ERR_BAD_ARG;
+    if (out_planes && ((split_cs & 3) || nsplit_out < 1 || nsplit_out > kMaxPlanes)) return ISTNET_ERR_BAD_ARG;
     ConvGemmParams p{};
     p.B = B; p.H = H; p.W = W;
     p.box_w = box_w; p.box_h = box_h; p.box_b = kTileM / (box_w * box_h);
     p.tiles_w = ceil_div(W, box_w); p.tiles_h = ceil_div(H, box_h); p.tiles_b = ceil_div(B, p.box_b);
     p.kh = kh; p.kw = kw;
     p.cin_blocks = ceil_div(Cin, kBlockK);
-    p.Cout = Cout; p.BN = pick_bn(Cout);
+    p.Cout = Cout; p.BN = pick_bn(Cout, nsplit);
+    p.nsplit = nsplit;
     p.bias = bias; p.relu = relu;
     p.out_f32 = out_f32; p.out_cs = out_cs;
-    p.out_hi = (__nv_bfloat16 *)out_hi; p.out_lo = (__nv_bfloat16 *)out_lo; p.split_cs = split_cs;
+    p.out_pl = (__nv_bfloat16 *)out_planes; p.out_pl_stride = out_plane_stride; p.split_cs = split_cs; p.nsplit_out = nsplit_out;
     p.tmem_cols = 32;
     while ((int)p.tmem_cols < p.BN) p.tmem_cols *= 2;
     const int num_k = kh * kw * p.cin_blocks;
-    const int stage_bytes = 2 * kATileBytes + 2 * p.BN * kBlockK * 2;
+    const int stage_bytes = nsplit * (kATileBytes + p.BN * kBlockK * 2);
     int max_stages = (225 * 1024 - 1024 - 256) / stage_bytes;
     if (max_stages > 6) max_stages = 6;
     p.stages = num_k < max_stages ? num_k : max_stages;
     if (p.stages < 1) return ISTNET_ERR_UNSUPPORTED;
     size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
 
-    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    CUtensorMap ta, tb;
     {
-        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-        uint64_t str[3] = {(uint64_t)act_cs * 2, (uint64_t)W * act_cs * 2, (uint64_t)H * W * act_cs * 2};
-        uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)box_w, (uint32_t)box_h, (uint32_t)p.box_b};
-        int e = istnet_make_tmap_bf16(&ta_hi, act_hi, 4, dims, str, box);
-        if (e) return e;
-        e = istnet_make_tmap_bf16(&ta_lo, act_lo, 4, dims, str, box);
+        uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B, (uint64_t)nsplit};
+        uint64_t str[4] = {(uint64_t)act_cs * 2, (uint64_t)W * act_cs * 2, (uint64_t)H * W * act_cs * 2, (uint64_t)act_plane_stride * 2};
+        uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)box_w, (uint32_t)box_h, (uint32_t)p.box_b, 1u};
+        int e = istnet_make_tmap_bf16(&ta, act_planes, 5, dims, str, box);
         if (e) return e;
     }
     {
-        uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
-        uint64_t str[2] = {(uint64_t)wgt_cs * 2, (uint64_t)Cout * wgt_cs * 2};
-        uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)p.BN, 1u};
-        int e = istnet_make_tmap_bf16(&tb_hi, wgt_hi, 3, dims, str, box);
-        if (e) return e;
-        e = istnet_make_tmap_bf16(&tb_lo, wgt_lo, 3, dims, str, box);
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw), (uint64_t)nsplit};
+        uint64_t str[3] = {(uint64_t)wgt_cs * 2, (uint64_t)Cout * wgt_cs * 2, (uint64_t)wgt_plane_stride * 2};
+        uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.BN, 1u, 1u};
+        int e = istnet_make_tmap_bf16(&tb, wgt_planes, 4, dims, str, box);
         if (e) return e;
     }
     ISTNET_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     dim3 grid(p.tiles_w * p.tiles_h * p.tiles_b, ceil_div(Cout, p.BN));
-    conv_gemm_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+    conv_gemm_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ta, tb, p);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }

@@ -16,17 +16,6 @@ namespace {
 
 constexpr int kEwThreads = 256;
 
-__device__ __forceinline__ void split_store4(__nv_bfloat16 *hi, __nv_bfloat16 *lo, float4 v) {
-    unsigned short h0, h1, h2, h3, l0, l1, l2, l3;
-    split_hi_lo(v.x, h0, l0); split_hi_lo(v.y, h1, l1); split_hi_lo(v.z, h2, l2); split_hi_lo(v.w, h3, l3);
-    uint2 ph, pl;
-    ph.x = (uint32_t)h0 | ((uint32_t)h1 << 16);
-    ph.y = (uint32_t)h2 | ((uint32_t)h3 << 16);
-    pl.x = (uint32_t)l0 | ((uint32_t)l1 << 16);
-    pl.y = (uint32_t)l2 | ((uint32_t)l3 << 16);
-    *reinterpret_cast<uint2 *>(hi) = ph;
-    *reinterpret_cast<uint2 *>(lo) = pl;
-}
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ float4 bf4_to_f4(const __nv_bfloat16 *p) {
     uint2 r = *reinterpret_cast<const uint2 *>(p);
@@ -120,8 +109,9 @@ struct ActFwdP {
     const float *noise;     // optional [B,C] Dropout2d scale
     long long HW;
     float *out_f32;         // optional [P,C]
-    __nv_bfloat16 *out_hi, *out_lo;  // optional [P,cs] (+ch_off)
-    int cs, ch_off;
+    __nv_bfloat16 *out_pl;  // optional operand planes [nsplit][P,cs] (+ch_off)
+    long long pl_stride;
+    int nsplit, cs, ch_off;
 };
 __device__ __forceinline__ float4 act_fwd4(float4 u, int act, float a) {
     if (act == 1) return make_float4(fmaxf(u.x, 0.f), fmaxf(u.y, 0.f), fmaxf(u.z, 0.f), fmaxf(u.w, 0.f));
@@ -146,7 +136,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_act_split_kernel(long long P, i
             z.x *= nz.x; z.y *= nz.y; z.z *= nz.z; z.w *= nz.w;
         }
         if (p.out_f32) *reinterpret_cast<float4 *>(p.out_f32 + r * C + c) = z;
-        if (p.out_hi) split_store4(p.out_hi + r * p.cs + p.ch_off + c, p.out_lo + r * p.cs + p.ch_off + c, z);
+        if (p.out_pl) store_planes4(p.out_pl + r * p.cs + p.ch_off + c, p.pl_stride, p.nsplit, z);
     }
 }
 
@@ -209,8 +199,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(long long P, 
 }
 // dy = gamma*invstd*(g - sum_g/P - xhat*sum_gx/P)  (BN)   or   dy = g   (no BN);  dy -> bf16 pair (+ optional FP32 copies)
 __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(long long P, int C, ActBwdP p, const double *__restrict__ ws,
-                                                                  __nv_bfloat16 *dy_hi, __nv_bfloat16 *dy_lo, int cs_dy, float *dy_f32,
-                                                                  float *g_out) {
+                                                                  __nv_bfloat16 *dy_pl, long long pl_stride, int nsplit, int cs_dy,
+                                                                  float *dy_f32, float *g_out) {
     const int lanes = C >> 2;
     const long long total = P * lanes;
     const float a = (p.act == 2) ? *p.prelu_a : 0.f;
@@ -232,23 +222,20 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(long long P, i
             dy.z = ga.z * s.z * (g.z - mg[2] - xh.z * mgx[2]);
             dy.w = ga.w * s.w * (g.w - mg[3] - xh.w * mgx[3]);
         }
-        if (dy_hi) split_store4(dy_hi + r * cs_dy + c, dy_lo + r * cs_dy + c, dy);
+        if (dy_pl) store_planes4(dy_pl + r * cs_dy + c, pl_stride, nsplit, dy);
         if (dy_f32) *reinterpret_cast<float4 *>(dy_f32 + r * C + c) = dy;
     }
 }
 
 // ------------------------------------------------------------------ generic FP32 -> bf16 pair (optionally NCHW -> NHWC), column sums
 __global__ void __launch_bounds__(kEwThreads) split_kernel(long long P, int C, const float *__restrict__ x, long long HW, int nchw,
-                                                           __nv_bfloat16 *hi, __nv_bfloat16 *lo, int cs, int ch_off) {
+                                                           __nv_bfloat16 *pl, long long pl_stride, int nsplit, int cs, int ch_off) {
     const long long total = P * C;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / C;
         const int c = (int)(i % C);
         float v = nchw ? x[((r / HW) * C + c) * HW + (r % HW)] : x[i];
-        unsigned short hv, lv;
-        split_hi_lo(v, hv, lv);
-        hi[r * cs + ch_off + c] = __ushort_as_bfloat16(hv);
-        lo[r * cs + ch_off + c] = __ushort_as_bfloat16(lv);
+        store_planes1(pl + r * cs + ch_off + c, pl_stride, nsplit, v);
     }
 }
 __global__ void __launch_bounds__(kEwThreads) colsum_kernel(const float *__restrict__ x, long long P, int C, double *ws) {
@@ -269,7 +256,7 @@ __device__ __forceinline__ void up_src(int o, int in, int out, int &i0, int &i1,
     l0 = 1.f - l1;
 }
 __global__ void __launch_bounds__(kEwThreads) upsample2x_split_kernel(int B, int H, int W, int C, const float *__restrict__ x,
-                                                                       __nv_bfloat16 *hi, __nv_bfloat16 *lo, int cs, float *out_f32) {
+                                                                       __nv_bfloat16 *pl, long long pl_stride, int nsplit, int cs, float *out_f32) {
     const int lanes = C >> 2, Ho = 2 * H, Wo = 2 * W;
     const long long total = (long long)B * Ho * Wo * lanes;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -291,7 +278,7 @@ __global__ void __launch_bounds__(kEwThreads) upsample2x_split_kernel(int B, int
         o.z = hl0 * (wl0 * a.z + wl1 * bq.z) + hl1 * (wl0 * cq.z + wl1 * d.z);
         o.w = hl0 * (wl0 * a.w + wl1 * bq.w) + hl1 * (wl0 * cq.w + wl1 * d.w);
         const size_t op = ((size_t)b * Ho + ho) * Wo + wo;
-        if (hi) split_store4(hi + op * cs + c, lo + op * cs + c, o);
+        if (pl) store_planes4(pl + op * cs + c, pl_stride, nsplit, o);
         if (out_f32) *reinterpret_cast<float4 *>(out_f32 + op * C + c) = o;
     }
 }
@@ -331,8 +318,8 @@ __global__ void __launch_bounds__(kEwThreads) upsample2x_bwd_kernel(int B, int H
 // ------------------------------------------------------------------ im2col (strided convs) and its adjoint
 // out[b,ho,wo,(r*kw+s)*C + c] = x[b, ho*stride+r-pad, wo*stride+s-pad, c]   (zero outside); x NHWC or NCHW
 __global__ void __launch_bounds__(kEwThreads) im2col_split_kernel(int B, int H, int W, int C, int kh, int kw, int stride, int pad, int Ho,
-                                                                   int Wo, const float *__restrict__ x, int nchw, __nv_bfloat16 *hi,
-                                                                   __nv_bfloat16 *lo, int cs) {
+                                                                   int Wo, const float *__restrict__ x, int nchw, __nv_bfloat16 *pl,
+                                                                   long long pl_stride, int nsplit, int cs) {
     const int K = kh * kw * C;
     const long long total = (long long)B * Ho * Wo * K;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -346,10 +333,7 @@ __global__ void __launch_bounds__(kEwThreads) im2col_split_kernel(int B, int H, 
         float v = 0.f;
         if (h >= 0 && h < H && w >= 0 && w < W) v = nchw ? x[(((size_t)b * C + c) * H + h) * W + w] : x[(((size_t)b * H + h) * W + w) * C + c];
         const size_t o = (((size_t)b * Ho + ho) * Wo + wo) * cs + k;
-        unsigned short hv, lv;
-        split_hi_lo(v, hv, lv);
-        hi[o] = __ushort_as_bfloat16(hv);
-        lo[o] = __ushort_as_bfloat16(lv);
+        store_planes1(pl + o, pl_stride, nsplit, v);
     }
 }
 // dx[b,h,w,c] (+)= sum over (r,s) with (h+pad-r) % stride == 0 ... of dcol[b,ho,wo,(r*kw+s)*C+c]
@@ -383,7 +367,7 @@ __global__ void __launch_bounds__(kEwThreads) col2im_kernel(int B, int H, int W,
 
 // ------------------------------------------------------------------ stem: BN + ReLU + MaxPool(3,2,1) fused
 __global__ void __launch_bounds__(kEwThreads) bn_relu_maxpool_kernel(int B, int H, int W, int C, const float *__restrict__ y, BnP bn,
-                                                                      float *out_f32, __nv_bfloat16 *hi, __nv_bfloat16 *lo, int cs,
+                                                                      float *out_f32, __nv_bfloat16 *pl, long long pl_stride, int nsplit, int cs,
                                                                       uint8_t *argmax) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1, lanes = C >> 2;
     const long long total = (long long)B * Ho * Wo * lanes;
@@ -411,7 +395,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_relu_maxpool_kernel(int B, int 
         const size_t op = ((size_t)b * Ho + ho) * Wo + wo;
         float4 z = make_float4(best[0], best[1], best[2], best[3]);
         if (out_f32) *reinterpret_cast<float4 *>(out_f32 + op * C + c) = z;
-        if (hi) split_store4(hi + op * cs + c, lo + op * cs + c, z);
+        if (pl) store_planes4(pl + op * cs + c, pl_stride, nsplit, z);
         *reinterpret_cast<uchar4 *>(argmax + op * C + c) = make_uchar4((uint8_t)bi[0], (uint8_t)bi[1], (uint8_t)bi[2], (uint8_t)bi[3]);
     }
 }
@@ -445,7 +429,7 @@ __global__ void __launch_bounds__(kEwThreads) maxpool_relu_bwd_kernel(int B, int
 }
 
 // ------------------------------------------------------------------ final head: BN + PReLU only at the chosen pixels
-// out[b,c,n] = prelu(bn(y[b, choose[b,n], c]))   (ist_net.py:42-45 gather after modules.py:64-66)
+// out[b,n,c] = prelu(bn(y[b, choose[b,n], c]))   (ist_net.py:42-45 gather after modules.py:64-66; row layout)
 __global__ void __launch_bounds__(kEwThreads) gather_bn_prelu_kernel(int B, long long HW, int C, int N, const float *__restrict__ y,
                                                                       const long long *__restrict__ choose, BnP bn, const float *prelu_a,
                                                                       float *out) {
@@ -459,10 +443,10 @@ __global__ void __launch_bounds__(kEwThreads) gather_bn_prelu_kernel(int B, long
         const long long px = choose[(long long)b * N + n];
         float yv = y[((long long)b * HW + px) * C + c];
         float u = bn.mean ? (yv - bn.mean[c]) * bn.invstd[c] * bn.gamma[c] + bn.beta[c] : yv;
-        out[((long long)b * C + c) * N + n] = u > 0.f ? u : a * u;
+        out[i] = u > 0.f ? u : a * u;  // rows: out[b][n][c]
     }
 }
-// g_dense[b, choose[b,n], c] += dout[b,c,n] * prelu'(u);  slope_ws[c] += dout*u*[u<=0]   (g_dense pre-zeroed)
+// g_dense[b, choose[b,n], c] += dout[b,n,c] * prelu'(u);  slope_ws[c] += dout*u*[u<=0]   (g_dense pre-zeroed)
 __global__ void __launch_bounds__(kEwThreads) gather_bn_prelu_bwd_kernel(int B, long long HW, int C, int N, const float *__restrict__ y,
                                                                           const long long *__restrict__ choose, BnP bn, const float *prelu_a,
                                                                           const float *__restrict__ dout, float *g_dense, double *slope_ws) {
@@ -477,7 +461,7 @@ __global__ void __launch_bounds__(kEwThreads) gather_bn_prelu_bwd_kernel(int B, 
         const long long src = ((long long)b * HW + px) * C + c;
         float yv = y[src];
         float u = bn.mean ? (yv - bn.mean[c]) * bn.invstd[c] * bn.gamma[c] + bn.beta[c] : yv;
-        float d = dout[((long long)b * C + c) * N + n];
+        float d = dout[i];
         atomicAdd(g_dense + src, u > 0.f ? d : a * d);
         if (!(u > 0.f) && slope_ws) atomicAdd(slope_ws + c, (double)(d * u));
     }
@@ -515,13 +499,14 @@ extern "C" int istnet_bn_stats(const float *y, long long P, int C, double *ws, f
 extern "C" int istnet_bn_act_split(const float *y, long long P, int C, long long HW, const float *mean, const float *invstd,
                                    const float *gamma, const float *beta, const float *res, const float *res_mean,
                                    const float *res_invstd, const float *res_gamma, const float *res_beta, int act, const float *prelu_a,
-                                   const float *noise, float *out_f32, void *out_hi, void *out_lo, int cs, int ch_off, void *stream) {
-    if (P <= 0 || C <= 0 || (C & 3) || (out_hi && ((cs & 3) || (ch_off & 3)))) return ISTNET_ERR_BAD_ARG;
+                                   const float *noise, float *out_f32, void *out_planes, long long plane_stride, int nsplit, int cs, int ch_off,
+                                   void *stream) {
+    if (P <= 0 || C <= 0 || (C & 3) || (out_planes && ((cs & 3) || (ch_off & 3) || nsplit < 1 || nsplit > kMaxPlanes))) return ISTNET_ERR_BAD_ARG;
     ActFwdP p{};
     p.y = y; p.bn = make_bn(mean, invstd, gamma, beta);
     p.res = res; p.res_bn = make_bn(res_mean, res_invstd, res_gamma, res_beta);
     p.act = act; p.prelu_a = prelu_a; p.noise = noise; p.HW = HW > 0 ? HW : 1;
-    p.out_f32 = out_f32; p.out_hi = (__nv_bfloat16 *)out_hi; p.out_lo = (__nv_bfloat16 *)out_lo; p.cs = cs; p.ch_off = ch_off;
+    p.out_f32 = out_f32; p.out_pl = (__nv_bfloat16 *)out_planes; p.pl_stride = plane_stride; p.nsplit = nsplit; p.cs = cs; p.ch_off = ch_off;
     bn_act_split_kernel<<<ew_grid(P * (C / 4)), kEwThreads, 0, ST>>>(P, C, p);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
@@ -529,8 +514,8 @@ extern "C" int istnet_bn_act_split(const float *y, long long P, int C, long long
 
 extern "C" int istnet_bn_act_bwd(const float *dz, const float *dz2, const float *y, long long P, int C, long long HW, const float *mean,
                                  const float *invstd, const float *gamma, const float *beta, int act, const float *prelu_a,
-                                 const void *z_hi, int cs_z, const float *noise, double *ws /*3C*/, void *dy_hi, void *dy_lo, int cs_dy,
-                                 float *dy_f32, float *g_out, void *stream) {
+                                 const void *z_hi, int cs_z, const float *noise, double *ws /*3C*/, void *dy_planes, long long plane_stride,
+                                 int nsplit, int cs_dy, float *dy_f32, float *g_out, void *stream) {
     if (P <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
     if (act == 1 && !z_hi) return ISTNET_ERR_BAD_ARG;
     ActBwdP p{};
@@ -539,15 +524,16 @@ extern "C" int istnet_bn_act_bwd(const float *dz, const float *dz2, const float 
     ISTNET_CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(double) * 3 * C, ST));
     bn_bwd_reduce_kernel<<<red_grid(P, C), kEwThreads, 0, ST>>>(P, C, p, ws);
     ISTNET_LAUNCH_CHECK();
-    bn_bwd_apply_kernel<<<ew_grid(P * (C / 4)), kEwThreads, 0, ST>>>(P, C, p, ws, (__nv_bfloat16 *)dy_hi, (__nv_bfloat16 *)dy_lo, cs_dy,
+    bn_bwd_apply_kernel<<<ew_grid(P * (C / 4)), kEwThreads, 0, ST>>>(P, C, p, ws, (__nv_bfloat16 *)dy_planes, plane_stride, nsplit, cs_dy,
                                                                      dy_f32, g_out);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
 
-extern "C" int istnet_split(const float *x, long long P, int C, long long HW, int nchw, void *hi, void *lo, int cs, int ch_off, void *stream) {
-    if (P <= 0 || C <= 0) return ISTNET_ERR_BAD_ARG;
-    split_kernel<<<ew_grid(P * C), kEwThreads, 0, ST>>>(P, C, x, HW > 0 ? HW : 1, nchw, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, cs, ch_off);
+extern "C" int istnet_split(const float *x, long long P, int C, long long HW, int nchw, void *planes, long long plane_stride, int nsplit,
+                            int cs, int ch_off, void *stream) {
+    if (P <= 0 || C <= 0 || nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
+    split_kernel<<<ew_grid(P * C), kEwThreads, 0, ST>>>(P, C, x, HW > 0 ? HW : 1, nchw, (__nv_bfloat16 *)planes, plane_stride, nsplit, cs, ch_off);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
@@ -560,10 +546,11 @@ extern "C" int istnet_colsum(const float *x, long long P, int C, double *ws, voi
     return ISTNET_OK;
 }
 
-extern "C" int istnet_upsample2x_split(const float *x, int B, int H, int W, int C, void *hi, void *lo, int cs, float *out_f32, void *stream) {
-    if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
-    upsample2x_split_kernel<<<ew_grid((long long)B * 4 * H * W * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, x, (__nv_bfloat16 *)hi,
-                                                                                               (__nv_bfloat16 *)lo, cs, out_f32);
+extern "C" int istnet_upsample2x_split(const float *x, int B, int H, int W, int C, void *planes, long long plane_stride, int nsplit, int cs,
+                                       float *out_f32, void *stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
+    upsample2x_split_kernel<<<ew_grid((long long)B * 4 * H * W * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, x, (__nv_bfloat16 *)planes,
+                                                                                               plane_stride, nsplit, cs, out_f32);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
@@ -574,12 +561,12 @@ extern "C" int istnet_upsample2x_bwd(const float *dout, int B, int H, int W, int
     return ISTNET_OK;
 }
 
-extern "C" int istnet_im2col_split(const float *x, int nchw, int B, int H, int W, int C, int kh, int kw, int stride, int pad, void *hi,
-                                   void *lo, int cs, void *stream) {
+extern "C" int istnet_im2col_split(const float *x, int nchw, int B, int H, int W, int C, int kh, int kw, int stride, int pad, void *planes,
+                                   long long plane_stride, int nsplit, int cs, void *stream) {
     const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
-    if (B <= 0 || Ho <= 0 || Wo <= 0 || cs < kh * kw * C) return ISTNET_ERR_BAD_ARG;
+    if (B <= 0 || Ho <= 0 || Wo <= 0 || cs < kh * kw * C || nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
     im2col_split_kernel<<<ew_grid((long long)B * Ho * Wo * kh * kw * C), kEwThreads, 0, ST>>>(B, H, W, C, kh, kw, stride, pad, Ho, Wo, x, nchw,
-                                                                                             (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, cs);
+                                                                                             (__nv_bfloat16 *)planes, plane_stride, nsplit, cs);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
@@ -593,11 +580,12 @@ extern "C" int istnet_col2im(const float *dcol, int B, int H, int W, int C, int 
 }
 
 extern "C" int istnet_bn_relu_maxpool(const float *y, int B, int H, int W, int C, const float *mean, const float *invstd, const float *gamma,
-                                      const float *beta, float *out_f32, void *hi, void *lo, int cs, uint8_t *argmax, void *stream) {
-    if (B <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
+                                      const float *beta, float *out_f32, void *planes, long long plane_stride, int nsplit, int cs,
+                                      uint8_t *argmax, void *stream) {
+    if (B <= 0 || (C & 3) || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     bn_relu_maxpool_kernel<<<ew_grid((long long)B * Ho * Wo * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, y, make_bn(mean, invstd, gamma, beta),
-                                                                                            out_f32, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, cs, argmax);
+                                                                                            out_f32, (__nv_bfloat16 *)planes, plane_stride, nsplit, cs, argmax);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }

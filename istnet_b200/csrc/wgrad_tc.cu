@@ -7,7 +7,7 @@
 // (SWIZZLE_128B, 8 KB) is exactly one canonical MN-major swizzle slab (8-pixel groups 1024 B apart), and
 // consecutive 64-channel slabs sit 8 KB apart (the descriptor's leading-byte-offset).  The tap shift and the
 // zero padding are the TMA coordinates / out-of-bounds fill, exactly as in the forward kernel.
-// Split-bf16 arithmetic as in conv_gemm_tc.cu: lo*hi + hi*lo + hi*hi.
+// bf16-plane arithmetic as in conv_gemm_tc.cu: all plane products dY_i * X_j with i + j < nsplit, smallest first.
 // K (pixels) is split across CTAs; each CTA writes its FP32 partial tile and a second tiny kernel reduces the
 // partials in a fixed order into the PyTorch weight layout [Cout][Cin][kh][kw] — deterministic, unlike the
 // atomics of the reference's custom grads (SURVEY.md §7 hard part 5).
@@ -27,20 +27,19 @@ struct WgradParams {
     int kh, kw;
     int Cout, Cin, BN;        // BN multiple of 64
     int n_ci_tiles;
-    int ksplit, stages;
+    int ksplit, stages, nsplit;
     float *partial;           // [ksplit][taps][Cout][Cin]
     uint32_t tmem_cols;
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_constant__ CUtensorMap tm_dy_lo,
-                const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo, const WgradParams p) {
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x, const WgradParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int n_slabs_b = p.BN / 64;
-    const int a_bytes = 2 * kSlabBytes;          // 128 output channels = 2 slabs (per hi / lo)
+    const int a_bytes = 2 * kSlabBytes;          // 128 output channels = 2 slabs (per plane)
     const int b_bytes = n_slabs_b * kSlabBytes;
-    const int stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const int stage_bytes = p.nsplit * (a_bytes + b_bytes);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
     uint64_t *empty_bar = full_bar + p.stages;
     uint64_t *tmem_full_bar = empty_bar + p.stages;
@@ -58,7 +57,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_const
     const int num_k = max(0, t_end - t_begin);
 
     if (warp == 0 && lane == 0) {
-        tc::prefetch_tmap(&tm_dy_hi); tc::prefetch_tmap(&tm_dy_lo); tc::prefetch_tmap(&tm_x_hi); tc::prefetch_tmap(&tm_x_lo);
+        tc::prefetch_tmap(&tm_dy); tc::prefetch_tmap(&tm_x);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
@@ -84,41 +83,39 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_const
                 tc::mbar_wait(&empty_bar[st], ph ^ 1);
                 uint8_t *sa = smem + (size_t)st * stage_bytes;
                 tc::mbar_arrive_expect_tx(&full_bar[st], stage_bytes);
-                for (int c = 0; c < 2; ++c) {
-                    tc::tma_load_4d(sa + c * kSlabBytes, &tm_dy_hi, &full_bar[st], co0 + c * 64, w0, h0, b0);
-                    tc::tma_load_4d(sa + a_bytes + c * kSlabBytes, &tm_dy_lo, &full_bar[st], co0 + c * 64, w0, h0, b0);
-                }
-                uint8_t *sb = sa + 2 * a_bytes;
-                for (int c = 0; c < n_slabs_b; ++c) {
-                    tc::tma_load_4d(sb + c * kSlabBytes, &tm_x_hi, &full_bar[st], ci0 + c * 64, w0 + s - pad_w, h0 + r - pad_h, b0);
-                    tc::tma_load_4d(sb + b_bytes + c * kSlabBytes, &tm_x_lo, &full_bar[st], ci0 + c * 64, w0 + s - pad_w, h0 + r - pad_h, b0);
+                uint8_t *sb = sa + p.nsplit * a_bytes;
+                for (int pl = 0; pl < p.nsplit; ++pl) {
+                    for (int c = 0; c < 2; ++c)
+                        tc::tma_load_5d(sa + pl * a_bytes + c * kSlabBytes, &tm_dy, &full_bar[st], co0 + c * 64, w0, h0, b0, pl);
+                    for (int c = 0; c < n_slabs_b; ++c)
+                        tc::tma_load_5d(sb + pl * b_bytes + c * kSlabBytes, &tm_x, &full_bar[st], ci0 + c * 64, w0 + s - pad_w, h0 + r - pad_h, b0, pl);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // both operands MN-major
-            const uint32_t id_hh = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 1, 1), id_hl = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 1, 1);
-            const uint32_t id_lh = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 1, 1), id_ll = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 1, 1);
+            const uint32_t idesc = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 1, 1);
             for (int it = 0; it < num_k; ++it) {
                 const int st = it % p.stages;
                 const uint32_t ph = (it / p.stages) & 1;
                 tc::mbar_wait(&full_bar[st], ph);
                 tc::tc_fence_after();
-                const uint32_t a_hi = tc::smem_u32(smem + (size_t)st * stage_bytes);
-                const uint32_t a_lo = a_hi + a_bytes;
-                const uint32_t b_hi = a_hi + 2 * a_bytes;
-                const uint32_t b_lo = b_hi + b_bytes;
+                const uint32_t a0 = tc::smem_u32(smem + (size_t)st * stage_bytes);
+                const uint32_t b0 = a0 + p.nsplit * a_bytes;
 #pragma unroll
                 for (int j = 0; j < kPixTile / 16; ++j) {  // 16 pixels (k) per MMA = 2 groups of 8 rows x 128 B
                     const uint32_t off = j * 2048;
-                    const uint64_t dah = tc::make_desc_sw128(a_hi + off, kSlabBytes, 1024);
-                    const uint64_t dal = tc::make_desc_sw128(a_lo + off, kSlabBytes, 1024);
-                    const uint64_t dbh = tc::make_desc_sw128(b_hi + off, kSlabBytes, 1024);
-                    const uint64_t dbl = tc::make_desc_sw128(b_lo + off, kSlabBytes, 1024);
-                    tc::umma_bf16(tmem_base, dal, dbh, id_lh, (it | j) != 0);
-                    tc::umma_bf16(tmem_base, dah, dbl, id_hl, 1);
-                    tc::umma_bf16(tmem_base, dah, dbh, id_hh, 1);
+                    uint32_t acc = (it | j) != 0;
+                    for (int sum = p.nsplit - 1; sum >= 0; --sum) {
+                        for (int ia = sum; ia >= 0; --ia) {
+                            const int ib = sum - ia;
+                            const uint64_t da = tc::make_desc_sw128(a0 + ia * a_bytes + off, kSlabBytes, 1024);
+                            const uint64_t db = tc::make_desc_sw128(b0 + ib * b_bytes + off, kSlabBytes, 1024);
+                            tc::umma_bf16(tmem_base, da, db, idesc, acc);
+                            acc = 1;
+                        }
+                    }
                 }
                 tc::umma_commit(&empty_bar[st]);
             }
@@ -180,14 +177,15 @@ __global__ void wgrad_reduce_kernel(int ksplit, int taps, int Cout, int Cin, con
 
 }  // namespace
 
-static int wgrad_pick_bn(int cin) {
+static int wgrad_pick_bn(int cin, int nsplit) {
     int bn = (cin + 63) / 64 * 64;
-    return bn > 256 ? 256 : bn;
+    const int cap = nsplit >= 3 ? 128 : 256;  // keep >= 2 pipeline stages
+    return bn > cap ? cap : bn;
 }
 
-extern "C" int istnet_wgrad_ksplit(int B, int H, int W, int Cout, int Cin, int kh, int kw) {
+extern "C" int istnet_wgrad_ksplit(int B, int H, int W, int Cout, int Cin, int kh, int kw, int nsplit) {
     // enough CTAs to fill the chip ~2x, at least 4 pixel tiles per CTA
-    const int bn = wgrad_pick_bn(Cin);
+    const int bn = wgrad_pick_bn(Cin, nsplit);
     const int base = ceil_div(Cout, kTileM) * ceil_div(Cin, bn) * kh * kw;
     const long long pix_tiles = ((long long)B * H * W + kPixTile - 1) / kPixTile;
     int ks = ceil_div(2 * kNumSMs, base);
@@ -197,10 +195,11 @@ extern "C" int istnet_wgrad_ksplit(int B, int H, int W, int Cout, int Cin, int k
     return ks;
 }
 
-extern "C" int istnet_conv_wgrad(const void *dy_hi, const void *dy_lo, int dy_cs, const void *x_hi, const void *x_lo, int x_cs, int B,
-                                 int H, int W, int Cout, int Cin, int kh, int kw, float *partial_ws, int ksplit, float *grad_w,
-                                 int box_w, int box_h, void *stream) {
+extern "C" int istnet_conv_wgrad(const void *dy_planes, long long dy_plane_stride, int dy_cs, const void *x_planes, long long x_plane_stride,
+                                 int x_cs, int nsplit, int B, int H, int W, int Cout, int Cin, int kh, int kw, float *partial_ws, int ksplit,
+                                 float *grad_w, int box_w, int box_h, void *stream) {
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || ksplit <= 0) return ISTNET_ERR_BAD_ARG;
+    if (nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
     if ((dy_cs & 7) || (x_cs & 7) || dy_cs < Cout || x_cs < Cin) return ISTNET_ERR_BAD_ARG;
     if (box_w <= 0 || box_h <= 0 || (kPixTile % (box_w * box_h)) != 0) return ISTNET_ERR_BAD_ARG;
     if ((kh & 1) == 0 || (kw & 1) == 0) return ISTNET_ERR_UNSUPPORTED;
@@ -210,13 +209,14 @@ extern "C" int istnet_conv_wgrad(const void *dy_hi, const void *dy_lo, int dy_cs
     p.tiles_w = ceil_div(W, box_w); p.tiles_h = ceil_div(H, box_h); p.tiles_b = ceil_div(B, p.box_b);
     p.num_pix_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
     p.kh = kh; p.kw = kw; p.Cout = Cout; p.Cin = Cin;
-    p.BN = wgrad_pick_bn(Cin);
+    p.nsplit = nsplit;
+    p.BN = wgrad_pick_bn(Cin, nsplit);
     p.n_ci_tiles = ceil_div(Cin, p.BN);
     p.ksplit = ksplit;
     p.partial = partial_ws;
     p.tmem_cols = 32;
     while ((int)p.tmem_cols < p.BN) p.tmem_cols *= 2;
-    const int stage_bytes = 2 * 2 * kSlabBytes + 2 * (p.BN / 64) * kSlabBytes;
+    const int stage_bytes = nsplit * (2 * kSlabBytes + (p.BN / 64) * kSlabBytes);
     int max_stages = (225 * 1024 - 1024 - 256) / stage_bytes;
     if (max_stages > 6) max_stages = 6;
     const int per = ceil_div(p.num_pix_tiles, ksplit);
@@ -224,27 +224,23 @@ extern "C" int istnet_conv_wgrad(const void *dy_hi, const void *dy_lo, int dy_cs
     if (p.stages < 1) p.stages = 1;
     size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
 
-    CUtensorMap t_dy_hi, t_dy_lo, t_x_hi, t_x_lo;
-    uint32_t box[4] = {64u, (uint32_t)box_w, (uint32_t)box_h, (uint32_t)p.box_b};
+    CUtensorMap t_dy, t_x;
+    uint32_t box[5] = {64u, (uint32_t)box_w, (uint32_t)box_h, (uint32_t)p.box_b, 1u};
     {
-        uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-        uint64_t str[3] = {(uint64_t)dy_cs * 2, (uint64_t)W * dy_cs * 2, (uint64_t)H * W * dy_cs * 2};
-        int e = istnet_make_tmap_bf16(&t_dy_hi, dy_hi, 4, dims, str, box);
-        if (e) return e;
-        e = istnet_make_tmap_bf16(&t_dy_lo, dy_lo, 4, dims, str, box);
+        uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B, (uint64_t)nsplit};
+        uint64_t str[4] = {(uint64_t)dy_cs * 2, (uint64_t)W * dy_cs * 2, (uint64_t)H * W * dy_cs * 2, (uint64_t)dy_plane_stride * 2};
+        int e = istnet_make_tmap_bf16(&t_dy, dy_planes, 5, dims, str, box);
         if (e) return e;
     }
     {
-        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-        uint64_t str[3] = {(uint64_t)x_cs * 2, (uint64_t)W * x_cs * 2, (uint64_t)H * W * x_cs * 2};
-        int e = istnet_make_tmap_bf16(&t_x_hi, x_hi, 4, dims, str, box);
-        if (e) return e;
-        e = istnet_make_tmap_bf16(&t_x_lo, x_lo, 4, dims, str, box);
+        uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B, (uint64_t)nsplit};
+        uint64_t str[4] = {(uint64_t)x_cs * 2, (uint64_t)W * x_cs * 2, (uint64_t)H * W * x_cs * 2, (uint64_t)x_plane_stride * 2};
+        int e = istnet_make_tmap_bf16(&t_x, x_planes, 5, dims, str, box);
         if (e) return e;
     }
     ISTNET_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     dim3 grid(ksplit, ceil_div(Cout, kTileM) * p.n_ci_tiles, kh * kw);
-    wgrad_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(t_dy_hi, t_dy_lo, t_x_hi, t_x_lo, p);
+    wgrad_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(t_dy, t_x, p);
     ISTNET_LAUNCH_CHECK();
     const long long total = (long long)kh * kw * Cout * Cin;
     int rgrid = (int)((total + 255) / 256);

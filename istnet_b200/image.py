@@ -160,6 +160,12 @@ class ModifiedResnet(nn.Module):
         passes, the head evaluated only at the chosen pixels).  There is no CPU path."""
         if not rgb.is_cuda:
             raise RuntimeError("istnet_b200: the image branch runs on CUDA only (no CPU fallback)")
+        return self.gather_rows(rgb, choose).transpose(1, 2).contiguous()
+
+    def gather_rows(self, rgb, choose):
+        """Same as gather() but channels-last: (B,N,128), the layout the per-point MLP kernels consume."""
+        if not rgb.is_cuda:
+            raise RuntimeError("istnet_b200: the image branch runs on CUDA only (no CPU fallback)")
         from .image_engine import image_branch
 
         return image_branch(self.model, rgb, choose)

@@ -17,10 +17,8 @@ from .nhwc import ACT_NONE, ACT_PRELU, ACT_RELU, Act, ConvUnit
 
 
 def _units(net):
-    """ConvUnit objects for every conv of Modified_PSPNet, keyed like the state dict (built once per module)."""
-    u = getattr(net, "_b200_units", None)
-    if u is not None:
-        return u
+    """ConvUnit views of every conv of Modified_PSPNet, keyed like the state dict.  Rebuilt per call (cheap) so that
+    module replicas (DataParallel) and re-materialised parameters are always the ones used."""
     f = net.feats
     u = {"conv1": ConvUnit(f.conv1.weight, None, f.bn1, ACT_RELU, k=7, stride=2, pad=3)}
     for li in (1, 2, 3, 4):
@@ -35,7 +33,6 @@ def _units(net):
         seq = getattr(net, name).conv
         u[name] = ConvUnit(seq[1].weight, seq[1].bias, seq[2], ACT_PRELU, prelu=seq[3].weight, k=3)
     u["final"] = ConvUnit(net.final[0].weight, net.final[0].bias, net.final[1], ACT_PRELU, prelu=net.final[2].weight, k=1)
-    net._b200_units = u
     return u
 
 
@@ -54,9 +51,9 @@ def _basic_block_fwd(u, pre, x, training, record, tape):
     return out
 
 
-def forward(net, rgb, choose, training, record):
-    """rgb (B,3,H,W) FP32 NCHW, choose (B,N) int64 -> rgb_local (B,128,N) FP32; tape (list) when record."""
-    u = _units(net)
+def forward(net, rgb, choose, training, record, u=None):
+    """rgb (B,3,H,W) FP32 NCHW, choose (B,N) int64 -> rgb_local rows (B,N,128) FP32; tape (list) when record."""
+    u = u or _units(net)
     dev = rgb.device
     B, _, H, W = rgb.shape
     tape = []
@@ -67,10 +64,10 @@ def forward(net, rgb, choose, training, record):
     st0 = r0["bn"]
     Hp, Wp = (y0.H - 1) // 2 + 1, (y0.W - 1) // 2 + 1
     z = Act(B, Hp, Wp, 64, torch.empty(B, Hp, Wp, 64, dtype=torch.float32, device=dev))
-    z.hi, z.lo = K.empty_pair(B, Hp, Wp, 64, dev)
+    z.pl = K.empty_planes(B, Hp, Wp, 64, dev)
     argmax = torch.empty(B, Hp, Wp, 64, dtype=torch.uint8, device=dev)
     _C.call("bn_relu_maxpool", ptr(y0.f32), c_int(B), c_int(y0.H), c_int(y0.W), c_int(64), ptr(st0.mean), ptr(st0.invstd), ptr(st0.gamma),
-            ptr(st0.beta), ptr(z.f32), ptr(z.hi), ptr(z.lo), c_int(z.cs), ptr(argmax))
+            ptr(st0.beta), ptr(z.f32), *K._pl_args(z.pl), c_int(z.cs), ptr(argmax))
     if record:
         tape.append(("stem", r0, argmax, (y0.H, y0.W)))
     # ---- layer1..4
@@ -85,10 +82,9 @@ def forward(net, rgb, choose, training, record):
         priors = [F.interpolate(stage(leaf), size=(Hf, Wf), mode="bilinear", align_corners=False) for stage in net.psp.stages]
         pri = torch.cat(priors, 1).permute(0, 2, 3, 1).contiguous()  # [B,Hf,Wf,2048] channels-last
     cat = Act(B, Hf, Wf, 2560)
-    cat.hi, cat.lo = K.empty_pair(B, Hf, Wf, 2560, dev)
-    K.split(pri.detach(), B * Hf * Wf, 2048, cat.hi, cat.lo, ch_off=0)
-    cat.hi[..., 2048:] = z.hi
-    cat.lo[..., 2048:] = z.lo
+    cat.pl = K.empty_planes(B, Hf, Wf, 2560, dev)
+    K.split(pri.detach(), B * Hf * Wf, 2048, cat.pl, ch_off=0)
+    cat.pl[..., 2048:] = z.pl
     noise = _draw_noise(net, B, training, dev)
     p, rb = u["bottleneck"].forward(cat, training, record, noise=noise[0], want_f32=True, want_pair=False)
     if record:
@@ -97,8 +93,8 @@ def forward(net, rgb, choose, training, record):
     for i, name in enumerate(("up_1", "up_2", "up_3")):
         cin = p.C
         xu = Act(B, 2 * p.H, 2 * p.W, cin)
-        xu.hi, xu.lo = K.empty_pair(B, xu.H, xu.W, cin, dev)
-        K.upsample2x(p.f32, B, p.H, p.W, cin, (xu.hi, xu.lo))
+        xu.pl = K.empty_planes(B, xu.H, xu.W, cin, dev)
+        K.upsample2x(p.f32, B, p.H, p.W, cin, xu.pl)
         last = name == "up_3"
         p, ru = u[name].forward(xu, training, record, noise=None if last else noise[i + 1], want_f32=not last, want_pair=last)
         if record:
@@ -107,7 +103,7 @@ def forward(net, rgb, choose, training, record):
     yf, rf = u["final"].forward(p, training, True, defer_act=True)
     stf = rf["bn"]
     N = choose.shape[1]
-    out = torch.empty(B, 128, N, dtype=torch.float32, device=dev)
+    out = torch.empty(B, N, 128, dtype=torch.float32, device=dev)
     choose = choose.contiguous()
     _C.call("gather_bn_prelu", ptr(yf.f32), c_int(B), c_ll(yf.H * yf.W), c_int(128), c_int(N), ptr(choose), ptr(stf.mean), ptr(stf.invstd),
             ptr(stf.gamma), ptr(stf.beta), ptr(u["final"].prelu), ptr(out))
@@ -131,9 +127,8 @@ def _draw_noise(net, B, training, dev):
     return out
 
 
-def backward(net, tape, d_out):
-    """d_out (B,128,N) -> {parameter: gradient} for every parameter of the branch that receives one."""
-    u = _units(net)
+def backward(net, tape, d_out, u):
+    """d_out (B,N,128) -> {id(parameter): gradient} for every parameter of the branch that receives one."""
     grads = {}
     dev = d_out.device
     d_out = d_out.contiguous()
@@ -149,8 +144,8 @@ def backward(net, tape, d_out):
             slope = torch.empty(128, dtype=torch.float64, device=dev)
             _C.call("gather_bn_prelu_bwd", ptr(rf["y"]), c_int(B), c_ll(HW), c_int(128), c_int(N), ptr(choose), ptr(st.mean), ptr(st.invstd),
                     ptr(st.gamma), ptr(st.beta), ptr(unit.prelu), ptr(d_out), ptr(g), ptr(slope))
-            dy = K.empty_pair(B, xin.H, xin.W, 128, dev)
-            ws = K.bn_act_bwd(g, None, rf["y"], rf["P"], 128, HW, st, ACT_NONE, None, None, None, dy_pair=dy)
+            dy = K.empty_planes(B, xin.H, xin.W, 128, dev)
+            ws = K.bn_act_bwd(g, None, rf["y"], rf["P"], 128, HW, st, ACT_NONE, None, None, None, dy_pl=dy)
             wsf = ws.float()
             grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = wsf[128:256], wsf[0:128]
             grads[id(unit.b)] = torch.zeros_like(unit.b)
@@ -190,8 +185,8 @@ def backward(net, tape, d_out):
             g0 = torch.empty(B, H0, W0, 64, dtype=torch.float32, device=dev)
             _C.call("maxpool_relu_bwd", ptr(r0["y"]), c_int(B), c_int(H0), c_int(W0), c_int(64), ptr(st.mean), ptr(st.invstd), ptr(st.gamma),
                     ptr(st.beta), ptr(dz), K._p(dz2), ptr(argmax), ptr(g0))
-            dy = K.empty_pair(B, H0, W0, 64, dev)
-            ws = K.bn_act_bwd(g0, None, r0["y"], r0["P"], 64, H0 * W0, st, ACT_NONE, None, None, None, dy_pair=dy)
+            dy = K.empty_planes(B, H0, W0, 64, dev)
+            ws = K.bn_act_bwd(g0, None, r0["y"], r0["P"], 64, H0 * W0, st, ACT_NONE, None, None, None, dy_pl=dy)
             wsf = ws.float()
             grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = wsf[64:128], wsf[0:64]
             unit.data_grads(r0, dy, False, grads)
@@ -201,19 +196,20 @@ def backward(net, tape, d_out):
 class _ImageBranchFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, rgb, choose, *params):
-        out, tape = forward(net, rgb, choose, net.training, True)
-        ctx.net, ctx.tape, ctx.params = net, tape, params
+        u = _units(net)
+        out, tape = forward(net, rgb, choose, net.training, True, u)
+        ctx.net, ctx.tape, ctx.params, ctx.units = net, tape, params, u
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        grads = backward(ctx.net, ctx.tape, d_out)
+        grads = backward(ctx.net, ctx.tape, d_out, ctx.units)
         ctx.tape = None
         return (None, None, None) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
 
 
 def image_branch(net, rgb, choose):
-    """Modified_PSPNet forward + pixel gather on the B200 kernels; differentiable w.r.t. the module's parameters."""
+    """Modified_PSPNet forward + pixel gather on the B200 kernels -> rows (B,N,128); differentiable w.r.t. the parameters."""
     params = tuple(p for n, p in net.named_parameters() if not n.startswith("feats.fc."))
     if torch.is_grad_enabled() and any(p.requires_grad for p in params):
         return _ImageBranchFn.apply(net, rgb, choose, *params)

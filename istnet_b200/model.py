@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import rows_engine as RE
 from .image import ModifiedResnet
 from .pointnet2 import PointNet2MSG
 
@@ -55,21 +56,37 @@ def gather_pixels(rgb_map, choose):
     return torch.gather(rgb_map.view(b, d, -1), 2, choose.unsqueeze(1).expand(-1, d, -1)).contiguous()
 
 
+def _rows(x_bnc):
+    """(B,N,C) -> contiguous row matrix (B*N, C)"""
+    b, n, c = x_bnc.shape
+    return x_bnc.reshape(b * n, c)
+
+
+def _mlp(seq, x_rows, training=False):
+    """nn.Sequential of Conv1d(k=1)(+ReLU) applied to a row matrix on the tcgen05 GEMM chain (rows_engine)."""
+    return RE.run_chain(RE.units_from_conv1d_seq(seq), x_rows, training)
+
+
+def _with_global(x_rows, b, n):
+    """cat([f, mean_over_points(f).expand]) of ist_net.py:172-173,257-258,325-326 on rows"""
+    f = x_rows.view(b, n, -1)
+    return torch.cat([f, f.mean(1, keepdim=True).expand_as(f)], 2).reshape(b * n, -1)
+
+
 class _PoseHeads(nn.Module):
     """pose_mlp1 -> global mean concat -> pose_mlp2 -> avg pool -> rotation / translation / size heads."""
 
-    def _tail(self, feat):
-        feat = self.pose_mlp1(feat)
-        glob = torch.mean(feat, 2, keepdim=True)
-        feat = torch.cat([feat, glob.expand_as(feat)], 1)
-        feat = self.pose_mlp2(feat).squeeze(2)
+    def _tail(self, feat_rows, b, n):
+        feat = _mlp(self.pose_mlp1, feat_rows)
+        feat = _mlp(self.pose_mlp2, _with_global(feat, b, n))
+        feat = feat.view(b, n, -1).mean(1)  # AdaptiveAvgPool1d(1)
         r6 = self.rotation_estimator(feat)
         r = ortho6d_to_mat(r6[:, :3].contiguous(), r6[:, 3:].contiguous()).view(-1, 3, 3)
         return r, self.translation_estimator(feat), self.size_estimator(feat)
 
 
 class LightEstimator(_PoseHeads):
-    """ist_net.py:202-264"""
+    """ist_net.py:202-264.  Inputs are rows: pts (B,N,3), rgb_local / pts_local (B,N,128)."""
 
     def __init__(self):
         super().__init__()
@@ -79,12 +96,13 @@ class LightEstimator(_PoseHeads):
         self.rotation_estimator, self.translation_estimator, self.size_estimator = _head(6), _head(3), _head(3)
 
     def forward(self, pts, rgb_local, pts_local):
-        e = self.pts_mlp(pts.transpose(1, 2))
-        return self._tail(torch.cat([rgb_local, e, pts_local], dim=1))
+        b, n, _ = pts.shape
+        e = _mlp(self.pts_mlp, _rows(pts))
+        return self._tail(torch.cat([_rows(rgb_local), e, _rows(pts_local)], dim=1), b, n)
 
 
 class HeavyEstimator(_PoseHeads):
-    """ist_net.py:267-332 (identical copy at posenet_gt.py:71-136)"""
+    """ist_net.py:267-332 (identical copy at posenet_gt.py:71-136).  Inputs are rows (B,N,C)."""
 
     def __init__(self):
         super().__init__()
@@ -95,13 +113,14 @@ class HeavyEstimator(_PoseHeads):
         self.rotation_estimator, self.translation_estimator, self.size_estimator = _head(6), _head(3), _head(3)
 
     def forward(self, pts, pts_w, rgb_local, pts_local, pts_w_local):
-        e1 = self.pts_mlp1(pts.transpose(1, 2))
-        e2 = self.pts_mlp2(pts_w.transpose(1, 2))
-        return self._tail(torch.cat([rgb_local, e1, pts_local, e2, pts_w_local], dim=1))
+        b, n, _ = pts.shape
+        e1 = _mlp(self.pts_mlp1, _rows(pts))
+        e2 = _mlp(self.pts_mlp2, _rows(pts_w))
+        return self._tail(torch.cat([_rows(rgb_local), e1, _rows(pts_local), e2, _rows(pts_w_local)], dim=1), b, n)
 
 
 class FeatureDeformer(nn.Module):
-    """Implicit space transformation (ist_net.py:125-183)."""
+    """Implicit space transformation (ist_net.py:125-183).  Inputs are rows; returns (pts_w_local rows (B,N,128), pts_w (B,N,3))."""
 
     def __init__(self, nclass=6):
         super().__init__()
@@ -111,15 +130,15 @@ class FeatureDeformer(nn.Module):
         self.deform_mlp2 = _pt_mlp(512, 384, 256, 128)
         self.pred_nocs = _pt_mlp(128, 256, 128, nclass * 3, last_relu=False)
 
-    def forward(self, pts, rgb_local, pts_local, index):
-        npoint = pts_local.size(2)
-        e = self.pts_mlp1(pts.transpose(1, 2))
-        x = self.deform_mlp1(torch.cat([e, pts_local, rgb_local], dim=1))
-        glob = torch.mean(x, 2, keepdim=True)
-        x = self.deform_mlp2(torch.cat([x, glob.expand_as(x)], 1))
-        q = self.pred_nocs(x).view(-1, 3, npoint).contiguous()
-        q = torch.index_select(q, 0, index).permute(0, 2, 1).contiguous()
-        return x, q
+    def forward(self, pts, rgb_local, pts_local, cls):
+        b, n, _ = pts.shape
+        e = _mlp(self.pts_mlp1, _rows(pts))
+        x = _mlp(self.deform_mlp1, torch.cat([e, _rows(pts_local), _rows(rgb_local)], dim=1))
+        x = _mlp(self.deform_mlp2, _with_global(x, b, n))
+        q = _mlp(self.pred_nocs, x).view(b, n, self.nclass, 3)
+        # ist_net.py:178-181: view(-1,3,N) + index_select(cls + nclass*b) == pick the class's 3 channels per instance
+        q = torch.gather(q, 2, cls.view(b, 1, 1, 1).expand(b, n, 1, 3)).squeeze(2)
+        return x.view(b, n, -1), q.contiguous()
 
 
 class ImplicitTransformation(nn.Module):
@@ -130,13 +149,13 @@ class ImplicitTransformation(nn.Module):
         self.nclass = nclass
         self.feature_refine = FeatureDeformer(nclass)
 
-    def forward(self, rgb_local, pts_local, pts, center, index):
-        pts_local_w, pts_w = self.feature_refine(pts, rgb_local, pts_local, index)
+    def forward(self, rgb_local, pts_local, pts, center, cls):
+        pts_local_w, pts_w = self.feature_refine(pts, rgb_local, pts_local, cls)
         return pts_w, pts_local_w
 
 
 class WorldSpaceEnhancer(nn.Module):
-    """ist_net.py:185-200"""
+    """ist_net.py:185-200 (rows in / rows out)"""
 
     def __init__(self, freeze=False):
         super().__init__()
@@ -146,7 +165,7 @@ class WorldSpaceEnhancer(nn.Module):
             self.pose_estimator = HeavyEstimator()
 
     def forward(self, pts, pts_w_gt, rgb_local, pts_local):
-        pts_w_local_gt = self.extractor(pts_w_gt)
+        pts_w_local_gt = self.extractor.forward_rows(pts_w_gt)
         if self.freeze:
             return None, None, None, pts_w_local_gt
         r, t, s = self.pose_estimator(pts, pts_w_gt, rgb_local.detach(), pts_local.detach(), pts_w_local_gt)
@@ -174,20 +193,19 @@ class IST_Net(nn.Module):
         cls = inputs["category_label"].reshape(-1)
         c = torch.mean(pts, 1, keepdim=True)
         pts = pts - c
-        b = pts.size(0)
-        index = cls + torch.arange(b, dtype=torch.long, device=pts.device) * self.nclass
-
-        rgb_local = self.rgb_cam_extractor.gather(rgb, choose)
-        pts_local = self.pts_cam_extractor(pts)
+        # everything below works on rows (B,N,C): the layout the GEMM kernels consume; the reference's (B,C,N)
+        # tensors appear only at the module boundary (end_points)
+        rgb_local = self.rgb_cam_extractor.gather_rows(rgb, choose)
+        pts_local = self.pts_cam_extractor.forward_rows(pts)
         if self.training:
             r_c, t_c, s_c = self.cam_enhancer(pts, rgb_local, pts_local)
-        pts_w, pts_w_local = self.implicit_transform(rgb_local, pts_local, pts, c, index)
+        pts_w, pts_w_local = self.implicit_transform(rgb_local, pts_local, pts, c, cls)
         r, t, s = self.main_estimator(pts, pts_w, rgb_local, pts_local, pts_w_local)
         end_points["pred_qo"] = pts_w
         if self.training:
             r_w, t_w, s_w, pts_w_local_gt = self.world_enhancer(pts, inputs["qo"], rgb_local, pts_local)
-            end_points["pts_w_local"] = pts_w_local
-            end_points["pts_w_local_gt"] = pts_w_local_gt
+            end_points["pts_w_local"] = pts_w_local.transpose(1, 2).contiguous()
+            end_points["pts_w_local_gt"] = pts_w_local_gt.transpose(1, 2).contiguous()
         end_points["pred_rotation"] = r
         end_points["pred_translation"] = t + c.squeeze(1)
         end_points["pred_size"] = s
@@ -219,11 +237,11 @@ class PoseNetGT(nn.Module):
         c = torch.mean(pts, 1, keepdim=True)
         pts = pts - c
         with torch.no_grad():  # outputs are detached in the reference (posenet_gt.py:43); same values, no graph
-            rgb_local = self.rgb_extractor.gather(rgb, choose)
-            pts_local = self.pts_extractor(pts)
-        gt_local = self.pts_gt_extractor(pts_w_gt)
+            rgb_local = self.rgb_extractor.gather_rows(rgb, choose)
+            pts_local = self.pts_extractor.forward_rows(pts)
+        gt_local = self.pts_gt_extractor.forward_rows(pts_w_gt)
         r, t, s = self.pose_estimator_aux(pts, pts_w_gt, rgb_local, pts_local, gt_local)
-        return {"pts_local_w_gt": gt_local, "pred_rotation": r, "pred_translation": t + c.squeeze(1), "pred_size": s}
+        return {"pts_local_w_gt": gt_local.transpose(1, 2).contiguous(), "pred_rotation": r, "pred_translation": t + c.squeeze(1), "pred_size": s}
 
 
 # --------------------------------------------------------------------------------------------- losses

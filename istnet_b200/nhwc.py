@@ -5,7 +5,7 @@ Everything here works on FP32 tensors [B,H,W,C] (or [1,1,rows,C] for point sets)
 pairs; see include/istnet_b200.h §3-§4 for the kernels.  The classes mirror what PyTorch autograd records for the
 reference modules (cuDNN conv fwd/dgrad/wgrad, BN fwd/bwd, ReLU/PReLU, Dropout2d), but as an explicit tape.
 """
-import ctypes
+import os
 
 import torch
 
@@ -13,6 +13,9 @@ from . import _C
 from ._C import c_float, c_int, c_ll, c_void_p, ptr
 
 NULL = c_void_p(0)
+# bf16 operand planes per FP32 tensor: 3 -> six tensor-core products, FP32-level accuracy (default, needed for the 1e-4
+# parity bar in train mode); 2 -> three products, ~3e-6 per product, twice the tensor-core throughput.
+NSPLIT = int(os.environ.get("ISTNET_NSPLIT", "3"))
 
 
 def _p(t):
@@ -24,12 +27,12 @@ def pad8(c):
 
 
 class Act:
-    """An activation tensor in channels-last layout: optional FP32 copy + optional bf16 (hi, lo) operand pair."""
+    """An activation tensor in channels-last layout: optional FP32 copy + optional bf16 operand planes [NSPLIT,B,H,W,cs]."""
 
-    __slots__ = ("f32", "hi", "lo", "B", "H", "W", "C")
+    __slots__ = ("f32", "pl", "B", "H", "W", "C")
 
-    def __init__(self, B, H, W, C, f32=None, hi=None, lo=None):
-        self.B, self.H, self.W, self.C, self.f32, self.hi, self.lo = B, H, W, C, f32, hi, lo
+    def __init__(self, B, H, W, C, f32=None, pl=None):
+        self.B, self.H, self.W, self.C, self.f32, self.pl = B, H, W, C, f32, pl
 
     @property
     def P(self):
@@ -37,21 +40,31 @@ class Act:
 
     @property
     def cs(self):
-        return self.hi.shape[-1]
+        return self.pl.shape[-1]
+
+    @property
+    def hi(self):
+        return self.pl[0] if self.pl is not None else None
 
 
-def empty_pair(B, H, W, C, dev, cs=None):
-    cs = cs or pad8(C)
-    return (torch.empty(B, H, W, cs, dtype=torch.bfloat16, device=dev), torch.empty(B, H, W, cs, dtype=torch.bfloat16, device=dev))
+def empty_planes(B, H, W, C, dev, cs=None):
+    return torch.empty(NSPLIT, B, H, W, cs or pad8(C), dtype=torch.bfloat16, device=dev)
+
+
+def _pl_args(pl):
+    """(pointer, plane stride in elements, nsplit) of an operand-plane tensor (or nulls)."""
+    if pl is None:
+        return NULL, c_ll(0), c_int(NSPLIT)
+    return ptr(pl), c_ll(pl.stride(0)), c_int(pl.shape[0])
 
 
 # ----------------------------------------------------------------------------------------- thin kernel wrappers
-def split(x_f32, P, C, hi, lo, ch_off=0, HW=1, nchw=False):
-    _C.call("split", ptr(x_f32), c_ll(P), c_int(C), c_ll(HW), c_int(1 if nchw else 0), ptr(hi), ptr(lo), c_int(hi.shape[-1]), c_int(ch_off))
+def split(x_f32, P, C, pl, ch_off=0, HW=1, nchw=False):
+    _C.call("split", ptr(x_f32), c_ll(P), c_int(C), c_ll(HW), c_int(1 if nchw else 0), *_pl_args(pl), c_int(pl.shape[-1]), c_int(ch_off))
 
 
 def prep_weight(w, transpose=False):
-    """Conv / linear weight [co, ci, kh, kw] (or [co, ci]) -> bf16 pair [taps, rows, pad8(cols)].
+    """Conv / linear weight [co, ci, kh, kw] (or [co, ci]) -> bf16 operand planes [NSPLIT, taps, rows, pad8(cols)].
     transpose=False: forward operand  [tap][co][ci];  transpose=True: data-gradient operand [flipped tap][ci][co]."""
     if w.dim() == 2:
         w = w[:, :, None, None]
@@ -63,11 +76,9 @@ def prep_weight(w, transpose=False):
     else:
         m = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
     taps, rows, cols = m.shape
-    cs = pad8(cols)
-    hi = torch.empty(taps, rows, cs, dtype=torch.bfloat16, device=w.device)
-    lo = torch.empty(taps, rows, cs, dtype=torch.bfloat16, device=w.device)
-    split(m, taps * rows, cols, hi, lo)
-    return hi, lo
+    pl = torch.empty(NSPLIT, taps, rows, pad8(cols), dtype=torch.bfloat16, device=w.device)
+    split(m, taps * rows, cols, pl)
+    return pl
 
 
 def pick_box(H, W):
@@ -78,27 +89,27 @@ def pick_box(H, W):
     return 8, 8
 
 
-def conv_gemm(x, w_pair, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pair=None):
-    """x: Act with (hi, lo); returns nothing — writes out_f32 [B,H,W,cout] and/or out_pair."""
+def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl=None):
+    """x: Act with operand planes; returns nothing — writes out_f32 [B,H,W,cout] and/or out_pl."""
     bw, bh = pick_box(x.H, x.W)
-    oh, ol = out_pair if out_pair is not None else (None, None)
     _C.call(
-        "conv_gemm", ptr(x.hi), ptr(x.lo), c_int(x.B), c_int(x.H), c_int(x.W), c_int(x.C), c_int(x.cs), ptr(w_pair[0]), ptr(w_pair[1]),
-        c_int(cout), c_int(w_pair[0].shape[-1]), c_int(kh), c_int(kw), _p(bias), c_int(1 if relu else 0), _p(out_f32),
-        c_int(out_f32.shape[-1] if out_f32 is not None else 0), _p(oh), _p(ol), c_int(oh.shape[-1] if oh is not None else 0), c_int(bw), c_int(bh),
+        "conv_gemm", ptr(x.pl), c_ll(x.pl.stride(0)), c_int(x.B), c_int(x.H), c_int(x.W), c_int(x.C), c_int(x.cs), ptr(w_pl),
+        c_ll(w_pl.stride(0)), c_int(cout), c_int(w_pl.shape[-1]), c_int(kh), c_int(kw), c_int(x.pl.shape[0]), _p(bias), c_int(1 if relu else 0),
+        _p(out_f32), c_int(out_f32.shape[-1] if out_f32 is not None else 0), *_pl_args(out_pl), c_int(out_pl.shape[-1] if out_pl is not None else 0),
+        c_int(bw), c_int(bh),
     )
 
 
-def conv_wgrad(dy_pair, cout, x, kh, kw):
-    """grad_w [cout, cin, kh, kw] from dy (hi, lo) [B,H,W,cs] and x: Act (hi, lo)."""
-    dev = x.hi.device
-    ks = _C.lib().istnet_wgrad_ksplit(x.B, x.H, x.W, cout, x.C, kh, kw)
+def conv_wgrad(dy_pl, cout, x, kh, kw):
+    """grad_w [cout, cin, kh, kw] from dy operand planes [NSPLIT,B,H,W,cs] and x: Act (planes)."""
+    dev = x.pl.device
+    ks = _C.lib().istnet_wgrad_ksplit(x.B, x.H, x.W, cout, x.C, kh, kw, x.pl.shape[0])
     ws = torch.empty(ks * kh * kw * cout * x.C, dtype=torch.float32, device=dev)
     gw = torch.empty(cout, x.C, kh, kw, dtype=torch.float32, device=dev)
     bw, bh = (64, 1) if x.H == 1 else (8, 8)
     _C.call(
-        "conv_wgrad", ptr(dy_pair[0]), ptr(dy_pair[1]), c_int(dy_pair[0].shape[-1]), ptr(x.hi), ptr(x.lo), c_int(x.cs), c_int(x.B), c_int(x.H),
-        c_int(x.W), c_int(cout), c_int(x.C), c_int(kh), c_int(kw), ptr(ws), c_int(ks), ptr(gw), c_int(bw), c_int(bh),
+        "conv_wgrad", ptr(dy_pl), c_ll(dy_pl.stride(0)), c_int(dy_pl.shape[-1]), ptr(x.pl), c_ll(x.pl.stride(0)), c_int(x.cs), c_int(x.pl.shape[0]),
+        c_int(x.B), c_int(x.H), c_int(x.W), c_int(cout), c_int(x.C), c_int(kh), c_int(kw), ptr(ws), c_int(ks), ptr(gw), c_int(bw), c_int(bh),
     )
     return gw
 
@@ -131,30 +142,28 @@ def bn_state(bn, y, P, C, training):
     return BnState(mean, invstd, bn.weight, bn.bias)
 
 
-def bn_act_split(y, P, C, HW, bn=None, res=None, res_bn=None, act=0, prelu=None, noise=None, out_f32=None, out_pair=None, ch_off=0):
-    oh, ol = out_pair if out_pair is not None else (None, None)
+def bn_act_split(y, P, C, HW, bn=None, res=None, res_bn=None, act=0, prelu=None, noise=None, out_f32=None, out_pl=None, ch_off=0):
     _C.call(
         "bn_act_split", ptr(y), c_ll(P), c_int(C), c_ll(HW), _p(bn.mean if bn else None), _p(bn.invstd if bn else None),
         _p(bn.gamma if bn else None), _p(bn.beta if bn else None), _p(res), _p(res_bn.mean if res_bn else None),
         _p(res_bn.invstd if res_bn else None), _p(res_bn.gamma if res_bn else None), _p(res_bn.beta if res_bn else None), c_int(act),
-        _p(prelu), _p(noise), _p(out_f32), _p(oh), _p(ol), c_int(oh.shape[-1] if oh is not None else 0), c_int(ch_off),
+        _p(prelu), _p(noise), _p(out_f32), *_pl_args(out_pl), c_int(out_pl.shape[-1] if out_pl is not None else 0), c_int(ch_off),
     )
 
 
-def bn_act_bwd(dz, dz2, y, P, C, HW, bn, act, prelu, z_hi, noise, dy_pair=None, dy_f32=None, g_out=None):
+def bn_act_bwd(dz, dz2, y, P, C, HW, bn, act, prelu, z_hi, noise, dy_pl=None, dy_f32=None, g_out=None):
     """Returns ws (3*C doubles): [sum g | sum g*xhat | PReLU slope partials]."""
     ws = torch.empty(3 * C, dtype=torch.float64, device=dz.device)
-    dh, dl = dy_pair if dy_pair is not None else (None, None)
     _C.call(
         "bn_act_bwd", ptr(dz), _p(dz2), _p(y), c_ll(P), c_int(C), c_ll(HW), _p(bn.mean if bn else None), _p(bn.invstd if bn else None),
         _p(bn.gamma if bn else None), _p(bn.beta if bn else None), c_int(act), _p(prelu), _p(z_hi), c_int(z_hi.shape[-1] if z_hi is not None else 0),
-        _p(noise), ptr(ws), _p(dh), _p(dl), c_int(dh.shape[-1] if dh is not None else 0), _p(dy_f32), _p(g_out),
+        _p(noise), ptr(ws), *_pl_args(dy_pl), c_int(dy_pl.shape[-1] if dy_pl is not None else 0), _p(dy_f32), _p(g_out),
     )
     return ws
 
 
-def upsample2x(x_f32, B, H, W, C, out_pair):
-    _C.call("upsample2x_split", ptr(x_f32), c_int(B), c_int(H), c_int(W), c_int(C), ptr(out_pair[0]), ptr(out_pair[1]), c_int(out_pair[0].shape[-1]), NULL)
+def upsample2x(x_f32, B, H, W, C, out_pl):
+    _C.call("upsample2x_split", ptr(x_f32), c_int(B), c_int(H), c_int(W), c_int(C), *_pl_args(out_pl), c_int(out_pl.shape[-1]), NULL)
 
 
 def upsample2x_bwd(dout, B, H, W, C):
@@ -166,10 +175,10 @@ def upsample2x_bwd(dout, B, H, W, C):
 def im2col(x_f32, nchw, B, H, W, C, k, stride, pad):
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
     K = k * k * C
-    hi, lo = empty_pair(B, Ho, Wo, K, x_f32.device)
+    pl = empty_planes(B, Ho, Wo, K, x_f32.device)
     _C.call("im2col_split", ptr(x_f32), c_int(1 if nchw else 0), c_int(B), c_int(H), c_int(W), c_int(C), c_int(k), c_int(k), c_int(stride),
-            c_int(pad), ptr(hi), ptr(lo), c_int(hi.shape[-1]))
-    return Act(B, Ho, Wo, K, None, hi, lo)
+            c_int(pad), *_pl_args(pl), c_int(pl.shape[-1]))
+    return Act(B, Ho, Wo, K, None, pl)
 
 
 def col2im(dcol, B, H, W, C, k, stride, pad, dx=None):
@@ -220,13 +229,20 @@ class ConvUnit:
             rec.update({"xin": xin, "y": y, "noise": noise, "kk": kk, "P": P, "HW": H * W, "in_shape": (x.B, x.H, x.W, x.C)})
         if defer_act:
             return Act(B, H, W, C, y), rec
+        if self.bn is None and self.act == ACT_NONE and noise is None and res is None:  # plain linear layer
+            out = Act(B, H, W, C, y)
+            if want_pair:
+                out.pl = empty_planes(B, H, W, C, dev)
+                split(y, P, C, out.pl)
+            if record:
+                rec["y"] = None
+            return out, rec
         out = Act(B, H, W, C)
         if want_f32:
             out.f32 = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
         if want_pair or (record and self.act == ACT_RELU):
-            out.hi, out.lo = empty_pair(B, H, W, C, dev)
-        bn_act_split(y, P, C, H * W, bn=st, res=res, res_bn=res_bn, act=self.act, prelu=self.prelu, noise=noise, out_f32=out.f32,
-                     out_pair=(out.hi, out.lo) if out.hi is not None else None)
+            out.pl = empty_planes(B, H, W, C, dev)
+        bn_act_split(y, P, C, H * W, bn=st, res=res, res_bn=res_bn, act=self.act, prelu=self.prelu, noise=noise, out_f32=out.f32, out_pl=out.pl)
         if record:
             rec["z_hi"] = out.hi
             if self.bn is None and self.act != ACT_PRELU:
@@ -239,9 +255,15 @@ class ConvUnit:
         dev = dz.device
         xin, P, C = rec["xin"], rec["P"], self.cout
         B, H, W = xin.B, xin.H, xin.W
-        dy = empty_pair(B, H, W, C, dev)
+        dy = empty_planes(B, H, W, C, dev)
+        if self.bn is None and self.act == ACT_NONE and rec["noise"] is None:  # plain linear layer
+            d = dz if dz2 is None else dz + dz2
+            split(d.contiguous(), P, C, dy)
+            if self.b is not None:
+                grads[id(self.b)] = d.reshape(P, C).sum(0)
+            return self.data_grads(rec, dy, need_dx, grads), (d if g_out else None)
         g = torch.empty(B, H, W, C, dtype=torch.float32, device=dev) if g_out else None
-        ws = bn_act_bwd(dz, dz2, rec["y"], P, C, rec["HW"], rec["bn"], self.act, self.prelu, rec.get("z_hi"), rec["noise"], dy_pair=dy, g_out=g)
+        ws = bn_act_bwd(dz, dz2, rec["y"], P, C, rec["HW"], rec["bn"], self.act, self.prelu, rec.get("z_hi"), rec["noise"], dy_pl=dy, g_out=g)
         self.param_grads(rec, ws, grads)
         dx = self.data_grads(rec, dy, need_dx, grads)
         return dx, g
@@ -268,15 +290,15 @@ class ConvUnit:
         grads[id(self.w)] = gw.reshape(self.w.shape)
         if not need_dx:
             return None
-        dyA = Act(xin.B, xin.H, xin.W, C, None, dy[0], dy[1])
+        dyA = Act(xin.B, xin.H, xin.W, C, None, dy)
         if kk != self.k or self.stride != 1:
             wm = self.w.permute(0, 2, 3, 1).reshape(C, -1)
             wd = prep_weight(wm, transpose=True)
-            dcol = torch.empty(xin.B, xin.H, xin.W, xin.C, dtype=torch.float32, device=dy[0].device)
+            dcol = torch.empty(xin.B, xin.H, xin.W, xin.C, dtype=torch.float32, device=dy.device)
             conv_gemm(dyA, wd, xin.C, 1, 1, out_f32=dcol)
             b, h, w, c = rec["in_shape"]
             return col2im(dcol, b, h, w, c, self.k, self.stride, self.pad)
         wd = prep_weight(self.w, transpose=True)
-        dx = torch.empty(xin.B, xin.H, xin.W, xin.C, dtype=torch.float32, device=dy[0].device)
+        dx = torch.empty(xin.B, xin.H, xin.W, xin.C, dtype=torch.float32, device=dy.device)
         conv_gemm(dyA, wd, xin.C, kk, kk, out_f32=dx)
         return dx

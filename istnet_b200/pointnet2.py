@@ -13,6 +13,7 @@ import torch.nn.functional as F
 
 from . import ext
 from . import functional as PF
+from . import rows_engine as RE
 
 
 class _NormLayer(nn.Sequential):
@@ -43,16 +44,17 @@ class SharedMLP(nn.Sequential):
 
 
 class QueryAndGroup(nn.Module):
-    """pointnet2_utils.py:294-377 (use_xyz=True, no normalize_xyz / sample_uniformly on this path)."""
+    """pointnet2_utils.py:294-377 (use_xyz=True, no normalize_xyz / sample_uniformly on this path).  Holds the ball
+    parameters; the grouping itself is fused into the first shared-MLP operand (rows_engine.sa_scale)."""
 
     def __init__(self, radius, nsample, use_xyz=True):
         super().__init__()
         self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
 
-    def forward(self, xyz, new_xyz, features=None, xyz_t=None):
+    def forward(self, xyz, new_xyz, features=None):
+        """Reference-layout result (B, 3+C, npoint, nsample) — API compatibility, not used by the fused path."""
         idx = PF.ball_query(self.radius, self.nsample, xyz, new_xyz)
-        if xyz_t is None:
-            xyz_t = xyz.transpose(1, 2).contiguous()
+        xyz_t = xyz.transpose(1, 2).contiguous()
         with torch.no_grad():
             grouped_xyz = ext.group_points(xyz_t, idx)
             grouped_xyz -= new_xyz.transpose(1, 2).unsqueeze(-1)
@@ -67,31 +69,34 @@ class PointnetSAModuleMSG(nn.Module):
 
     def __init__(self, npoint, radii, nsamples, mlps, bn=True, use_xyz=True):
         super().__init__()
-        assert len(radii) == len(nsamples) == len(mlps)
+        assert len(radii) == len(nsamples) == len(mlps) and use_xyz
         self.npoint = npoint
         self.groupers = nn.ModuleList()
         self.mlps = nn.ModuleList()
         for r, ns, spec in zip(radii, nsamples, mlps):
             self.groupers.append(QueryAndGroup(r, ns, use_xyz=use_xyz))
             spec = list(spec)
-            if use_xyz:
-                spec[0] += 3
+            spec[0] += 3
             self.mlps.append(SharedMLP(spec, bn=bn))
 
-    def forward(self, xyz, features=None, new_xyz=None):
-        """xyz (B,N,3), features (B,C,N) -> new_xyz (B,npoint,3), new_features (B,sum mlp[-1],npoint).
-        `new_xyz` may be supplied by a caller that already ran the fused FPS chain."""
+    def forward_rows(self, xyz, feats_rows=None, new_xyz=None):
+        """xyz (B,N,3), feats_rows (B,N,C) channels-last -> new_xyz (B,npoint,3), new feats (B,npoint,sum mlp[-1])."""
         xyz = xyz.contiguous()
-        xyz_t = xyz.transpose(1, 2).contiguous()
         if new_xyz is None:
-            fidx = PF.furthest_point_sample(xyz, self.npoint)
-            new_xyz = ext.gather_points(xyz_t, fidx).transpose(1, 2).contiguous()
+            with torch.no_grad():
+                _, cent = ext.fps_chain(xyz, (self.npoint,))
+            new_xyz = cent[0]
         outs = []
         for grouper, mlp in zip(self.groupers, self.mlps):
-            g = grouper(xyz, new_xyz, features, xyz_t)
-            g = mlp(g)
-            outs.append(F.max_pool2d(g, kernel_size=[1, g.size(3)]).squeeze(-1))
-        return new_xyz, torch.cat(outs, dim=1)
+            idx = PF.ball_query(grouper.radius, grouper.nsample, xyz, new_xyz)
+            outs.append(RE.sa_scale(RE.units_from_shared_mlp(mlp), self.training, xyz, new_xyz, idx, feats_rows))
+        return new_xyz, torch.cat(outs, dim=2)
+
+    def forward(self, xyz, features=None, new_xyz=None):
+        """Reference layout (pointnet2_modules.py:29-73): features (B,C,N) -> (B,sum mlp[-1],npoint)."""
+        fr = features.transpose(1, 2).contiguous() if features is not None else None
+        new_xyz, out = self.forward_rows(xyz, fr, new_xyz)
+        return new_xyz, out.transpose(1, 2).contiguous()
 
 
 class PointnetFPModule(nn.Module):
@@ -101,12 +106,19 @@ class PointnetFPModule(nn.Module):
         super().__init__()
         self.mlp = SharedMLP(mlp, bn=bn)
 
-    def forward(self, unknown, known, unknow_feats, known_feats):
+    def forward_rows(self, unknown, known, unknown_rows, known_rows):
+        """unknown (B,n,3), known (B,m,3), unknown_rows (B,n,C1) or None, known_rows (B,m,C2) -> (B,n,mlp[-1])"""
         idx, weight = PF.three_nn_weights(unknown, known)
-        x = PF.three_interpolate(known_feats, idx, weight)
-        if unknow_feats is not None:
-            x = torch.cat([x, unknow_feats], dim=1)
-        return self.mlp(x.unsqueeze(-1)).squeeze(-1)
+        x = RE.interp_rows(known_rows, idx, weight)
+        if unknown_rows is not None:
+            x = torch.cat([x, unknown_rows], dim=2)
+        B, n, C = x.shape
+        return RE.run_chain(RE.units_from_shared_mlp(self.mlp), x.reshape(B * n, C), self.training).view(B, n, -1)
+
+    def forward(self, unknown, known, unknow_feats, known_feats):
+        ur = unknow_feats.transpose(1, 2).contiguous() if unknow_feats is not None else None
+        out = self.forward_rows(unknown, known, ur, known_feats.transpose(1, 2).contiguous())
+        return out.transpose(1, 2).contiguous()
 
 
 class PointNet2MSG(nn.Module):
@@ -132,17 +144,22 @@ class PointNet2MSG(nn.Module):
         self.FP_modules.append(PointnetFPModule(mlp=[512 + outs[1], 256, 256]))
         self.FP_modules.append(PointnetFPModule(mlp=[outs[3] + outs[2], 512, 512]))
 
-    def forward(self, pointcloud):
+    def forward_rows(self, pointcloud):
+        """(B,N,3[+C]) -> per-point features as rows (B,N,128)."""
         xyz = pointcloud[..., 0:3].contiguous()
-        features = pointcloud[..., 3:].transpose(1, 2).contiguous() if pointcloud.size(-1) > 3 else None
+        feats = pointcloud[..., 3:].contiguous() if pointcloud.size(-1) > 3 else None
         # all four FPS levels + centroid gathers in ONE launch (the reference runs 4 FPS + 4 gather kernels)
         with torch.no_grad():
             _, centroids = ext.fps_chain(xyz, self.NPOINT)
-        l_xyz, l_feats = [xyz], [features]
+        l_xyz, l_feats = [xyz], [feats]
         for i, sa in enumerate(self.SA_modules):
-            nx, nf = sa(l_xyz[i], l_feats[i], new_xyz=centroids[i])
+            nx, nf = sa.forward_rows(l_xyz[i], l_feats[i], new_xyz=centroids[i])
             l_xyz.append(nx)
             l_feats.append(nf)
         for i in range(-1, -(len(self.FP_modules) + 1), -1):
-            l_feats[i - 1] = self.FP_modules[i](l_xyz[i - 1], l_xyz[i], l_feats[i - 1], l_feats[i])
+            l_feats[i - 1] = self.FP_modules[i].forward_rows(l_xyz[i - 1], l_xyz[i], l_feats[i - 1], l_feats[i])
         return l_feats[0]
+
+    def forward(self, pointcloud):
+        """Reference layout (modules.py:311-327): (B,128,N)."""
+        return self.forward_rows(pointcloud).transpose(1, 2).contiguous()

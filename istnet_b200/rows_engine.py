@@ -1,0 +1,195 @@
+"""Point-set layers ("rows": one row per point, channels contiguous) on the B200 kernels: chains of 1x1 convolutions
+(SharedMLP conv+BN+ReLU, Conv1d+bias+ReLU) as tcgen05 GEMMs with fused BN / activation passes and hand-written
+backward; the set-abstraction scale (group -> 3-layer MLP -> max over neighbours) and the three-NN interpolation.
+
+Replaces, for the reference: pytorch_utils.SharedMLP on (B,C,npoint,nsample) tensors (cuDNN 1x1 convs + BN + ReLU +
+F.max_pool2d, pointnet2_modules.py:60-69), grouping_operation / three_interpolate on channel-first tensors, and the
+nn.Conv1d(k=1) stacks of ist_net.py:125-332.
+"""
+import torch
+
+from . import _C
+from . import nhwc as K
+from ._C import c_int, c_ll, ptr
+from .nhwc import ACT_NONE, ACT_RELU, Act, ConvUnit
+
+
+def units_from_shared_mlp(mlp):
+    """pytorch_utils.SharedMLP (conv1x1 no bias -> BN2d -> ReLU) * n  ->  [ConvUnit]"""
+    return [ConvUnit(layer.conv.weight, None, layer.normlayer.bn, ACT_RELU, k=1) for layer in mlp]
+
+
+def units_from_conv1d_seq(seq):
+    """nn.Sequential of Conv1d(k=1) [+ ReLU] pairs -> [ConvUnit] (bias, optional ReLU)"""
+    mods = [m for m in seq if not isinstance(m, torch.nn.AdaptiveAvgPool1d)]
+    units = []
+    for i, m in enumerate(mods):
+        if isinstance(m, torch.nn.Conv1d):
+            relu = i + 1 < len(mods) and isinstance(mods[i + 1], torch.nn.ReLU)
+            units.append(ConvUnit(m.weight, m.bias, None, ACT_RELU if relu else ACT_NONE, k=1))
+    return units
+
+
+def _unit_params(units):
+    ps = []
+    for u in units:
+        ps.append(u.w)
+        if u.b is not None:
+            ps.append(u.b)
+        if u.bn is not None:
+            ps += [u.bn.weight, u.bn.bias]
+    return ps
+
+
+def _chain_forward(units, a, training, record, last_f32=True, last_pair=False):
+    tape = []
+    for i, u in enumerate(units):
+        last = i + 1 == len(units)
+        a, rec = u.forward(a, training, record, want_f32=last and last_f32, want_pair=(not last) or last_pair)
+        tape.append(rec)
+    return a, tape
+
+
+def _chain_backward(units, tape, dz, grads, need_dx_first):
+    for i in range(len(units) - 1, -1, -1):
+        dz, _ = units[i].backward(tape[i], dz, None, need_dx=(i > 0 or need_dx_first), grads=grads)
+    return dz
+
+
+class _ChainFn(torch.autograd.Function):
+    """x [rows, Cin] FP32 -> [rows, Cout] FP32 through a list of ConvUnits."""
+
+    @staticmethod
+    def forward(ctx, units, training, x, *params):
+        rows, cin = x.shape
+        a = Act(1, 1, rows, cin, x)
+        a.pl = K.empty_planes(1, 1, rows, cin, x.device)
+        K.split(x, rows, cin, a.pl)
+        out, tape = _chain_forward(units, a, training, True)
+        ctx.units, ctx.tape, ctx.params, ctx.need_dx = units, tape, params, x.requires_grad
+        return out.f32.view(rows, -1)
+
+    @staticmethod
+    def backward(ctx, dz):
+        grads = {}
+        dx = _chain_backward(ctx.units, ctx.tape, dz.contiguous().view(1, 1, dz.shape[0], dz.shape[1]), grads, ctx.need_dx)
+        ctx.tape = None
+        return (None, None, dx.view(dx.shape[2], dx.shape[3]) if dx is not None else None) + tuple(
+            grads.get(id(p)) if p.requires_grad else None for p in ctx.params
+        )
+
+
+def run_chain(units, x, training):
+    """Differentiable chain of 1x1-conv units on a row matrix x [rows, Cin] (contiguous FP32)."""
+    x = x.contiguous()
+    params = _unit_params(units)
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
+        return _ChainFn.apply(units, training, x, *params)
+    rows, cin = x.shape
+    a = Act(1, 1, rows, cin, x)
+    a.pl = K.empty_planes(1, 1, rows, cin, x.device)
+    K.split(x, rows, cin, a.pl)
+    out, _ = _chain_forward(units, a, training, False)
+    return out.f32.view(rows, -1)
+
+
+# ------------------------------------------------------------------------------------------ set abstraction scale
+class _SAScaleFn(torch.autograd.Function):
+    """One (radius, nsample) scale of PointnetSAModuleMSG (pointnet2_modules.py:60-69) in channels-last form:
+    grouped rows -> 3 x [1x1 conv GEMM, BN, ReLU] -> max over the nsample axis."""
+
+    @staticmethod
+    def forward(ctx, units, training, xyz, new_xyz, idx, feats, *params):
+        out, saved = sa_scale_forward(units, training, xyz, new_xyz, idx, feats, True)
+        ctx.units, ctx.saved, ctx.params = units, saved, params
+        ctx.has_feats = feats is not None and feats.requires_grad
+        ctx.shape = (xyz.shape[0], xyz.shape[1], new_xyz.shape[1], idx.shape[2], 0 if feats is None else feats.shape[2])
+        ctx.idx = idx
+        return out
+
+    @staticmethod
+    def backward(ctx, dz):
+        units, (tape, argmax, G, ns) = ctx.units, ctx.saved
+        B, N, M, _, C = ctx.shape
+        grads = {}
+        dz = dz.contiguous()
+        last = units[-1]
+        rec = tape[-1]
+        Cl = last.cout
+        gsel = torch.empty(1, 1, G * ns, Cl, dtype=torch.float32, device=dz.device)
+        st = rec["bn"]
+        _C.call("maxrows_bwd", ptr(rec["y"]), c_ll(G), c_int(ns), c_int(Cl), ptr(st.mean), ptr(st.invstd), ptr(st.gamma), ptr(st.beta), ptr(dz),
+                c_int(Cl), c_int(0), ptr(argmax), ptr(gsel))
+        dy = K.empty_planes(1, 1, G * ns, Cl, dz.device)
+        ws = K.bn_act_bwd(gsel, None, rec["y"], G * ns, Cl, 1, st, ACT_NONE, None, None, None, dy_pl=dy)
+        wsf = ws.float()
+        grads[id(last.bn.weight)], grads[id(last.bn.bias)] = wsf[Cl : 2 * Cl], wsf[0:Cl]
+        d = last.data_grads(rec, dy, True, grads)
+        d = _chain_backward(units[:-1], tape[:-1], d, grads, ctx.has_feats)
+        d_feats = None
+        if ctx.has_feats:
+            d_feats = torch.empty(B, N, C, dtype=torch.float32, device=dz.device)
+            _C.call("group_rows_bwd", c_int(B), c_int(N), c_int(M), c_int(ns), c_int(C), ptr(d), ptr(ctx.idx), ptr(d_feats))
+        ctx.saved = None
+        return (None, None, None, None, None, d_feats) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
+
+
+def sa_scale_forward(units, training, xyz, new_xyz, idx, feats, record):
+    B, N, _ = xyz.shape
+    M, ns = idx.shape[1], idx.shape[2]
+    C = 0 if feats is None else feats.shape[2]
+    rows = B * M * ns
+    dev = xyz.device
+    a = Act(1, 1, rows, 3 + C)
+    a.pl = K.empty_planes(1, 1, rows, 3 + C, dev)
+    _C.call("group_rows_split", c_int(B), c_int(N), c_int(M), c_int(ns), c_int(C), ptr(xyz), ptr(new_xyz), K._p(feats), ptr(idx), *K._pl_args(a.pl),
+            c_int(a.cs))
+    a, tape = _chain_forward(units[:-1], a, training, record, last_f32=False, last_pair=True)
+    last = units[-1]
+    y, rec = last.forward(a, training, record, defer_act=True)
+    tape.append(rec)
+    st = rec["bn"]
+    Cl = last.cout
+    out = torch.empty(B, M, Cl, dtype=torch.float32, device=dev)
+    argmax = torch.empty(B * M, Cl, dtype=torch.uint8, device=dev)
+    _C.call("bn_relu_maxrows", ptr(y.f32), c_ll(B * M), c_int(ns), c_int(Cl), ptr(st.mean), ptr(st.invstd), ptr(st.gamma), ptr(st.beta), ptr(out),
+            c_int(Cl), c_int(0), ptr(argmax))
+    return out, (tape, argmax, B * M, ns)
+
+
+def sa_scale(units, training, xyz, new_xyz, idx, feats):
+    """xyz (B,N,3), new_xyz (B,M,3), idx int32 (B,M,ns), feats (B,N,C) channels-last or None -> (B,M,Cout)"""
+    params = _unit_params(units)
+    if feats is not None:
+        feats = feats.contiguous()
+    if torch.is_grad_enabled() and ((feats is not None and feats.requires_grad) or any(p.requires_grad for p in params)):
+        return _SAScaleFn.apply(units, training, xyz, new_xyz, idx, feats, *params)
+    out, _ = sa_scale_forward(units, training, xyz, new_xyz, idx, feats, False)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ three-NN interpolation on rows
+class _InterpRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, idx, weight):
+        B, m, C = feats.shape
+        n = idx.shape[1]
+        out = torch.empty(B, n, C, dtype=torch.float32, device=feats.device)
+        _C.call("interp_rows", c_int(B), c_int(m), c_int(n), c_int(C), ptr(feats), ptr(idx), ptr(weight), ptr(out), c_int(C), c_int(0))
+        ctx.save_for_backward(idx, weight)
+        ctx.m = m
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        idx, weight = ctx.saved_tensors
+        dout = dout.contiguous()
+        B, n, C = dout.shape
+        d = torch.empty(B, ctx.m, C, dtype=torch.float32, device=dout.device)
+        _C.call("interp_rows_bwd", c_int(B), c_int(ctx.m), c_int(n), c_int(C), ptr(dout), c_int(C), c_int(0), ptr(idx), ptr(weight), ptr(d))
+        return d, None, None
+
+
+def interp_rows(feats, idx, weight):
+    """three_interpolate on channels-last features: feats (B,m,C), idx/weight (B,n,3) -> (B,n,C)"""
+    return _InterpRowsFn.apply(feats.contiguous(), idx, weight)

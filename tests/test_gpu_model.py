@@ -11,6 +11,10 @@ from istnet_b200.synth import make_batch
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
+# Gradients of a train-mode network with tiny batches (B=2..4) are BatchNorm-amplified: the reference's own FP32 result
+# moves by ~5e-4 (relative, per tensor) between its CPU and GPU library back-ends on these cases (measured, see
+# DESIGN.md "Parity"), so parameter gradients are held to 2e-3 of each tensor's max / norm; outputs and the loss to 1e-4.
+GRAD_TOL = 2e-3
 LABELS = ("qo", "rotation_label", "translation_label", "size_label")
 
 
@@ -62,10 +66,10 @@ def test_train_step_matches_reference_golden():
         if k.startswith("grad_"):
             e = rel_err(params[k[5:]].grad, z[k])
             worst = max(worst, e)
-            assert e < 5 * TOL, (k, e)  # individual small gradient tensors (BN-amplified rounding)
+            assert e < GRAD_TOL, (k, e)
         elif k.startswith("gradnorm_"):
             g = params[k[9:]].grad
-            assert abs(g.double().norm().item() - float(z[k])) <= 5 * TOL * float(z[k]) + 1e-10, k
+            assert abs(g.double().norm().item() - float(z[k])) <= GRAD_TOL * float(z[k]) + 1e-10, k
         elif k.startswith("stat_"):
             assert rel_err(sd[k[5:]], z[k]) < TOL, k
     for n in z["nograd"]:
@@ -87,7 +91,7 @@ def test_posenet_gt_matches_reference_golden():
         assert params[str(n)].grad is None, n
     for k in z:
         if k.startswith("gradnorm_"):
-            assert abs(params[k[9:]].grad.double().norm().item() - float(z[k])) <= 5 * TOL * float(z[k]) + 1e-10, k
+            assert abs(params[k[9:]].grad.double().norm().item() - float(z[k])) <= GRAD_TOL * float(z[k]) + 1e-10, k
 
 
 def test_full_resolution_train_step_matches_oracle_port():
@@ -118,6 +122,6 @@ def test_full_resolution_train_step_matches_oracle_port():
             assert p.grad is None, n
             continue
         e = rel_err(p.grad, go)
-        if e > 10 * TOL:
+        if e > GRAD_TOL:
             bad.append((n, e))
     assert not bad, bad[:10]

@@ -16,9 +16,9 @@ def check(B, H, W, cin, cout, k, bias, relu, split):
     if relu:
         ref = ref.relu()
     ref = ref.permute(0, 2, 3, 1)
-    ah, al = tc.split_bf16_torch(x.permute(0, 2, 3, 1).contiguous())
-    wh, wl = tc.split_bf16_torch(w.permute(2, 3, 0, 1).reshape(k * k, cout, cin).contiguous())
-    out, sp = tc.conv_gemm(ah, al, cin, wh, wl, cout, k, k, bias=bvec, relu=relu, out_f32=True, out_split=split)
+    ap = tc.split_planes_torch(x.permute(0, 2, 3, 1).contiguous())
+    wp = tc.split_planes_torch(w.permute(2, 3, 0, 1).reshape(k * k, cout, cin).contiguous())
+    out, sp = tc.conv_gemm(ap, cin, wp, cout, k, k, bias=bvec, relu=relu, out_split=split)
     torch.cuda.synchronize()
     err = ((out.double() - ref).abs().max() / ref.abs().max()).item()
     tf = F.conv2d(x, w, bvec, padding=k // 2)
@@ -27,7 +27,7 @@ def check(B, H, W, cin, cout, k, bias, relu, split):
     err_t = ((tf.permute(0, 2, 3, 1).double() - ref).abs().max() / ref.abs().max()).item()
     msg = f"B{B} {H}x{W} {cin}->{cout} k{k} bias{int(bias)} relu{int(relu)}: rel err {err:.2e} (torch fp32 {err_t:.2e})"
     if split:
-        rs = sp[0].float() + sp[1].float()
+        rs = sp.float().sum(0)
         e2 = ((rs[..., :cout].double() - ref).abs().max() / ref.abs().max()).item()
         msg += f" split {e2:.2e}"
     print(msg, flush=True)
@@ -52,11 +52,11 @@ print("worst", worst)
 # quick timing of the big shapes
 def bench(B, H, W, cin, cout, k, n=10):
     x = torch.randn(B, H, W, cin, device=dev); w = torch.randn(k * k, cout, cin, device=dev) * 0.02
-    ah, al = tc.split_bf16_torch(x); wh, wl = tc.split_bf16_torch(w)
-    for _ in range(3): tc.conv_gemm(ah, al, cin, wh, wl, cout, k, k)
+    ap = tc.split_planes_torch(x); wp = tc.split_planes_torch(w)
+    for _ in range(3): tc.conv_gemm(ap, cin, wp, cout, k, k)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n): tc.conv_gemm(ah, al, cin, wh, wl, cout, k, k)
+    for _ in range(n): tc.conv_gemm(ap, cin, wp, cout, k, k)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     fl = 2.0 * B * H * W * cin * cout * k * k

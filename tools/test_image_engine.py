@@ -42,7 +42,7 @@ def run(B, S, N, train):
             grads[name] = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
         stats[name] = {n: b.clone() for n, b in m.named_buffers()}
     with torch.set_grad_enabled(train):
-        o = image_branch(net, rgb, choose)
+        o = image_branch(net, rgb, choose).transpose(1, 2)
     torch.cuda.synchronize()
     print(f"--- B{B} {S}x{S} N{N} train={train}: out rel err engine {rel(o, outs['f64']):.2e} | torch-fp32 {rel(outs['f32'], outs['f64']):.2e}")
     if train:

@@ -14,9 +14,9 @@ def check(B, H, W, cin, cout, k):
     y = F.conv2d(x, w, None, padding=k // 2)
     dy = torch.randn_like(y)
     (gw_ref,) = torch.autograd.grad(y, w, dy)
-    xh, xl = tc.split_bf16_torch(x.float().permute(0, 2, 3, 1).contiguous())
-    dh, dl = tc.split_bf16_torch(dy.float().permute(0, 2, 3, 1).contiguous())
-    gw = tc.conv_wgrad(dh, dl, cout, xh, xl, cin, k, k)
+    xp = tc.split_planes_torch(x.float().permute(0, 2, 3, 1).contiguous())
+    dp = tc.split_planes_torch(dy.float().permute(0, 2, 3, 1).contiguous())
+    gw = tc.conv_wgrad(dp, cout, xp, cin, k, k)
     torch.cuda.synchronize()
     err = ((gw.double() - gw_ref).abs().max() / gw_ref.abs().max()).item()
     wf = w.detach().float().requires_grad_(True)
@@ -33,11 +33,11 @@ print("worst", worst)
 
 def bench(B, H, W, cin, cout, k, n=10):
     x = torch.randn(B, H, W, cin, device=dev); dy = torch.randn(B, H, W, cout, device=dev)
-    xh, xl = tc.split_bf16_torch(x); dh, dl = tc.split_bf16_torch(dy)
-    for _ in range(3): tc.conv_wgrad(dh, dl, cout, xh, xl, cin, k, k)
+    xp = tc.split_planes_torch(x); dp = tc.split_planes_torch(dy)
+    for _ in range(3): tc.conv_wgrad(dp, cout, xp, cin, k, k)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n): tc.conv_wgrad(dh, dl, cout, xh, xl, cin, k, k)
+    for _ in range(n): tc.conv_wgrad(dp, cout, xp, cin, k, k)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     fl = 2.0 * B * H * W * cin * cout * k * k
