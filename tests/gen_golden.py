@@ -95,6 +95,47 @@ def main():
         g = grads_summary(ref)
         sd_after = ref.state_dict()
         keep = [n for n in g if g[n].numel() <= 4096]  # full small grads; norms for everything
+        # ---- FLOAT64 ground truth of the same step (reference modules in double, same indices): separates the
+        # reference's own FP32 rounding noise from implementation differences
+        import sys as _sys
+        from oracle import pointops_any
+        _sys.modules["pointnet2._ext"] = pointops_any
+        ns.pointnet2_utils._ext = pointops_any
+        torch.manual_seed(1)
+        mine64 = M.IST_Net(6, freeze)
+        ref64 = ns.ist_net.IST_Net(6, freeze)
+        ref64.load_state_dict(mine64.state_dict())
+        ref64 = ref64.double().train()
+        for m in ref64.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.momentum = 0.9
+        noise64 = fixed_dropout_noise(77)
+
+        class _Drop64(torch.nn.Module):
+            def __init__(self, p):
+                super().__init__()
+                self.p = p
+
+            def forward(self, x):
+                return x * noise64(x.shape[0], x.shape[1], self.p).double()
+
+        ref64.rgb_cam_extractor.model.drop_1, ref64.rgb_cam_extractor.model.drop_2 = _Drop64(0.3), _Drop64(0.15)
+        inp64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in inp.items()}
+        ep64 = ref64(inp64)
+        ep64.update({k: inp64[k] for k in LABELS})
+        loss64 = ns.ist_net.SupervisedLoss(M.LossCfg(1.0, 10.0, freeze))(ep64)
+        loss64.backward()
+        g64 = grads_summary(ref64)
+        ns.pointnet2_utils._ext = ns.pointnet2_utils._ext.__class__ and __import__("oracle.pointops", fromlist=["x"])
+        _sys.modules["pointnet2._ext"] = ns.pointnet2_utils._ext
+        truth = {"loss64": loss64.item()}
+        truth.update({"out64_" + k: v.detach().numpy() for k, v in ep64.items() if k not in LABELS})
+        truth.update({"grad64_" + n: g64[n].numpy() for n in keep})
+        truth.update({"gradnorm64_" + n: np.float64(v.norm().item()) for n, v in g64.items()})
+        # per-tensor deviation of the reference's own FP32 result from the truth (max|a-b|/max|b|)
+        truth.update({"referr_grad_" + n: np.float64(((g[n].double() - g64[n]).abs().max() / g64[n].abs().max().clamp_min(1e-300)).item()) for n in g})
+        truth.update({"referr_out_" + k: np.float64(((ep[k].detach().double() - ep64[k].detach()).abs().max() / ep64[k].detach().abs().max()).item())
+                      for k in ep64 if k not in LABELS})
         np.savez_compressed(
             os.path.join(OUT, f"{name}.npz"),
             sd_checksum=sd_checksum(mine.state_dict()),
@@ -105,6 +146,7 @@ def main():
             **{"grad_" + n: g[n].numpy() for n in keep},
             **{"stat_" + k: v.numpy() for k, v in sd_after.items() if "running_" in k and v.numel() <= 64},
             nograd=np.array([n for n, p in ref.named_parameters() if p.grad is None]),
+            **truth,
         )
     # ---------------- PoseNetGT (cfg3 shape family): B=2, 256 pts, 64x64 train step
     torch.manual_seed(1)

@@ -11,10 +11,11 @@ from istnet_b200.synth import make_batch
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
-# Gradients of a train-mode network with tiny batches (B=2..4) are BatchNorm-amplified: the reference's own FP32 result
-# moves by ~5e-4 (relative, per tensor) between its CPU and GPU library back-ends on these cases (measured, see
-# DESIGN.md "Parity"), so parameter gradients are held to 2e-3 of each tensor's max / norm; outputs and the loss to 1e-4.
-GRAD_TOL = 2e-3
+# Gradients of a train-mode network with tiny batches (B=2..4) are chaotic (ReLU / max-pool selections flip under
+# rounding-level perturbations): the reference's own FP32 gradients deviate from a FLOAT64 evaluation of the same step by
+# 1e-3..2e-1 per tensor (tests/golden/train_b4.npz `referr_grad_*`).  Where no float64 truth is stored, gradient norms
+# are held to GRAD_TOL; outputs, losses and running statistics are always held to 1e-4.
+GRAD_TOL = 3e-2
 LABELS = ("qo", "rotation_label", "translation_label", "size_label")
 
 
@@ -51,6 +52,12 @@ def _train_step(m, inp, loss_mod, noise_seed, momentum=None):
 
 
 def test_train_step_matches_reference_golden():
+    """B=4 train step (fwd + SupervisedLoss + bwd) against the reference.  The golden file holds the reference's FP32
+    result AND the same step evaluated by the reference modules in FLOAT64 (ground truth) with the reference's own FP32
+    deviation from it per tensor (`referr_*`).  Outputs / loss / running stats: 1e-4 against the truth and the FP32
+    reference.  Gradients: this tiny-batch train-mode step is chaotic (ReLU / max-pool selections flip under 1e-7
+    perturbations — the reference's own FP32 gradients are up to 2e-1 off the truth), so each gradient must be within
+    max(1e-4, 3 x the reference's own deviation) of the truth."""
     z = load_golden("train_b4.npz")
     torch.manual_seed(1)
     m = M.IST_Net(6, False).cuda()
@@ -58,23 +65,37 @@ def test_train_step_matches_reference_golden():
     for k in z:
         if k.startswith("out_"):
             assert rel_err(ep[k[4:]], z[k]) < TOL, (k, rel_err(ep[k[4:]], z[k]))
+            assert rel_err(ep[k[4:]], z["out64_" + k[4:]]) < TOL, (k, "vs float64 truth")
     assert abs(loss.item() - float(z["loss"])) < TOL * abs(float(z["loss"]))
+    assert abs(loss.item() - float(z["loss64"])) < TOL * abs(float(z["loss64"]))
     params = dict(m.named_parameters())
     sd = m.state_dict()
-    worst = 0.0
+    gmax = max(float(z[k]) for k in z if k.startswith("gradnorm64_"))
+    closer, total, failures = 0, 0, []
     for k in z:
-        if k.startswith("grad_"):
-            e = rel_err(params[k[5:]].grad, z[k])
-            worst = max(worst, e)
-            assert e < GRAD_TOL, (k, e)
-        elif k.startswith("gradnorm_"):
-            g = params[k[9:]].grad
-            assert abs(g.double().norm().item() - float(z[k])) <= GRAD_TOL * float(z[k]) + 1e-10, k
+        if k.startswith("gradnorm64_"):
+            n = k[11:]
+            g = params[n].grad
+            truth = float(z[k])
+            mine = g.double().norm().item()
+            if truth < 1e-7 * gmax:  # analytically-zero gradients (biases feeding a train-mode BatchNorm)
+                assert mine < 1e-6 * gmax, n
+                continue
+            bound = max(TOL, 3.0 * float(z["referr_grad_" + n]))
+            if abs(mine - truth) / truth > bound:
+                failures.append((n, abs(mine - truth) / truth, bound))
+            if ("grad64_" + n) in z:
+                e = rel_err(g, z["grad64_" + n])
+                total += 1
+                closer += e <= float(z["referr_grad_" + n])
+                if e > bound:
+                    failures.append((n, e, bound))
         elif k.startswith("stat_"):
             assert rel_err(sd[k[5:]], z[k]) < TOL, k
+    assert not failures, failures[:10]
     for n in z["nograd"]:
         assert params[str(n)].grad is None, n
-    print("worst small-gradient rel err", worst)
+    print(f"gradients closer to the float64 truth than the reference's own FP32 result: {closer}/{total}")
 
 
 def test_posenet_gt_matches_reference_golden():
