@@ -46,10 +46,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int split = blockIdx.x;
+    // the filter tap is the fastest grid index: the kh*kw CTAs that read the same dY / (shifted) X pixel tiles are
+    // co-scheduled and share them through L2
+    const int tap = blockIdx.x;
     const int co0 = (blockIdx.y / p.n_ci_tiles) * kTileM;
     const int ci0 = (blockIdx.y % p.n_ci_tiles) * p.BN;
-    const int tap = blockIdx.z;
+    const int split = blockIdx.z;
     const int r = tap / p.kw, s = tap % p.kw;
     const int per = (p.num_pix_tiles + p.ksplit - 1) / p.ksplit;
     const int t_begin = split * per;
@@ -239,7 +241,7 @@ extern "C" int istnet_conv_wgrad(const void *dy_planes, long long dy_plane_strid
         if (e) return e;
     }
     ISTNET_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    dim3 grid(ksplit, ceil_div(Cout, kTileM) * p.n_ci_tiles, kh * kw);
+    dim3 grid(kh * kw, ceil_div(Cout, kTileM) * p.n_ci_tiles, ksplit);
     wgrad_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(t_dy, t_x, p);
     ISTNET_LAUNCH_CHECK();
     const long long total = (long long)kh * kw * Cout * Cin;

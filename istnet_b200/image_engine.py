@@ -144,7 +144,7 @@ def backward(net, tape, d_out, u):
             slope = torch.empty(128, dtype=torch.float64, device=dev)
             _C.call("gather_bn_prelu_bwd", ptr(rf["y"]), c_int(B), c_ll(HW), c_int(128), c_int(N), ptr(choose), ptr(st.mean), ptr(st.invstd),
                     ptr(st.gamma), ptr(st.beta), ptr(unit.prelu), ptr(d_out), ptr(g), ptr(slope))
-            dy = K.empty_planes(B, xin.H, xin.W, 128, dev)
+            dy = K.empty_planes(B, xin.H, xin.W, 128, dev, nsplit=K.NSPLIT_BWD)
             ws = K.bn_act_bwd(g, None, rf["y"], rf["P"], 128, HW, st, ACT_NONE, None, None, None, dy_pl=dy)
             wsf = ws.float()
             grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = wsf[128:256], wsf[0:128]
@@ -185,7 +185,7 @@ def backward(net, tape, d_out, u):
             g0 = torch.empty(B, H0, W0, 64, dtype=torch.float32, device=dev)
             _C.call("maxpool_relu_bwd", ptr(r0["y"]), c_int(B), c_int(H0), c_int(W0), c_int(64), ptr(st.mean), ptr(st.invstd), ptr(st.gamma),
                     ptr(st.beta), ptr(dz), K._p(dz2), ptr(argmax), ptr(g0))
-            dy = K.empty_planes(B, H0, W0, 64, dev)
+            dy = K.empty_planes(B, H0, W0, 64, dev, nsplit=K.NSPLIT_BWD)
             ws = K.bn_act_bwd(g0, None, r0["y"], r0["P"], 64, H0 * W0, st, ACT_NONE, None, None, None, dy_pl=dy)
             wsf = ws.float()
             grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = wsf[64:128], wsf[0:64]

@@ -16,6 +16,9 @@ NULL = c_void_p(0)
 # bf16 operand planes per FP32 tensor: 3 -> six tensor-core products, FP32-level accuracy (default, needed for the 1e-4
 # parity bar in train mode); 2 -> three products, ~3e-6 per product, twice the tensor-core throughput.
 NSPLIT = int(os.environ.get("ISTNET_NSPLIT", "3"))
+# The backward contractions (dgrad / wgrad) use the first NSPLIT_BWD planes only: 3 products, ~3e-6 per product —
+# orders of magnitude below the FP32 noise floor of the gradients themselves (tests/golden `referr_grad_*`).
+NSPLIT_BWD = min(NSPLIT, int(os.environ.get("ISTNET_NSPLIT_BWD", "2")))
 
 
 def _p(t):
@@ -47,8 +50,8 @@ class Act:
         return self.pl[0] if self.pl is not None else None
 
 
-def empty_planes(B, H, W, C, dev, cs=None):
-    return torch.empty(NSPLIT, B, H, W, cs or pad8(C), dtype=torch.bfloat16, device=dev)
+def empty_planes(B, H, W, C, dev, cs=None, nsplit=None):
+    return torch.empty(nsplit or NSPLIT, B, H, W, cs or pad8(C), dtype=torch.bfloat16, device=dev)
 
 
 def _pl_args(pl):
@@ -63,7 +66,7 @@ def split(x_f32, P, C, pl, ch_off=0, HW=1, nchw=False):
     _C.call("split", ptr(x_f32), c_ll(P), c_int(C), c_ll(HW), c_int(1 if nchw else 0), *_pl_args(pl), c_int(pl.shape[-1]), c_int(ch_off))
 
 
-def prep_weight(w, transpose=False):
+def prep_weight(w, transpose=False, nsplit=None):
     """Conv / linear weight [co, ci, kh, kw] (or [co, ci]) -> bf16 operand planes [NSPLIT, taps, rows, pad8(cols)].
     transpose=False: forward operand  [tap][co][ci];  transpose=True: data-gradient operand [flipped tap][ci][co]."""
     if w.dim() == 2:
@@ -76,7 +79,7 @@ def prep_weight(w, transpose=False):
     else:
         m = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
     taps, rows, cols = m.shape
-    pl = torch.empty(NSPLIT, taps, rows, pad8(cols), dtype=torch.bfloat16, device=w.device)
+    pl = torch.empty(nsplit or NSPLIT, taps, rows, pad8(cols), dtype=torch.bfloat16, device=w.device)
     split(m, taps * rows, cols, pl)
     return pl
 
@@ -103,12 +106,13 @@ def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl
 def conv_wgrad(dy_pl, cout, x, kh, kw):
     """grad_w [cout, cin, kh, kw] from dy operand planes [NSPLIT,B,H,W,cs] and x: Act (planes)."""
     dev = x.pl.device
-    ks = _C.lib().istnet_wgrad_ksplit(x.B, x.H, x.W, cout, x.C, kh, kw, x.pl.shape[0])
+    xpl = x.pl[: dy_pl.shape[0]]  # planes are nested: the first n planes are the n-plane representation
+    ks = _C.lib().istnet_wgrad_ksplit(x.B, x.H, x.W, cout, x.C, kh, kw, xpl.shape[0])
     ws = torch.empty(ks * kh * kw * cout * x.C, dtype=torch.float32, device=dev)
     gw = torch.empty(cout, x.C, kh, kw, dtype=torch.float32, device=dev)
     bw, bh = (64, 1) if x.H == 1 else (8, 8)
     _C.call(
-        "conv_wgrad", ptr(dy_pl), c_ll(dy_pl.stride(0)), c_int(dy_pl.shape[-1]), ptr(x.pl), c_ll(x.pl.stride(0)), c_int(x.cs), c_int(x.pl.shape[0]),
+        "conv_wgrad", ptr(dy_pl), c_ll(dy_pl.stride(0)), c_int(dy_pl.shape[-1]), ptr(xpl), c_ll(xpl.stride(0)), c_int(x.cs), c_int(xpl.shape[0]),
         c_int(x.B), c_int(x.H), c_int(x.W), c_int(cout), c_int(x.C), c_int(kh), c_int(kw), ptr(ws), c_int(ks), ptr(gw), c_int(bw), c_int(bh),
     )
     return gw
@@ -255,7 +259,7 @@ class ConvUnit:
         dev = dz.device
         xin, P, C = rec["xin"], rec["P"], self.cout
         B, H, W = xin.B, xin.H, xin.W
-        dy = empty_planes(B, H, W, C, dev)
+        dy = empty_planes(B, H, W, C, dev, nsplit=NSPLIT_BWD)
         if self.bn is None and self.act == ACT_NONE and rec["noise"] is None:  # plain linear layer
             d = dz if dz2 is None else dz + dz2
             split(d.contiguous(), P, C, dy)
@@ -293,12 +297,12 @@ class ConvUnit:
         dyA = Act(xin.B, xin.H, xin.W, C, None, dy)
         if kk != self.k or self.stride != 1:
             wm = self.w.permute(0, 2, 3, 1).reshape(C, -1)
-            wd = prep_weight(wm, transpose=True)
+            wd = prep_weight(wm, transpose=True, nsplit=dy.shape[0])
             dcol = torch.empty(xin.B, xin.H, xin.W, xin.C, dtype=torch.float32, device=dy.device)
             conv_gemm(dyA, wd, xin.C, 1, 1, out_f32=dcol)
             b, h, w, c = rec["in_shape"]
             return col2im(dcol, b, h, w, c, self.k, self.stride, self.pad)
-        wd = prep_weight(self.w, transpose=True)
+        wd = prep_weight(self.w, transpose=True, nsplit=dy.shape[0])
         dx = torch.empty(xin.B, xin.H, xin.W, xin.C, dtype=torch.float32, device=dy.device)
         conv_gemm(dyA, wd, xin.C, kk, kk, out_f32=dx)
         return dx

@@ -15,6 +15,8 @@ for r in csv.DictReader(lines):
         rows.append((r["Kernel Name"], v * scale))
 agg = defaultdict(lambda: [0, 0.0])
 for name, us in rows:
+    name = name.replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
+    name = re.sub(r"\(.*", "", name)
     name = re.sub(r"<.*", "", name)[:90]
     agg[name][0] += 1
     agg[name][1] += us
