@@ -1,0 +1,178 @@
+"""Tight, well-conditioned GPU checks of the individual dense / fused kernels (through the C ABI) against FLOAT64 PyTorch
+evaluations of the reference ops they replace.  Tolerances are written per test; the float target of the path is 1e-4
+relative (max|a-b| / max|b|)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    from istnet_b200 import nhwc
+
+    return nhwc
+
+
+@pytest.fixture(scope="module")
+def tc():
+    from istnet_b200 import tc as t
+
+    return t
+
+
+CONV_CASES = [(2, 8, 8, 64, 64, 1), (2, 8, 8, 64, 64, 3), (2, 24, 24, 128, 256, 3), (3, 24, 24, 512, 512, 3), (1, 1, 1000, 320, 384, 1),
+              (1, 1, 4096, 67, 32, 1), (1, 1, 300, 3, 16, 1), (2, 48, 48, 1024, 256, 3), (2, 16, 16, 128, 18, 1), (1, 1, 512, 2560, 1024, 1),
+              (1, 8, 8, 512, 512, 3)]
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,k", CONV_CASES)
+def test_conv_gemm_matches_float64_conv2d(tc, B, H, W, cin, cout, k):
+    """tcgen05 implicit GEMM (nn.Conv2d / Conv1d / Linear call sites) — 1e-4; odd batch, K tails, N tails, 1x1 and 3x3."""
+    g = torch.Generator(device="cuda").manual_seed(B * 131 + cin + cout)
+    x = torch.randn(B, cin, H, W, device="cuda", generator=g)
+    w = torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, device="cuda", generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=k // 2).relu().permute(0, 2, 3, 1)
+    ap = tc.split_planes_torch(x.permute(0, 2, 3, 1).contiguous())
+    wp = tc.split_planes_torch(w.permute(2, 3, 0, 1).reshape(k * k, cout, cin).contiguous())
+    out, planes = tc.conv_gemm(ap, cin, wp, cout, k, k, bias=b, relu=True, out_split=True)
+    assert rel_err(out, ref) < 1e-4
+    assert rel_err(planes.float().sum(0)[..., :cout], ref) < 1e-4  # fused operand-plane epilogue
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,k", [(2, 8, 8, 64, 64, 1), (2, 8, 8, 64, 128, 3), (4, 24, 24, 128, 256, 3), (2, 24, 24, 512, 512, 3),
+                                               (1, 1, 4096, 320, 384, 1), (1, 1, 1000, 67, 32, 1), (3, 16, 16, 128, 18, 1), (1, 1, 512, 3, 16, 1)])
+def test_wgrad_matches_float64_autograd(tc, B, H, W, cin, cout, k):
+    """tcgen05 weight gradient (MN-major operands, split-K, deterministic reduce) — 2e-5."""
+    g = torch.Generator(device="cuda").manual_seed(cin * 7 + cout)
+    x = torch.randn(B, cin, H, W, device="cuda", dtype=torch.float64, generator=g)
+    w = torch.randn(cout, cin, k, k, device="cuda", dtype=torch.float64, generator=g).requires_grad_(True)
+    y = F.conv2d(x, w, None, padding=k // 2)
+    dy = torch.randn(y.shape, device="cuda", dtype=torch.float64, generator=g)
+    (gw_ref,) = torch.autograd.grad(y, w, dy)
+    xp = tc.split_planes_torch(x.float().permute(0, 2, 3, 1).contiguous())
+    dp = tc.split_planes_torch(dy.float().permute(0, 2, 3, 1).contiguous())
+    gw = tc.conv_wgrad(dp, cout, xp, cin, k, k)
+    gw2 = tc.conv_wgrad(dp, cout, xp, cin, k, k)
+    assert torch.equal(gw, gw2)  # deterministic
+    assert rel_err(gw, gw_ref) < 2e-5
+
+
+def _unit_vs_torch(K, B, H, W, cin, cout, k, stride, bn, act, bias, noise, seed):
+    from istnet_b200.nhwc import Act, ConvUnit
+
+    torch.manual_seed(seed)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    conv = torch.nn.Conv2d(cin, cout, k, stride=stride, padding=k // 2, bias=bias).cuda()
+    bnm = torch.nn.BatchNorm2d(cout).cuda() if bn else None
+    prelu = torch.nn.PReLU().cuda() if act == 2 else None
+    # keep every pre-activation far from the PReLU kink (alternating +-8 offsets per channel): the derivative is
+    # discontinuous there and a rounding-level sign flip would change single gradient elements by O(1)
+    sign = (torch.arange(cout, device="cuda") % 2 * 2 - 1).float()
+    if bnm is not None:
+        torch.nn.init.uniform_(bnm.weight, 0.5, 1.0)
+        with torch.no_grad():
+            bnm.bias.copy_(8.0 * sign if act != 0 else 0.3 * torch.randn(cout, device="cuda"))
+        bnm.momentum = 0.7
+    elif bias and act != 0:
+        with torch.no_grad():
+            conv.bias.copy_(8.0 * sign)
+    x = torch.randn(B, cin, H, W, device="cuda", generator=g)
+    nz = (torch.rand(B, cout, device="cuda", generator=g) > 0.3).float() / 0.7 if noise else None
+    # float64 reference
+    import copy
+
+    c64, b64, p64 = copy.deepcopy(conv).double(), copy.deepcopy(bnm).double() if bnm else None, copy.deepcopy(prelu).double() if prelu else None
+    x64 = x.double().requires_grad_(True)
+    u = c64(x64)
+    if b64 is not None:
+        u = b64.train()(u)
+    z = u if act == 0 else (p64(u) if act == 2 else u.relu())
+    if nz is not None:
+        z = z * nz.double()[:, :, None, None]
+    dz = torch.randn(z.shape, device="cuda", dtype=torch.float64, generator=g)
+    z.backward(dz)
+    # B200 unit
+    unit = ConvUnit(conv.weight, conv.bias, bnm, act, prelu=prelu.weight if prelu else None, k=k, stride=stride)
+    xin = Act(B, H, W, cin, x.permute(0, 2, 3, 1).contiguous())
+    xin.pl = K.empty_planes(B, H, W, cin, "cuda")
+    K.split(xin.f32, B * H * W, cin, xin.pl)
+    out, rec = unit.forward(xin, True, True, noise=nz, want_f32=True)
+    grads = {}
+    dx, _ = unit.backward(rec, dz.float().permute(0, 2, 3, 1).contiguous(), None, need_dx=True, grads=grads)
+    res = {"z": (out.f32, z.detach().permute(0, 2, 3, 1)), "dx": (dx, x64.grad.permute(0, 2, 3, 1)), "dw": (grads[id(conv.weight)], c64.weight.grad)}
+    if bnm is not None:
+        res["dgamma"] = (grads[id(bnm.weight)], b64.weight.grad)
+        res["dbeta"] = (grads[id(bnm.bias)], b64.bias.grad)
+        res["running_mean"] = (bnm.running_mean, b64.running_mean)
+        res["running_var"] = (bnm.running_var, b64.running_var)
+    elif bias:
+        res["dbias"] = (grads[id(conv.bias)], c64.bias.grad)
+    if prelu is not None:
+        res["dslope"] = (grads[id(prelu.weight)], p64.weight.grad)
+    return res
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=4, H=16, W=16, cin=64, cout=128, k=3, stride=1, bn=True, act=0, bias=False, noise=False),   # conv + BN(train)
+    dict(B=4, H=16, W=16, cin=64, cout=64, k=3, stride=1, bn=True, act=2, bias=True, noise=True),      # PSPUpsample tail
+    dict(B=2, H=1, W=2048, cin=320, cout=256, k=1, stride=1, bn=False, act=2, bias=True, noise=False),  # per-point layer
+    dict(B=4, H=16, W=16, cin=64, cout=128, k=3, stride=2, bn=True, act=0, bias=False, noise=False),   # strided (im2col) conv
+    dict(B=4, H=16, W=16, cin=64, cout=128, k=1, stride=2, bn=True, act=0, bias=False, noise=False),   # strided downsample
+])
+def test_conv_bn_act_unit_forward_backward(K, cfg):
+    """conv (+bias) -> BatchNorm(train) -> PReLU -> Dropout2d scale, forward and hand-written backward, vs float64 autograd.
+    Pre-activations are kept away from the activation kink (see _unit_vs_torch): 1e-4 on everything, including the BN
+    running statistics."""
+    res = _unit_vs_torch(K, seed=11, **cfg)
+    for name, (a, b) in res.items():
+        assert rel_err(a, b) < 1e-4, (name, rel_err(a, b))
+
+
+def test_upsample2x_and_adjoint(K):
+    """nn.Upsample(x2, bilinear, align_corners=True) fused with the operand split, and its gather-form adjoint — 1e-6."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(3, 64, 12, 12, device="cuda", generator=g, dtype=torch.float64).requires_grad_(True)
+    ref = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+    d = torch.randn(ref.shape, device="cuda", generator=g, dtype=torch.float64)
+    ref.backward(d)
+    pl = K.empty_planes(3, 24, 24, 64, "cuda")
+    K.upsample2x(x.detach().float().permute(0, 2, 3, 1).contiguous(), 3, 12, 12, 64, pl)
+    assert rel_err(pl.float().sum(0), ref.detach().permute(0, 2, 3, 1)) < 1e-6
+    dx = K.upsample2x_bwd(d.float().permute(0, 2, 3, 1).contiguous(), 3, 12, 12, 64)
+    assert rel_err(dx, x.grad.permute(0, 2, 3, 1)) < 1e-6
+
+
+def test_sa_scale_and_interp_rows_match_reference_flow():
+    """Fused set-abstraction scale (group -> 3 x [GEMM, BN, ReLU] -> max) and row interpolation vs the reference dataflow
+    (grouping_operation + SharedMLP + max_pool2d, three_interpolate) evaluated in float64 — forward 1e-4."""
+    from istnet_b200 import ext, rows_engine as RE
+    from istnet_b200.pointnet2 import SharedMLP
+    from istnet_b200.synth import make_batch
+
+    d = make_batch(4, 512, 8, seed=3)
+    xyz = (d["pts"] - d["pts"].mean(1, keepdim=True)).cuda().contiguous()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    feats = torch.randn(4, 512, 64, device="cuda", generator=g)
+    idx_f = ext.furthest_point_sampling(xyz, 128)
+    new_xyz = torch.gather(xyz, 1, idx_f.long()[..., None].expand(-1, -1, 3)).contiguous()
+    idx = ext.ball_query(new_xyz, xyz, 0.04, 32)
+    mlp = SharedMLP([67, 32, 32, 64]).cuda().train()
+    out = RE.sa_scale(RE.units_from_shared_mlp(mlp), True, xyz, new_xyz, idx, feats)
+    m64 = SharedMLP([67, 32, 32, 64]).cuda().double().train()
+    m64.load_state_dict(mlp.state_dict())
+    gi = idx.long()
+    gx = torch.gather(xyz.double()[:, None].expand(-1, 128, -1, -1), 2, gi[..., None].expand(-1, -1, -1, 3)) - new_xyz.double()[:, :, None]
+    gf = torch.gather(feats.double()[:, None].expand(-1, 128, -1, -1), 2, gi[..., None].expand(-1, -1, -1, 64))
+    grouped = torch.cat([gx, gf], -1).permute(0, 3, 1, 2)  # (B, 3+C, npoint, nsample)
+    ref = F.max_pool2d(m64(grouped), kernel_size=[1, 32]).squeeze(-1).transpose(1, 2)
+    assert rel_err(out, ref) < 1e-4
+    d2, i3 = ext.three_nn(xyz, new_xyz)
+    w = torch.rand(4, 512, 3, device="cuda", generator=g)
+    got = RE.interp_rows(out.detach().contiguous(), i3, w)
+    want = sum(torch.gather(out.detach(), 1, i3[..., q].long()[..., None].expand(-1, -1, 64)) * w[..., q : q + 1] for q in range(3))
+    assert rel_err(got, want) < 1e-6
