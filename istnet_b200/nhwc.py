@@ -92,15 +92,32 @@ def pick_box(H, W):
     return 8, 8
 
 
+# bench.py sets PROFILE = [] to time every tensor-core launch with CUDA events on the launching stream:
+# entries are (kernel name, start event, end event, algorithmic FLOPs, nsplit)
+PROFILE = None
+
+
+def _prof(name, flops, nsplit):
+    if PROFILE is None:
+        return None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    PROFILE.append((name, e0, e1, flops, nsplit))
+    e0.record()
+    return e1
+
+
 def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl=None):
     """x: Act with operand planes; returns nothing — writes out_f32 [B,H,W,cout] and/or out_pl."""
     bw, bh = pick_box(x.H, x.W)
+    ev = _prof("conv_gemm_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, x.pl.shape[0])
     _C.call(
         "conv_gemm", ptr(x.pl), c_ll(x.pl.stride(0)), c_int(x.B), c_int(x.H), c_int(x.W), c_int(x.C), c_int(x.cs), ptr(w_pl),
         c_ll(w_pl.stride(0)), c_int(cout), c_int(w_pl.shape[-1]), c_int(kh), c_int(kw), c_int(x.pl.shape[0]), _p(bias), c_int(1 if relu else 0),
         _p(out_f32), c_int(out_f32.shape[-1] if out_f32 is not None else 0), *_pl_args(out_pl), c_int(out_pl.shape[-1] if out_pl is not None else 0),
         c_int(bw), c_int(bh),
     )
+    if ev is not None:
+        ev.record()
 
 
 def conv_wgrad(dy_pl, cout, x, kh, kw):
@@ -111,10 +128,13 @@ def conv_wgrad(dy_pl, cout, x, kh, kw):
     ws = torch.empty(ks * kh * kw * cout * x.C, dtype=torch.float32, device=dev)
     gw = torch.empty(cout, x.C, kh, kw, dtype=torch.float32, device=dev)
     bw, bh = (64, 1) if x.H == 1 else (8, 8)
+    ev = _prof("wgrad_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, xpl.shape[0])
     _C.call(
         "conv_wgrad", ptr(dy_pl), c_ll(dy_pl.stride(0)), c_int(dy_pl.shape[-1]), ptr(xpl), c_ll(xpl.stride(0)), c_int(x.cs), c_int(xpl.shape[0]),
         c_int(x.B), c_int(x.H), c_int(x.W), c_int(cout), c_int(x.C), c_int(kh), c_int(kw), ptr(ws), c_int(ks), ptr(gw), c_int(bw), c_int(bh),
     )
+    if ev is not None:
+        ev.record()
     return gw
 
 
