@@ -16,13 +16,13 @@
 //            and nsplit weight boxes (64 x BN) into a SWIZZLE_128B ring, completion on mbarriers
 //   warp 1 : MMA issuer    — one elected thread, 4 k-steps x 3|6 products per stage, tcgen05.commit frees the stage
 //   warps 2-5 : epilogue   — tcgen05.ld 32x32b, + bias, ReLU, FP32 and/or bf16-plane stores (NHWC rows)
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kBlockK = 64;                          // bf16 elements = 128 B = one swizzle row
-constexpr int kATileBytes = kTileM * kBlockK * 2;    // 16 KB
 constexpr int kThreads = 192;
 
 struct ConvGemmParams {
@@ -30,7 +30,8 @@ struct ConvGemmParams {
     int box_w, box_h, box_b;  // pixel tile, box_w*box_h*box_b == 128
     int tiles_w, tiles_h, tiles_b;
     int kh, kw;               // taps (1x1 or 3x3 ...), padding = k/2
-    int cin_blocks;           // ceil(Cin / 64)
+    int cin_blocks;           // ceil(Cin / block_k)
+    int block_k;              // K elements per pipeline stage: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows)
     int Cout, BN;             // logical output channels, tile width (multiple of 16, <= 256)
     int stages;
     const float *bias;        // [Cout] or null
@@ -48,6 +49,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const ConvGemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int kBlockK = p.block_k;
+    const int kATileBytes = kTileM * kBlockK * 2;
     const int b_tile_bytes = p.BN * kBlockK * 2;
     const int stage_bytes = p.nsplit * (kATileBytes + b_tile_bytes);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
@@ -114,15 +117,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 tc::tc_fence_after();
                 const uint32_t a0 = tc::smem_u32(smem + (size_t)st * stage_bytes);
                 const uint32_t b0 = a0 + p.nsplit * kATileBytes;
-#pragma unroll
+                const uint32_t ltype = kBlockK == 64 ? 2u : 4u;   // SWIZZLE_128B | SWIZZLE_64B
+                const uint32_t sbo = 8u * kBlockK * 2u;           // 8 rows of one swizzle atom
                 for (int j = 0; j < kBlockK / 16; ++j) {
                     uint32_t acc = (it | j) != 0;
                     // all plane products a_i * b_j with i + j < nsplit, smallest magnitude first
                     for (int sum = p.nsplit - 1; sum >= 0; --sum) {
                         for (int ia = sum; ia >= 0; --ia) {
                             const int ib = sum - ia;
-                            const uint64_t da = tc::make_desc_sw128(a0 + ia * kATileBytes + j * 32, 16, 1024);
-                            const uint64_t db = tc::make_desc_sw128(b0 + ib * b_tile_bytes + j * 32, 16, 1024);
+                            const uint64_t da = tc::make_desc_swz(a0 + ia * kATileBytes + j * 32, 16, sbo, ltype);
+                            const uint64_t db = tc::make_desc_swz(b0 + ib * b_tile_bytes + j * 32, 16, sbo, ltype);
                             tc::umma_bf16(tmem_base, da, db, idesc, acc);
                             acc = 1;
                         }
@@ -203,7 +207,7 @@ PFN_tmapEncodeTiled istnet_get_tmap_encoder() {
 }
 
 int istnet_make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
-                          const uint32_t *box) {
+                          const uint32_t *box, int swizzle_bytes) {
     PFN_tmapEncodeTiled enc = istnet_get_tmap_encoder();
     if (!enc) return ISTNET_ERR_UNSUPPORTED;
     cuuint64_t gd[5], gs[4];
@@ -211,13 +215,26 @@ int istnet_make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const ui
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? ISTNET_OK : ISTNET_ERR_BAD_ARG;
 }
 
-static int pick_bn(int cout, int nsplit) {
-    const int cap = nsplit >= 3 ? 128 : 256;  // keep >= 2 pipeline stages in 227 KB of shared memory
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+// Tile shape: N = 256 keeps the MMA off the shared-memory-bandwidth limit (an M=128 x N=128 x K=16 MMA reads 8 KB in 64
+// cycles = the full 128 B/clk); with 3 operand planes a 64-wide K block would leave a single 144 KB stage, so K = 32
+// (SWIZZLE_64B rows) is used there: 72 KB stages, 3 in flight.
+static int pick_block_k(int cout, int nsplit) {
+    const int force = env_int("ISTNET_BK", 0);
+    if (force == 32 || force == 64) return force;
+    return (nsplit >= 3 && cout > 128) ? 32 : 64;
+}
+static int pick_bn(int cout, int nsplit, int block_k) {
+    const int cap = (nsplit >= 3 && block_k == 64) ? 128 : 256;  // keep >= 2 pipeline stages in 227 KB of shared memory
     if (cout >= cap) return cap;
     int bn = (cout + 15) / 16 * 16;
     return bn < 16 ? 16 : bn;
@@ -238,8 +255,11 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     p.box_w = box_w; p.box_h = box_h; p.box_b = kTileM / (box_w * box_h);
     p.tiles_w = ceil_div(W, box_w); p.tiles_h = ceil_div(H, box_h); p.tiles_b = ceil_div(B, p.box_b);
     p.kh = kh; p.kw = kw;
+    const int kBlockK = pick_block_k(Cout, nsplit);
+    const int kATileBytes = kTileM * kBlockK * 2;
+    p.block_k = kBlockK;
     p.cin_blocks = ceil_div(Cin, kBlockK);
-    p.Cout = Cout; p.BN = pick_bn(Cout, nsplit);
+    p.Cout = Cout; p.BN = pick_bn(Cout, nsplit, kBlockK);
     p.nsplit = nsplit;
     p.bias = bias; p.relu = relu;
     p.out_f32 = out_f32; p.out_cs = out_cs;
@@ -259,14 +279,14 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
         uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B, (uint64_t)nsplit};
         uint64_t str[4] = {(uint64_t)act_cs * 2, (uint64_t)W * act_cs * 2, (uint64_t)H * W * act_cs * 2, (uint64_t)act_plane_stride * 2};
         uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)box_w, (uint32_t)box_h, (uint32_t)p.box_b, 1u};
-        int e = istnet_make_tmap_bf16(&ta, act_planes, 5, dims, str, box);
+        int e = istnet_make_tmap_bf16(&ta, act_planes, 5, dims, str, box, kBlockK * 2);
         if (e) return e;
     }
     {
         uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw), (uint64_t)nsplit};
         uint64_t str[3] = {(uint64_t)wgt_cs * 2, (uint64_t)Cout * wgt_cs * 2, (uint64_t)wgt_plane_stride * 2};
         uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.BN, 1u, 1u};
-        int e = istnet_make_tmap_bf16(&tb, wgt_planes, 4, dims, str, box);
+        int e = istnet_make_tmap_bf16(&tb, wgt_planes, 4, dims, str, box, kBlockK * 2);
         if (e) return e;
     }
     ISTNET_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -107,14 +107,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   K-major  operand: rows of 128 B (64 bf16 along K), 8-row groups 1024 B apart  -> LBO unused(1), SBO = 1024 B
 //   MN-major operand: rows of 128 B (64 bf16 along M/N) indexed by k, 8-k groups 1024 B apart (SBO),
 //                     consecutive 64-wide M/N chunks `lbo_bytes` apart (LBO)
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc_swz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-    d |= (uint64_t)1 << 46;  // version = 1
-    d |= (uint64_t)2 << 61;  // layout_type = SWIZZLE_128B
+    d |= (uint64_t)1 << 46;            // version = 1
+    d |= (uint64_t)layout_type << 61;  // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
     return d;
+}
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return make_desc_swz(smem_addr, lbo_bytes, sbo_bytes, 2);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16, FP32 accumulate.
 // a_bf16 / b_bf16: 1 = BF16 operand, 0 = FP16 operand (the formats may differ between A and B).
@@ -150,4 +153,4 @@ PFN_tmapEncodeTiled istnet_get_tmap_encoder();
 
 // bf16 tensor map with SWIZZLE_128B and zero OOB fill. dims/strides innermost first; strides in BYTES for dims 1..rank-1.
 int istnet_make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
-                          const uint32_t *box);
+                          const uint32_t *box, int swizzle_bytes = 128);
