@@ -231,7 +231,7 @@ static int env_int(const char *name, int dflt) {
 static int pick_block_k(int cout, int nsplit) {
     const int force = env_int("ISTNET_BK", 0);
     if (force == 32 || force == 64) return force;
-    return (nsplit >= 3 && cout > 128) ? 32 : 64;
+    return nsplit >= 3 ? 32 : 64;
 }
 static int pick_bn(int cout, int nsplit, int block_k) {
     const int cap = (nsplit >= 3 && block_k == 64) ? 128 : 256;  // keep >= 2 pipeline stages in 227 KB of shared memory
@@ -268,10 +268,18 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     while ((int)p.tmem_cols < p.BN) p.tmem_cols *= 2;
     const int num_k = kh * kw * p.cin_blocks;
     const int stage_bytes = nsplit * (kATileBytes + p.BN * kBlockK * 2);
-    int max_stages = (225 * 1024 - 1024 - 256) / stage_bytes;
+    // Shared-memory budget per CTA.  Wide tiles (BN = 256) are MMA-bound with one CTA per SM and a deep ring.  Narrow
+    // tiles (BN <= 128: small-channel layers, per-point MLPs) have short K loops and are latency-bound when the TMA ->
+    // MMA -> epilogue chain of a single resident CTA is serial, so they get a smaller ring and two CTAs share the SM
+    // (measured on up_3, 64->64 3x3 @192^2: 1.52 ms -> 0.88 ms; profiles/r1_conv_small_tiles.txt).
+    const long long n_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b * ceil_div(Cout, p.BN);
+    int budget_kb = (p.BN <= 128 && n_tiles >= 2 * kNumSMs) ? 110 : 225;
+    budget_kb = env_int("ISTNET_CG_SMEM_KB", budget_kb);
+    int max_stages = (budget_kb * 1024 - 1024 - 256) / stage_bytes;
+    if (max_stages < 1) max_stages = 1;
     if (max_stages > 6) max_stages = 6;
     p.stages = num_k < max_stages ? num_k : max_stages;
-    if (p.stages < 1) return ISTNET_ERR_UNSUPPORTED;
+    if ((size_t)p.stages * stage_bytes + 1280 > 227 * 1024) return ISTNET_ERR_UNSUPPORTED;
     size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
 
     CUtensorMap ta, tb;

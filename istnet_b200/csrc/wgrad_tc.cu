@@ -11,18 +11,19 @@
 // K (pixels) is split across CTAs; each CTA writes its FP32 partial tile and a second tiny kernel reduces the
 // partials in a fixed order into the PyTorch weight layout [Cout][Cin][kh][kw] — deterministic, unlike the
 // atomics of the reference's custom grads (SURVEY.md §7 hard part 5).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace {
 
-constexpr int kPixTile = 64;                     // pixels per pipeline stage (K of the GEMM)
-constexpr int kSlabBytes = kPixTile * 64 * 2;    // 64 pixels x 64 channels bf16 = 8 KB
 constexpr int kTileM = 128;
 constexpr int kThreads = 192;
 
 struct WgradParams {
     int B, H, W;
-    int box_w, box_h, box_b;  // box_w*box_h*box_b == 64
+    int pix_tile;             // pixels per pipeline stage (K of the GEMM): 64 or 32
+    int box_w, box_h, box_b;  // box_w*box_h*box_b == pix_tile
     int tiles_w, tiles_h, tiles_b, num_pix_tiles;
     int kh, kw;
     int Cout, Cin, BN;        // BN multiple of 64
@@ -36,6 +37,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x, const WgradParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int kPixTile = p.pix_tile;
+    const int kSlabBytes = kPixTile * 64 * 2;    // pix_tile pixels x 64 channels bf16
     const int n_slabs_b = p.BN / 64;
     const int a_bytes = 2 * kSlabBytes;          // 128 output channels = 2 slabs (per plane)
     const int b_bytes = n_slabs_b * kSlabBytes;
@@ -105,7 +108,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
                 tc::tc_fence_after();
                 const uint32_t a0 = tc::smem_u32(smem + (size_t)st * stage_bytes);
                 const uint32_t b0 = a0 + p.nsplit * a_bytes;
-#pragma unroll
                 for (int j = 0; j < kPixTile / 16; ++j) {  // 16 pixels (k) per MMA = 2 groups of 8 rows x 128 B
                     const uint32_t off = j * 2048;
                     uint32_t acc = (it | j) != 0;
@@ -179,9 +181,19 @@ __global__ void wgrad_reduce_kernel(int ksplit, int taps, int Cout, int Cin, con
 
 }  // namespace
 
+static int wg_env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+static int wgrad_pick_pix() {
+    const int f = wg_env_int("ISTNET_WG_PIX", 0);
+    return (f == 32 || f == 64) ? f : 64;
+}
 static int wgrad_pick_bn(int cin, int nsplit) {
     int bn = (cin + 63) / 64 * 64;
-    const int cap = nsplit >= 3 ? 128 : 256;  // keep >= 2 pipeline stages
+    int cap = nsplit >= 3 ? 128 : 256;  // keep >= 2 pipeline stages
+    const int f = wg_env_int("ISTNET_WG_BN", 0);
+    if (f == 64 || f == 128 || f == 256) cap = f;
     return bn > cap ? cap : bn;
 }
 
@@ -189,6 +201,7 @@ extern "C" int istnet_wgrad_ksplit(int B, int H, int W, int Cout, int Cin, int k
     // enough CTAs to fill the chip ~2x, at least 4 pixel tiles per CTA
     const int bn = wgrad_pick_bn(Cin, nsplit);
     const int base = ceil_div(Cout, kTileM) * ceil_div(Cin, bn) * kh * kw;
+    const int kPixTile = wgrad_pick_pix();
     const long long pix_tiles = ((long long)B * H * W + kPixTile - 1) / kPixTile;
     int ks = ceil_div(2 * kNumSMs, base);
     if (ks > pix_tiles / 4) ks = (int)(pix_tiles / 4);
@@ -203,9 +216,15 @@ extern "C" int istnet_conv_wgrad(const void *dy_planes, long long dy_plane_strid
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || ksplit <= 0) return ISTNET_ERR_BAD_ARG;
     if (nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
     if ((dy_cs & 7) || (x_cs & 7) || dy_cs < Cout || x_cs < Cin) return ISTNET_ERR_BAD_ARG;
+    const int kPixTile = wgrad_pick_pix();
+    const int kSlabBytes = kPixTile * 64 * 2;
+    if (kPixTile == 32) {  // halve the caller's 64-pixel box
+        if (box_h > 1) box_h /= 2; else box_w /= 2;
+    }
     if (box_w <= 0 || box_h <= 0 || (kPixTile % (box_w * box_h)) != 0) return ISTNET_ERR_BAD_ARG;
     if ((kh & 1) == 0 || (kw & 1) == 0) return ISTNET_ERR_UNSUPPORTED;
     WgradParams p{};
+    p.pix_tile = kPixTile;
     p.B = B; p.H = H; p.W = W;
     p.box_w = box_w; p.box_h = box_h; p.box_b = kPixTile / (box_w * box_h);
     p.tiles_w = ceil_div(W, box_w); p.tiles_h = ceil_div(H, box_h); p.tiles_b = ceil_div(B, p.box_b);
