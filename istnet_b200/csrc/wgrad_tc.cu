@@ -197,16 +197,31 @@ static int wgrad_pick_bn(int cin, int nsplit) {
     return bn > cap ? cap : bn;
 }
 
+// Shared-memory budget per CTA: wide tiles run one deep-ring CTA per SM; narrow multi-tap tiles (small channel counts)
+// are bound by L2->SM delivery / latency and do better with several shallow CTAs per SM (measured).
+static int wgrad_budget_kb(int bn, int taps) {
+    return wg_env_int("ISTNET_WG_SMEM_KB", (bn <= 128 && taps > 1) ? 60 : 225);
+}
+static int wgrad_stage_bytes(int bn, int nsplit, int pix) { return nsplit * (2 + bn / 64) * pix * 64 * 2; }
+
 extern "C" int istnet_wgrad_ksplit(int B, int H, int W, int Cout, int Cin, int kh, int kw, int nsplit) {
-    // enough CTAs to fill the chip ~2x, at least 4 pixel tiles per CTA
+    // fill the chip with an integral number of co-resident CTA "waves", at least 4 pixel tiles per CTA
+    const int pix = wgrad_pick_pix();
     const int bn = wgrad_pick_bn(Cin, nsplit);
     const int base = ceil_div(Cout, kTileM) * ceil_div(Cin, bn) * kh * kw;
-    const int kPixTile = wgrad_pick_pix();
-    const long long pix_tiles = ((long long)B * H * W + kPixTile - 1) / kPixTile;
-    int ks = ceil_div(2 * kNumSMs, base);
+    const long long pix_tiles = ((long long)B * H * W + pix - 1) / pix;
+    const int stage_bytes = wgrad_stage_bytes(bn, nsplit, pix);
+    int stages = (wgrad_budget_kb(bn, kh * kw) * 1024 - 1280) / stage_bytes;
+    if (stages < 1) stages = 1;
+    if (stages > 6) stages = 6;
+    int per_sm = (227 * 1024) / (stages * stage_bytes + 1280);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    const int capacity = kNumSMs * per_sm;
+    int ks = capacity / base;
     if (ks > pix_tiles / 4) ks = (int)(pix_tiles / 4);
     if (ks < 1) ks = 1;
-    if (ks > 64) ks = 64;
+    if (ks > 96) ks = 96;
     return ks;
 }
 
@@ -238,7 +253,9 @@ extern "C" int istnet_conv_wgrad(const void *dy_planes, long long dy_plane_strid
     p.tmem_cols = 32;
     while ((int)p.tmem_cols < p.BN) p.tmem_cols *= 2;
     const int stage_bytes = nsplit * (2 * kSlabBytes + (p.BN / 64) * kSlabBytes);
-    int max_stages = (225 * 1024 - 1024 - 256) / stage_bytes;
+    int budget_kb = wgrad_budget_kb(p.BN, kh * kw);
+    int max_stages = (budget_kb * 1024 - 1024 - 256) / stage_bytes;
+    if (max_stages < 1) max_stages = 1;
     if (max_stages > 6) max_stages = 6;
     const int per = ceil_div(p.num_pix_tiles, ksplit);
     p.stages = per < max_stages ? per : max_stages;
