@@ -195,15 +195,20 @@ def main():
     eager_step(resident)
     launches_per_step = _C.LAUNCHES - l_probe
     graphed = None
-    if not args.eager and world == 1:
+    if not args.eager:
         from istnet_b200.graph import GraphedTrainStep
 
-        graphed = GraphedTrainStep(model, loss_fn, resident, MODEL_IN, LABELS)
+        if world > 1:  # the first eager step built the flat gradient buckets; the graph writes into them, NCCL reduces them
+            reducer.remove_hooks()
+        graphed = GraphedTrainStep(model, loss_fn, resident, MODEL_IN, LABELS, keep_grads=world > 1)
 
     def step(data):
         if graphed is None:
             return eager_step(data)
-        return graphed()
+        loss = graphed()
+        if world > 1:
+            reducer.reduce_all()
+        return loss
 
     def barrier():
         if world > 1:
@@ -218,7 +223,7 @@ def main():
             if e2e:
                 if graphed is not None:
                     graphed.load(host)  # pinned host -> static device buffers (inside the timed region)
-                    loss = graphed()
+                    loss = step(None)
                 else:
                     loss = step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
                 _ = loss.item()  # device->host read of the step's result
@@ -249,7 +254,12 @@ def main():
     from istnet_b200 import nhwc
 
     nhwc.PROFILE = []
-    eager_step(resident)
+    if world > 1 and graphed is not None:  # hooks were removed for the graph path: plain forward+backward is enough here
+        ep_ = model({k: resident[k] for k in MODEL_IN})
+        ep_.update({k: resident[k] for k in LABELS})
+        loss_fn(ep_).backward()
+    else:
+        eager_step(resident)
     torch.cuda.synchronize()
     prof, nhwc.PROFILE = nhwc.PROFILE, None
     kstat = {}

@@ -126,16 +126,22 @@ int istnet_bn_act_split(const float *y, long long P, int C, long long HW, const 
                         long long plane_stride, int nsplit, int cs, int ch_off, void *stream);
 
 /* Backward of the unit above: g = (dz + dz2) * noise * act'(u);  ws[0:C] = sum g, ws[C:2C] = sum g*xhat, ws[2C:3C] = PReLU
- * slope partials;  dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))  (or g without BN) written as bf16 operand planes and/or FP32;
+ * slope partials;  dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))  (batch_stats=1; gamma*invstd*g with running
+ * statistics, batch_stats=0; g without BN) written as bf16 operand planes and/or FP32;
  * g_out (optional) receives g (the residual branch's gradient).  ReLU masks come from plane 0 (z_hi) of the saved forward output. */
 int istnet_bn_act_bwd(const float *dz, const float *dz2, const float *y, long long P, int C, long long HW, const float *mean,
                       const float *invstd, const float *gamma, const float *beta, int act, const float *prelu_a, const void *z_hi,
-                      int cs_z, const float *noise, double *ws, void *dy_planes, long long plane_stride, int nsplit, int cs_dy,
-                      float *dy_f32, float *g_out, void *stream);
+                      int cs_z, const float *noise, int batch_stats, double *ws, void *dy_planes, long long plane_stride, int nsplit,
+                      int cs_dy, float *dy_f32, float *g_out, void *stream);
 
 /* FP32 [P][C] (or NCHW with HW pixels per image when nchw != 0) -> bf16 operand planes [nsplit][P][cs] at channel offset ch_off */
 int istnet_split(const float *x, long long P, int C, long long HW, int nchw, void *planes, long long plane_stride, int nsplit, int cs,
                  int ch_off, void *stream);
+/* Weight re-layout + split in one pass: PyTorch [Cout][Cin][kh][kw] FP32 -> operand planes
+ *   transpose=0: [nsplit][tap][Cout][cs] (forward);  transpose=1: [nsplit][flipped tap][Cin][cs] (data gradient);
+ *   im2col=1: the strided-conv form, one tap with K = (r*kw+s)*Cin + ci  ([Cout][cs] or, transposed, [K][cs]). */
+int istnet_prep_weight(const float *w, int Cout, int Cin, int kh, int kw, int transpose, int im2col, void *planes, long long plane_stride,
+                       int nsplit, int cs, void *stream);
 /* ws[c] = sum_p x[p][c] (double; bias gradients) */
 int istnet_colsum(const float *x, long long P, int C, double *ws, void *stream);
 

@@ -149,6 +149,7 @@ struct ActBwdP {
     const float *prelu_a;
     const __nv_bfloat16 *z_hi;  // ReLU mask source (saved forward output), [P,cs_z]
     int cs_z;
+    int batch_stats;            // 1: BN used batch statistics (train) -> full backward; 0: running statistics -> dy = gamma*invstd*g
     const float *noise;
     long long HW;
 };
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(long long P, i
             float mg[4], mgx[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) { mg[k] = (float)(ws[c + k] * invP); mgx[k] = (float)(ws[C + c + k] * invP); }
+            if (!p.batch_stats) { mg[0] = mg[1] = mg[2] = mg[3] = 0.f; mgx[0] = mgx[1] = mgx[2] = mgx[3] = 0.f; }
             dy.x = ga.x * s.x * (g.x - mg[0] - xh.x * mgx[0]);
             dy.y = ga.y * s.y * (g.y - mg[1] - xh.y * mgx[1]);
             dy.z = ga.z * s.z * (g.z - mg[2] - xh.z * mgx[2]);
@@ -236,6 +238,47 @@ __global__ void __launch_bounds__(kEwThreads) split_kernel(long long P, int C, c
         const int c = (int)(i % C);
         float v = nchw ? x[((r / HW) * C + c) * HW + (r % HW)] : x[i];
         store_planes1(pl + r * cs + ch_off + c, pl_stride, nsplit, v);
+    }
+}
+// PyTorch weight [co][ci][kh][kw] -> operand planes [nsplit][tap][rows][cs]:
+//   transpose = 0 (forward operand):        rows = co, cols = ci, tap = r*kw + s
+//   transpose = 1 (data-gradient operand):  rows = ci, cols = co, tap = flipped (kh-1-r, kw-1-s)
+//   im2col   = 1 (strided convs as 1x1 GEMM over patches): one tap, K index = (r*kw + s)*ci_total + ci
+__global__ void __launch_bounds__(kEwThreads) prep_weight_kernel(int co_n, int ci_n, int kh, int kw, const float *__restrict__ w, int transpose,
+                                                                 int im2col, __nv_bfloat16 *pl, long long pl_stride, int nsplit, int cs) {
+    const long long total = (long long)co_n * ci_n * kh * kw;
+    const int taps = kh * kw;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        // iterate in OUTPUT order so that stores are coalesced
+        long long o;
+        float v;
+        if (im2col) {
+            const int K = taps * ci_n;
+            if (!transpose) {  // [co][K]
+                const int k = (int)(i % K), co = (int)(i / K);
+                const int tap = k / ci_n, ci = k % ci_n;
+                v = w[((long long)co * ci_n + ci) * taps + tap];
+                o = (long long)co * cs + k;
+            } else {  // [K][co]
+                const int co = (int)(i % co_n), k = (int)(i / co_n);
+                const int tap = k / ci_n, ci = k % ci_n;
+                v = w[((long long)co * ci_n + ci) * taps + tap];
+                o = (long long)k * cs + co;
+            }
+        } else if (!transpose) {  // [tap][co][ci]
+            const int ci = (int)(i % ci_n);
+            const long long r = i / ci_n;
+            const int co = (int)(r % co_n), tap = (int)(r / co_n);
+            v = w[((long long)co * ci_n + ci) * taps + tap];
+            o = ((long long)tap * co_n + co) * cs + ci;
+        } else {  // [flipped tap][ci][co]
+            const int co = (int)(i % co_n);
+            const long long r = i / co_n;
+            const int ci = (int)(r % ci_n), tap = (int)(r / ci_n);
+            v = w[((long long)co * ci_n + ci) * taps + (taps - 1 - tap)];
+            o = ((long long)tap * ci_n + ci) * cs + co;
+        }
+        store_planes1(pl + o, pl_stride, nsplit, v);
     }
 }
 __global__ void __launch_bounds__(kEwThreads) colsum_kernel(const float *__restrict__ x, long long P, int C, double *ws) {
@@ -473,9 +516,11 @@ inline int ew_grid(long long total) {
     return (int)(g < 1 ? 1 : (g < cap ? g : cap));
 }
 inline int red_grid(long long P, int C) {
+    // every CTA ends with one double atomic per channel and accumulator: give each thread >= 16 rows so that small
+    // tensors do not pay hundreds of contended atomics per address
     int lanes = C / 4;
     int rows_per_iter = lanes <= kEwThreads ? kEwThreads / lanes : 1;
-    long long g = (P + rows_per_iter - 1) / rows_per_iter;
+    long long g = (P + (long long)rows_per_iter * 16 - 1) / ((long long)rows_per_iter * 16);
     long long cap = (long long)kNumSMs * 4;
     return (int)(g < 1 ? 1 : (g < cap ? g : cap));
 }
@@ -514,13 +559,14 @@ extern "C" int istnet_bn_act_split(const float *y, long long P, int C, long long
 
 extern "C" int istnet_bn_act_bwd(const float *dz, const float *dz2, const float *y, long long P, int C, long long HW, const float *mean,
                                  const float *invstd, const float *gamma, const float *beta, int act, const float *prelu_a,
-                                 const void *z_hi, int cs_z, const float *noise, double *ws /*3C*/, void *dy_planes, long long plane_stride,
-                                 int nsplit, int cs_dy, float *dy_f32, float *g_out, void *stream) {
+                                 const void *z_hi, int cs_z, const float *noise, int batch_stats, double *ws /*3C*/, void *dy_planes,
+                                 long long plane_stride, int nsplit, int cs_dy, float *dy_f32, float *g_out, void *stream) {
     if (P <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
     if (act == 1 && !z_hi) return ISTNET_ERR_BAD_ARG;
     ActBwdP p{};
     p.dz = dz; p.dz2 = dz2; p.y = y; p.bn = make_bn(mean, invstd, gamma, beta);
     p.act = act; p.prelu_a = prelu_a; p.z_hi = (const __nv_bfloat16 *)z_hi; p.cs_z = cs_z; p.noise = noise; p.HW = HW > 0 ? HW : 1;
+    p.batch_stats = batch_stats;
     ISTNET_CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(double) * 3 * C, ST));
     bn_bwd_reduce_kernel<<<red_grid(P, C), kEwThreads, 0, ST>>>(P, C, p, ws);
     ISTNET_LAUNCH_CHECK();
@@ -534,6 +580,15 @@ extern "C" int istnet_split(const float *x, long long P, int C, long long HW, in
                             int cs, int ch_off, void *stream) {
     if (P <= 0 || C <= 0 || nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
     split_kernel<<<ew_grid(P * C), kEwThreads, 0, ST>>>(P, C, x, HW > 0 ? HW : 1, nchw, (__nv_bfloat16 *)planes, plane_stride, nsplit, cs, ch_off);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+
+extern "C" int istnet_prep_weight(const float *w, int Cout, int Cin, int kh, int kw, int transpose, int im2col, void *planes, long long plane_stride,
+                                  int nsplit, int cs, void *stream) {
+    if (Cout <= 0 || Cin <= 0 || kh <= 0 || kw <= 0 || nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
+    prep_weight_kernel<<<ew_grid((long long)Cout * Cin * kh * kw), kEwThreads, 0, ST>>>(Cout, Cin, kh, kw, w, transpose, im2col, (__nv_bfloat16 *)planes,
+                                                                                       plane_stride, nsplit, cs);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }

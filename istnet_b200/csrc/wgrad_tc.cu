@@ -174,7 +174,15 @@ __global__ void wgrad_reduce_kernel(int ksplit, int taps, int Cout, int Cin, con
         const int co = (int)(rest % Cout);
         const int tap = (int)(rest / Cout);
         float acc = 0.f;
-        for (int sp = 0; sp < ksplit; ++sp) acc += partial[(size_t)sp * total + i];
+        int sp = 0;
+        for (; sp + 8 <= ksplit; sp += 8) {  // 8 independent loads in flight, summed in a fixed order
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = partial[(size_t)(sp + u) * total + i];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += v[u];
+        }
+        for (; sp < ksplit; ++sp) acc += partial[(size_t)sp * total + i];
         grad_w[((size_t)co * Cin + ci) * taps + tap] = acc;
     }
 }

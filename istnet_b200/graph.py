@@ -9,9 +9,11 @@ import torch
 
 
 class GraphedTrainStep:
-    """step = GraphedTrainStep(model, loss_fn, example_batch); loss = step(batch)  (gradients are left in p.grad)."""
+    """step = GraphedTrainStep(model, loss_fn, example_batch); loss = step(batch)  (gradients are left in p.grad).
+    keep_grads=True captures with the existing `.grad` tensors (e.g. views into GradAllReducer's flat buckets, so that the
+    NCCL all-reduce after the replay works on the same memory)."""
 
-    def __init__(self, model, loss_fn, example, model_keys, label_keys, warmup=3, after_backward=None):
+    def __init__(self, model, loss_fn, example, model_keys, label_keys, warmup=3, after_backward=None, keep_grads=False):
         self.model, self.loss_fn = model, loss_fn
         self.model_keys, self.label_keys = tuple(model_keys), tuple(label_keys)
         self.static = {k: example[k].clone() for k in self.model_keys + tuple(k for k in self.label_keys if k not in self.model_keys)}
@@ -24,9 +26,10 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        for p in model.parameters():  # gradients are accumulated into static tensors that the graph zeroes itself
-            if p.grad is not None:
-                p.grad = torch.zeros_like(p.grad)
+        if not keep_grads:  # gradients are accumulated into static tensors that the graph zeroes itself
+            for p in model.parameters():
+                if p.grad is not None:
+                    p.grad = torch.zeros_like(p.grad)
         with torch.cuda.graph(self.graph):
             self.loss = self._eager()
 

@@ -148,7 +148,7 @@ def backward(net, tape, d_out, u):
             ws = K.bn_act_bwd(g, None, rf["y"], rf["P"], 128, HW, st, ACT_NONE, None, None, None, dy_pl=dy)
             wsf = ws.float()
             grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = wsf[128:256], wsf[0:128]
-            grads[id(unit.b)] = torch.zeros_like(unit.b)
+            grads[id(unit.b)] = torch.zeros_like(unit.b) if st.batch else (st.gamma * st.invstd * wsf[0:128]).detach()
             grads[id(unit.prelu)] = slope.sum().float().reshape(1)
             dz = unit.data_grads(rf, dy, True, grads)
             dz2 = None

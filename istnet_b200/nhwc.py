@@ -66,21 +66,24 @@ def split(x_f32, P, C, pl, ch_off=0, HW=1, nchw=False):
     _C.call("split", ptr(x_f32), c_ll(P), c_int(C), c_ll(HW), c_int(1 if nchw else 0), *_pl_args(pl), c_int(pl.shape[-1]), c_int(ch_off))
 
 
-def prep_weight(w, transpose=False, nsplit=None):
-    """Conv / linear weight [co, ci, kh, kw] (or [co, ci]) -> bf16 operand planes [NSPLIT, taps, rows, pad8(cols)].
-    transpose=False: forward operand  [tap][co][ci];  transpose=True: data-gradient operand [flipped tap][ci][co]."""
+def prep_weight(w, transpose=False, nsplit=None, im2col=False):
+    """Conv / linear weight [co, ci, kh, kw] (or [co, ci(,1)]) -> bf16 operand planes, one fused kernel:
+    transpose=False: forward operand [ns, tap, co, pad8(ci)];  transpose=True: data-gradient operand [ns, flipped tap, ci, pad8(co)];
+    im2col=True (strided convs run as a 1x1 GEMM over patches): [ns, 1, co, pad8(kh*kw*ci)] / transposed [ns, 1, kh*kw*ci, pad8(co)]."""
     if w.dim() == 2:
-        w = w[:, :, None, None]
+        co, ci, kh, kw = w.shape[0], w.shape[1], 1, 1
     elif w.dim() == 3:
-        w = w[:, :, :, None]
-    co, ci, kh, kw = w.shape
-    if transpose:
-        m = w.flip(2, 3).permute(2, 3, 1, 0).reshape(kh * kw, ci, co).contiguous()
+        co, ci, kh, kw = w.shape[0], w.shape[1], w.shape[2], 1
     else:
-        m = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
-    taps, rows, cols = m.shape
-    pl = torch.empty(nsplit or NSPLIT, taps, rows, pad8(cols), dtype=torch.bfloat16, device=w.device)
-    split(m, taps * rows, cols, pl)
+        co, ci, kh, kw = w.shape
+    taps = kh * kw
+    if im2col:
+        shape = (1, taps * ci, pad8(co)) if transpose else (1, co, pad8(taps * ci))
+    else:
+        shape = (taps, ci, pad8(co)) if transpose else (taps, co, pad8(ci))
+    pl = torch.empty(nsplit or NSPLIT, *shape, dtype=torch.bfloat16, device=w.device)
+    _C.call("prep_weight", ptr(w), c_int(co), c_int(ci), c_int(kh), c_int(kw), c_int(1 if transpose else 0), c_int(1 if im2col else 0),
+            *_pl_args(pl), c_int(shape[-1]))
     return pl
 
 
@@ -141,16 +144,16 @@ def conv_wgrad(dy_pl, cout, x, kh, kw):
 class BnState:
     """Per-call BatchNorm quantities: batch (train) or running (eval) mean / invstd + affine parameters."""
 
-    __slots__ = ("mean", "invstd", "gamma", "beta")
+    __slots__ = ("mean", "invstd", "gamma", "beta", "batch")
 
-    def __init__(self, mean, invstd, gamma, beta):
-        self.mean, self.invstd, self.gamma, self.beta = mean, invstd, gamma, beta
+    def __init__(self, mean, invstd, gamma, beta, batch=True):
+        self.mean, self.invstd, self.gamma, self.beta, self.batch = mean, invstd, gamma, beta, batch
 
 
 def bn_state(bn, y, P, C, training):
     """Reads momentum / eps / running stats from the nn.BatchNorm2d at call time (BNMomentumScheduler, scheduler.py:277-303)."""
     dev = y.device
-    if training:
+    if training and bn.training:  # each BatchNorm module's own flag decides, as in nn.BatchNorm2d.forward
         mean = torch.empty(C, dtype=torch.float32, device=dev)
         invstd = torch.empty(C, dtype=torch.float32, device=dev)
         ws = torch.empty(2 * C, dtype=torch.float64, device=dev)
@@ -161,9 +164,8 @@ def bn_state(bn, y, P, C, training):
         if track:
             bn.num_batches_tracked += 1
     else:
-        mean = bn.running_mean
-        invstd = torch.rsqrt(bn.running_var + bn.eps)
-    return BnState(mean, invstd, bn.weight, bn.bias)
+        return BnState(bn.running_mean, torch.rsqrt(bn.running_var + bn.eps), bn.weight, bn.bias, batch=False)
+    return BnState(mean, invstd, bn.weight, bn.bias, batch=True)
 
 
 def bn_act_split(y, P, C, HW, bn=None, res=None, res_bn=None, act=0, prelu=None, noise=None, out_f32=None, out_pl=None, ch_off=0):
@@ -181,7 +183,7 @@ def bn_act_bwd(dz, dz2, y, P, C, HW, bn, act, prelu, z_hi, noise, dy_pl=None, dy
     _C.call(
         "bn_act_bwd", ptr(dz), _p(dz2), _p(y), c_ll(P), c_int(C), c_ll(HW), _p(bn.mean if bn else None), _p(bn.invstd if bn else None),
         _p(bn.gamma if bn else None), _p(bn.beta if bn else None), c_int(act), _p(prelu), _p(z_hi), c_int(z_hi.shape[-1] if z_hi is not None else 0),
-        _p(noise), ptr(ws), *_pl_args(dy_pl), c_int(dy_pl.shape[-1] if dy_pl is not None else 0), _p(dy_f32), _p(g_out),
+        _p(noise), c_int(1 if (bn is not None and bn.batch) else 0), ptr(ws), *_pl_args(dy_pl), c_int(dy_pl.shape[-1] if dy_pl is not None else 0), _p(dy_f32), _p(g_out),
     )
     return ws
 
@@ -238,7 +240,7 @@ class ConvUnit:
         if self.stride != 1 or x_f32_nchw is not None:
             src = x_f32_nchw if x_f32_nchw is not None else x.f32
             xin = im2col(src, x_f32_nchw is not None, x.B, x.H, x.W, x.C, self.k, self.stride, self.pad)
-            wp = prep_weight(self.w.permute(0, 2, 3, 1).reshape(self.cout, -1))  # [co, (r,s,c)] = the im2col K order
+            wp = prep_weight(self.w, im2col=True)  # [co, (r,s,c)] = the im2col K order
             kk = 1
         else:
             xin, kk = x, self.k
@@ -299,7 +301,10 @@ class ConvUnit:
             grads[id(self.bn.weight)] = wsf[C : 2 * C]
             grads[id(self.bn.bias)] = wsf[0:C]
             if self.b is not None:  # a bias feeding a train-mode BatchNorm has an identically zero gradient
-                grads[id(self.b)] = torch.zeros_like(self.b)
+                if rec["bn"].batch:
+                    grads[id(self.b)] = torch.zeros_like(self.b)
+                else:  # running statistics: d bias = sum_p dy = gamma*invstd*sum g
+                    grads[id(self.b)] = (rec["bn"].gamma * rec["bn"].invstd * wsf[0:C]).detach()
         elif self.b is not None:
             grads[id(self.b)] = wsf[0:C]
         if self.act == ACT_PRELU:
@@ -316,8 +321,7 @@ class ConvUnit:
             return None
         dyA = Act(xin.B, xin.H, xin.W, C, None, dy)
         if kk != self.k or self.stride != 1:
-            wm = self.w.permute(0, 2, 3, 1).reshape(C, -1)
-            wd = prep_weight(wm, transpose=True, nsplit=dy.shape[0])
+            wd = prep_weight(self.w, transpose=True, nsplit=dy.shape[0], im2col=True)
             dcol = torch.empty(xin.B, xin.H, xin.W, xin.C, dtype=torch.float32, device=dy.device)
             conv_gemm(dyA, wd, xin.C, 1, 1, out_f32=dcol)
             b, h, w, c = rec["in_shape"]

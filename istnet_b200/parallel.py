@@ -91,6 +91,24 @@ class GradAllReducer:
             b["flat"].div_(self.world)
         self._handles = []
 
+    def reduce_all(self):
+        """All-reduce every bucket now (used after a CUDA-graph replay of forward+backward, where the hooks do not run):
+        the bucket all-reduces are enqueued back to back and overlap each other on the NCCL stream."""
+        if self.buckets is None:
+            self._discover_and_build()
+            return
+        if self.world == 1:
+            return
+        hs = [dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True) for b in self.buckets]
+        for h, b in zip(hs, self.buckets):
+            h.wait()
+            b["flat"].div_(self.world)
+
+    def remove_hooks(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
     def num_buckets(self):
         return 0 if self.buckets is None else len(self.buckets)
 

@@ -19,7 +19,7 @@ from . import pointops as _cpu_ops
 class Ctx:
     """Run-time switches shared by all functions: train/eval, BN momentum source, dropout masks."""
 
-    def __init__(self, sd, training, ops=None, bn_momentum=0.1, dropout_noise=None, update_stats=True):
+    def __init__(self, sd, training, ops=None, bn_momentum=0.1, dropout_noise=None, update_stats=True, bn_training=None):
         self.sd = sd
         self.training = training
         self.ops = ops or _cpu_ops
@@ -27,6 +27,7 @@ class Ctx:
         self.dropout_noise = dropout_noise  # optional list of (B,C,1,1) tensors consumed in call order
         self._drop_i = 0
         self.update_stats = update_stats
+        self.bn_training = training if bn_training is None else bn_training  # BatchNorm modules may be in eval() alone
 
     def p(self, key):
         return self.sd[key]
@@ -35,10 +36,10 @@ class Ctx:
 def batch_norm(cx, x, prefix):
     """nn.BatchNorm2d forward (eps 1e-5); train: batch stats + running update."""
     rm, rv = cx.p(prefix + ".running_mean"), cx.p(prefix + ".running_var")
-    if cx.training and not cx.update_stats:
+    if cx.bn_training and not cx.update_stats:
         rm, rv = rm.clone(), rv.clone()
-    y = F.batch_norm(x, rm, rv, cx.p(prefix + ".weight"), cx.p(prefix + ".bias"), cx.training, cx.bn_momentum, 1e-5)
-    if cx.training and cx.update_stats:
+    y = F.batch_norm(x, rm, rv, cx.p(prefix + ".weight"), cx.p(prefix + ".bias"), cx.bn_training, cx.bn_momentum, 1e-5)
+    if cx.bn_training and cx.update_stats:
         cx.sd[prefix + ".num_batches_tracked"] += 1
     return y
 

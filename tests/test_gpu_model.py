@@ -117,11 +117,23 @@ def test_posenet_gt_matches_reference_golden():
 
 
 def test_full_resolution_train_step_matches_oracle_port():
-    """B=2 at the bench resolution (1024 pts, 192x192): oracle port on the host CPU vs the CUDA path."""
+    """B=2 at the bench resolution (1024 pts, 192x192): oracle port on the host CPU vs the CUDA path, forward + loss +
+    backward through the training branch of IST_Net with the BatchNorm layers in eval() (running statistics): this removes
+    the batch-statistics amplification that makes tiny-batch train-mode gradients chaotic, so gradients can be held to a
+    much tighter bound than in train mode.  What remains are ReLU / max-pool selection flips between the two FP32
+    evaluations (measured: median 3.5e-4, 90 % 1.4e-3, max 1.5e-2; identical with 3-plane backward contractions, i.e. not a
+    precision effect of the kernels) — bounds: median 2e-3, no tensor beyond 5e-2."""
     from oracle import istnet_port as port
 
     torch.manual_seed(1)
     m = M.IST_Net(6, False)
+    g = torch.Generator().manual_seed(3)
+    for mod in m.modules():  # non-trivial running statistics / affine parameters
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_(0.1 * torch.randn(mod.num_features, generator=g))
+            mod.running_var.copy_(0.5 + torch.rand(mod.num_features, generator=g))
+            mod.weight.data.copy_(0.5 + torch.rand(mod.num_features, generator=g))
+            mod.bias.data.copy_(0.1 * torch.randn(mod.num_features, generator=g))
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     for k, v in sd.items():
         if v.is_floating_point() and "running_" not in k:
@@ -129,11 +141,18 @@ def test_full_resolution_train_step_matches_oracle_port():
     inp = make_batch(2, 1024, 192, seed=21, quantize=True)
     noise = fixed_dropout_noise(5)
     masks = [noise(2, 1024, 0.3), noise(2, 256, 0.15), noise(2, 64, 0.15)]
-    ep_o = port.ist_net_forward(sd, inp, training=True, dropout_noise=masks)
+    ep_o = port.ist_net_forward(sd, inp, training=True, dropout_noise=masks, bn_training=False)
     loss_o = port.ist_net_loss(ep_o, inp)
     loss_o.backward()
-    m = m.cuda()
-    ep, loss = _train_step(m, inp, M.SupervisedLoss(M.LossCfg()), 5)
+    m = m.cuda().train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.eval()
+    m.rgb_cam_extractor.model.dropout_noise_fn = fixed_dropout_noise(5)
+    ep = m(cuda_inputs(inp))
+    ep.update({k: inp[k].cuda() for k in LABELS})
+    loss = M.SupervisedLoss(M.LossCfg())(ep)
+    loss.backward()
     for k in ep_o:
         assert rel_err(ep[k], ep_o[k]) < TOL, (k, rel_err(ep[k], ep_o[k]))
     assert abs(loss.item() - loss_o.item()) < TOL * abs(loss_o.item())
@@ -143,14 +162,9 @@ def test_full_resolution_train_step_matches_oracle_port():
         if go is None:
             assert p.grad is None, n
             continue
-        if go.abs().max() < 1e-7:  # analytically-zero gradients (biases feeding a train-mode BatchNorm)
-            assert p.grad.abs().max() < 1e-5, n
-            continue
         errs.append((rel_err(p.grad, go), n))
     errs.sort()
     med = errs[len(errs) // 2][0]
-    # FP32-vs-FP32 comparison of a chaotic B=2 train step (see test_train_step_matches_reference_golden): the bulk of the
-    # gradients must agree closely, no tensor may be grossly off (wrong sign / scale / missing term would give O(1))
-    assert med < 2e-3, med
-    assert errs[-1][0] < 0.3, errs[-5:]
     print(f"gradient rel err vs oracle port: median {med:.2e}, 90% {errs[int(0.9 * len(errs))][0]:.2e}, max {errs[-1][0]:.2e} ({errs[-1][1]})")
+    assert med < 2e-3, med
+    assert errs[-1][0] < 5e-2, errs[-5:]
