@@ -5,6 +5,8 @@ Same class names, constructor signatures, forward dict keys, train/eval behaviou
 `compat/` is on sys.path.  Differences from the reference are deliberate and documented:
 no hard-coded `.cuda()` (everything follows the input's device), no weight download.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -15,6 +17,47 @@ from .pointnet2 import PointNet2MSG
 
 CAM_RADII = [[0.01, 0.02], [0.02, 0.04], [0.04, 0.08], [0.08, 0.16]]  # ist_net.py:16, posenet_gt.py:18
 WORLD_RADII = [[0.05, 0.10], [0.10, 0.20], [0.20, 0.30], [0.30, 0.40]]  # ist_net.py:189, posenet_gt.py:19
+
+
+# --------------------------------------------------------------------------------------------- stream-level concurrency
+USE_SIDE_STREAMS = os.environ.get("ISTNET_STREAMS", "1") != "0"
+
+
+class _Branches:
+    """Runs independent sub-networks (image branch, camera-space extractor, NOCS-space extractor) on side CUDA streams so
+    that the latency-bound point-cloud kernels overlap the tensor-core-bound image branch.  Autograd replays each
+    backward node on its forward stream, so the overlap carries over to the backward pass; under CUDA-graph capture the
+    fork / join become graph dependencies."""
+
+    def __init__(self, device, n):
+        self.main = torch.cuda.current_stream(device)
+        self.on = USE_SIDE_STREAMS and device.type == "cuda"
+        self.side = []
+        if self.on:
+            pool = _Branches._pool.setdefault(device, [])
+            while len(pool) < n:
+                pool.append(torch.cuda.Stream(device))
+            self.side = pool[:n]
+            for st in self.side:
+                st.wait_stream(self.main)
+        self.results = []
+
+    _pool = {}
+
+    def run(self, i, fn):
+        if not self.on:
+            return fn()
+        with torch.cuda.stream(self.side[i]):
+            out = fn()
+        self.results.append((self.side[i], out))
+        return out
+
+    def join(self):
+        for st, out in self.results:
+            self.main.wait_stream(st)
+            for t in out if isinstance(out, (tuple, list)) else (out,):
+                if isinstance(t, torch.Tensor):
+                    t.record_stream(self.main)
 
 
 # --------------------------------------------------------------------------------------------- small pieces
@@ -164,8 +207,9 @@ class WorldSpaceEnhancer(nn.Module):
         if not freeze:
             self.pose_estimator = HeavyEstimator()
 
-    def forward(self, pts, pts_w_gt, rgb_local, pts_local):
-        pts_w_local_gt = self.extractor.forward_rows(pts_w_gt)
+    def forward(self, pts, pts_w_gt, rgb_local, pts_local, pts_w_local_gt=None):
+        if pts_w_local_gt is None:  # (IST_Net runs the extractor on a side stream and passes its output in)
+            pts_w_local_gt = self.extractor.forward_rows(pts_w_gt)
         if self.freeze:
             return None, None, None, pts_w_local_gt
         r, t, s = self.pose_estimator(pts, pts_w_gt, rgb_local.detach(), pts_local.detach(), pts_w_local_gt)
@@ -195,15 +239,23 @@ class IST_Net(nn.Module):
         pts = pts - c
         # everything below works on rows (B,N,C): the layout the GEMM kernels consume; the reference's (B,C,N)
         # tensors appear only at the module boundary (end_points)
+        br = _Branches(pts.device, 2)
+        pts_local = br.run(0, lambda: self.pts_cam_extractor.forward_rows(pts))
+        if self.training:  # the NOCS-space extractor only depends on the ground-truth coordinates
+            gt_feats = br.run(1, lambda: self.world_enhancer.extractor.forward_rows(inputs["qo"]))
         rgb_local = self.rgb_cam_extractor.gather_rows(rgb, choose)
-        pts_local = self.pts_cam_extractor.forward_rows(pts)
+        br.join()
+        # the three pose heads are independent of each other: camera-space enhancer and world-space enhancer on the side
+        # streams, implicit space transformation -> main estimator on the main stream
+        br2 = _Branches(pts.device, 2)
         if self.training:
-            r_c, t_c, s_c = self.cam_enhancer(pts, rgb_local, pts_local)
+            r_c, t_c, s_c = br2.run(0, lambda: self.cam_enhancer(pts, rgb_local, pts_local))
+            r_w, t_w, s_w, pts_w_local_gt = br2.run(1, lambda: self.world_enhancer(pts, inputs["qo"], rgb_local, pts_local, gt_feats))
         pts_w, pts_w_local = self.implicit_transform(rgb_local, pts_local, pts, c, cls)
         r, t, s = self.main_estimator(pts, pts_w, rgb_local, pts_local, pts_w_local)
+        br2.join()
         end_points["pred_qo"] = pts_w
         if self.training:
-            r_w, t_w, s_w, pts_w_local_gt = self.world_enhancer(pts, inputs["qo"], rgb_local, pts_local)
             end_points["pts_w_local"] = pts_w_local.transpose(1, 2).contiguous()
             end_points["pts_w_local_gt"] = pts_w_local_gt.transpose(1, 2).contiguous()
         end_points["pred_rotation"] = r
@@ -236,10 +288,17 @@ class PoseNetGT(nn.Module):
         rgb, pts, choose, pts_w_gt = inputs["rgb"], inputs["pts"], inputs["choose"], inputs["qo"]
         c = torch.mean(pts, 1, keepdim=True)
         pts = pts - c
+        br = _Branches(pts.device, 2)
+
+        def _cam():
+            with torch.no_grad():
+                return self.pts_extractor.forward_rows(pts)
+
+        pts_local = br.run(0, _cam)
+        gt_local = br.run(1, lambda: self.pts_gt_extractor.forward_rows(pts_w_gt))
         with torch.no_grad():  # outputs are detached in the reference (posenet_gt.py:43); same values, no graph
             rgb_local = self.rgb_extractor.gather_rows(rgb, choose)
-            pts_local = self.pts_extractor.forward_rows(pts)
-        gt_local = self.pts_gt_extractor.forward_rows(pts_w_gt)
+        br.join()
         r, t, s = self.pose_estimator_aux(pts, pts_w_gt, rgb_local, pts_local, gt_local)
         return {"pts_local_w_gt": gt_local.transpose(1, 2).contiguous(), "pred_rotation": r, "pred_translation": t + c.squeeze(1), "pred_size": s}
 
