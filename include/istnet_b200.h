@@ -113,8 +113,10 @@ int istnet_conv_wgrad(const void *dy_planes, long long dy_plane_stride, int dy_c
 
 /* nn.BatchNorm2d training statistics (resnet.py:129, modules.py:43,65, pytorch_utils.py:53-71): per-channel mean and
  * 1/sqrt(biased var + eps) over P rows; running stats updated in place with `momentum` (unbiased variance) when the
- * pointers are non-null.  ws: 2*C doubles of scratch. */
-int istnet_bn_stats(const float *y, long long P, int C, double *ws, float eps, float momentum, float *running_mean,
+ * pointers are non-null.  part_ws: istnet_reduce_ws_floats(P, C, 2) floats of scratch (per-CTA partial sums, summed in a
+ * fixed order by a second tiny kernel: no atomics, deterministic). */
+int istnet_reduce_ws_floats(long long P, int C, int nacc); /* floats of partial-sum scratch for a per-channel reduction */
+int istnet_bn_stats(const float *y, long long P, int C, float *part_ws, float eps, float momentum, float *running_mean,
                     float *running_var, float *mean, float *invstd, void *stream);
 
 /* z = noise[b,c] * act( bn(y) + bn_res(res) )  written as FP32 and/or as bf16 operand planes (channel stride cs, offset ch_off).
@@ -125,14 +127,14 @@ int istnet_bn_act_split(const float *y, long long P, int C, long long HW, const 
                         const float *res_beta, int act, const float *prelu_a, const float *noise, float *out_f32, void *out_planes,
                         long long plane_stride, int nsplit, int cs, int ch_off, void *stream);
 
-/* Backward of the unit above: g = (dz + dz2) * noise * act'(u);  ws[0:C] = sum g, ws[C:2C] = sum g*xhat, ws[2C:3C] = PReLU
+/* Backward of the unit above (part_ws: istnet_reduce_ws_floats(P, C, 3) floats): g = (dz + dz2) * noise * act'(u);  ws[0:C] = sum g, ws[C:2C] = sum g*xhat, ws[2C:3C] = PReLU
  * slope partials;  dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))  (batch_stats=1; gamma*invstd*g with running
  * statistics, batch_stats=0; g without BN) written as bf16 operand planes and/or FP32;
  * g_out (optional) receives g (the residual branch's gradient).  ReLU masks come from plane 0 (z_hi) of the saved forward output. */
 int istnet_bn_act_bwd(const float *dz, const float *dz2, const float *y, long long P, int C, long long HW, const float *mean,
                       const float *invstd, const float *gamma, const float *beta, int act, const float *prelu_a, const void *z_hi,
-                      int cs_z, const float *noise, int batch_stats, double *ws, void *dy_planes, long long plane_stride, int nsplit,
-                      int cs_dy, float *dy_f32, float *g_out, void *stream);
+                      int cs_z, const float *noise, int batch_stats, float *part_ws, double *ws, void *dy_planes, long long plane_stride,
+                      int nsplit, int cs_dy, float *dy_f32, float *g_out, void *stream);
 
 /* FP32 [P][C] (or NCHW with HW pixels per image when nchw != 0) -> bf16 operand planes [nsplit][P][cs] at channel offset ch_off */
 int istnet_split(const float *x, long long P, int C, long long HW, int nchw, void *planes, long long plane_stride, int nsplit, int cs,

@@ -20,10 +20,11 @@
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
-// Squared distance in the exact operation order of the reference's SASS:
-// three FADDs, FMUL, FFMA, FFMA.  Explicit intrinsics so that nvcc neither adds nor removes a contraction.
+// Squared distance in the exact operation order of the reference's sm_100a SASS for `dx*dx + dy*dy + dz*dz`:
+// FMUL dy*dy, FFMA dx*dx + ., FFMA dz*dz + .  (cuobjdump of the reference build under oracle/_ref; the plain multiply
+// is on the middle term).  Explicit intrinsics so that nvcc neither adds nor removes a contraction.
 __device__ __forceinline__ float sqdist_ref(float dx, float dy, float dz) {
-    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
 constexpr int kNumSMs = 148;

@@ -37,8 +37,12 @@ __device__ __forceinline__ float4 bn4(float4 y, const BnP &b, int c) {
 // ------------------------------------------------------------------ per-channel reductions
 // Each thread owns 4 channels (float4) of rows r = row0 + i*rows_per_iter; partial sums are combined through shared
 // memory and flushed with double atomics (one per channel per CTA).
-template <int NACC, typename F>
-__device__ void column_reduce(long long P, int C, double *ws, F row_fn) {
+// Each thread owns 4 channels (float4) of rows r = row0 + i*rows_per_iter; partial sums are combined through shared
+// memory.  ATOMIC = true: flushed with double atomics into ws[a*C + c] (ws pre-zeroed).  ATOMIC = false: every CTA
+// writes its FP32 partial to part[(a*gridDim.x + blockIdx.x)*C + c]; a finalize kernel sums the partials in a fixed
+// order — no atomics (hundreds of CTAs hammering a few dozen addresses cost ~25 us per call), no memset, deterministic.
+template <int NACC, bool ATOMIC, typename F>
+__device__ void column_reduce(long long P, int C, double *ws, float *part, F row_fn) {
     const int lanes = C >> 2;  // float4 lanes per row
     __shared__ float red[kEwThreads * 4];
     float acc[NACC][4];
@@ -59,7 +63,8 @@ __device__ void column_reduce(long long P, int C, double *ws, F row_fn) {
                 for (int k = 0; k < 4; ++k) {
                     float s = 0.f;
                     for (int q = 0; q < rows_per_iter; ++q) s += red[(q * lanes + threadIdx.x) * 4 + k];
-                    atomicAdd(ws + (size_t)a * C + threadIdx.x * 4 + k, (double)s);
+                    if (ATOMIC) atomicAdd(ws + (size_t)a * C + threadIdx.x * 4 + k, (double)s);
+                    else part[((size_t)a * gridDim.x + blockIdx.x) * C + threadIdx.x * 4 + k] = s;
                 }
             }
         }
@@ -69,25 +74,51 @@ __device__ void column_reduce(long long P, int C, double *ws, F row_fn) {
             for (int a = 0; a < NACC; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
             for (long long r = blockIdx.x; r < P; r += gridDim.x) row_fn(r, cv * 4, acc);
             for (int a = 0; a < NACC; ++a)
-                for (int k = 0; k < 4; ++k) atomicAdd(ws + (size_t)a * C + cv * 4 + k, (double)acc[a][k]);
+                for (int k = 0; k < 4; ++k) {
+                    if (ATOMIC) atomicAdd(ws + (size_t)a * C + cv * 4 + k, (double)acc[a][k]);
+                    else part[((size_t)a * gridDim.x + blockIdx.x) * C + cv * 4 + k] = acc[a][k];
+                }
         }
     }
 }
+// tot[a*C + c] = sum_g part[(a*G + g)*C + c]  in double, fixed order: block = 32 channels x 8 partial-slices
+template <int NACC>
+__device__ void sum_partials(const float *__restrict__ part, int G, int C, double (&out)[NACC]) {
+    __shared__ double sred[NACC][8][32];
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + l;
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+        double s = 0.0;
+        if (c < C)
+            for (int g = w; g < G; g += 8) s += (double)part[((size_t)a * G + g) * C + c];
+        sred[a][w][l] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+        double s = 0.0;
+        for (int q = 0; q < 8; ++q) s += sred[a][q][l];
+        out[a] = s;
+    }
+}
 
-__global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const float *__restrict__ y, long long P, int C, double *ws) {
-    column_reduce<2>(P, C, ws, [&](long long r, int c, float (*acc)[4]) {
+__global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const float *__restrict__ y, long long P, int C, float *part) {
+    column_reduce<2, false>(P, C, nullptr, part, [&](long long r, int c, float (*acc)[4]) {
         float4 v = ld4(y + r * C + c);
         acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
         acc[1][0] += v.x * v.x; acc[1][1] += v.y * v.y; acc[1][2] += v.z * v.z; acc[1][3] += v.w * v.w;
     });
 }
 
-__global__ void bn_finalize_kernel(const double *__restrict__ ws, long long P, int C, float eps, float momentum, float *running_mean,
-                                   float *running_var, float *mean, float *invstd) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double m = ws[c] / (double)P;
-    double var = ws[C + c] / (double)P - m * m;
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float *__restrict__ part, int G, long long P, int C, float eps, float momentum,
+                                                          float *running_mean, float *running_var, float *mean, float *invstd) {
+    double t[2];
+    sum_partials<2>(part, G, C, t);
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    if (threadIdx.x >= 32 || c >= C) return;
+    double m = t[0] / (double)P;
+    double var = t[1] / (double)P - m * m;
     if (var < 0.0) var = 0.0;
     mean[c] = (float)m;
     invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -96,6 +127,15 @@ __global__ void bn_finalize_kernel(const double *__restrict__ ws, long long P, i
         running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
         running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
     }
+}
+__global__ void __launch_bounds__(256) bwd_finalize_kernel(const float *__restrict__ part, int G, int C, double *ws) {
+    double t[3];
+    sum_partials<3>(part, G, C, t);
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    if (threadIdx.x >= 32 || c >= C) return;
+    ws[c] = t[0];
+    ws[C + c] = t[1];
+    ws[2 * C + c] = t[2];
 }
 
 // ------------------------------------------------------------------ forward: BN + residual + act + noise + split
@@ -188,9 +228,9 @@ __device__ __forceinline__ void act_bwd4(const ActBwdP &p, long long r, int c, i
     }
 }
 // ws[0:C] = sum g, ws[C:2C] = sum g*xhat, ws[2C:3C] = PReLU slope partial
-__global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(long long P, int C, ActBwdP p, double *ws) {
+__global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(long long P, int C, ActBwdP p, float *part) {
     const float a = (p.act == 2) ? *p.prelu_a : 0.f;
-    column_reduce<3>(P, C, ws, [&](long long r, int c, float (*acc)[4]) {
+    column_reduce<3, false>(P, C, nullptr, part, [&](long long r, int c, float (*acc)[4]) {
         float4 g, xh, ex;
         act_bwd4(p, r, c, C, a, g, xh, ex);
         acc[0][0] += g.x; acc[0][1] += g.y; acc[0][2] += g.z; acc[0][3] += g.w;
@@ -282,7 +322,7 @@ __global__ void __launch_bounds__(kEwThreads) prep_weight_kernel(int co_n, int c
     }
 }
 __global__ void __launch_bounds__(kEwThreads) colsum_kernel(const float *__restrict__ x, long long P, int C, double *ws) {
-    column_reduce<1>(P, C, ws, [&](long long r, int c, float (*acc)[4]) {
+    column_reduce<1, true>(P, C, ws, nullptr, [&](long long r, int c, float (*acc)[4]) {
         float4 v = ld4(x + r * C + c);
         acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
     });
@@ -516,11 +556,10 @@ inline int ew_grid(long long total) {
     return (int)(g < 1 ? 1 : (g < cap ? g : cap));
 }
 inline int red_grid(long long P, int C) {
-    // every CTA ends with one double atomic per channel and accumulator: give each thread >= 16 rows so that small
-    // tensors do not pay hundreds of contended atomics per address
+    // >= 4 rows per thread, at most 4 CTAs per SM; every CTA writes one partial vector (no atomics)
     int lanes = C / 4;
     int rows_per_iter = lanes <= kEwThreads ? kEwThreads / lanes : 1;
-    long long g = (P + (long long)rows_per_iter * 16 - 1) / ((long long)rows_per_iter * 16);
+    long long g = (P + (long long)rows_per_iter * 4 - 1) / ((long long)rows_per_iter * 4);
     long long cap = (long long)kNumSMs * 4;
     return (int)(g < 1 ? 1 : (g < cap ? g : cap));
 }
@@ -530,13 +569,15 @@ inline BnP make_bn(const float *mean, const float *invstd, const float *gamma, c
 
 #define ST ((cudaStream_t)stream)
 
-extern "C" int istnet_bn_stats(const float *y, long long P, int C, double *ws, float eps, float momentum, float *running_mean,
+extern "C" int istnet_reduce_ws_floats(long long P, int C, int nacc) { return red_grid(P, C) * nacc * C; }
+
+extern "C" int istnet_bn_stats(const float *y, long long P, int C, float *part_ws, float eps, float momentum, float *running_mean,
                                float *running_var, float *mean, float *invstd, void *stream) {
     if (P <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
-    ISTNET_CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, ST));
-    bn_stats_kernel<<<red_grid(P, C), kEwThreads, 0, ST>>>(y, P, C, ws);
+    const int G = red_grid(P, C);
+    bn_stats_kernel<<<G, kEwThreads, 0, ST>>>(y, P, C, part_ws);
     ISTNET_LAUNCH_CHECK();
-    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, ST>>>(ws, P, C, eps, momentum, running_mean, running_var, mean, invstd);
+    bn_finalize_kernel<<<ceil_div(C, 32), 256, 0, ST>>>(part_ws, G, P, C, eps, momentum, running_mean, running_var, mean, invstd);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
@@ -559,16 +600,18 @@ extern "C" int istnet_bn_act_split(const float *y, long long P, int C, long long
 
 extern "C" int istnet_bn_act_bwd(const float *dz, const float *dz2, const float *y, long long P, int C, long long HW, const float *mean,
                                  const float *invstd, const float *gamma, const float *beta, int act, const float *prelu_a,
-                                 const void *z_hi, int cs_z, const float *noise, int batch_stats, double *ws /*3C*/, void *dy_planes,
-                                 long long plane_stride, int nsplit, int cs_dy, float *dy_f32, float *g_out, void *stream) {
+                                 const void *z_hi, int cs_z, const float *noise, int batch_stats, float *part_ws, double *ws /*3C*/,
+                                 void *dy_planes, long long plane_stride, int nsplit, int cs_dy, float *dy_f32, float *g_out, void *stream) {
     if (P <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
     if (act == 1 && !z_hi) return ISTNET_ERR_BAD_ARG;
     ActBwdP p{};
     p.dz = dz; p.dz2 = dz2; p.y = y; p.bn = make_bn(mean, invstd, gamma, beta);
     p.act = act; p.prelu_a = prelu_a; p.z_hi = (const __nv_bfloat16 *)z_hi; p.cs_z = cs_z; p.noise = noise; p.HW = HW > 0 ? HW : 1;
     p.batch_stats = batch_stats;
-    ISTNET_CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(double) * 3 * C, ST));
-    bn_bwd_reduce_kernel<<<red_grid(P, C), kEwThreads, 0, ST>>>(P, C, p, ws);
+    const int G = red_grid(P, C);
+    bn_bwd_reduce_kernel<<<G, kEwThreads, 0, ST>>>(P, C, p, part_ws);
+    ISTNET_LAUNCH_CHECK();
+    bwd_finalize_kernel<<<ceil_div(C, 32), 256, 0, ST>>>(part_ws, G, C, ws);
     ISTNET_LAUNCH_CHECK();
     bn_bwd_apply_kernel<<<ew_grid(P * (C / 4)), kEwThreads, 0, ST>>>(P, C, p, ws, (__nv_bfloat16 *)dy_planes, plane_stride, nsplit, cs_dy,
                                                                      dy_f32, g_out);

@@ -373,7 +373,7 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__
     idx[o + 0] = i1; idx[o + 1] = i2; idx[o + 2] = i3;
 }
 
-// out[(bi*c + l)*n + j] = fma(p[i3], w3, fma(p[i2], w2, p[i1]*w1)),  p = points + (bi*c + l)*m
+// out[(bi*c + l)*n + j] = fma(p[i3], w3, fma(p[i1], w1, p[i2]*w2)) (the reference's SASS contraction),  p = points + (bi*c + l)*m
 __global__ void three_interpolate_kernel(long long total, int c, int m, int n, const float *__restrict__ points,
                                          const int32_t *__restrict__ idx, const float *__restrict__ weight, float *__restrict__ out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -382,7 +382,7 @@ __global__ void three_interpolate_kernel(long long total, int c, int m, int n, c
         int bi = (int)(row / c);
         long long o = ((long long)bi * n + j) * 3;
         const float *p = points + row * m;
-        out[i] = __fmaf_rn(p[idx[o + 2]], weight[o + 2], __fmaf_rn(p[idx[o + 1]], weight[o + 1], __fmul_rn(p[idx[o + 0]], weight[o + 0])));
+        out[i] = __fmaf_rn(p[idx[o + 2]], weight[o + 2], __fmaf_rn(p[idx[o + 0]], weight[o + 0], __fmul_rn(p[idx[o + 1]], weight[o + 1])));
     }
 }
 __global__ void three_interpolate_grad_kernel(long long total, int c, int n, int m, const float *__restrict__ grad_out,

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kThreads) maxrows_bwd_kernel(long long G, int 
     }
 }
 
-// out[b, j, off + c] = fma(p3, w3, fma(p2, w2, p1*w1)),  p_q = feats[b, idx[b,j,q], c]   (interpolate_gpu.cu:77-106 on rows)
+// out[b, j, off + c] = fma(p3, w3, fma(p1, w1, p2*w2)),  p_q = feats[b, idx[b,j,q], c]   (interpolate_gpu.cu:77-106 on rows)
 __global__ void __launch_bounds__(kThreads) interp_rows_kernel(int B, int m, int n, int C, const float *__restrict__ feats,
                                                                 const int32_t *__restrict__ idx, const float *__restrict__ w, float *out, int out_ld,
                                                                 int out_off) {
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kThreads) interp_rows_kernel(int B, int m, int
         const float *f = feats + (long long)b * m * C + c;
         const long long o = bj * 3;
         out[bj * out_ld + out_off + c] = __fmaf_rn(f[(long long)idx[o + 2] * C], w[o + 2],
-                                                   __fmaf_rn(f[(long long)idx[o + 1] * C], w[o + 1], __fmul_rn(f[(long long)idx[o] * C], w[o])));
+                                                   __fmaf_rn(f[(long long)idx[o] * C], w[o], __fmul_rn(f[(long long)idx[o + 1] * C], w[o + 1])));
     }
 }
 // d_feats[b, idx[b,j,q], c] += dout[b, j, off + c] * w_q   (d_feats pre-zeroed)

@@ -156,7 +156,7 @@ def bn_state(bn, y, P, C, training):
     if training and bn.training:  # each BatchNorm module's own flag decides, as in nn.BatchNorm2d.forward
         mean = torch.empty(C, dtype=torch.float32, device=dev)
         invstd = torch.empty(C, dtype=torch.float32, device=dev)
-        ws = torch.empty(2 * C, dtype=torch.float64, device=dev)
+        ws = torch.empty(_C.lib().istnet_reduce_ws_floats(c_ll(P), C, 2), dtype=torch.float32, device=dev)
         mom = bn.momentum if bn.momentum is not None else 0.1
         track = bn.track_running_stats and bn.running_mean is not None
         _C.call("bn_stats", ptr(y), c_ll(P), c_int(C), ptr(ws), c_float(bn.eps), c_float(mom), _p(bn.running_mean if track else None),
@@ -180,10 +180,11 @@ def bn_act_split(y, P, C, HW, bn=None, res=None, res_bn=None, act=0, prelu=None,
 def bn_act_bwd(dz, dz2, y, P, C, HW, bn, act, prelu, z_hi, noise, dy_pl=None, dy_f32=None, g_out=None):
     """Returns ws (3*C doubles): [sum g | sum g*xhat | PReLU slope partials]."""
     ws = torch.empty(3 * C, dtype=torch.float64, device=dz.device)
+    part = torch.empty(_C.lib().istnet_reduce_ws_floats(c_ll(P), C, 3), dtype=torch.float32, device=dz.device)
     _C.call(
         "bn_act_bwd", ptr(dz), _p(dz2), _p(y), c_ll(P), c_int(C), c_ll(HW), _p(bn.mean if bn else None), _p(bn.invstd if bn else None),
         _p(bn.gamma if bn else None), _p(bn.beta if bn else None), c_int(act), _p(prelu), _p(z_hi), c_int(z_hi.shape[-1] if z_hi is not None else 0),
-        _p(noise), c_int(1 if (bn is not None and bn.batch) else 0), ptr(ws), *_pl_args(dy_pl), c_int(dy_pl.shape[-1] if dy_pl is not None else 0), _p(dy_f32), _p(g_out),
+        _p(noise), c_int(1 if (bn is not None and bn.batch) else 0), ptr(part), ptr(ws), *_pl_args(dy_pl), c_int(dy_pl.shape[-1] if dy_pl is not None else 0), _p(dy_f32), _p(g_out),
     )
     return ws
 

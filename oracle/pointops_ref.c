@@ -27,9 +27,12 @@ int ref_opt_n_threads(int work_size) {
     return v;
 }
 
-/* squared distance as the reference SASS evaluates it: FADD x3, FMUL, FFMA, FFMA */
+/* Squared distance exactly as the reference's sm_100a SASS evaluates `dx*dx + dy*dy + dz*dz` (nvcc -fmad=true):
+ *   FMUL t = dy*dy ; FFMA t = dx*dx + t ; FFMA d = dz*dz + t        (read from oracle/_ref/build/*_gpu.cuda.o with
+ * cuobjdump -sass for furthest_point_sampling_kernel, query_ball_point_kernel and three_nn_kernel — the plain multiply is
+ * on the MIDDLE term; SURVEY.md Appendix A has the first and second terms swapped). */
 static inline float sqdist(float dx, float dy, float dz) {
-    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
 }
 
 /*
@@ -172,7 +175,7 @@ void ref_three_nn(int b, int n, int m, const float *unknown, const float *known,
     }
 }
 
-/* interpolate_gpu.cu:77-106 — out = fma(p3,w3, fma(p2,w2, p1*w1)) */
+/* interpolate_gpu.cu:77-106 — `p1*w1 + p2*w2 + p3*w3` contracts to fma(p3,w3, fma(p1,w1, p2*w2)) (same SASS pattern) */
 void ref_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx, const float *weight, float *out) {
     for (int bi = 0; bi < b; ++bi)
         for (int l = 0; l < c; ++l)
@@ -180,7 +183,7 @@ void ref_three_interpolate(int b, int c, int m, int n, const float *points, cons
                 size_t o = ((size_t)bi * n + j) * 3;
                 const float *p = points + ((size_t)bi * c + l) * m;
                 out[((size_t)bi * c + l) * n + j] =
-                    fmaf(p[idx[o + 2]], weight[o + 2], fmaf(p[idx[o + 1]], weight[o + 1], p[idx[o + 0]] * weight[o + 0]));
+                    fmaf(p[idx[o + 2]], weight[o + 2], fmaf(p[idx[o + 0]], weight[o + 0], p[idx[o + 1]] * weight[o + 1]));
             }
 }
 

@@ -12,10 +12,10 @@ f32 = np.float32
 
 
 def _sq(dx, dy, dz):
-    # fmaf(dz,dz,fmaf(dy,dy,dx*dx)) evaluated exactly: products/sums in float64 are exact for float32 inputs
-    # up to the single rounding of each fused step.
-    t = f32(f32(dx) * f32(dx))
-    t = f32(np.float64(dy) * np.float64(dy) + np.float64(t))
+    # fmaf(dz,dz,fmaf(dx,dx,dy*dy)) (the reference's SASS order) evaluated exactly: products/sums in float64 are exact
+    # for float32 inputs up to the single rounding of each fused step.
+    t = f32(f32(dy) * f32(dy))
+    t = f32(np.float64(dx) * np.float64(dx) + np.float64(t))
     return f32(np.float64(dz) * np.float64(dz) + np.float64(t))
 
 
