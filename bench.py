@@ -25,7 +25,7 @@ import torch.distributed as dist  # noqa: E402
 LABELS = ("qo", "rotation_label", "translation_label", "size_label")
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's largest launch (up_1 conv, B=32) from one
 # `ncu --set full` capture (profiles/), bytes per launch; None until captured for the current kernel version
-ROOFLINE_TRAFFIC = None
+ROOFLINE_TRAFFIC = 583.1e6  # profiles/r1_conv_up1_ns3_bk32.txt: 510.9 MB read + 72.2 MB written (algorithmic: 453 MB operand planes + 75.5 MB output)
 MODEL_IN = ("rgb", "pts", "choose", "category_label", "qo")
 WORKLOADS = {
     "cfg1": dict(model="ist_net", batch=32, npts=1024, img=192, desc="ist_net_default.yaml train fwd+bwd, 32 x (1024 pts + 192x192 RGB) per GPU"),
