@@ -33,6 +33,8 @@ struct ConvGemmParams {
     int cin_blocks;           // ceil(Cin / block_k)
     int block_k;              // K elements per pipeline stage: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows)
     int Cout, BN;             // logical output channels, tile width (multiple of 16, <= 256)
+    int n_tiles_n;            // ceil(Cout / BN)
+    int acc_stride;           // TMEM columns between the two accumulators (BN rounded up to 32)
     int stages;
     const float *bias;        // [Cout] or null
     int relu;
@@ -55,25 +57,24 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const int stage_bytes = p.nsplit * (kATileBytes + b_tile_bytes);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
     uint64_t *empty_bar = full_bar + p.stages;
-    uint64_t *tmem_full_bar = empty_bar + p.stages;
-    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+    uint64_t *tmem_full_bar = empty_bar + p.stages;   // [2] accumulator ready for the epilogue
+    uint64_t *tmem_empty_bar = tmem_full_bar + 2;     // [2] accumulator drained by the epilogue
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // tile coordinates
-    int mt = blockIdx.x;
-    const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-    const int th = mt % p.tiles_h; mt /= p.tiles_h;
-    const int tb = mt;
-    const int w0 = tw * p.box_w, h0 = th * p.box_h, b0 = tb * p.box_b;
-    const int n0 = blockIdx.y * p.BN;
     const int num_k = p.kh * p.kw * p.cin_blocks;
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+    const int n_tiles = m_tiles * p.n_tiles_n;
+    // PERSISTENT: this CTA processes tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The shared-memory ring keeps running
+    // across tiles and the accumulator is double-buffered in tensor memory, so the epilogue of tile i overlaps the TMA /
+    // MMA main loop of tile i+1 and the per-CTA set-up (TMEM allocation, barrier init, descriptor prefetch) is paid once.
 
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tm_a); tc::prefetch_tmap(&tm_b);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-        tc::mbar_init(tmem_full_bar, 1);
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&tmem_full_bar[s], 1); tc::mbar_init(&tmem_empty_bar[s], 4); }
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc(tmem_holder, p.tmem_cols);
@@ -87,21 +88,28 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         if (lane == 0) {
             const int pad_h = p.kh / 2, pad_w = p.kw / 2;
             int it = 0;
-            // channel block OUTER, filter tap INNER: the nine shifted boxes of one 64-channel slab are fetched back to
-            // back, so taps 1..8 hit in L2 (tap-outer order re-streamed the whole activation tensor from HBM per tap:
-            // 6.9 GB instead of 0.9 GB for up_1 at B=32, ncu profiles/r1_conv_up1_taporder.txt)
-            for (int kb = 0; kb < p.cin_blocks; ++kb) {
-                for (int tap = 0; tap < p.kh * p.kw; ++tap, ++it) {
-                    const int r = tap / p.kw, s = tap % p.kw;
-                    const int st = it % p.stages;
-                    const uint32_t ph = (it / p.stages) & 1;
-                    tc::mbar_wait(&empty_bar[st], ph ^ 1);
-                    uint8_t *sa = smem + (size_t)st * stage_bytes;
-                    tc::mbar_arrive_expect_tx(&full_bar[st], stage_bytes);
-                    uint8_t *sb = sa + p.nsplit * kATileBytes;
-                    for (int pl = 0; pl < p.nsplit; ++pl) {
-                        tc::tma_load_5d(sa + pl * kATileBytes, &tm_a, &full_bar[st], kb * kBlockK, w0 + s - pad_w, h0 + r - pad_h, b0, pl);
-                        tc::tma_load_4d(sb + pl * b_tile_bytes, &tm_b, &full_bar[st], kb * kBlockK, n0, tap, pl);
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                int mt = tile % m_tiles;
+                const int n0 = (tile / m_tiles) * p.BN;
+                const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+                const int th = mt % p.tiles_h; mt /= p.tiles_h;
+                const int w0 = tw * p.box_w, h0 = th * p.box_h, b0 = mt * p.box_b;
+                // channel block OUTER, filter tap INNER: the nine shifted boxes of one channel slab are fetched back to
+                // back, so taps 1..8 hit in L2 (tap-outer order re-streamed the activation tensor from HBM per tap:
+                // 6.9 GB instead of 0.5 GB for up_1 at B=32, profiles/r1_conv_up1_taporder_before.txt)
+                for (int kb = 0; kb < p.cin_blocks; ++kb) {
+                    for (int tap = 0; tap < p.kh * p.kw; ++tap, ++it) {
+                        const int r = tap / p.kw, s = tap % p.kw;
+                        const int st = it % p.stages;
+                        const uint32_t ph = (it / p.stages) & 1;
+                        tc::mbar_wait(&empty_bar[st], ph ^ 1);
+                        uint8_t *sa = smem + (size_t)st * stage_bytes;
+                        tc::mbar_arrive_expect_tx(&full_bar[st], stage_bytes);
+                        uint8_t *sb = sa + p.nsplit * kATileBytes;
+                        for (int pl = 0; pl < p.nsplit; ++pl) {
+                            tc::tma_load_5d(sa + pl * kATileBytes, &tm_a, &full_bar[st], kb * kBlockK, w0 + s - pad_w, h0 + r - pad_h, b0, pl);
+                            tc::tma_load_4d(sb + pl * b_tile_bytes, &tm_b, &full_bar[st], kb * kBlockK, n0, tap, pl);
+                        }
                     }
                 }
             }
@@ -110,31 +118,39 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = tc::make_idesc_f16(kTileM, p.BN, 1, 1, 0, 0);
-            for (int it = 0; it < num_k; ++it) {
-                const int st = it % p.stages;
-                const uint32_t ph = (it / p.stages) & 1;
-                tc::mbar_wait(&full_bar[st], ph);
+            const uint32_t ltype = kBlockK == 64 ? 2u : 4u;   // SWIZZLE_128B | SWIZZLE_64B
+            const uint32_t sbo = 8u * kBlockK * 2u;           // 8 rows of one swizzle atom
+            int it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+                const int buf = lt & 1;
+                const uint32_t use = (uint32_t)(lt >> 1);
+                tc::mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);  // epilogue has drained this accumulator
                 tc::tc_fence_after();
-                const uint32_t a0 = tc::smem_u32(smem + (size_t)st * stage_bytes);
-                const uint32_t b0 = a0 + p.nsplit * kATileBytes;
-                const uint32_t ltype = kBlockK == 64 ? 2u : 4u;   // SWIZZLE_128B | SWIZZLE_64B
-                const uint32_t sbo = 8u * kBlockK * 2u;           // 8 rows of one swizzle atom
-                for (int j = 0; j < kBlockK / 16; ++j) {
-                    uint32_t acc = (it | j) != 0;
-                    // all plane products a_i * b_j with i + j < nsplit, smallest magnitude first
-                    for (int sum = p.nsplit - 1; sum >= 0; --sum) {
-                        for (int ia = sum; ia >= 0; --ia) {
-                            const int ib = sum - ia;
-                            const uint64_t da = tc::make_desc_swz(a0 + ia * kATileBytes + j * 32, 16, sbo, ltype);
-                            const uint64_t db = tc::make_desc_swz(b0 + ib * b_tile_bytes + j * 32, 16, sbo, ltype);
-                            tc::umma_bf16(tmem_base, da, db, idesc, acc);
-                            acc = 1;
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * p.acc_stride);
+                for (int kk = 0; kk < num_k; ++kk, ++it) {
+                    const int st = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1;
+                    tc::mbar_wait(&full_bar[st], ph);
+                    tc::tc_fence_after();
+                    const uint32_t a0 = tc::smem_u32(smem + (size_t)st * stage_bytes);
+                    const uint32_t b0 = a0 + p.nsplit * kATileBytes;
+                    for (int j = 0; j < kBlockK / 16; ++j) {
+                        uint32_t acc = (kk | j) != 0;
+                        // all plane products a_i * b_j with i + j < nsplit, smallest magnitude first
+                        for (int sum = p.nsplit - 1; sum >= 0; --sum) {
+                            for (int ia = sum; ia >= 0; --ia) {
+                                const int ib = sum - ia;
+                                const uint64_t da = tc::make_desc_swz(a0 + ia * kATileBytes + j * 32, 16, sbo, ltype);
+                                const uint64_t db = tc::make_desc_swz(b0 + ib * b_tile_bytes + j * 32, 16, sbo, ltype);
+                                tc::umma_bf16(tacc, da, db, idesc, acc);
+                                acc = 1;
+                            }
                         }
                     }
+                    tc::umma_commit(&empty_bar[st]);  // frees the smem stage once these MMAs retire
                 }
-                tc::umma_commit(&empty_bar[st]);  // frees the smem stage once these MMAs retire
+                tc::umma_commit(&tmem_full_bar[buf]);
             }
-            tc::umma_commit(tmem_full_bar);
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
@@ -143,47 +159,59 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         const int pb = row / (p.box_w * p.box_h);
         const int ph_ = (row / p.box_w) % p.box_h;
         const int pw = row % p.box_w;
-        const int b = b0 + pb, h = h0 + ph_, w = w0 + pw;
-        const bool row_ok = (b < p.B) && (h < p.H) && (w < p.W);
-        const size_t pix = ((size_t)b * p.H + h) * p.W + w;
-        tc::mbar_wait(tmem_full_bar, 0);
-        tc::tc_fence_after();
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
-            uint32_t v[32];
-            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            tc::tmem_ld_wait();
-            if (!row_ok) continue;
-            const int n = n0 + c0;
-            if (n >= p.Cout) continue;
-            float f[32];
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            int mt = tile % m_tiles;
+            const int n0 = (tile / m_tiles) * p.BN;
+            const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+            const int th = mt % p.tiles_h; mt /= p.tiles_h;
+            const int b = mt * p.box_b + pb, h = th * p.box_h + ph_, w = tw * p.box_w + pw;
+            const bool row_ok = (b < p.B) && (h < p.H) && (w < p.W);
+            const size_t pix = ((size_t)b * p.H + h) * p.W + w;
+            const int buf = lt & 1;
+            tc::mbar_wait(&tmem_full_bar[buf], (uint32_t)(lt >> 1) & 1);
+            tc::tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)(buf * p.acc_stride) + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(tacc + (uint32_t)c0, v);
+                tc::tmem_ld_wait();
+                if (!row_ok) continue;
+                const int n = n0 + c0;
+                if (n >= p.Cout) continue;
+                float f[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float x = __uint_as_float(v[i]);
-                if (p.bias != nullptr && n + i < p.Cout) x += __ldg(p.bias + n + i);
-                if (p.relu) x = fmaxf(x, 0.f);
-                f[i] = x;
-            }
-            const int valid = min(32, p.Cout - n);
-            if (p.out_f32) {
-                float *o = p.out_f32 + pix * p.out_cs + n;
-                if (valid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                for (int i = 0; i < 32; ++i) {
+                    float x = __uint_as_float(v[i]);
+                    if (p.bias != nullptr && n + i < p.Cout) x += __ldg(p.bias + n + i);
+                    if (p.relu) x = fmaxf(x, 0.f);
+                    f[i] = x;
+                }
+                const int valid = min(32, p.Cout - n);
+                if (p.out_f32) {
+                    float *o = p.out_f32 + pix * p.out_cs + n;
+                    if (valid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                } else {
-                    for (int i = 0; i < valid; ++i) o[i] = f[i];
+                        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                    } else {
+                        for (int i = 0; i < valid; ++i) o[i] = f[i];
+                    }
+                }
+                if (p.out_pl) {
+                    __nv_bfloat16 *o = p.out_pl + pix * p.split_cs + n;
+                    if (valid == 32 && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) store_planes4(o + i, p.out_pl_stride, p.nsplit_out, make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]));
+                    } else {
+                        for (int i = 0; i < valid; ++i) store_planes1(o + i, p.out_pl_stride, p.nsplit_out, f[i]);
+                    }
                 }
             }
-            if (p.out_pl) {
-                __nv_bfloat16 *o = p.out_pl + pix * p.split_cs + n;
-                if (valid == 32 && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) store_planes4(o + i, p.out_pl_stride, p.nsplit_out, make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]));
-                } else {
-                    for (int i = 0; i < valid; ++i) store_planes1(o + i, p.out_pl_stride, p.nsplit_out, f[i]);
-                }
-            }
+            // this warp is done reading the accumulator: hand it back to the MMA issuer (4 arrivals, one per warp)
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[buf]);
         }
-        tc::tc_fence_before();
     }
     __syncthreads();
     if (warp == 2) {
@@ -264,8 +292,10 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     p.bias = bias; p.relu = relu;
     p.out_f32 = out_f32; p.out_cs = out_cs;
     p.out_pl = (__nv_bfloat16 *)out_planes; p.out_pl_stride = out_plane_stride; p.split_cs = split_cs; p.nsplit_out = nsplit_out;
+    p.n_tiles_n = ceil_div(Cout, p.BN);
     p.tmem_cols = 32;
-    while ((int)p.tmem_cols < p.BN) p.tmem_cols *= 2;
+    p.acc_stride = (p.BN + 31) / 32 * 32;
+    while ((int)p.tmem_cols < 2 * p.acc_stride) p.tmem_cols *= 2;  // two accumulators (double buffering across tiles)
     const int num_k = kh * kw * p.cin_blocks;
     const int stage_bytes = nsplit * (kATileBytes + p.BN * kBlockK * 2);
     // Shared-memory budget per CTA.  Wide tiles (BN = 256) are MMA-bound with one CTA per SM and a deep ring.  Narrow
@@ -298,8 +328,13 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
         if (e) return e;
     }
     ISTNET_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    dim3 grid(p.tiles_w * p.tiles_h * p.tiles_b, ceil_div(Cout, p.BN));
-    conv_gemm_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ta, tb, p);
+    int ctas_per_sm = (int)((227 * 1024) / smem);
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctas_per_sm > 512 / (int)p.tmem_cols) ctas_per_sm = 512 / (int)p.tmem_cols;  // tensor memory: 512 columns per SM
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    long long grid_x = (long long)kNumSMs * ctas_per_sm;
+    if (grid_x > n_tiles) grid_x = n_tiles;
+    conv_gemm_tc_kernel<<<(unsigned)grid_x, kThreads, smem, (cudaStream_t)stream>>>(ta, tb, p);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }

@@ -204,6 +204,7 @@ class _ImageBranchFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out):
         grads = backward(ctx.net, ctx.tape, d_out, ctx.units)
+        K.join_side_streams()
         ctx.tape = None
         return (None, None, None) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
 

@@ -95,6 +95,26 @@ def pick_box(H, W):
     return 8, 8
 
 
+WGRAD_SIDE_STREAM = os.environ.get("ISTNET_WGRAD_STREAM", "1") != "0"
+_SIDE = {}
+_PENDING_JOINS = []
+
+
+def _side_stream(dev):
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    st = _SIDE.get(key)
+    if st is None:
+        st = _SIDE[key] = torch.cuda.Stream(dev)
+    return st
+
+
+def join_side_streams():
+    """Makes every stream that forked a weight-gradient side stream wait for it (called once per backward of a tape)."""
+    while _PENDING_JOINS:
+        main, side = _PENDING_JOINS.pop()
+        main.wait_stream(side)
+
+
 # bench.py sets PROFILE = [] to time every tensor-core launch with CUDA events on the launching stream:
 # entries are (kernel name, start event, end event, algorithmic FLOPs, nsplit)
 PROFILE = None
@@ -248,6 +268,20 @@ class ConvUnit:
             wp = prep_weight(self.w)
         B, H, W = xin.B, xin.H, xin.W
         P, C = B * H * W, self.cout
+        if self.bn is None and self.act == ACT_RELU and noise is None and res is None and not defer_act:
+            # Conv1d/Linear + bias + ReLU (per-point MLPs): bias, ReLU and the operand split of the NEXT layer are the
+            # GEMM's epilogue; nothing else touches the activation
+            out = Act(B, H, W, C)
+            if want_f32:
+                out.f32 = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
+            if want_pair or record:
+                out.pl = empty_planes(B, H, W, C, dev)
+            conv_gemm(xin, wp, C, kk, kk, bias=self.b, relu=True, out_f32=out.f32, out_pl=out.pl)
+            rec = {"bn": None}
+            if record:
+                rec.update({"xin": xin, "y": None, "noise": None, "kk": kk, "P": P, "HW": H * W, "in_shape": (x.B, x.H, x.W, x.C),
+                            "z_hi": out.hi})
+            return out, rec
         y = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
         conv_gemm(xin, wp, C, kk, kk, bias=self.b, out_f32=y)
         st = bn_state(self.bn, y, P, C, training) if self.bn is not None else None
@@ -313,11 +347,22 @@ class ConvUnit:
 
     def data_grads(self, rec, dy, need_dx, grads):
         xin, kk, C = rec["xin"], rec["kk"], self.cout
-        gw = conv_wgrad(dy, C, xin, kk, kk)
-        if kk != self.k or self.stride != 1:  # im2col path: [co, (r,s,c)] -> [co, c, r, s]
-            cin = self.w.shape[1]
-            gw = gw.reshape(C, self.k, self.k, cin).permute(0, 3, 1, 2).contiguous()
+        # weight gradient and data gradient are independent: wgrad goes to a side stream and overlaps the dgrad GEMM
+        main = torch.cuda.current_stream()
+        side = _side_stream(dy.device) if (need_dx and WGRAD_SIDE_STREAM) else None
+        if side is not None:
+            side.wait_stream(main)
+        with torch.cuda.stream(side if side is not None else main):
+            gw = conv_wgrad(dy, C, xin, kk, kk)
+            if kk != self.k or self.stride != 1:  # im2col path: [co, (r,s,c)] -> [co, c, r, s]
+                cin = self.w.shape[1]
+                gw = gw.reshape(C, self.k, self.k, cin).permute(0, 3, 1, 2).contiguous()
         grads[id(self.w)] = gw.reshape(self.w.shape)
+        if side is not None:
+            dy.record_stream(side)
+            xin.pl.record_stream(side)
+            gw.record_stream(main)
+            _PENDING_JOINS.append((main, side))
         if not need_dx:
             return None
         dyA = Act(xin.B, xin.H, xin.W, C, None, dy)

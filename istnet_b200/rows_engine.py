@@ -73,6 +73,7 @@ class _ChainFn(torch.autograd.Function):
     def backward(ctx, dz):
         grads = {}
         dx = _chain_backward(ctx.units, ctx.tape, dz.contiguous().view(1, 1, dz.shape[0], dz.shape[1]), grads, ctx.need_dx)
+        K.join_side_streams()
         ctx.tape = None
         return (None, None, dx.view(dx.shape[2], dx.shape[3]) if dx is not None else None) + tuple(
             grads.get(id(p)) if p.requires_grad else None for p in ctx.params
@@ -130,6 +131,7 @@ class _SAScaleFn(torch.autograd.Function):
         if ctx.has_feats:
             d_feats = torch.empty(B, N, C, dtype=torch.float32, device=dz.device)
             _C.call("group_rows_bwd", c_int(B), c_int(N), c_int(M), c_int(ns), c_int(C), ptr(d), ptr(ctx.idx), ptr(d_feats))
+        K.join_side_streams()
         ctx.saved = None
         return (None, None, None, None, None, d_feats) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
 
