@@ -249,11 +249,15 @@ def main():
     value = world * B * args.steps / (ms / 1000.0)
     e2e_value = world * B * args.steps / (ms_e2e / 1000.0)
 
-    # ---- roofline of the dominant kernel (conv_gemm_tc_kernel: ~35 % of device time, profiles/): one extra eager step,
-    # outside the timed region, with CUDA events around every tensor-core launch on the launching stream
+    # ---- roofline of the dominant kernel (conv_gemm_tc_kernel: ~31 % of device time, profiles/): one extra eager step,
+    # outside the timed region, with CUDA events on the launching stream around every tensor-core launch (each re-issued
+    # 3x back to back between the events so the device-side duration is measured, not the host's launch latency)
     from istnet_b200 import nhwc
 
+    from istnet_b200 import model as model_mod
+
     nhwc.PROFILE = []
+    model_mod.USE_SIDE_STREAMS, nhwc.WGRAD_SIDE_STREAM = False, False  # time each kernel alone on its launching stream
     if world > 1 and graphed is not None:  # hooks were removed for the graph path: plain forward+backward is enough here
         ep_ = model({k: resident[k] for k in MODEL_IN})
         ep_.update({k: resident[k] for k in LABELS})
@@ -263,9 +267,9 @@ def main():
     torch.cuda.synchronize()
     prof, nhwc.PROFILE = nhwc.PROFILE, None
     kstat = {}
-    for name, e0, e1, fl, ns in prof:
+    for name, e0, e1, reps, fl, ns in prof:
         d = kstat.setdefault(name, {"ms": 0.0, "flop": 0.0, "mma_flop": 0.0, "n": 0})
-        d["ms"] += e0.elapsed_time(e1)
+        d["ms"] += e0.elapsed_time(e1) / reps
         d["flop"] += fl
         d["mma_flop"] += fl * (ns * (ns + 1) // 2)
         d["n"] += 1

@@ -91,11 +91,13 @@ int istnet_fps_chain(int b, int n, int nlevels, const int *npoint, const float *
 /* Stride-1 "same" convolution / GEMM:  out[b,h,w,n] = bias[n] + sum_{r,s,c} act[b,h+r-kh/2,w+s-kw/2,c] * wgt[r*kw+s][n][c]
  * (replaces nn.Conv2d / nn.Conv1d(k=1) / nn.Linear call sites: resnet.py:34-35, modules.py:17-25,41-44,64-66,
  * ist_net.py:130-160).  wgt planes: bf16 [nsplit][kh*kw][Cout][wgt_cs].  Any of out_f32 / out_planes may be null.
- * (box_w, box_h): pixel tile; box_w*box_h must divide 128 (images: 8x8 -> 2 images per tile; row matrices: 128x1). */
+ * (box_w, box_h): pixel tile; box_w*box_h must divide 128 (images: 8x8 -> 2 images per tile; row matrices: 128x1).
+ * stat_part (optional, >= 2*296*Cout floats): the epilogue also accumulates the per-channel sum / sum of squares of the
+ * output (train-mode BatchNorm statistics) per CTA; *grid_out receives the number of CTAs G, finish with istnet_bn_finalize. */
 int istnet_conv_gemm(const void *act_planes, long long act_plane_stride, int B, int H, int W, int Cin, int act_cs,
                      const void *wgt_planes, long long wgt_plane_stride, int Cout, int wgt_cs, int kh, int kw, int nsplit,
                      const float *bias, int relu, float *out_f32, int out_cs, void *out_planes, long long out_plane_stride,
-                     int nsplit_out, int split_cs, int box_w, int box_h, void *stream);
+                     int nsplit_out, int split_cs, int box_w, int box_h, float *stat_part, int *grid_out, void *stream);
 
 /* Weight gradient of the layer above (cuDNN wgrad in the reference):
  *   grad_w[co][ci][r][s] = sum_{b,h,w} dy[b,h,w,co] * x[b,h+r-kh/2,w+s-kw/2,ci]       (PyTorch weight layout, FP32)
@@ -118,6 +120,9 @@ int istnet_conv_wgrad(const void *dy_planes, long long dy_plane_stride, int dy_c
 int istnet_reduce_ws_floats(long long P, int C, int nacc); /* floats of partial-sum scratch for a per-channel reduction */
 int istnet_bn_stats(const float *y, long long P, int C, float *part_ws, float eps, float momentum, float *running_mean,
                     float *running_var, float *mean, float *invstd, void *stream);
+
+int istnet_bn_finalize(const float *part, int G, long long P, int C, float eps, float momentum, float *running_mean, float *running_var,
+                       float *mean, float *invstd, void *stream);
 
 /* z = noise[b,c] * act( bn(y) + bn_res(res) )  written as FP32 and/or as bf16 operand planes (channel stride cs, offset ch_off).
  * mean==NULL: no BN.  res==NULL: no residual; res_mean==NULL: raw residual.  act: 0 none, 1 ReLU, 2 PReLU(*prelu_a).

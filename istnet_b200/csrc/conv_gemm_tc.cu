@@ -44,6 +44,7 @@ struct ConvGemmParams {
     long long out_pl_stride;
     int split_cs, nsplit_out;
     int nsplit;               // planes of the input operands
+    float *stat_part;         // optional [gridDim.x][2][Cout]: per-CTA column sums / sums of squares of the output (BN statistics)
     uint32_t tmem_cols;
 };
 
@@ -60,6 +61,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     uint64_t *tmem_full_bar = empty_bar + p.stages;   // [2] accumulator ready for the epilogue
     uint64_t *tmem_empty_bar = tmem_full_bar + 2;     // [2] accumulator drained by the epilogue
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+    float *s_stat = reinterpret_cast<float *>(smem + (size_t)p.stages * stage_bytes + 256);  // [4 warps][2][Cout] when stat_part != null
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = p.kh * p.kw * p.cin_blocks;
@@ -78,6 +80,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc(tmem_holder, p.tmem_cols);
+    if (p.stat_part)
+        for (int i = threadIdx.x; i < 8 * p.Cout; i += kThreads) s_stat[i] = 0.f;
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -176,9 +180,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 uint32_t v[32];
                 tc::tmem_ld_32x32(tacc + (uint32_t)c0, v);
                 tc::tmem_ld_wait();
-                if (!row_ok) continue;
                 const int n = n0 + c0;
-                if (n >= p.Cout) continue;
+                if (n >= p.Cout) continue;  // warp-uniform
                 float f[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -187,6 +190,32 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     if (p.relu) x = fmaxf(x, 0.f);
                     f[i] = x;
                 }
+                if (p.stat_part) {
+                    // BatchNorm statistics of this 32-row x 32-column block: butterfly transpose-reduce over the warp
+                    // (31 shuffles per quantity), lane l ends with the column (c0 + l) totals and adds them to this WARP's
+                    // private shared-memory slot (no atomics: fixed summation order, bitwise reproducible); the CTA
+                    // flushes the sum of its four slots once, after its last tile
+                    float a[32], q2[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { a[i] = row_ok ? f[i] : 0.f; q2[i] = a[i] * a[i]; }
+#pragma unroll
+                    for (int half = 16; half >= 1; half >>= 1) {
+                        const bool up = (lane & half) != 0;
+#pragma unroll
+                        for (int i = 0; i < half; ++i) {
+                            // keep the half of the columns selected by this lane's bit, send the other half
+                            float keep_a = up ? a[i + half] : a[i], send_a = up ? a[i] : a[i + half];
+                            float keep_q = up ? q2[i + half] : q2[i], send_q = up ? q2[i] : q2[i + half];
+                            a[i] = keep_a + __shfl_xor_sync(0xffffffffu, send_a, half);
+                            q2[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, half);
+                        }
+                    }
+                    if (n + lane < p.Cout) {
+                        s_stat[(q * 2 + 0) * p.Cout + n + lane] += a[0];
+                        s_stat[(q * 2 + 1) * p.Cout + n + lane] += q2[0];
+                    }
+                }
+                if (!row_ok) continue;
                 const int valid = min(32, p.Cout - n);
                 if (p.out_f32) {
                     float *o = p.out_f32 + pix * p.out_cs + n;
@@ -214,6 +243,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         }
     }
     __syncthreads();
+    if (p.stat_part)
+        for (int i = threadIdx.x; i < 2 * p.Cout; i += kThreads) {
+            // layout expected by the finalize kernel: part[(a*G + g)*C + c]
+            const int a = i / p.Cout, c = i % p.Cout;
+            const float tot = ((s_stat[(0 * 2 + a) * p.Cout + c] + s_stat[(1 * 2 + a) * p.Cout + c]) + s_stat[(2 * 2 + a) * p.Cout + c]) +
+                              s_stat[(3 * 2 + a) * p.Cout + c];
+            p.stat_part[((size_t)a * gridDim.x + blockIdx.x) * p.Cout + c] = tot;
+        }
     if (warp == 2) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, p.tmem_cols);
@@ -271,7 +308,7 @@ static int pick_bn(int cout, int nsplit, int block_k) {
 extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stride, int B, int H, int W, int Cin, int act_cs,
                                 const void *wgt_planes, long long wgt_plane_stride, int Cout, int wgt_cs, int kh, int kw, int nsplit,
                                 const float *bias, int relu, float *out_f32, int out_cs, void *out_planes, long long out_plane_stride,
-                                int nsplit_out, int split_cs, int box_w, int box_h, void *stream) {
+                                int nsplit_out, int split_cs, int box_w, int box_h, float *stat_part, int *grid_out, void *stream) {
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return ISTNET_ERR_BAD_ARG;
     if (nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
     if ((act_cs & 7) || (wgt_cs & 7) || act_cs < Cin || wgt_cs < Cin) return ISTNET_ERR_BAD_ARG;
@@ -290,6 +327,7 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     p.Cout = Cout; p.BN = pick_bn(Cout, nsplit, kBlockK);
     p.nsplit = nsplit;
     p.bias = bias; p.relu = relu;
+    p.stat_part = stat_part;
     p.out_f32 = out_f32; p.out_cs = out_cs;
     p.out_pl = (__nv_bfloat16 *)out_planes; p.out_pl_stride = out_plane_stride; p.split_cs = split_cs; p.nsplit_out = nsplit_out;
     p.n_tiles_n = ceil_div(Cout, p.BN);
@@ -305,12 +343,13 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     const long long n_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b * ceil_div(Cout, p.BN);
     int budget_kb = (p.BN <= 128 && n_tiles >= 2 * kNumSMs) ? 110 : 225;
     budget_kb = env_int("ISTNET_CG_SMEM_KB", budget_kb);
-    int max_stages = (budget_kb * 1024 - 1024 - 256) / stage_bytes;
+    const int stat_bytes = stat_part ? 8 * Cout * (int)sizeof(float) : 0;
+    int max_stages = (budget_kb * 1024 - 1024 - 256 - stat_bytes) / stage_bytes;
     if (max_stages < 1) max_stages = 1;
     if (max_stages > 6) max_stages = 6;
     p.stages = num_k < max_stages ? num_k : max_stages;
-    if ((size_t)p.stages * stage_bytes + 1280 > 227 * 1024) return ISTNET_ERR_UNSUPPORTED;
-    size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+    size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256 + stat_bytes;
+    if (smem > 227 * 1024) return ISTNET_ERR_UNSUPPORTED;
 
     CUtensorMap ta, tb;
     {
@@ -332,8 +371,10 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     if (ctas_per_sm > 512 / (int)p.tmem_cols) ctas_per_sm = 512 / (int)p.tmem_cols;  // tensor memory: 512 columns per SM
     if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctas_per_sm > 2) ctas_per_sm = 2;  // grid <= 2 * 148 = 296: the size callers give the statistics scratch (stat_part)
     long long grid_x = (long long)kNumSMs * ctas_per_sm;
     if (grid_x > n_tiles) grid_x = n_tiles;
+    if (grid_out) *grid_out = (int)grid_x;
     conv_gemm_tc_kernel<<<(unsigned)grid_x, kThreads, smem, (cudaStream_t)stream>>>(ta, tb, p);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;

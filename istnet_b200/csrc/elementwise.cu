@@ -90,8 +90,18 @@ __device__ void sum_partials(const float *__restrict__ part, int G, int C, doubl
 #pragma unroll
     for (int a = 0; a < NACC; ++a) {
         double s = 0.0;
-        if (c < C)
-            for (int g = w; g < G; g += 8) s += (double)part[((size_t)a * G + g) * C + c];
+        if (c < C) {
+            const float *src = part + (size_t)a * G * C + c;
+            int g = w;
+            for (; g + 56 < G; g += 64) {  // 8 independent loads in flight per thread
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(g + 8 * u) * C];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += (double)v[u];
+            }
+            for (; g < G; g += 8) s += (double)src[(size_t)g * C];
+        }
         sred[a][w][l] = s;
     }
     __syncthreads();
@@ -556,11 +566,11 @@ inline int ew_grid(long long total) {
     return (int)(g < 1 ? 1 : (g < cap ? g : cap));
 }
 inline int red_grid(long long P, int C) {
-    // >= 4 rows per thread, at most 4 CTAs per SM; every CTA writes one partial vector (no atomics)
+    // >= 4 rows per thread, at most 2 CTAs per SM; every CTA writes one partial vector (no atomics)
     int lanes = C / 4;
     int rows_per_iter = lanes <= kEwThreads ? kEwThreads / lanes : 1;
     long long g = (P + (long long)rows_per_iter * 4 - 1) / ((long long)rows_per_iter * 4);
-    long long cap = (long long)kNumSMs * 4;
+    long long cap = (long long)kNumSMs * 2;
     return (int)(g < 1 ? 1 : (g < cap ? g : cap));
 }
 inline BnP make_bn(const float *mean, const float *invstd, const float *gamma, const float *beta) { return BnP{mean, invstd, gamma, beta}; }
@@ -578,6 +588,15 @@ extern "C" int istnet_bn_stats(const float *y, long long P, int C, float *part_w
     bn_stats_kernel<<<G, kEwThreads, 0, ST>>>(y, P, C, part_ws);
     ISTNET_LAUNCH_CHECK();
     bn_finalize_kernel<<<ceil_div(C, 32), 256, 0, ST>>>(part_ws, G, P, C, eps, momentum, running_mean, running_var, mean, invstd);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+
+// second stage of a BN-statistics reduction whose per-CTA partials [2][G][C] were produced elsewhere (the conv epilogue)
+extern "C" int istnet_bn_finalize(const float *part, int G, long long P, int C, float eps, float momentum, float *running_mean,
+                                  float *running_var, float *mean, float *invstd, void *stream) {
+    if (G <= 0 || P <= 0 || C <= 0) return ISTNET_ERR_BAD_ARG;
+    bn_finalize_kernel<<<ceil_div(C, 32), 256, 0, ST>>>(part, G, P, C, eps, momentum, running_mean, running_var, mean, invstd);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }

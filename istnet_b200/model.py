@@ -35,8 +35,8 @@ class _Branches:
         self.side = []
         if self.on:
             pool = _Branches._pool.setdefault(device, [])
-            while len(pool) < n:
-                pool.append(torch.cuda.Stream(device))
+            while len(pool) < n:  # stream #2 is the high-priority one (lower number = higher priority)
+                pool.append(torch.cuda.Stream(device, priority=-1 if len(pool) == 2 else 0))
             self.side = pool[:n]
             for st in self.side:
                 st.wait_stream(self.main)
@@ -239,11 +239,12 @@ class IST_Net(nn.Module):
         pts = pts - c
         # everything below works on rows (B,N,C): the layout the GEMM kernels consume; the reference's (B,C,N)
         # tensors appear only at the module boundary (end_points)
-        br = _Branches(pts.device, 2)
+        br = _Branches(pts.device, 3)
+        # the image branch is the critical path: it gets the high-priority stream, the (latency-bound) extractors fill in
+        rgb_local = br.run(2, lambda: self.rgb_cam_extractor.gather_rows(rgb, choose))
         pts_local = br.run(0, lambda: self.pts_cam_extractor.forward_rows(pts))
         if self.training:  # the NOCS-space extractor only depends on the ground-truth coordinates
             gt_feats = br.run(1, lambda: self.world_enhancer.extractor.forward_rows(inputs["qo"]))
-        rgb_local = self.rgb_cam_extractor.gather_rows(rgb, choose)
         br.join()
         # the three pose heads are independent of each other: camera-space enhancer and world-space enhancer on the side
         # streams, implicit space transformation -> main estimator on the main stream

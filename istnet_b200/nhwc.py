@@ -5,6 +5,7 @@ Everything here works on FP32 tensors [B,H,W,C] (or [1,1,rows,C] for point sets)
 pairs; see include/istnet_b200.h §3-§4 for the kernels.  The classes mirror what PyTorch autograd records for the
 reference modules (cuDNN conv fwd/dgrad/wgrad, BN fwd/bwd, ReLU/PReLU, Dropout2d), but as an explicit tape.
 """
+import ctypes
 import os
 
 import torch
@@ -95,6 +96,7 @@ def pick_box(H, W):
     return 8, 8
 
 
+FUSE_BN_STATS = os.environ.get("ISTNET_FUSE_BN_STATS", "1") != "0"
 WGRAD_SIDE_STREAM = os.environ.get("ISTNET_WGRAD_STREAM", "1") != "0"
 _SIDE = {}
 _PENDING_JOINS = []
@@ -108,6 +110,17 @@ def _side_stream(dev):
     return st
 
 
+def side_stream_for(dev, slot):
+    """A per-(current stream, slot) side stream (slot 0 is used by the weight-gradient overlap)."""
+    if dev.type != "cuda":
+        return None
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream, slot)
+    st = _SIDE.get(key)
+    if st is None:
+        st = _SIDE[key] = torch.cuda.Stream(dev)
+    return st
+
+
 def join_side_streams():
     """Makes every stream that forked a weight-gradient side stream wait for it (called once per backward of a tape)."""
     while _PENDING_JOINS:
@@ -115,32 +128,39 @@ def join_side_streams():
         main.wait_stream(side)
 
 
-# bench.py sets PROFILE = [] to time every tensor-core launch with CUDA events on the launching stream:
-# entries are (kernel name, start event, end event, algorithmic FLOPs, nsplit)
+# bench.py sets PROFILE = [] to time every tensor-core launch with CUDA events on the launching stream.  Each profiled
+# call is re-issued PROFILE_REPS times back to back between the two events (the kernels are pure functions of their
+# inputs), so that the measurement is the device-side duration and not the host's launch latency on an idle stream.
+# entries: (kernel name, start event, end event, repetitions, algorithmic FLOPs, nsplit)
 PROFILE = None
+PROFILE_REPS = 3
 
 
-def _prof(name, flops, nsplit):
+def _timed(name, flops, nsplit, launch):
+    launch()
     if PROFILE is None:
-        return None
+        return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    PROFILE.append((name, e0, e1, flops, nsplit))
     e0.record()
-    return e1
+    for _ in range(PROFILE_REPS):
+        launch()
+    e1.record()
+    PROFILE.append((name, e0, e1, PROFILE_REPS, flops, nsplit))
 
 
-def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl=None):
-    """x: Act with operand planes; returns nothing — writes out_f32 [B,H,W,cout] and/or out_pl."""
+def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl=None, stat_part=None):
+    """x: Act with operand planes; writes out_f32 [B,H,W,cout] and/or out_pl.  With stat_part (float buffer of
+    >= 2*296*cout) the epilogue also leaves per-CTA BN-statistics partials there; returns the CTA count G."""
     bw, bh = pick_box(x.H, x.W)
-    ev = _prof("conv_gemm_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, x.pl.shape[0])
-    _C.call(
-        "conv_gemm", ptr(x.pl), c_ll(x.pl.stride(0)), c_int(x.B), c_int(x.H), c_int(x.W), c_int(x.C), c_int(x.cs), ptr(w_pl),
+    grid = ctypes.c_int(0)
+    args = (
+        ptr(x.pl), c_ll(x.pl.stride(0)), c_int(x.B), c_int(x.H), c_int(x.W), c_int(x.C), c_int(x.cs), ptr(w_pl),
         c_ll(w_pl.stride(0)), c_int(cout), c_int(w_pl.shape[-1]), c_int(kh), c_int(kw), c_int(x.pl.shape[0]), _p(bias), c_int(1 if relu else 0),
         _p(out_f32), c_int(out_f32.shape[-1] if out_f32 is not None else 0), *_pl_args(out_pl), c_int(out_pl.shape[-1] if out_pl is not None else 0),
-        c_int(bw), c_int(bh),
+        c_int(bw), c_int(bh), _p(stat_part), ctypes.byref(grid),
     )
-    if ev is not None:
-        ev.record()
+    _timed("conv_gemm_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, x.pl.shape[0], lambda: _C.call("conv_gemm", *args))
+    return grid.value
 
 
 def conv_wgrad(dy_pl, cout, x, kh, kw):
@@ -151,13 +171,11 @@ def conv_wgrad(dy_pl, cout, x, kh, kw):
     ws = torch.empty(ks * kh * kw * cout * x.C, dtype=torch.float32, device=dev)
     gw = torch.empty(cout, x.C, kh, kw, dtype=torch.float32, device=dev)
     bw, bh = (64, 1) if x.H == 1 else (8, 8)
-    ev = _prof("wgrad_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, xpl.shape[0])
-    _C.call(
-        "conv_wgrad", ptr(dy_pl), c_ll(dy_pl.stride(0)), c_int(dy_pl.shape[-1]), ptr(xpl), c_ll(xpl.stride(0)), c_int(x.cs), c_int(xpl.shape[0]),
+    args = (
+        ptr(dy_pl), c_ll(dy_pl.stride(0)), c_int(dy_pl.shape[-1]), ptr(xpl), c_ll(xpl.stride(0)), c_int(x.cs), c_int(xpl.shape[0]),
         c_int(x.B), c_int(x.H), c_int(x.W), c_int(cout), c_int(x.C), c_int(kh), c_int(kw), ptr(ws), c_int(ks), ptr(gw), c_int(bw), c_int(bh),
     )
-    if ev is not None:
-        ev.record()
+    _timed("wgrad_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, xpl.shape[0], lambda: _C.call("conv_wgrad", *args))
     return gw
 
 
@@ -170,17 +188,26 @@ class BnState:
         self.mean, self.invstd, self.gamma, self.beta, self.batch = mean, invstd, gamma, beta, batch
 
 
-def bn_state(bn, y, P, C, training):
-    """Reads momentum / eps / running stats from the nn.BatchNorm2d at call time (BNMomentumScheduler, scheduler.py:277-303)."""
+def bn_uses_batch_stats(bn, training):
+    return bn is not None and training and bn.training  # each BatchNorm module's own flag decides, as in nn.BatchNorm2d.forward
+
+
+def bn_state(bn, y, P, C, training, part=None, G=0):
+    """Reads momentum / eps / running stats from the nn.BatchNorm2d at call time (BNMomentumScheduler, scheduler.py:277-303).
+    `part`/`G`: per-CTA statistics partials already produced by the convolution's epilogue (else a reduction pass over y)."""
     dev = y.device
-    if training and bn.training:  # each BatchNorm module's own flag decides, as in nn.BatchNorm2d.forward
+    if bn_uses_batch_stats(bn, training):
         mean = torch.empty(C, dtype=torch.float32, device=dev)
         invstd = torch.empty(C, dtype=torch.float32, device=dev)
-        ws = torch.empty(_C.lib().istnet_reduce_ws_floats(c_ll(P), C, 2), dtype=torch.float32, device=dev)
         mom = bn.momentum if bn.momentum is not None else 0.1
         track = bn.track_running_stats and bn.running_mean is not None
-        _C.call("bn_stats", ptr(y), c_ll(P), c_int(C), ptr(ws), c_float(bn.eps), c_float(mom), _p(bn.running_mean if track else None),
-                _p(bn.running_var if track else None), ptr(mean), ptr(invstd))
+        if part is not None:
+            _C.call("bn_finalize", ptr(part), c_int(G), c_ll(P), c_int(C), c_float(bn.eps), c_float(mom), _p(bn.running_mean if track else None),
+                    _p(bn.running_var if track else None), ptr(mean), ptr(invstd))
+        else:
+            ws = torch.empty(_C.lib().istnet_reduce_ws_floats(c_ll(P), C, 2), dtype=torch.float32, device=dev)
+            _C.call("bn_stats", ptr(y), c_ll(P), c_int(C), ptr(ws), c_float(bn.eps), c_float(mom), _p(bn.running_mean if track else None),
+                    _p(bn.running_var if track else None), ptr(mean), ptr(invstd))
         if track:
             bn.num_batches_tracked += 1
     else:
@@ -283,8 +310,11 @@ class ConvUnit:
                             "z_hi": out.hi})
             return out, rec
         y = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
-        conv_gemm(xin, wp, C, kk, kk, bias=self.b, out_f32=y)
-        st = bn_state(self.bn, y, P, C, training) if self.bn is not None else None
+        part = None
+        if FUSE_BN_STATS and bn_uses_batch_stats(self.bn, training):
+            part = torch.empty(2 * 296 * C, dtype=torch.float32, device=dev)  # per-CTA partials from the GEMM epilogue
+        G = conv_gemm(xin, wp, C, kk, kk, bias=self.b, out_f32=y, stat_part=part)
+        st = bn_state(self.bn, y, P, C, training, part, G) if self.bn is not None else None
         rec = {"bn": st}
         if record:
             rec.update({"xin": xin, "y": y, "noise": noise, "kk": kk, "P": P, "HW": H * W, "in_shape": (x.B, x.H, x.W, x.C)})
