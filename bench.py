@@ -122,6 +122,52 @@ def cpu_reference_rate(wl, sample_batch, steps, warmup):
     return sample_batch * len(times) / sum(times), cores
 
 
+def gpu_reference_rate(wl, dev, steps=3, warmup=2):
+    """Secondary bar: what the UNMODIFIED reference does on this GPU — its module dataflow (oracle port =
+    the reference's torch ops, verified bit-identical to the reference modules) on cuDNN/cuBLAS with PyTorch defaults (TF32
+    convolutions) + the reference's own CUDA extension compiled from /root/reference (oracle/_ref).  Not parity-grade
+    (TF32 misses the 1e-4 bar); reported for context only.  Returns inst/s or None when oracle/_ref is absent."""
+    import importlib.util
+
+    so = os.path.join(ROOT, "oracle", "_ref", "pointnet2_ref", "_ext.so")
+    if not os.path.exists(so):
+        return None
+    from istnet_b200 import model as M
+    from istnet_b200.synth import make_batch
+    from oracle import istnet_port as port
+
+    spec = importlib.util.spec_from_file_location("_ext", so)
+    ref_ext = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_ext)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = True  # PyTorch default, what the reference runs with
+    try:
+        torch.manual_seed(1)
+        mod = M.IST_Net(6, False) if wl["model"] == "ist_net" else M.PoseNetGT(6)
+        sd = {k: v.clone().to(dev) for k, v in mod.state_dict().items()}
+        for k, v in sd.items():
+            if v.is_floating_point() and "running_" not in k:
+                v.requires_grad_(True)
+        data = {k: v.to(dev) for k, v in make_batch(wl["batch"], wl["npts"], wl["img"], seed=1).items()}
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(warmup + steps):
+            if it == warmup:
+                torch.cuda.synchronize()
+                ev0.record()
+            for v in sd.values():
+                v.grad = None
+            if wl["model"] == "ist_net":
+                loss = port.ist_net_loss(port.ist_net_forward(sd, data, True, ops=ref_ext), data)
+            else:
+                loss = port.posenet_gt_loss(port.posenet_gt_forward(sd, data, True, ops=ref_ext), data)
+            loss.backward()
+        ev1.record()
+        torch.cuda.synchronize()
+        return wl["batch"] * steps / (ev0.elapsed_time(ev1) / 1000.0)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -307,6 +353,13 @@ def main():
             rate, cores = cpu_reference_rate(wl, 2, 2, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "instances/s", "cores": cores, "kind": "port",
                                     "sample": "2 timed steps of fwd+loss+bwd on a batch of 2 (same shapes), oracle port on host threads"}
+            try:
+                g = gpu_reference_rate(wl, dev)
+            except Exception as e:  # context only: never fail the bench on it
+                g = None
+                line["reference_gpu_path_error"] = str(e)[:200]
+            if g is not None:
+                line["reference_gpu_path"] = {"value": g, "unit": "instances/s", "what": "reference dataflow (oracle port) on cuDNN TF32 defaults + the reference's own CUDA extension (oracle/_ref), eager, same GPU; context only, not parity-grade"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
