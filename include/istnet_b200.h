@@ -135,11 +135,13 @@ int istnet_bn_act_split(const float *y, long long P, int C, long long HW, const 
 /* Backward of the unit above (part_ws: istnet_reduce_ws_floats(P, C, 3) floats): g = (dz + dz2) * noise * act'(u);  ws[0:C] = sum g, ws[C:2C] = sum g*xhat, ws[2C:3C] = PReLU
  * slope partials;  dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))  (batch_stats=1; gamma*invstd*g with running
  * statistics, batch_stats=0; g without BN) written as bf16 operand planes and/or FP32;
- * g_out (optional) receives g (the residual branch's gradient).  ReLU masks come from plane 0 (z_hi) of the saved forward output. */
+ * g_out (optional) receives g (the residual branch's gradient).  ReLU masks come from plane 0 (z_hi) of the saved forward output.
+ * act = 3: BN + ReLU + max over `ns` consecutive rows (the last SharedMLP layer of a set-abstraction scale): dz is [P/ns][C]
+ * and is routed to the arg-max row of each group (argmax from istnet_bn_relu_maxrows). */
 int istnet_bn_act_bwd(const float *dz, const float *dz2, const float *y, long long P, int C, long long HW, const float *mean,
                       const float *invstd, const float *gamma, const float *beta, int act, const float *prelu_a, const void *z_hi,
-                      int cs_z, const float *noise, int batch_stats, float *part_ws, double *ws, void *dy_planes, long long plane_stride,
-                      int nsplit, int cs_dy, float *dy_f32, float *g_out, void *stream);
+                      int cs_z, const float *noise, int batch_stats, const uint8_t *argmax, int ns, float *part_ws, double *ws,
+                      void *dy_planes, long long plane_stride, int nsplit, int cs_dy, float *dy_f32, float *g_out, void *stream);
 
 /* FP32 [P][C] (or NCHW with HW pixels per image when nchw != 0) -> bf16 operand planes [nsplit][P][cs] at channel offset ch_off */
 int istnet_split(const float *x, long long P, int C, long long HW, int nchw, void *planes, long long plane_stride, int nsplit, int cs,

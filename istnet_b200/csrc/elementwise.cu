@@ -200,12 +200,23 @@ struct ActBwdP {
     const __nv_bfloat16 *z_hi;  // ReLU mask source (saved forward output), [P,cs_z]
     int cs_z;
     int batch_stats;            // 1: BN used batch statistics (train) -> full backward; 0: running statistics -> dy = gamma*invstd*g
+    const uint8_t *argmax;      // act == 3 (BN + ReLU + max over `ns` consecutive rows): dz is [P/ns][C], routed to the arg-max row
+    int ns;
     const float *noise;
     long long HW;
 };
 // returns g (gradient w.r.t. u = bn(y) [+res]) and xhat; extra = dz*noise*u*[u<=0] (PReLU slope gradient)
 __device__ __forceinline__ void act_bwd4(const ActBwdP &p, long long r, int c, int C, float a, float4 &g, float4 &xh, float4 &extra) {
-    float4 d = ld4(p.dz + r * C + c);
+    float4 d;
+    if (p.act == 3) {  // gradient of the max over the neighbour axis: only the selected row of each group receives dz
+        const long long grp = r / p.ns;
+        const int l = (int)(r % p.ns);
+        const uchar4 am = *reinterpret_cast<const uchar4 *>(p.argmax + grp * C + c);
+        const float4 dg = ld4(p.dz + grp * C + c);
+        d = make_float4(am.x == l ? dg.x : 0.f, am.y == l ? dg.y : 0.f, am.z == l ? dg.z : 0.f, am.w == l ? dg.w : 0.f);
+    } else {
+        d = ld4(p.dz + r * C + c);
+    }
     if (p.dz2) {
         float4 d2 = ld4(p.dz2 + r * C + c);
         d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
@@ -220,7 +231,7 @@ __device__ __forceinline__ void act_bwd4(const ActBwdP &p, long long r, int c, i
     if (p.bn.mean) {
         float4 yv = ld4(p.y + r * C + c), m = ld4(p.bn.mean + c), s = ld4(p.bn.invstd + c);
         xh = make_float4((yv.x - m.x) * s.x, (yv.y - m.y) * s.y, (yv.z - m.z) * s.z, (yv.w - m.w) * s.w);
-        if (p.act == 2) {
+        if (p.act == 2 || p.act == 3) {
             float4 ga = ld4(p.bn.gamma + c), be = ld4(p.bn.beta + c);
             u = make_float4(xh.x * ga.x + be.x, xh.y * ga.y + be.y, xh.z * ga.z + be.z, xh.w * ga.w + be.w);
         }
@@ -230,6 +241,8 @@ __device__ __forceinline__ void act_bwd4(const ActBwdP &p, long long r, int c, i
     if (p.act == 1) {
         float4 z = bf4_to_f4(p.z_hi + r * p.cs_z + c);
         g = make_float4(z.x > 0.f ? d.x : 0.f, z.y > 0.f ? d.y : 0.f, z.z > 0.f ? d.z : 0.f, z.w > 0.f ? d.w : 0.f);
+    } else if (p.act == 3) {
+        g = make_float4(u.x > 0.f ? d.x : 0.f, u.y > 0.f ? d.y : 0.f, u.z > 0.f ? d.z : 0.f, u.w > 0.f ? d.w : 0.f);
     } else if (p.act == 2) {
         g = make_float4(u.x > 0.f ? d.x : a * d.x, u.y > 0.f ? d.y : a * d.y, u.z > 0.f ? d.z : a * d.z, u.w > 0.f ? d.w : a * d.w);
         extra = make_float4(u.x > 0.f ? 0.f : d.x * u.x, u.y > 0.f ? 0.f : d.y * u.y, u.z > 0.f ? 0.f : d.z * u.z, u.w > 0.f ? 0.f : d.w * u.w);
@@ -619,14 +632,17 @@ extern "C" int istnet_bn_act_split(const float *y, long long P, int C, long long
 
 extern "C" int istnet_bn_act_bwd(const float *dz, const float *dz2, const float *y, long long P, int C, long long HW, const float *mean,
                                  const float *invstd, const float *gamma, const float *beta, int act, const float *prelu_a,
-                                 const void *z_hi, int cs_z, const float *noise, int batch_stats, float *part_ws, double *ws /*3C*/,
-                                 void *dy_planes, long long plane_stride, int nsplit, int cs_dy, float *dy_f32, float *g_out, void *stream) {
+                                 const void *z_hi, int cs_z, const float *noise, int batch_stats, const uint8_t *argmax, int ns,
+                                 float *part_ws, double *ws /*3C*/, void *dy_planes, long long plane_stride, int nsplit, int cs_dy,
+                                 float *dy_f32, float *g_out, void *stream) {
     if (P <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
     if (act == 1 && !z_hi) return ISTNET_ERR_BAD_ARG;
+    if (act == 3 && (!argmax || ns <= 0 || !mean || dz2)) return ISTNET_ERR_BAD_ARG;
     ActBwdP p{};
     p.dz = dz; p.dz2 = dz2; p.y = y; p.bn = make_bn(mean, invstd, gamma, beta);
     p.act = act; p.prelu_a = prelu_a; p.z_hi = (const __nv_bfloat16 *)z_hi; p.cs_z = cs_z; p.noise = noise; p.HW = HW > 0 ? HW : 1;
     p.batch_stats = batch_stats;
+    p.argmax = argmax; p.ns = ns;
     const int G = red_grid(P, C);
     bn_bwd_reduce_kernel<<<G, kEwThreads, 0, ST>>>(P, C, p, part_ws);
     ISTNET_LAUNCH_CHECK();

@@ -224,14 +224,14 @@ def bn_act_split(y, P, C, HW, bn=None, res=None, res_bn=None, act=0, prelu=None,
     )
 
 
-def bn_act_bwd(dz, dz2, y, P, C, HW, bn, act, prelu, z_hi, noise, dy_pl=None, dy_f32=None, g_out=None):
+def bn_act_bwd(dz, dz2, y, P, C, HW, bn, act, prelu, z_hi, noise, dy_pl=None, dy_f32=None, g_out=None, argmax=None, ns=0):
     """Returns ws (3*C doubles): [sum g | sum g*xhat | PReLU slope partials]."""
     ws = torch.empty(3 * C, dtype=torch.float64, device=dz.device)
     part = torch.empty(_C.lib().istnet_reduce_ws_floats(c_ll(P), C, 3), dtype=torch.float32, device=dz.device)
     _C.call(
         "bn_act_bwd", ptr(dz), _p(dz2), _p(y), c_ll(P), c_int(C), c_ll(HW), _p(bn.mean if bn else None), _p(bn.invstd if bn else None),
         _p(bn.gamma if bn else None), _p(bn.beta if bn else None), c_int(act), _p(prelu), _p(z_hi), c_int(z_hi.shape[-1] if z_hi is not None else 0),
-        _p(noise), c_int(1 if (bn is not None and bn.batch) else 0), ptr(part), ptr(ws), *_pl_args(dy_pl), c_int(dy_pl.shape[-1] if dy_pl is not None else 0), _p(dy_f32), _p(g_out),
+        _p(noise), c_int(1 if (bn is not None and bn.batch) else 0), _p(argmax), c_int(ns), ptr(part), ptr(ws), *_pl_args(dy_pl), c_int(dy_pl.shape[-1] if dy_pl is not None else 0), _p(dy_f32), _p(g_out),
     )
     return ws
 
@@ -264,7 +264,7 @@ def col2im(dcol, B, H, W, C, k, stride, pad, dx=None):
 
 
 # ----------------------------------------------------------------------------------------- the conv+BN+act unit
-ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_PRELU, ACT_RELU_MAXROWS = 0, 1, 2, 3
 
 
 class ConvUnit:

@@ -117,12 +117,10 @@ class _SAScaleFn(torch.autograd.Function):
         last = units[-1]
         rec = tape[-1]
         Cl = last.cout
-        gsel = torch.empty(1, 1, G * ns, Cl, dtype=torch.float32, device=dz.device)
         st = rec["bn"]
-        _C.call("maxrows_bwd", ptr(rec["y"]), c_ll(G), c_int(ns), c_int(Cl), ptr(st.mean), ptr(st.invstd), ptr(st.gamma), ptr(st.beta), ptr(dz),
-                c_int(Cl), c_int(0), ptr(argmax), ptr(gsel))
         dy = K.empty_planes(1, 1, G * ns, Cl, dz.device, nsplit=K.NSPLIT_BWD)
-        ws = K.bn_act_bwd(gsel, None, rec["y"], G * ns, Cl, 1, st, ACT_NONE, None, None, None, dy_pl=dy)
+        # max-pool routing + ReLU mask + BN backward in one reduce / apply pair (no materialised [rows, C] selection tensor)
+        ws = K.bn_act_bwd(dz, None, rec["y"], G * ns, Cl, 1, st, K.ACT_RELU_MAXROWS, None, None, None, dy_pl=dy, argmax=argmax, ns=ns)
         wsf = ws.float()
         grads[id(last.bn.weight)], grads[id(last.bn.bias)] = wsf[Cl : 2 * Cl], wsf[0:Cl]
         d = last.data_grads(rec, dy, True, grads)
