@@ -313,13 +313,19 @@ def main():
     torch.cuda.synchronize()
     prof, nhwc.PROFILE = nhwc.PROFILE, None
     kstat = {}
-    for name, e0, e1, reps, fl, ns in prof:
+    table = []
+    for name, e0, e1, reps, fl, ns, desc in prof:
         d = kstat.setdefault(name, {"ms": 0.0, "flop": 0.0, "mma_flop": 0.0, "n": 0})
+        table.append((e0.elapsed_time(e1) / reps, name, ns, fl, desc))
         d["ms"] += e0.elapsed_time(e1) / reps
         d["flop"] += fl
         d["mma_flop"] += fl * (ns * (ns + 1) // 2)
         d["n"] += 1
 
+    if rank == 0 and os.environ.get("ISTNET_KERNEL_TABLE"):  # per-launch table of the tensor-core kernels (tools / profiles)
+        with open(os.environ["ISTNET_KERNEL_TABLE"], "w") as f:
+            for ms_, name, ns, fl, desc in table:
+                f.write(f"{ms_ * 1000:9.1f} us  {name:22s} ns={ns}  {fl * (ns * (ns + 1) // 2) / (ms_ * 1e-3) / 1e12:7.1f} MMA-TFLOP/s  {desc}\n")
     if rank == 0:
         pk, pk_src = peaks()
         gflop = flops_per_instance(wl["model"], wl["npts"], True)

@@ -151,6 +151,10 @@ int istnet_split(const float *x, long long P, int C, long long HW, int nchw, voi
  *   im2col=1: the strided-conv form, one tap with K = (r*kw+s)*Cin + ci  ([Cout][cs] or, transposed, [K][cs]). */
 int istnet_prep_weight(const float *w, int Cout, int Cin, int kh, int kw, int transpose, int im2col, void *planes, long long plane_stride,
                        int nsplit, int cs, void *stream);
+/* Timeline marker: one thread stores %globaltimer (ns) into stamps[slot] in stream order.  A node like any other inside a
+ * captured CUDA graph, so phase boundaries of the real (graph-replayed, multi-stream) step can be read back (tools/timeline.py);
+ * the reference has no counterpart (its solver times whole iterations with time.time(), utils/solver.py:153). */
+int istnet_marker(unsigned long long *stamps, int slot, void *stream);
 /* ws[c] = sum_p x[p][c] (double; bias gradients) */
 int istnet_colsum(const float *x, long long P, int C, double *ws, void *stream);
 

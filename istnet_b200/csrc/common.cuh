@@ -56,15 +56,34 @@ __device__ __forceinline__ void store_planes1(__nv_bfloat16 *base, long long pla
     for (int i = 0; i < kMaxPlanes; ++i)
         if (i < n) base[i * plane_stride] = __ushort_as_bfloat16(o[i]);
 }
+// two values at once: one packed round-to-nearest conversion per plane (F2FP.BF16.F32.PACK_AB), the packed word is the
+// store payload and, shifted / masked back to FP32, the subtrahend of the residual — same bits as split_planes
+__device__ __forceinline__ void split_planes_pair(float a, float b, uint32_t (&out)[kMaxPlanes], int n) {
+    float ra = a, rb = b;
+#pragma unroll
+    for (int i = 0; i < kMaxPlanes; ++i) {
+        if (i < n) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(ra, rb);  // .x (low half) = ra, .y (high half) = rb
+            const uint32_t pk = *reinterpret_cast<const uint32_t *>(&h);
+            out[i] = pk;
+            ra -= __uint_as_float(pk << 16);
+            rb -= __uint_as_float(pk & 0xffff0000u);
+        }
+    }
+}
 __device__ __forceinline__ void store_planes4(__nv_bfloat16 *base, long long plane_stride, int n, float4 v) {
-    unsigned short a[kMaxPlanes], b[kMaxPlanes], c[kMaxPlanes], d[kMaxPlanes];
-    split_planes(v.x, a, n); split_planes(v.y, b, n); split_planes(v.z, c, n); split_planes(v.w, d, n);
+    uint32_t lo[kMaxPlanes], hi[kMaxPlanes];
+    split_planes_pair(v.x, v.y, lo, n); split_planes_pair(v.z, v.w, hi, n);
 #pragma unroll
     for (int i = 0; i < kMaxPlanes; ++i)
-        if (i < n) {
-            uint2 p;
-            p.x = (uint32_t)a[i] | ((uint32_t)b[i] << 16);
-            p.y = (uint32_t)c[i] | ((uint32_t)d[i] << 16);
-            *reinterpret_cast<uint2 *>(base + i * plane_stride) = p;
-        }
+        if (i < n) *reinterpret_cast<uint2 *>(base + i * plane_stride) = make_uint2(lo[i], hi[i]);
+}
+// 8 consecutive channels -> one 16-byte store per plane (base 16-byte aligned, plane_stride % 8 == 0)
+__device__ __forceinline__ void store_planes8(__nv_bfloat16 *base, long long plane_stride, int n, const float (&v)[8]) {
+    uint32_t a[kMaxPlanes], b[kMaxPlanes], c[kMaxPlanes], d[kMaxPlanes];
+    split_planes_pair(v[0], v[1], a, n); split_planes_pair(v[2], v[3], b, n);
+    split_planes_pair(v[4], v[5], c, n); split_planes_pair(v[6], v[7], d, n);
+#pragma unroll
+    for (int i = 0; i < kMaxPlanes; ++i)
+        if (i < n) *reinterpret_cast<uint4 *>(base + i * plane_stride) = make_uint4(a[i], b[i], c[i], d[i]);
 }

@@ -23,7 +23,8 @@
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;      // 2 + 4 epilogue warps: tiles narrow enough for two CTAs per SM
+constexpr int kThreadsWide = 320;  // 2 + 8 epilogue warps: one CTA per SM
 
 struct ConvGemmParams {
     int B, H, W;              // output (= input) extent
@@ -48,7 +49,7 @@ struct ConvGemmParams {
     uint32_t tmem_cols;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsWide, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const ConvGemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -76,12 +77,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { tc::mbar_init(&tmem_full_bar[s], 1); tc::mbar_init(&tmem_empty_bar[s], 4); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&tmem_full_bar[s], 1); tc::mbar_init(&tmem_empty_bar[s], (blockDim.x >> 5) - 2); }
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc(tmem_holder, p.tmem_cols);
     if (p.stat_part)
-        for (int i = threadIdx.x; i < 8 * p.Cout; i += kThreads) s_stat[i] = 0.f;
+        for (int i = threadIdx.x; i < 8 * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -157,12 +158,21 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2 .. 2+n_epi-1) =====================
+        // A warp may only read the TMEM lane quarter (warp % 4).  With 8 epilogue warps (one CTA per SM) two warps share a
+        // quarter and take alternate 32-column chunks: the epilogue is a dependent ALU chain (bias, ReLU, operand split),
+        // so its speed is set by how many warps each scheduler can interleave (measured with ONE warp per scheduler:
+        // 92k cycles per 128x256 tile against a 34k-cycle main loop at K = 512, profiles/r1_rowsgemm_epilogue_before.txt).
+        const int groups = ((int)(blockDim.x >> 5) - 2) >> 2;  // warps per lane quarter: 1 or 2
+        const int grp = (warp - 2) >> 2;
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
         const int pb = row / (p.box_w * p.box_h);
         const int ph_ = (row / p.box_w) % p.box_h;
         const int pw = row % p.box_w;
+        const bool pl_vec8 = p.out_pl && ((p.out_pl_stride & 7) == 0) && ((p.split_cs & 7) == 0) &&
+                             ((reinterpret_cast<uintptr_t>(p.out_pl) & 15) == 0);
+        const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
         int lt = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
             int mt = tile % m_tiles;
@@ -176,25 +186,38 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             tc::mbar_wait(&tmem_full_bar[buf], (uint32_t)(lt >> 1) & 1);
             tc::tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(buf * p.acc_stride) + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            for (int c0 = grp * 32; c0 < p.BN; c0 += 32 * groups) {
+                const int n = n0 + c0;
+                if (n >= p.Cout) break;  // warp-uniform
                 uint32_t v[32];
                 tc::tmem_ld_32x32(tacc + (uint32_t)c0, v);
                 tc::tmem_ld_wait();
-                const int n = n0 + c0;
-                if (n >= p.Cout) continue;  // warp-uniform
+                const int valid = min(32, p.Cout - n);
                 float f[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float x = __uint_as_float(v[i]);
-                    if (p.bias != nullptr && n + i < p.Cout) x += __ldg(p.bias + n + i);
-                    if (p.relu) x = fmaxf(x, 0.f);
-                    f[i] = x;
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                if (p.bias != nullptr) {
+                    if (valid == 32 && bias_vec) {  // n is a multiple of 32: 16-byte aligned, uniform (broadcast) loads
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + n + i));
+                            f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < valid) f[i] += __ldg(p.bias + n + i);
+                    }
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
                 }
                 if (p.stat_part) {
                     // BatchNorm statistics of this 32-row x 32-column block: butterfly transpose-reduce over the warp
-                    // (31 shuffles per quantity), lane l ends with the column (c0 + l) totals and adds them to this WARP's
-                    // private shared-memory slot (no atomics: fixed summation order, bitwise reproducible); the CTA
-                    // flushes the sum of its four slots once, after its last tile
+                    // (31 shuffles per quantity), lane l ends with the column (c0 + l) totals and adds them to this lane
+                    // QUARTER's shared-memory slot (warps of one quarter own disjoint columns; no atomics: fixed summation
+                    // order, bitwise reproducible); the CTA flushes the sum of its four slots once, after its last tile
                     float a[32], q2[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) { a[i] = row_ok ? f[i] : 0.f; q2[i] = a[i] * a[i]; }
@@ -216,27 +239,36 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     }
                 }
                 if (!row_ok) continue;
-                const int valid = min(32, p.Cout - n);
                 if (p.out_f32) {
                     float *o = p.out_f32 + pix * p.out_cs + n;
                     if (valid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
                     } else {
-                        for (int i = 0; i < valid; ++i) o[i] = f[i];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)  // predicated, fully unrolled: a dynamic index would put f[] in local memory
+                            if (i < valid) o[i] = f[i];
                     }
                 }
                 if (p.out_pl) {
                     __nv_bfloat16 *o = p.out_pl + pix * p.split_cs + n;
-                    if (valid == 32 && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
+                    if (valid == 32 && pl_vec8) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            const float g8[8] = {f[i], f[i + 1], f[i + 2], f[i + 3], f[i + 4], f[i + 5], f[i + 6], f[i + 7]};
+                            store_planes8(o + i, p.out_pl_stride, p.nsplit_out, g8);
+                        }
+                    } else if (valid == 32 && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) store_planes4(o + i, p.out_pl_stride, p.nsplit_out, make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]));
                     } else {
-                        for (int i = 0; i < valid; ++i) store_planes1(o + i, p.out_pl_stride, p.nsplit_out, f[i]);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < valid) store_planes1(o + i, p.out_pl_stride, p.nsplit_out, f[i]);
                     }
                 }
             }
-            // this warp is done reading the accumulator: hand it back to the MMA issuer (4 arrivals, one per warp)
+            // this warp is done reading the accumulator: hand it back to the MMA issuer (one arrival per epilogue warp)
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[buf]);
@@ -244,7 +276,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     __syncthreads();
     if (p.stat_part)
-        for (int i = threadIdx.x; i < 2 * p.Cout; i += kThreads) {
+        for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) {
             // layout expected by the finalize kernel: part[(a*G + g)*C + c]
             const int a = i / p.Cout, c = i % p.Cout;
             const float tot = ((s_stat[(0 * 2 + a) * p.Cout + c] + s_stat[(1 * 2 + a) * p.Cout + c]) + s_stat[(2 * 2 + a) * p.Cout + c]) +
@@ -375,7 +407,9 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     long long grid_x = (long long)kNumSMs * ctas_per_sm;
     if (grid_x > n_tiles) grid_x = n_tiles;
     if (grid_out) *grid_out = (int)grid_x;
-    conv_gemm_tc_kernel<<<(unsigned)grid_x, kThreads, smem, (cudaStream_t)stream>>>(ta, tb, p);
+    int threads = ctas_per_sm >= 2 ? kThreads : kThreadsWide;
+    threads = env_int("ISTNET_CG_THREADS", threads);
+    conv_gemm_tc_kernel<<<(unsigned)grid_x, threads, smem, (cudaStream_t)stream>>>(ta, tb, p);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }

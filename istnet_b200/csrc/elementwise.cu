@@ -36,15 +36,32 @@ __device__ __forceinline__ float4 bn4(float4 y, const BnP &b, int c) {
 
 // ------------------------------------------------------------------ per-channel reductions
 // Each thread owns 4 channels (float4) of rows r = row0 + i*rows_per_iter; partial sums are combined through shared
-// memory and flushed with double atomics (one per channel per CTA).
-// Each thread owns 4 channels (float4) of rows r = row0 + i*rows_per_iter; partial sums are combined through shared
 // memory.  ATOMIC = true: flushed with double atomics into ws[a*C + c] (ws pre-zeroed).  ATOMIC = false: every CTA
 // writes its FP32 partial to part[(a*gridDim.x + blockIdx.x)*C + c]; a finalize kernel sums the partials in a fixed
 // order — no atomics (hundreds of CTAs hammering a few dozen addresses cost ~25 us per call), no memset, deterministic.
+// Cross-thread part of a column reduction for lanes <= kEwThreads: thread (rr, cv) holds the partial sums of 4 channels
+// over its rows; the `rows_per_iter` row groups are combined through shared memory in a fixed order.
+template <int NACC, bool ATOMIC>
+__device__ __forceinline__ void column_flush(float (&acc)[NACC][4], int lanes, int rows_per_iter, bool active, int C, double *ws, float *part) {
+    __shared__ float red[kEwThreads * 4];
+    for (int a = 0; a < NACC; ++a) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) red[threadIdx.x * 4 + k] = active ? acc[a][k] : 0.f;
+        __syncthreads();
+        if (threadIdx.x < lanes) {
+            for (int k = 0; k < 4; ++k) {
+                float s = 0.f;
+                for (int q = 0; q < rows_per_iter; ++q) s += red[(q * lanes + threadIdx.x) * 4 + k];
+                if (ATOMIC) atomicAdd(ws + (size_t)a * C + threadIdx.x * 4 + k, (double)s);
+                else part[((size_t)a * gridDim.x + blockIdx.x) * C + threadIdx.x * 4 + k] = s;
+            }
+        }
+    }
+}
 template <int NACC, bool ATOMIC, typename F>
 __device__ void column_reduce(long long P, int C, double *ws, float *part, F row_fn) {
     const int lanes = C >> 2;  // float4 lanes per row
-    __shared__ float red[kEwThreads * 4];
     float acc[NACC][4];
 #pragma unroll
     for (int a = 0; a < NACC; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
@@ -54,20 +71,7 @@ __device__ void column_reduce(long long P, int C, double *ws, float *part, F row
         if (rr < rows_per_iter) {
             for (long long r = (long long)blockIdx.x * rows_per_iter + rr; r < P; r += (long long)gridDim.x * rows_per_iter) row_fn(r, cv * 4, acc);
         }
-        for (int a = 0; a < NACC; ++a) {
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < 4; ++k) red[threadIdx.x * 4 + k] = (rr < rows_per_iter) ? acc[a][k] : 0.f;
-            __syncthreads();
-            if (threadIdx.x < lanes) {
-                for (int k = 0; k < 4; ++k) {
-                    float s = 0.f;
-                    for (int q = 0; q < rows_per_iter; ++q) s += red[(q * lanes + threadIdx.x) * 4 + k];
-                    if (ATOMIC) atomicAdd(ws + (size_t)a * C + threadIdx.x * 4 + k, (double)s);
-                    else part[((size_t)a * gridDim.x + blockIdx.x) * C + threadIdx.x * 4 + k] = s;
-                }
-            }
-        }
+        column_flush<NACC, ATOMIC>(acc, lanes, rows_per_iter, rr < rows_per_iter, C, ws, part);
     } else {
         for (int cv = threadIdx.x; cv < lanes; cv += kEwThreads) {
 #pragma unroll
@@ -148,6 +152,18 @@ __global__ void __launch_bounds__(256) bwd_finalize_kernel(const float *__restri
     ws[2 * C + c] = t[2];
 }
 
+// Per-thread channel constants: with lanes = C/4 dividing the CTA, a thread keeps the same 4 channels for every row it
+// visits, so the BatchNorm parameters live in registers and the row loop contains no division.
+struct Chan4 {
+    float4 m, s, ga, be;
+};
+__device__ __forceinline__ Chan4 load_chan(const BnP &b, int c) {
+    Chan4 ch;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    ch.m = z; ch.s = z; ch.ga = z; ch.be = z;
+    if (b.mean) { ch.m = ld4(b.mean + c); ch.s = ld4(b.invstd + c); ch.ga = ld4(b.gamma + c); ch.be = ld4(b.beta + c); }
+    return ch;
+}
 // ------------------------------------------------------------------ forward: BN + residual + act + noise + split
 struct ActFwdP {
     const float *y;         // [P,C]
@@ -168,25 +184,62 @@ __device__ __forceinline__ float4 act_fwd4(float4 u, int act, float a) {
     if (act == 2) return make_float4(u.x > 0.f ? u.x : a * u.x, u.y > 0.f ? u.y : a * u.y, u.z > 0.f ? u.z : a * u.z, u.w > 0.f ? u.w : a * u.w);
     return u;
 }
-__global__ void __launch_bounds__(kEwThreads) bn_act_split_kernel(long long P, int C, ActFwdP p) {
+__device__ __forceinline__ void act_fwd_store(const ActFwdP &p, long long r, int c, int C, float a, float4 u, bool has_res, float4 rv, bool has_nz,
+                                              float4 nz) {
+    if (has_res) { u.x += rv.x; u.y += rv.y; u.z += rv.z; u.w += rv.w; }
+    float4 z = act_fwd4(u, p.act, a);
+    if (has_nz) { z.x *= nz.x; z.y *= nz.y; z.z *= nz.z; z.w *= nz.w; }
+    if (p.out_f32) *reinterpret_cast<float4 *>(p.out_f32 + r * C + c) = z;
+    if (p.out_pl) store_planes4(p.out_pl + r * p.cs + p.ch_off + c, p.pl_stride, p.nsplit, z);
+}
+constexpr int kFwdUnroll = 4;
+__global__ void __launch_bounds__(kEwThreads, 2) bn_act_split_kernel(long long P, int C, ActFwdP p) {
     const int lanes = C >> 2;
-    const long long total = P * lanes;
     const float a = (p.act == 2) ? *p.prelu_a : 0.f;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / lanes;
-        const int c = (int)(i % lanes) * 4;
-        float4 u = bn4(ld4(p.y + r * C + c), p.bn, c);
-        if (p.res) {
-            float4 rv = bn4(ld4(p.res + r * C + c), p.res_bn, c);
-            u.x += rv.x; u.y += rv.y; u.z += rv.z; u.w += rv.w;
+    if (lanes > kEwThreads || kEwThreads % lanes != 0) {  // generic flat (row, lane) loop
+        const long long total = P * lanes;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const long long r = i / lanes;
+            const int c = (int)(i % lanes) * 4;
+            const float4 u = bn4(ld4(p.y + r * C + c), p.bn, c);
+            float4 rv = u, nz = u;
+            if (p.res) rv = bn4(ld4(p.res + r * C + c), p.res_bn, c);
+            if (p.noise) nz = ld4(p.noise + (r / p.HW) * C + c);
+            act_fwd_store(p, r, c, C, a, u, p.res != nullptr, rv, p.noise != nullptr, nz);
         }
-        float4 z = act_fwd4(u, p.act, a);
-        if (p.noise) {
-            float4 nz = ld4(p.noise + (r / p.HW) * C + c);
-            z.x *= nz.x; z.y *= nz.y; z.z *= nz.z; z.w *= nz.w;
+        return;
+    }
+    // lanes divides the CTA: a thread keeps its 4 channels, BatchNorm parameters stay in registers, kFwdUnroll rows in flight
+    const int rows_per_iter = kEwThreads / lanes;
+    const int c = (threadIdx.x % lanes) * 4, rr = threadIdx.x / lanes;
+    const Chan4 ch = load_chan(p.bn, c), rch = load_chan(p.res_bn, c);
+    const long long stride = (long long)gridDim.x * rows_per_iter;
+    for (long long r0 = (long long)blockIdx.x * rows_per_iter + rr; r0 < P; r0 += stride * kFwdUnroll) {
+        float4 yv[kFwdUnroll], rv[kFwdUnroll], nz[kFwdUnroll];
+#pragma unroll
+        for (int u = 0; u < kFwdUnroll; ++u) {
+            const long long r = r0 + u * stride;
+            if (r < P) {
+                yv[u] = ld4(p.y + r * C + c);
+                if (p.res) rv[u] = ld4(p.res + r * C + c);
+                if (p.noise) nz[u] = ld4(p.noise + (r / p.HW) * C + c);
+            }
         }
-        if (p.out_f32) *reinterpret_cast<float4 *>(p.out_f32 + r * C + c) = z;
-        if (p.out_pl) store_planes4(p.out_pl + r * p.cs + p.ch_off + c, p.pl_stride, p.nsplit, z);
+#pragma unroll
+        for (int u = 0; u < kFwdUnroll; ++u) {
+            const long long r = r0 + u * stride;
+            if (r < P) {
+                float4 v = yv[u], q = rv[u];
+                // same operation order as ATen's batch_norm transform: (x - mean) * invstd * weight + bias
+                if (p.bn.mean)
+                    v = make_float4((v.x - ch.m.x) * ch.s.x * ch.ga.x + ch.be.x, (v.y - ch.m.y) * ch.s.y * ch.ga.y + ch.be.y,
+                                    (v.z - ch.m.z) * ch.s.z * ch.ga.z + ch.be.z, (v.w - ch.m.w) * ch.s.w * ch.ga.w + ch.be.w);
+                if (p.res && p.res_bn.mean)
+                    q = make_float4((q.x - rch.m.x) * rch.s.x * rch.ga.x + rch.be.x, (q.y - rch.m.y) * rch.s.y * rch.ga.y + rch.be.y,
+                                    (q.z - rch.m.z) * rch.s.z * rch.ga.z + rch.be.z, (q.w - rch.m.w) * rch.s.w * rch.ga.w + rch.be.w);
+                act_fwd_store(p, r, c, C, a, v, p.res != nullptr, q, p.noise != nullptr, nz[u]);
+            }
+        }
     }
 }
 
@@ -205,41 +258,50 @@ struct ActBwdP {
     const float *noise;
     long long HW;
 };
-// returns g (gradient w.r.t. u = bn(y) [+res]) and xhat; extra = dz*noise*u*[u<=0] (PReLU slope gradient)
-__device__ __forceinline__ void act_bwd4(const ActBwdP &p, long long r, int c, int C, float a, float4 &g, float4 &xh, float4 &extra) {
-    float4 d;
+// The raw operands of one (row, 4-channel) element of the backward pass.  Loading (bwd_load) is separated from the
+// arithmetic (bwd_finish) so that an unrolled row loop issues all its 16-byte loads before the first use.
+struct RowIn {
+    float4 d, y;
+    uint2 zh;
+};
+__device__ __forceinline__ void bwd_load(const ActBwdP &p, long long r, int c, int C, RowIn &in) {
     if (p.act == 3) {  // gradient of the max over the neighbour axis: only the selected row of each group receives dz
-        const long long grp = r / p.ns;
-        const int l = (int)(r % p.ns);
-        const uchar4 am = *reinterpret_cast<const uchar4 *>(p.argmax + grp * C + c);
-        const float4 dg = ld4(p.dz + grp * C + c);
-        d = make_float4(am.x == l ? dg.x : 0.f, am.y == l ? dg.y : 0.f, am.z == l ? dg.z : 0.f, am.w == l ? dg.w : 0.f);
+        const unsigned grp = (unsigned)r / (unsigned)p.ns;  // rows < 2^31 (checked by the launcher)
+        const int l = (int)((unsigned)r - grp * (unsigned)p.ns);
+        const uchar4 am = *reinterpret_cast<const uchar4 *>(p.argmax + (size_t)grp * C + c);
+        const float4 dg = ld4(p.dz + (size_t)grp * C + c);
+        in.d = make_float4(am.x == l ? dg.x : 0.f, am.y == l ? dg.y : 0.f, am.z == l ? dg.z : 0.f, am.w == l ? dg.w : 0.f);
     } else {
-        d = ld4(p.dz + r * C + c);
+        in.d = ld4(p.dz + r * C + c);
     }
     if (p.dz2) {
-        float4 d2 = ld4(p.dz2 + r * C + c);
-        d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
+        const float4 d2 = ld4(p.dz2 + r * C + c);
+        in.d.x += d2.x; in.d.y += d2.y; in.d.z += d2.z; in.d.w += d2.w;
     }
     if (p.noise) {
-        float4 nz = ld4(p.noise + (r / p.HW) * C + c);
-        d.x *= nz.x; d.y *= nz.y; d.z *= nz.z; d.w *= nz.w;
+        const float4 nz = ld4(p.noise + (size_t)((unsigned)r / (unsigned)p.HW) * C + c);
+        in.d.x *= nz.x; in.d.y *= nz.y; in.d.z *= nz.z; in.d.w *= nz.w;
     }
+    if (p.bn.mean || p.act == 2) in.y = ld4(p.y + r * C + c);
+    if (p.act == 1) in.zh = *reinterpret_cast<const uint2 *>(p.z_hi + r * p.cs_z + c);
+}
+// returns g (gradient w.r.t. u = bn(y) [+res]) and xhat; extra = dz*noise*u*[u<=0] (PReLU slope gradient)
+__device__ __forceinline__ void bwd_finish(const ActBwdP &p, const Chan4 &ch, float a, const RowIn &in, float4 &g, float4 &xh, float4 &extra) {
+    const float4 d = in.d;
     xh = make_float4(0.f, 0.f, 0.f, 0.f);
     extra = xh;
     float4 u = xh;
     if (p.bn.mean) {
-        float4 yv = ld4(p.y + r * C + c), m = ld4(p.bn.mean + c), s = ld4(p.bn.invstd + c);
-        xh = make_float4((yv.x - m.x) * s.x, (yv.y - m.y) * s.y, (yv.z - m.z) * s.z, (yv.w - m.w) * s.w);
-        if (p.act == 2 || p.act == 3) {
-            float4 ga = ld4(p.bn.gamma + c), be = ld4(p.bn.beta + c);
-            u = make_float4(xh.x * ga.x + be.x, xh.y * ga.y + be.y, xh.z * ga.z + be.z, xh.w * ga.w + be.w);
-        }
+        const float4 yv = in.y;
+        xh = make_float4((yv.x - ch.m.x) * ch.s.x, (yv.y - ch.m.y) * ch.s.y, (yv.z - ch.m.z) * ch.s.z, (yv.w - ch.m.w) * ch.s.w);
+        if (p.act == 2 || p.act == 3)
+            u = make_float4(xh.x * ch.ga.x + ch.be.x, xh.y * ch.ga.y + ch.be.y, xh.z * ch.ga.z + ch.be.z, xh.w * ch.ga.w + ch.be.w);
     } else if (p.act == 2) {
-        u = ld4(p.y + r * C + c);
+        u = in.y;
     }
     if (p.act == 1) {
-        float4 z = bf4_to_f4(p.z_hi + r * p.cs_z + c);
+        const float4 z = make_float4(__uint_as_float(in.zh.x << 16), __uint_as_float(in.zh.x & 0xffff0000u), __uint_as_float(in.zh.y << 16),
+                                     __uint_as_float(in.zh.y & 0xffff0000u));
         g = make_float4(z.x > 0.f ? d.x : 0.f, z.y > 0.f ? d.y : 0.f, z.z > 0.f ? d.z : 0.f, z.w > 0.f ? d.w : 0.f);
     } else if (p.act == 3) {
         g = make_float4(u.x > 0.f ? d.x : 0.f, u.y > 0.f ? d.y : 0.f, u.z > 0.f ? d.z : 0.f, u.w > 0.f ? d.w : 0.f);
@@ -250,45 +312,114 @@ __device__ __forceinline__ void act_bwd4(const ActBwdP &p, long long r, int c, i
         g = d;
     }
 }
+__device__ __forceinline__ void act_bwd4(const ActBwdP &p, long long r, int c, int C, float a, float4 &g, float4 &xh, float4 &extra) {
+    RowIn in;
+    bwd_load(p, r, c, C, in);
+    bwd_finish(p, load_chan(p.bn, c), a, in, g, xh, extra);
+}
+constexpr int kBwdUnroll = 4;  // rows in flight per thread: 4 x (2..3) independent 16-byte loads
 // ws[0:C] = sum g, ws[C:2C] = sum g*xhat, ws[2C:3C] = PReLU slope partial
-__global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(long long P, int C, ActBwdP p, float *part) {
+__global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_reduce_kernel(long long P, int C, ActBwdP p, float *part) {
     const float a = (p.act == 2) ? *p.prelu_a : 0.f;
-    column_reduce<3, false>(P, C, nullptr, part, [&](long long r, int c, float (*acc)[4]) {
-        float4 g, xh, ex;
-        act_bwd4(p, r, c, C, a, g, xh, ex);
-        acc[0][0] += g.x; acc[0][1] += g.y; acc[0][2] += g.z; acc[0][3] += g.w;
-        acc[1][0] += g.x * xh.x; acc[1][1] += g.y * xh.y; acc[1][2] += g.z * xh.z; acc[1][3] += g.w * xh.w;
-        acc[2][0] += ex.x; acc[2][1] += ex.y; acc[2][2] += ex.z; acc[2][3] += ex.w;
-    });
+    const int lanes = C >> 2;
+    if (lanes > kEwThreads) {  // very wide rows: generic path
+        column_reduce<3, false>(P, C, nullptr, part, [&](long long r, int c, float (*acc)[4]) {
+            float4 g, xh, ex;
+            act_bwd4(p, r, c, C, a, g, xh, ex);
+            acc[0][0] += g.x; acc[0][1] += g.y; acc[0][2] += g.z; acc[0][3] += g.w;
+            acc[1][0] += g.x * xh.x; acc[1][1] += g.y * xh.y; acc[1][2] += g.z * xh.z; acc[1][3] += g.w * xh.w;
+            acc[2][0] += ex.x; acc[2][1] += ex.y; acc[2][2] += ex.z; acc[2][3] += ex.w;
+        });
+        return;
+    }
+    float acc[3][4];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+    const int rows_per_iter = kEwThreads / lanes;
+    const int cv = threadIdx.x % lanes, rr = threadIdx.x / lanes;
+    if (rr < rows_per_iter) {
+        const int c = cv * 4;
+        const Chan4 ch = load_chan(p.bn, c);
+        const long long stride = (long long)gridDim.x * rows_per_iter;
+        for (long long r0 = (long long)blockIdx.x * rows_per_iter + rr; r0 < P; r0 += stride * kBwdUnroll) {
+            RowIn in[kBwdUnroll];
+#pragma unroll
+            for (int u = 0; u < kBwdUnroll; ++u)
+                if (r0 + u * stride < P) bwd_load(p, r0 + u * stride, c, C, in[u]);
+#pragma unroll
+            for (int u = 0; u < kBwdUnroll; ++u)
+                if (r0 + u * stride < P) {
+                    float4 g, xh, ex;
+                    bwd_finish(p, ch, a, in[u], g, xh, ex);
+                    acc[0][0] += g.x; acc[0][1] += g.y; acc[0][2] += g.z; acc[0][3] += g.w;
+                    acc[1][0] += g.x * xh.x; acc[1][1] += g.y * xh.y; acc[1][2] += g.z * xh.z; acc[1][3] += g.w * xh.w;
+                    acc[2][0] += ex.x; acc[2][1] += ex.y; acc[2][2] += ex.z; acc[2][3] += ex.w;
+                }
+        }
+    }
+    column_flush<3, false>(acc, lanes, rows_per_iter, rr < rows_per_iter, C, nullptr, part);
 }
 // dy = gamma*invstd*(g - sum_g/P - xhat*sum_gx/P)  (BN)   or   dy = g   (no BN);  dy -> bf16 pair (+ optional FP32 copies)
-__global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(long long P, int C, ActBwdP p, const double *__restrict__ ws,
-                                                                  __nv_bfloat16 *dy_pl, long long pl_stride, int nsplit, int cs_dy,
-                                                                  float *dy_f32, float *g_out) {
-    const int lanes = C >> 2;
-    const long long total = P * lanes;
-    const float a = (p.act == 2) ? *p.prelu_a : 0.f;
+__device__ __forceinline__ void bwd_apply_store(const ActBwdP &p, const Chan4 &ch, float a, const RowIn &in, const float (&mg)[4],
+                                                const float (&mgx)[4], long long r, int c, int C, __nv_bfloat16 *dy_pl, long long pl_stride,
+                                                int nsplit, int cs_dy, float *dy_f32, float *g_out) {
+    float4 g, xh, ex;
+    bwd_finish(p, ch, a, in, g, xh, ex);
+    if (g_out) *reinterpret_cast<float4 *>(g_out + r * C + c) = g;
+    float4 dy = g;
+    if (p.bn.mean) {
+        dy.x = ch.ga.x * ch.s.x * (g.x - mg[0] - xh.x * mgx[0]);
+        dy.y = ch.ga.y * ch.s.y * (g.y - mg[1] - xh.y * mgx[1]);
+        dy.z = ch.ga.z * ch.s.z * (g.z - mg[2] - xh.z * mgx[2]);
+        dy.w = ch.ga.w * ch.s.w * (g.w - mg[3] - xh.w * mgx[3]);
+    }
+    if (dy_pl) store_planes4(dy_pl + r * cs_dy + c, pl_stride, nsplit, dy);
+    if (dy_f32) *reinterpret_cast<float4 *>(dy_f32 + r * C + c) = dy;
+}
+__device__ __forceinline__ void bwd_apply_consts(const ActBwdP &p, const double *__restrict__ ws, long long P, int C, int c, float (&mg)[4],
+                                                 float (&mgx)[4]) {
     const double invP = 1.0 / (double)P;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / lanes;
-        const int c = (int)(i % lanes) * 4;
-        float4 g, xh, ex;
-        act_bwd4(p, r, c, C, a, g, xh, ex);
-        if (g_out) *reinterpret_cast<float4 *>(g_out + r * C + c) = g;
-        float4 dy = g;
-        if (p.bn.mean) {
-            float4 s = ld4(p.bn.invstd + c), ga = ld4(p.bn.gamma + c);
-            float mg[4], mgx[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { mg[k] = (float)(ws[c + k] * invP); mgx[k] = (float)(ws[C + c + k] * invP); }
-            if (!p.batch_stats) { mg[0] = mg[1] = mg[2] = mg[3] = 0.f; mgx[0] = mgx[1] = mgx[2] = mgx[3] = 0.f; }
-            dy.x = ga.x * s.x * (g.x - mg[0] - xh.x * mgx[0]);
-            dy.y = ga.y * s.y * (g.y - mg[1] - xh.y * mgx[1]);
-            dy.z = ga.z * s.z * (g.z - mg[2] - xh.z * mgx[2]);
-            dy.w = ga.w * s.w * (g.w - mg[3] - xh.w * mgx[3]);
+    for (int k = 0; k < 4; ++k) {
+        mg[k] = mgx[k] = 0.f;
+        if (p.bn.mean && p.batch_stats) { mg[k] = (float)(ws[c + k] * invP); mgx[k] = (float)(ws[C + c + k] * invP); }
+    }
+}
+__global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_apply_kernel(long long P, int C, ActBwdP p, const double *__restrict__ ws,
+                                                                     __nv_bfloat16 *dy_pl, long long pl_stride, int nsplit, int cs_dy,
+                                                                     float *dy_f32, float *g_out) {
+    const int lanes = C >> 2;
+    const float a = (p.act == 2) ? *p.prelu_a : 0.f;
+    if (lanes > kEwThreads) {  // very wide rows: flat (row, lane) loop
+        const long long total = P * lanes;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const long long r = i / lanes;
+            const int c = (int)(i % lanes) * 4;
+            float mg[4], mgx[4];
+            bwd_apply_consts(p, ws, P, C, c, mg, mgx);
+            RowIn in;
+            bwd_load(p, r, c, C, in);
+            bwd_apply_store(p, load_chan(p.bn, c), a, in, mg, mgx, r, c, C, dy_pl, pl_stride, nsplit, cs_dy, dy_f32, g_out);
         }
-        if (dy_pl) store_planes4(dy_pl + r * cs_dy + c, pl_stride, nsplit, dy);
-        if (dy_f32) *reinterpret_cast<float4 *>(dy_f32 + r * C + c) = dy;
+        return;
+    }
+    const int rows_per_iter = kEwThreads / lanes;
+    const int cv = threadIdx.x % lanes, rr = threadIdx.x / lanes;
+    if (rr >= rows_per_iter) return;
+    const int c = cv * 4;
+    const Chan4 ch = load_chan(p.bn, c);
+    float mg[4], mgx[4];
+    bwd_apply_consts(p, ws, P, C, c, mg, mgx);
+    const long long stride = (long long)gridDim.x * rows_per_iter;
+    for (long long r0 = (long long)blockIdx.x * rows_per_iter + rr; r0 < P; r0 += stride * kBwdUnroll) {
+        RowIn in[kBwdUnroll];
+#pragma unroll
+        for (int u = 0; u < kBwdUnroll; ++u)
+            if (r0 + u * stride < P) bwd_load(p, r0 + u * stride, c, C, in[u]);
+#pragma unroll
+        for (int u = 0; u < kBwdUnroll; ++u)
+            if (r0 + u * stride < P)
+                bwd_apply_store(p, ch, a, in[u], mg, mgx, r0 + u * stride, c, C, dy_pl, pl_stride, nsplit, cs_dy, dy_f32, g_out);
     }
 }
 
@@ -586,6 +717,15 @@ inline int red_grid(long long P, int C) {
     long long cap = (long long)kNumSMs * 2;
     return (int)(g < 1 ? 1 : (g < cap ? g : cap));
 }
+// grid of a row-streaming kernel whose CTA covers kEwThreads/lanes rows per iteration, `unroll` iterations in flight
+inline int row_grid(long long P, int C, int unroll) {
+    const int lanes = C / 4;
+    if (lanes > kEwThreads) return ew_grid(P * lanes);
+    const long long rows = (long long)(kEwThreads / lanes) * unroll;
+    long long g = (P + rows - 1) / rows;
+    const long long cap = (long long)kNumSMs * 4;
+    return (int)(g < 1 ? 1 : (g < cap ? g : cap));
+}
 inline BnP make_bn(const float *mean, const float *invstd, const float *gamma, const float *beta) { return BnP{mean, invstd, gamma, beta}; }
 
 }  // namespace
@@ -625,7 +765,7 @@ extern "C" int istnet_bn_act_split(const float *y, long long P, int C, long long
     p.res = res; p.res_bn = make_bn(res_mean, res_invstd, res_gamma, res_beta);
     p.act = act; p.prelu_a = prelu_a; p.noise = noise; p.HW = HW > 0 ? HW : 1;
     p.out_f32 = out_f32; p.out_pl = (__nv_bfloat16 *)out_planes; p.pl_stride = plane_stride; p.nsplit = nsplit; p.cs = cs; p.ch_off = ch_off;
-    bn_act_split_kernel<<<ew_grid(P * (C / 4)), kEwThreads, 0, ST>>>(P, C, p);
+    bn_act_split_kernel<<<((C / 4) <= kEwThreads && kEwThreads % (C / 4) == 0) ? row_grid(P, C, kFwdUnroll) : ew_grid(P * (C / 4)), kEwThreads, 0, ST>>>(P, C, p);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
@@ -638,6 +778,7 @@ extern "C" int istnet_bn_act_bwd(const float *dz, const float *dz2, const float 
     if (P <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
     if (act == 1 && !z_hi) return ISTNET_ERR_BAD_ARG;
     if (act == 3 && (!argmax || ns <= 0 || !mean || dz2)) return ISTNET_ERR_BAD_ARG;
+    if (P > 0x7fffffffLL) return ISTNET_ERR_BAD_ARG;  // group / instance indices are derived with 32-bit divisions
     ActBwdP p{};
     p.dz = dz; p.dz2 = dz2; p.y = y; p.bn = make_bn(mean, invstd, gamma, beta);
     p.act = act; p.prelu_a = prelu_a; p.z_hi = (const __nv_bfloat16 *)z_hi; p.cs_z = cs_z; p.noise = noise; p.HW = HW > 0 ? HW : 1;
@@ -648,8 +789,8 @@ extern "C" int istnet_bn_act_bwd(const float *dz, const float *dz2, const float 
     ISTNET_LAUNCH_CHECK();
     bwd_finalize_kernel<<<ceil_div(C, 32), 256, 0, ST>>>(part_ws, G, C, ws);
     ISTNET_LAUNCH_CHECK();
-    bn_bwd_apply_kernel<<<ew_grid(P * (C / 4)), kEwThreads, 0, ST>>>(P, C, p, ws, (__nv_bfloat16 *)dy_planes, plane_stride, nsplit, cs_dy,
-                                                                     dy_f32, g_out);
+    bn_bwd_apply_kernel<<<row_grid(P, C, kBwdUnroll), kEwThreads, 0, ST>>>(P, C, p, ws, (__nv_bfloat16 *)dy_planes, plane_stride, nsplit, cs_dy,
+                                                                            dy_f32, g_out);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
@@ -671,6 +812,17 @@ extern "C" int istnet_prep_weight(const float *w, int Cout, int Cin, int kh, int
     return ISTNET_OK;
 }
 
+__global__ void marker_kernel(unsigned long long *stamps, int slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    stamps[slot] = t;
+}
+extern "C" int istnet_marker(unsigned long long *stamps, int slot, void *stream) {
+    if (!stamps || slot < 0) return ISTNET_ERR_BAD_ARG;
+    marker_kernel<<<1, 1, 0, ST>>>(stamps, slot);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
 extern "C" int istnet_colsum(const float *x, long long P, int C, double *ws, void *stream) {
     if (P <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
     ISTNET_CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(double) * C, ST));

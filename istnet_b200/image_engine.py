@@ -12,6 +12,7 @@ import torch.nn.functional as F
 
 from . import _C
 from . import nhwc as K
+from . import trace
 from ._C import c_int, c_ll, ptr
 from .nhwc import ACT_NONE, ACT_PRELU, ACT_RELU, Act, ConvUnit
 
@@ -70,10 +71,12 @@ def forward(net, rgb, choose, training, record, u=None):
             ptr(st0.beta), ptr(z.f32), *K._pl_args(z.pl), c_int(z.cs), ptr(argmax))
     if record:
         tape.append(("stem", r0, argmax, (y0.H, y0.W)))
+    trace.mark("image: stem done")
     # ---- layer1..4
     for li in (1, 2, 3, 4):
         for bi in (0, 1):
             z = _basic_block_fwd(u, f"layer{li}.{bi}", z, training, record, tape)
+    trace.mark("image: layers done")
     # ---- PSP: priors on tiny pooled maps stay in torch (autograd sub-graph), concat buffer feeds the bottleneck GEMM
     Hf, Wf = z.H, z.W
     feats_nchw = z.f32.permute(0, 3, 1, 2)  # free view of the channels-last tensor
@@ -89,6 +92,7 @@ def forward(net, rgb, choose, training, record, u=None):
     p, rb = u["bottleneck"].forward(cat, training, record, noise=noise[0], want_f32=True, want_pair=False)
     if record:
         tape.append(("psp", rb, leaf, pri))
+    trace.mark("image: psp done")
     # ---- up_1..3: bilinear x2 (align_corners=True) fused with the operand split, conv3x3, BN, PReLU, Dropout2d scale
     for i, name in enumerate(("up_1", "up_2", "up_3")):
         cin = p.C
@@ -99,6 +103,7 @@ def forward(net, rgb, choose, training, record, u=None):
         p, ru = u[name].forward(xu, training, record, noise=None if last else noise[i + 1], want_f32=not last, want_pair=last)
         if record:
             tape.append(("up", name, ru))
+    trace.mark("image: ups done")
     # ---- head: final 1x1 conv, BN statistics over every pixel, BN + PReLU only at the chosen pixels
     yf, rf = u["final"].forward(p, training, True, defer_act=True)
     stf = rf["bn"]
@@ -135,6 +140,7 @@ def backward(net, tape, d_out, u):
     dz, dz2 = None, None
     for entry in reversed(tape):
         kind = entry[0]
+        trace.mark("image bwd: " + kind + ("" if kind in ("final", "psp", "stem") else " " + str(entry[1])))
         if kind == "final":
             _, rf, choose, N = entry
             unit = u["final"]
@@ -203,8 +209,10 @@ class _ImageBranchFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
+        trace.mark("image bwd>")
         grads = backward(ctx.net, ctx.tape, d_out, ctx.units)
         K.join_side_streams()
+        trace.mark("image bwd<")
         ctx.tape = None
         return (None, None, None) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
 

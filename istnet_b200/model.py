@@ -12,6 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import rows_engine as RE
+from . import trace
 from .image import ModifiedResnet
 from .pointnet2 import PointNet2MSG
 
@@ -241,20 +242,22 @@ class IST_Net(nn.Module):
         # tensors appear only at the module boundary (end_points)
         br = _Branches(pts.device, 3)
         # the image branch is the critical path: it gets the high-priority stream, the (latency-bound) extractors fill in
-        rgb_local = br.run(2, lambda: self.rgb_cam_extractor.gather_rows(rgb, choose))
-        pts_local = br.run(0, lambda: self.pts_cam_extractor.forward_rows(pts))
+        ph = trace.phase
+        rgb_local = br.run(2, lambda: ph("image", lambda: self.rgb_cam_extractor.gather_rows(rgb, choose)))
+        pts_local = br.run(0, lambda: ph("cam_extractor", lambda: self.pts_cam_extractor.forward_rows(pts)))
         if self.training:  # the NOCS-space extractor only depends on the ground-truth coordinates
-            gt_feats = br.run(1, lambda: self.world_enhancer.extractor.forward_rows(inputs["qo"]))
+            gt_feats = br.run(1, lambda: ph("world_extractor", lambda: self.world_enhancer.extractor.forward_rows(inputs["qo"])))
         br.join()
         # the three pose heads are independent of each other: camera-space enhancer and world-space enhancer on the side
         # streams, implicit space transformation -> main estimator on the main stream
         br2 = _Branches(pts.device, 2)
         if self.training:
-            r_c, t_c, s_c = br2.run(0, lambda: self.cam_enhancer(pts, rgb_local, pts_local))
-            r_w, t_w, s_w, pts_w_local_gt = br2.run(1, lambda: self.world_enhancer(pts, inputs["qo"], rgb_local, pts_local, gt_feats))
-        pts_w, pts_w_local = self.implicit_transform(rgb_local, pts_local, pts, c, cls)
-        r, t, s = self.main_estimator(pts, pts_w, rgb_local, pts_local, pts_w_local)
+            r_c, t_c, s_c = br2.run(0, lambda: ph("cam_enhancer", lambda: self.cam_enhancer(pts, rgb_local, pts_local)))
+            r_w, t_w, s_w, pts_w_local_gt = br2.run(1, lambda: ph("world_enhancer", lambda: self.world_enhancer(pts, inputs["qo"], rgb_local, pts_local, gt_feats)))
+        pts_w, pts_w_local = ph("implicit_transform", lambda: self.implicit_transform(rgb_local, pts_local, pts, c, cls))
+        r, t, s = ph("main_estimator", lambda: self.main_estimator(pts, pts_w, rgb_local, pts_local, pts_w_local))
         br2.join()
+        trace.mark("forward joined")
         end_points["pred_qo"] = pts_w
         if self.training:
             end_points["pts_w_local"] = pts_w_local.transpose(1, 2).contiguous()

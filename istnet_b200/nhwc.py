@@ -131,12 +131,12 @@ def join_side_streams():
 # bench.py sets PROFILE = [] to time every tensor-core launch with CUDA events on the launching stream.  Each profiled
 # call is re-issued PROFILE_REPS times back to back between the two events (the kernels are pure functions of their
 # inputs), so that the measurement is the device-side duration and not the host's launch latency on an idle stream.
-# entries: (kernel name, start event, end event, repetitions, algorithmic FLOPs, nsplit)
+# entries: (kernel name, start event, end event, repetitions, algorithmic FLOPs, nsplit, shape description)
 PROFILE = None
 PROFILE_REPS = 3
 
 
-def _timed(name, flops, nsplit, launch):
+def _timed(name, flops, nsplit, launch, desc=""):
     launch()
     if PROFILE is None:
         return
@@ -145,7 +145,7 @@ def _timed(name, flops, nsplit, launch):
     for _ in range(PROFILE_REPS):
         launch()
     e1.record()
-    PROFILE.append((name, e0, e1, PROFILE_REPS, flops, nsplit))
+    PROFILE.append((name, e0, e1, PROFILE_REPS, flops, nsplit, desc))
 
 
 def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl=None, stat_part=None):
@@ -159,7 +159,8 @@ def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl
         _p(out_f32), c_int(out_f32.shape[-1] if out_f32 is not None else 0), *_pl_args(out_pl), c_int(out_pl.shape[-1] if out_pl is not None else 0),
         c_int(bw), c_int(bh), _p(stat_part), ctypes.byref(grid),
     )
-    _timed("conv_gemm_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, x.pl.shape[0], lambda: _C.call("conv_gemm", *args))
+    _timed("conv_gemm_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, x.pl.shape[0], lambda: _C.call("conv_gemm", *args),
+           f"P={x.P} {x.H}x{x.W} cin={x.C} cout={cout} k={kh}")
     return grid.value
 
 
@@ -175,7 +176,8 @@ def conv_wgrad(dy_pl, cout, x, kh, kw):
         ptr(dy_pl), c_ll(dy_pl.stride(0)), c_int(dy_pl.shape[-1]), ptr(xpl), c_ll(xpl.stride(0)), c_int(x.cs), c_int(xpl.shape[0]),
         c_int(x.B), c_int(x.H), c_int(x.W), c_int(cout), c_int(x.C), c_int(kh), c_int(kw), ptr(ws), c_int(ks), ptr(gw), c_int(bw), c_int(bh),
     )
-    _timed("wgrad_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, xpl.shape[0], lambda: _C.call("conv_wgrad", *args))
+    _timed("wgrad_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, xpl.shape[0], lambda: _C.call("conv_wgrad", *args),
+           f"P={x.P} {x.H}x{x.W} cin={x.C} cout={cout} k={kh} ks={ks}")
     return gw
 
 

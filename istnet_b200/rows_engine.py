@@ -10,6 +10,7 @@ import torch
 
 from . import _C
 from . import nhwc as K
+from . import trace
 from ._C import c_int, c_ll, ptr
 from .nhwc import ACT_NONE, ACT_RELU, Act, ConvUnit
 
@@ -72,8 +73,10 @@ class _ChainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dz):
         grads = {}
+        trace.mark(f"chain bwd> rows={dz.shape[0]} cout={dz.shape[1]}")
         dx = _chain_backward(ctx.units, ctx.tape, dz.contiguous().view(1, 1, dz.shape[0], dz.shape[1]), grads, ctx.need_dx)
         K.join_side_streams()
+        trace.mark("chain bwd<")
         ctx.tape = None
         return (None, None, dx.view(dx.shape[2], dx.shape[3]) if dx is not None else None) + tuple(
             grads.get(id(p)) if p.requires_grad else None for p in ctx.params

@@ -12,6 +12,11 @@ dy = tc.split_planes_torch(torch.randn(B, H, W, cout, device="cuda"), ns)
 for _ in range(5):
     if mode == "fwd":
         tc.conv_gemm(ap, cin, wp, cout, k, k)
+    elif mode == "fwdpl":  # per-point MLP layer: bias + ReLU + operand planes of the next layer, no FP32 output
+        from istnet_b200 import nhwc as K
+        from istnet_b200.nhwc import Act
+        opl = K.empty_planes(B, H, W, cout, "cuda")
+        K.conv_gemm(Act(B, H, W, cin, None, ap), wp, cout, k, k, bias=torch.zeros(cout, device="cuda"), relu=True, out_pl=opl)
     else:
         tc.conv_wgrad(dy, cout, ap, cin, k, k)
 torch.cuda.synchronize()
