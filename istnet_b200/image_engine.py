@@ -29,7 +29,6 @@ def _units(net):
             u[pre + ".conv2"] = ConvUnit(blk.conv2.weight, None, blk.bn2, ACT_RELU, k=3)
             if blk.downsample is not None:
                 u[pre + ".down"] = ConvUnit(blk.downsample[0].weight, None, blk.downsample[1], ACT_NONE, k=1, stride=blk.stride, pad=0)
-    u["bottleneck"] = ConvUnit(net.psp.bottleneck.weight, net.psp.bottleneck.bias, None, ACT_RELU, k=1)
     for name in ("up_1", "up_2", "up_3"):
         seq = getattr(net, name).conv
         u[name] = ConvUnit(seq[1].weight, seq[1].bias, seq[2], ACT_PRELU, prelu=seq[3].weight, k=3)
@@ -77,21 +76,35 @@ def forward(net, rgb, choose, training, record, u=None):
         for bi in (0, 1):
             z = _basic_block_fwd(u, f"layer{li}.{bi}", z, training, record, tape)
     trace.mark("image: layers done")
-    # ---- PSP: priors on tiny pooled maps stay in torch (autograd sub-graph), concat buffer feeds the bottleneck GEMM
+    # ---- PSP (modules.py:27-34).  Bilinear up-sampling acts per channel, so it commutes with the 1x1 bottleneck:
+    #   bottleneck(cat(up(stage_i(feats)) ..., feats)) = Wb_x * feats + sum_i up(Wb_i * stage_i(feats)) + bias
+    # The priors therefore stay on their tiny pooled maps (<= 36 pixels per instance) through BOTH 1x1 convolutions (torch
+    # autograd sub-graph, a few hundred kFLOP), only their 1024-channel result is up-sampled, and the tensor-core GEMM
+    # contracts K = 512 instead of 2560: the 2048-channel prior tensor (151 MB at B = 32), its concat / permute / operand
+    # split, and 80 % of the bottleneck's forward, data-gradient and weight-gradient FLOPs are never executed.
     Hf, Wf = z.H, z.W
-    feats_nchw = z.f32.permute(0, 3, 1, 2)  # free view of the channels-last tensor
-    with torch.enable_grad():
-        leaf = feats_nchw.detach().requires_grad_(record)
-        priors = [F.interpolate(stage(leaf), size=(Hf, Wf), mode="bilinear", align_corners=False) for stage in net.psp.stages]
-        pri = torch.cat(priors, 1).permute(0, 2, 3, 1).contiguous()  # [B,Hf,Wf,2048] channels-last
-    cat = Act(B, Hf, Wf, 2560)
-    cat.pl = K.empty_planes(B, Hf, Wf, 2560, dev)
-    K.split(pri.detach(), B * Hf * Wf, 2048, cat.pl, ch_off=0)
-    cat.pl[..., 2048:] = z.pl
+    wb = net.psp.bottleneck.weight  # [1024, 2560, 1, 1]: columns 512*i .. of stage i, the last 512 of feats (cat order)
+    nst = len(net.psp.stages)
+    cf = z.C
+    with torch.enable_grad() if record else torch.no_grad():
+        leaf = z.f32.permute(0, 3, 1, 2).detach().requires_grad_(record)  # NCHW view of the channels-last tensor
+        prior = None
+        for i, stage in enumerate(net.psp.stages):
+            pooled = stage[0](leaf)  # AdaptiveAvgPool2d -> (B,512,s,s)
+            sz = pooled.shape[-1]
+            rows = pooled.permute(0, 2, 3, 1).reshape(-1, cf)
+            t = (rows @ stage[1].weight.view(cf, cf).t()) @ wb[:, i * cf : (i + 1) * cf, 0, 0].t()  # (B*s*s, 1024)
+            if sz == 1:
+                up = t.view(B, 1, 1, -1)  # a 1x1 map up-samples to a constant
+            else:
+                up = F.interpolate(t.view(B, sz, sz, -1).permute(0, 3, 1, 2), size=(Hf, Wf), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+            prior = up if prior is None else prior + up
+        prior = prior.expand(B, Hf, Wf, wb.shape[0]).contiguous()
     noise = _draw_noise(net, B, training, dev)
-    p, rb = u["bottleneck"].forward(cat, training, record, noise=noise[0], want_f32=True, want_pair=False)
+    ub = ConvUnit(wb[:, nst * cf :].detach().contiguous(), net.psp.bottleneck.bias, None, ACT_RELU, k=1)
+    p, rb = ub.forward(z, training, record, noise=noise[0], res=prior.detach(), want_f32=True, want_pair=False)
     if record:
-        tape.append(("psp", rb, leaf, pri))
+        tape.append(("psp", rb, leaf, prior, ub))
     trace.mark("image: psp done")
     # ---- up_1..3: bilinear x2 (align_corners=True) fused with the operand split, conv3x3, BN, PReLU, Dropout2d scale
     for i, name in enumerate(("up_1", "up_2", "up_3")):
@@ -138,6 +151,7 @@ def backward(net, tape, d_out, u):
     dev = d_out.device
     d_out = d_out.contiguous()
     dz, dz2 = None, None
+    pending_wb = None
     for entry in reversed(tape):
         kind = entry[0]
         trace.mark("image bwd: " + kind + ("" if kind in ("final", "psp", "stem") else " " + str(entry[1])))
@@ -165,13 +179,17 @@ def backward(net, tape, d_out, u):
             dz = K.upsample2x_bwd(dxu, xin.B, xin.H // 2, xin.W // 2, xin.C)
             dz2 = None
         elif kind == "psp":
-            _, rb, leaf, pri = entry
-            dcat, _ = u["bottleneck"].backward(rb, dz, dz2, need_dx=True, grads=grads)
+            _, rb, leaf, prior, ub = entry
+            # g = gradient w.r.t. (GEMM output + priors): the GEMM's dy and the priors' incoming gradient at once
+            dxf, g = ub.backward(rb, dz, dz2, need_dx=True, g_out=True, grads=grads)
             stage_w = [s[1].weight for s in net.psp.stages]
-            gs = torch.autograd.grad(pri, [leaf] + stage_w, dcat[..., :2048])
-            for w_, g_ in zip(stage_w, gs[1:]):
+            wb = net.psp.bottleneck.weight
+            gs = torch.autograd.grad(prior, [leaf, wb] + stage_w, g)
+            grads[id(wb)] = gs[1]
+            pending_wb = (gs[1], len(stage_w) * leaf.shape[1], id(ub.w))  # + the GEMM's weight gradient (side stream): added after the join
+            for w_, g_ in zip(stage_w, gs[2:]):
                 grads[id(w_)] = g_
-            dz = dcat[..., 2048:].contiguous()
+            dz = dxf
             dz2 = gs[0].permute(0, 2, 3, 1).contiguous()
         elif kind == "block":
             _, pre, r1, r2, rd = entry
@@ -196,6 +214,10 @@ def backward(net, tape, d_out, u):
             wsf = ws.float()
             grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = wsf[64:128], wsf[0:64]
             unit.data_grads(r0, dy, False, grads)
+    K.join_side_streams()
+    if pending_wb is not None:
+        gwb, col0, key = pending_wb
+        gwb[:, col0:] += grads.pop(key).reshape(gwb.shape[0], -1, 1, 1)
     return grads
 
 

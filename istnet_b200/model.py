@@ -22,6 +22,15 @@ WORLD_RADII = [[0.05, 0.10], [0.10, 0.20], [0.20, 0.30], [0.30, 0.40]]  # ist_ne
 
 # --------------------------------------------------------------------------------------------- stream-level concurrency
 USE_SIDE_STREAMS = os.environ.get("ISTNET_STREAMS", "1") != "0"
+# "points": the two point-cloud streams (extractors, enhancer heads) outrank the image stream.  Their kernels are short and
+# latency-bound; behind the image branch's persistent full-GPU kernels they starve (measured: the 5 ms camera-extractor
+# backward stretched over 15.6 ms and ended 3 ms after the image backward, tools/timeline.py), ahead of them they cost the
+# image branch little.  "image": the image stream outranks them (round-1 default until this measurement).  "none": equal.
+PRIORITY_MODE = os.environ.get("ISTNET_PRIO", "image")
+# pose heads: enqueue the main path (implicit transformation -> main estimator) before the two enhancer heads so that
+# autograd (which replays nodes newest-first and makes a consumer stream wait for everything already enqueued on the
+# producer stream) starts the enhancers' backward passes right after the loss instead of behind the main path's backward
+HEADS_MAIN_FIRST = os.environ.get("ISTNET_HEADS_MAIN_FIRST", "1") != "0"
 
 
 class _Branches:
@@ -36,8 +45,10 @@ class _Branches:
         self.side = []
         if self.on:
             pool = _Branches._pool.setdefault(device, [])
-            while len(pool) < n:  # stream #2 is the high-priority one (lower number = higher priority)
-                pool.append(torch.cuda.Stream(device, priority=-1 if len(pool) == 2 else 0))
+            while len(pool) < n:  # lower number = higher priority; PRIORITY_MODE picks who wins when CTAs compete for an SM
+                i = len(pool)
+                hi = (i == 2) if PRIORITY_MODE == "image" else (i < 2) if PRIORITY_MODE == "points" else False
+                pool.append(torch.cuda.Stream(device, priority=-1 if hi else 0))
             self.side = pool[:n]
             for st in self.side:
                 st.wait_stream(self.main)
@@ -241,7 +252,6 @@ class IST_Net(nn.Module):
         # everything below works on rows (B,N,C): the layout the GEMM kernels consume; the reference's (B,C,N)
         # tensors appear only at the module boundary (end_points)
         br = _Branches(pts.device, 3)
-        # the image branch is the critical path: it gets the high-priority stream, the (latency-bound) extractors fill in
         ph = trace.phase
         rgb_local = br.run(2, lambda: ph("image", lambda: self.rgb_cam_extractor.gather_rows(rgb, choose)))
         pts_local = br.run(0, lambda: ph("cam_extractor", lambda: self.pts_cam_extractor.forward_rows(pts)))
@@ -250,12 +260,19 @@ class IST_Net(nn.Module):
         br.join()
         # the three pose heads are independent of each other: camera-space enhancer and world-space enhancer on the side
         # streams, implicit space transformation -> main estimator on the main stream
-        br2 = _Branches(pts.device, 2)
+        br2 = _Branches(pts.device, 2)  # the side streams' wait on the main stream is taken here, before the main path is enqueued
+
+        def _main_path():
+            pw, pwl = ph("implicit_transform", lambda: self.implicit_transform(rgb_local, pts_local, pts, c, cls))
+            return (pw, pwl) + tuple(ph("main_estimator", lambda: self.main_estimator(pts, pw, rgb_local, pts_local, pwl)))
+
+        if HEADS_MAIN_FIRST:
+            pts_w, pts_w_local, r, t, s = _main_path()
         if self.training:
             r_c, t_c, s_c = br2.run(0, lambda: ph("cam_enhancer", lambda: self.cam_enhancer(pts, rgb_local, pts_local)))
             r_w, t_w, s_w, pts_w_local_gt = br2.run(1, lambda: ph("world_enhancer", lambda: self.world_enhancer(pts, inputs["qo"], rgb_local, pts_local, gt_feats)))
-        pts_w, pts_w_local = ph("implicit_transform", lambda: self.implicit_transform(rgb_local, pts_local, pts, c, cls))
-        r, t, s = ph("main_estimator", lambda: self.main_estimator(pts, pts_w, rgb_local, pts_local, pts_w_local))
+        if not HEADS_MAIN_FIRST:
+            pts_w, pts_w_local, r, t, s = _main_path()
         br2.join()
         trace.mark("forward joined")
         end_points["pred_qo"] = pts_w

@@ -333,8 +333,10 @@ class ConvUnit:
         out = Act(B, H, W, C)
         if want_f32:
             out.f32 = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
-        if want_pair or (record and self.act == ACT_RELU):
+        if want_pair:
             out.pl = empty_planes(B, H, W, C, dev)
+        elif record and self.act == ACT_RELU:
+            out.pl = empty_planes(B, H, W, C, dev, nsplit=1)  # plane 0 only: the ReLU mask of the backward pass
         bn_act_split(y, P, C, H * W, bn=st, res=res, res_bn=res_bn, act=self.act, prelu=self.prelu, noise=noise, out_f32=out.f32, out_pl=out.pl)
         if record:
             rec["z_hi"] = out.hi
