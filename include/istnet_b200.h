@@ -151,6 +151,12 @@ int istnet_split(const float *x, long long P, int C, long long HW, int nchw, voi
  *   im2col=1: the strided-conv form, one tap with K = (r*kw+s)*Cin + ci  ([Cout][cs] or, transposed, [K][cs]). */
 int istnet_prep_weight(const float *w, int Cout, int Cin, int kh, int kw, int transpose, int im2col, void *planes, long long plane_stride,
                        int nsplit, int cs, void *stream);
+/* ws[c] = sum_p sum_i planes[i][p][c] (double): column sums of a tensor held only as bf16 operand planes.  With the Gram matrix
+ * X^T X (istnet_conv_wgrad of the planes against themselves) this gives the train-mode BatchNorm statistics of the head's 1x1
+ * convolution (modules.py:64-66: Conv2d(64,128,1) -> BatchNorm2d -> PReLU) without materialising its 192x192x128 output: the
+ * head is only read at the `choose`d pixels (ist_net.py:42-45).  part_ws: istnet_reduce_ws_floats(P, C, 1) floats. */
+int istnet_colsum_planes(const void *planes, long long plane_stride, int nsplit, long long P, int C, int cs, float *part_ws, double *ws,
+                         void *stream);
 /* Timeline marker: one thread stores %globaltimer (ns) into stamps[slot] in stream order.  A node like any other inside a
  * captured CUDA graph, so phase boundaries of the real (graph-replayed, multi-stream) step can be read back (tools/timeline.py);
  * the reference has no counterpart (its solver times whole iterations with time.time(), utils/solver.py:153). */

@@ -812,6 +812,32 @@ extern "C" int istnet_prep_weight(const float *w, int Cout, int Cin, int kh, int
     return ISTNET_OK;
 }
 
+// column sums of a tensor that only exists as operand planes: part[g*C + c] = sum over CTA g's rows of (p0 + p1 + ...)[r][c]
+__global__ void __launch_bounds__(kEwThreads) colsum_planes_kernel(const __nv_bfloat16 *__restrict__ pl, long long pl_stride, int nsplit, long long P,
+                                                                   int C, int cs, float *part) {
+    column_reduce<1, false>(P, C, nullptr, part, [&](long long r, int c, float (*acc)[4]) {
+        for (int i = 0; i < nsplit; ++i) {
+            const float4 v = bf4_to_f4(pl + (size_t)i * pl_stride + r * cs + c);
+            acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
+        }
+    });
+}
+__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float *__restrict__ part, int G, int C, double *ws) {
+    double t[1];
+    sum_partials<1>(part, G, C, t);
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    if (threadIdx.x < 32 && c < C) ws[c] = t[0];
+}
+extern "C" int istnet_colsum_planes(const void *planes, long long plane_stride, int nsplit, long long P, int C, int cs, float *part_ws,
+                                    double *ws, void *stream) {
+    if (!planes || P <= 0 || C <= 0 || (C & 3) || (cs & 3) || nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
+    const int G = red_grid(P, C);
+    colsum_planes_kernel<<<G, kEwThreads, 0, ST>>>((const __nv_bfloat16 *)planes, plane_stride, nsplit, P, C, cs, part_ws);
+    ISTNET_LAUNCH_CHECK();
+    colsum_finalize_kernel<<<ceil_div(C, 32), 256, 0, ST>>>(part_ws, G, C, ws);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
 __global__ void marker_kernel(unsigned long long *stamps, int slot) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -7,6 +7,8 @@ implicit-GEMM tcgen05 kernel; BN statistics, BN-apply + residual + ReLU + operan
 operand split -> conv3x3 GEMM -> BN + PReLU (+Dropout2d scale)] -> final 1x1 GEMM -> BN + PReLU evaluated only at the
 `choose`d pixels, directly in the reference's (B,128,N) layout (ist_net.py:41-45).
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -49,6 +51,97 @@ def _basic_block_fwd(u, pre, x, training, record, tape):
     if record:
         tape.append(("block", pre, r1, r2, rd))
     return out
+
+
+# ISTNET_DENSE_HEAD=1 keeps the round-1 head (dense 192x192x128 convolution output, statistics over it, dense BN backward)
+DENSE_HEAD = os.environ.get("ISTNET_DENSE_HEAD", "0") == "1"
+
+
+def _head_forward(unit, x, choose, training):
+    """modules.py:64-66 + ist_net.py:42-45: y = W x + b on every pixel, train-mode BatchNorm over all B*H*W pixels, PReLU,
+    then only the `choose`d pixels are used.  y is affine in x, so its batch statistics follow from the first two moments
+    of x:  mean_y = W mean_x + b,  var_y[c] = w_c^T Cov(x) w_c  with  Cov = X^T X / P - mean_x mean_x^T.  X^T X is a
+    64x64 tensor-core contraction over the pixels (the weight-gradient kernel applied to x against itself); the
+    convolution itself runs on the B*N gathered rows only.  Returns (rows (B,N,128) FP32, record)."""
+    dev = x.pl.device
+    B, HW, C, Co = x.B, x.H * x.W, x.C, unit.cout
+    P, N = B * HW, choose.shape[1]
+    flat = (choose + torch.arange(B, device=dev, dtype=choose.dtype).view(B, 1) * HW).reshape(-1)
+    xg = Act(1, 1, B * N, C, None, x.pl.view(x.pl.shape[0], P, x.cs).index_select(1, flat).view(x.pl.shape[0], 1, 1, B * N, x.cs))
+    yg = torch.empty(1, 1, B * N, Co, dtype=torch.float32, device=dev)
+    K.conv_gemm(xg, K.prep_weight(unit.w), Co, 1, 1, bias=unit.b, out_f32=yg)
+    bn = unit.bn
+    rec = {"x": x, "xg": xg, "yg": yg, "flat": flat, "P": P, "N": N}
+    if K.bn_uses_batch_stats(bn, training):
+        xpl = x.pl[: K.NSPLIT_BWD]  # two planes: the plane-rounding errors are unbiased and average out over ~1e6 pixels
+        S = K.conv_wgrad(xpl, C, Act(x.B, x.H, x.W, C, None, xpl), 1, 1).view(C, C).double()
+        part = torch.empty(_C.lib().istnet_reduce_ws_floats(c_ll(P), C, 1), dtype=torch.float32, device=dev)
+        sx = torch.empty(C, dtype=torch.float64, device=dev)
+        _C.call("colsum_planes", ptr(xpl), c_ll(xpl.stride(0)), c_int(xpl.shape[0]), c_ll(P), c_int(C), c_int(x.cs), ptr(part), ptr(sx))
+        with torch.no_grad():
+            W64, b64 = unit.w.view(Co, C).double(), unit.b.double()
+            mx = sx / P
+            cov = S / P - torch.outer(mx, mx)
+            mean = W64 @ mx + b64
+            var = ((W64 @ cov) * W64).sum(1).clamp_min_(0.0)
+            invstd = torch.rsqrt(var + bn.eps)
+            if bn.track_running_stats and bn.running_mean is not None:
+                mom = bn.momentum if bn.momentum is not None else 0.1
+                bn.running_mean.copy_(((1.0 - mom) * bn.running_mean.double() + mom * mean).float())
+                bn.running_var.copy_(((1.0 - mom) * bn.running_var.double() + mom * var * (P / max(P - 1, 1))).float())
+                bn.num_batches_tracked += 1
+        st = K.BnState(mean.float(), invstd.float(), bn.weight, bn.bias, batch=True)
+        rec.update({"sx": sx, "S": S})
+    else:
+        st = K.BnState(bn.running_mean, torch.rsqrt(bn.running_var + bn.eps), bn.weight, bn.bias, batch=False)
+    rec["bn"] = st
+    out = torch.empty(B, N, Co, dtype=torch.float32, device=dev)
+    K.bn_act_split(yg, B * N, Co, 1, bn=st, act=ACT_PRELU, prelu=unit.prelu, out_f32=out)
+    return out, rec
+
+
+def _head_backward(unit, rec, d_out, grads):
+    """Backward of _head_forward.  With g = d_out * PReLU'(u) on the gathered rows (zero elsewhere) the train-mode BatchNorm
+    backward  dy_p = gamma*invstd*(g_p - sum(g)/P - xhat_p*sum(g*xhat)/P)  is a sparse term plus a term AFFINE in x_p:
+      dW = [sum_s (gamma*invstd*g_s) x_s^T] - a sx^T - diag(d) (W S + (b - mu) sx^T)
+      dx_p = [W^T (gamma*invstd*g_p)] - A x_p - c,   A = W^T diag(d) W,  c = W^T (a + d*(b - mu))
+    with a = gamma*invstd*sum(g)/P, d = gamma*invstd^2*sum(g*xhat)/P, S = X^T X, sx = sum_p x_p.  The bracketed terms are
+    GEMMs over the B*N gathered rows; -A x - c is one 64->64 1x1 convolution over the feature map.  Returns dx (B,H,W,C)."""
+    x, xg, yg, st, flat, P, N = rec["x"], rec["xg"], rec["yg"], rec["bn"], rec["flat"], rec["P"], rec["N"]
+    dev = d_out.device
+    C, Co, R = x.C, unit.cout, xg.W
+    dys = K.empty_planes(1, 1, R, Co, dev, nsplit=K.NSPLIT_BWD)
+    st_rows = K.BnState(st.mean, st.invstd, st.gamma, st.beta, batch=False)  # apply pass: dys = gamma*invstd*g (the sparse term)
+    ws = K.bn_act_bwd(d_out.view(1, 1, R, Co), None, yg, R, Co, 1, st_rows, ACT_PRELU, unit.prelu, None, None, dy_pl=dys)
+    sg, sgx = ws[0:Co], ws[Co : 2 * Co]
+    grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = sgx.float(), sg.float()
+    grads[id(unit.prelu)] = ws[2 * Co : 3 * Co].sum().float().reshape(1)
+    gw_s = K.conv_wgrad(dys, Co, Act(1, 1, R, C, None, xg.pl), 1, 1).view(Co, C)
+    ds = torch.empty(1, 1, R, C, dtype=torch.float32, device=dev)
+    K.conv_gemm(Act(1, 1, R, Co, None, dys), K.prep_weight(unit.w, transpose=True, nsplit=dys.shape[0]), C, 1, 1, out_f32=ds)
+    if st.batch:
+        with torch.no_grad():
+            W64, b64 = unit.w.view(Co, C).double(), unit.b.double()
+            gi = st.gamma.double() * st.invstd.double()
+            a = gi * sg / P
+            d = gi * st.invstd.double() * sgx / P
+            bm = b64 - st.mean.double()
+            sx, S = rec["sx"], rec["S"]
+            gw = gw_s.double() - torch.outer(a, sx) - d[:, None] * (W64 @ S + torch.outer(bm, sx))
+            A = W64.t() @ (d[:, None] * W64)
+            c = W64.t() @ (a + d * bm)
+        grads[id(unit.w)] = gw.float().view_as(unit.w)
+        grads[id(unit.b)] = torch.zeros_like(unit.b)  # a bias feeding a train-mode BatchNorm has an identically zero gradient
+        xb = x.pl[: K.NSPLIT_BWD]
+        dx = torch.empty(x.B, x.H, x.W, C, dtype=torch.float32, device=dev)
+        K.conv_gemm(Act(x.B, x.H, x.W, C, None, xb), K.prep_weight((-A).float().contiguous(), nsplit=xb.shape[0]), C, 1, 1,
+                    bias=(-c).float().contiguous(), out_f32=dx)
+    else:
+        grads[id(unit.w)] = gw_s.view_as(unit.w)
+        grads[id(unit.b)] = (st.gamma * st.invstd * sg.float()).detach()
+        dx = torch.zeros(x.B, x.H, x.W, C, dtype=torch.float32, device=dev)
+    dx.view(P, C).index_add_(0, flat, ds.view(R, C))  # gather backward: float atomics, as torch.gather's backward in the reference
+    return dx
 
 
 def forward(net, rgb, choose, training, record, u=None):
@@ -117,16 +210,21 @@ def forward(net, rgb, choose, training, record, u=None):
         if record:
             tape.append(("up", name, ru))
     trace.mark("image: ups done")
-    # ---- head: final 1x1 conv, BN statistics over every pixel, BN + PReLU only at the chosen pixels
-    yf, rf = u["final"].forward(p, training, True, defer_act=True)
-    stf = rf["bn"]
-    N = choose.shape[1]
-    out = torch.empty(B, N, 128, dtype=torch.float32, device=dev)
-    choose = choose.contiguous()
-    _C.call("gather_bn_prelu", ptr(yf.f32), c_int(B), c_ll(yf.H * yf.W), c_int(128), c_int(N), ptr(choose), ptr(stf.mean), ptr(stf.invstd),
-            ptr(stf.gamma), ptr(stf.beta), ptr(u["final"].prelu), ptr(out))
-    if record:
-        tape.append(("final", rf, choose, N))
+    # ---- head: final 1x1 conv + BN + PReLU, evaluated only at the `choose`d pixels (see _head_forward)
+    if DENSE_HEAD:
+        yf, rf = u["final"].forward(p, training, True, defer_act=True)
+        stf = rf["bn"]
+        N = choose.shape[1]
+        out = torch.empty(B, N, 128, dtype=torch.float32, device=dev)
+        choose = choose.contiguous()
+        _C.call("gather_bn_prelu", ptr(yf.f32), c_int(B), c_ll(yf.H * yf.W), c_int(128), c_int(N), ptr(choose), ptr(stf.mean), ptr(stf.invstd),
+                ptr(stf.gamma), ptr(stf.beta), ptr(u["final"].prelu), ptr(out))
+        if record:
+            tape.append(("final", rf, choose, N))
+    else:
+        out, rh = _head_forward(u["final"], p, choose, training)
+        if record:
+            tape.append(("head", rh))
     return out, (tape if record else None)
 
 
@@ -154,7 +252,7 @@ def backward(net, tape, d_out, u):
     pending_wb = None
     for entry in reversed(tape):
         kind = entry[0]
-        trace.mark("image bwd: " + kind + ("" if kind in ("final", "psp", "stem") else " " + str(entry[1])))
+        trace.mark("image bwd: " + kind + ("" if kind in ("final", "head", "psp", "stem") else " " + str(entry[1])))
         if kind == "final":
             _, rf, choose, N = entry
             unit = u["final"]
@@ -172,6 +270,8 @@ def backward(net, tape, d_out, u):
             grads[id(unit.prelu)] = slope.sum().float().reshape(1)
             dz = unit.data_grads(rf, dy, True, grads)
             dz2 = None
+        elif kind == "head":
+            dz, dz2 = _head_backward(u["final"], entry[1], d_out, grads), None
         elif kind == "up":
             _, name, ru = entry
             dxu, _ = u[name].backward(ru, dz, dz2, need_dx=True, grads=grads)
