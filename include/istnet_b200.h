@@ -151,6 +151,18 @@ int istnet_split(const float *x, long long P, int C, long long HW, int nchw, voi
  *   im2col=1: the strided-conv form, one tap with K = (r*kw+s)*Cin + ci  ([Cout][cs] or, transposed, [K][cs]). */
 int istnet_prep_weight(const float *w, int Cout, int Cin, int kh, int kw, int transpose, int im2col, void *planes, long long plane_stride,
                        int nsplit, int cs, void *stream);
+/* First shared-MLP layer of a set-abstraction scale evaluated on the POINTS (pointnet2_modules.py:60-66 applied to
+ * QueryAndGroup's [xyz_j - c_i | f_j], pointnet2_utils.py:335-367): y0[(b,i,k), :] = u[b, idx[b,i,k], :] + Wx (xyz_j - c_i),
+ * with u = F Wf^T a GEMM over the N points (u may be null: level 1 has no features) and Wx = w0[:, 0:3] (row stride ldw).
+ * Replaces group_points + the grouped 1x1 convolution; also leaves the train-mode BatchNorm statistics partials of y0 in
+ * stat_part (>= 2*296*C0 floats, layout of istnet_bn_finalize; *grid_out = number of partial rows G). */
+int istnet_sa_gather_l0(int B, int N, int M, int ns, int C0, const float *xyz, const float *new_xyz, const int32_t *idx, const float *u,
+                        const float *w0, int ldw, float *y0, float *stat_part, int *grid_out, void *stream);
+/* Backward of istnet_sa_gather_l0: dU[b, idx, :] += dy0[row, :] (zeroed here; float atomics like group_points_grad,
+ * group_points_gpu.cu:48-69; may be null) and ws[d*C0 + c] = sum_rows dy0[row, c] * (xyz_j - c_i)[d] (double, fixed summation
+ * order; ws holds 3*C0).  part_ws: istnet_reduce_ws_floats(rows, C0, 3) floats. */
+int istnet_sa_scatter_l0(int B, int N, int M, int ns, int C0, const float *dy0, const float *xyz, const float *new_xyz, const int32_t *idx,
+                         float *dU, float *part_ws, double *ws, void *stream);
 /* ws[c] = sum_p sum_i planes[i][p][c] (double): column sums of a tensor held only as bf16 operand planes.  With the Gram matrix
  * X^T X (istnet_conv_wgrad of the planes against themselves) this gives the train-mode BatchNorm statistics of the head's 1x1
  * convolution (modules.py:64-66: Conv2d(64,128,1) -> BatchNorm2d -> PReLU) without materialising its 192x192x128 output: the

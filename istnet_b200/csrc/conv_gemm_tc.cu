@@ -378,8 +378,12 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     const int stat_bytes = stat_part ? 8 * Cout * (int)sizeof(float) : 0;
     int max_stages = (budget_kb * 1024 - 1024 - 256 - stat_bytes) / stage_bytes;
     if (max_stages < 1) max_stages = 1;
-    if (max_stages > 6) max_stages = 6;
-    p.stages = num_k < max_stages ? num_k : max_stages;
+    if (max_stages > 8) max_stages = 8;
+    // The ring runs across the tiles of a persistent CTA, so its depth is bounded by the k-iterations of ALL the CTA's
+    // tiles, not of one: short-K layers (num_k = 1..4: the set-abstraction MLPs and their data gradients) would otherwise
+    // get a 1-deep ring and serialise TMA latency -> MMA -> stage release per tile.
+    const long long iters_per_cta = (long long)num_k * ceil_div_ll(n_tiles, kNumSMs);
+    p.stages = iters_per_cta < max_stages ? (int)iters_per_cta : max_stages;
     size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256 + stat_bytes;
     if (smem > 227 * 1024) return ISTNET_ERR_UNSUPPORTED;
 

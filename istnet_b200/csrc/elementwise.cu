@@ -704,6 +704,113 @@ __global__ void __launch_bounds__(kEwThreads) gather_bn_prelu_bwd_kernel(int B, 
     }
 }
 
+// ------------------------------------------------------------------ set-abstraction layer 0 on the POINTS instead of the grouped rows
+// The first shared-MLP layer of a set-abstraction scale (pointnet2_modules.py:60-66 on QueryAndGroup's output,
+// pointnet2_utils.py:335-367) is linear in the grouped row [xyz_j - c_i | f_j]:
+//     y0[(i,k), :] = Wx (xyz_j - c_i) + Wf f_j ,   j = idx[i,k]
+// so Wf f_j is a GEMM over the N points (u = F Wf^T, 16..32x fewer rows than the M*nsample grouped rows) and the grouped
+// tensor never exists: this kernel gathers u[j], adds the 3-term FP32 product with the relative coordinates, writes y0 and
+// leaves the per-CTA BatchNorm-statistics partials (same layout as the GEMM epilogue: part[(a*G + g)*C0 + c]).
+constexpr int kSaUnroll = 4;
+__global__ void __launch_bounds__(kEwThreads, 2) sa_gather_l0_kernel(int N, int M, int ns, int C0, long long rows, const float *__restrict__ xyz,
+                                                                     const float *__restrict__ new_xyz, const int32_t *__restrict__ idx,
+                                                                     const float *__restrict__ u, const float *__restrict__ w0, int ldw,
+                                                                     float *__restrict__ y0, float *part) {
+    const int lanes = C0 >> 2;  // <= kEwThreads (launcher)
+    const int rows_per_iter = kEwThreads / lanes;
+    const int cv = threadIdx.x % lanes, rr = threadIdx.x / lanes;
+    const int c = cv * 4;
+    float acc[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
+    if (rr < rows_per_iter) {
+        float wx[4][3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) wx[k][d] = w0[(size_t)(c + k) * ldw + d];
+        const long long stride = (long long)gridDim.x * rows_per_iter;
+        for (long long r0 = (long long)blockIdx.x * rows_per_iter + rr; r0 < rows; r0 += stride * kSaUnroll) {
+            float rel[kSaUnroll][3];
+            float4 uv[kSaUnroll];
+#pragma unroll
+            for (int q = 0; q < kSaUnroll; ++q) {
+                const long long r = r0 + q * stride;
+                if (r < rows) {
+                    const unsigned bj = (unsigned)r / (unsigned)ns;  // rows < 2^31 (launcher)
+                    const unsigned b = bj / (unsigned)M;
+                    const size_t src = (size_t)b * N + idx[r];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) rel[q][d] = __fsub_rn(xyz[src * 3 + d], new_xyz[(size_t)bj * 3 + d]);
+                    uv[q] = u ? ld4(u + src * C0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kSaUnroll; ++q) {
+                const long long r = r0 + q * stride;
+                if (r < rows) {
+                    float v[4] = {uv[q].x, uv[q].y, uv[q].z, uv[q].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        v[k] = __fmaf_rn(wx[k][0], rel[q][0], __fmaf_rn(wx[k][1], rel[q][1], __fmaf_rn(wx[k][2], rel[q][2], v[k])));
+                        acc[0][k] += v[k];
+                        acc[1][k] += v[k] * v[k];
+                    }
+                    *reinterpret_cast<float4 *>(y0 + r * C0 + c) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        }
+    }
+    column_flush<2, false>(acc, lanes, rows_per_iter, rr < rows_per_iter, C0, nullptr, part);
+}
+// Backward of the above for one scale: dU[j, :] += dy0[(i,k), :] (float atomics, as group_points_grad in the reference) and
+// the per-CTA partials of dWx[c][d] = sum_rows dy0[row, c] * (xyz_j - c_i)[d]  (part[(d*G + g)*C0 + c], summed in fixed order).
+__global__ void __launch_bounds__(kEwThreads, 2) sa_scatter_l0_kernel(int N, int M, int ns, int C0, long long rows, const float *__restrict__ dy0,
+                                                                      const float *__restrict__ xyz, const float *__restrict__ new_xyz,
+                                                                      const int32_t *__restrict__ idx, float *dU, float *part) {
+    const int lanes = C0 >> 2;
+    const int rows_per_iter = kEwThreads / lanes;
+    const int cv = threadIdx.x % lanes, rr = threadIdx.x / lanes;
+    const int c = cv * 4;
+    float acc[3][4];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
+    if (rr < rows_per_iter) {
+        const long long stride = (long long)gridDim.x * rows_per_iter;
+        for (long long r0 = (long long)blockIdx.x * rows_per_iter + rr; r0 < rows; r0 += stride * kSaUnroll) {
+            float rel[kSaUnroll][3];
+            float4 dv[kSaUnroll];
+            size_t src[kSaUnroll];
+#pragma unroll
+            for (int q = 0; q < kSaUnroll; ++q) {
+                const long long r = r0 + q * stride;
+                if (r < rows) {
+                    const unsigned bj = (unsigned)r / (unsigned)ns;
+                    const unsigned b = bj / (unsigned)M;
+                    src[q] = (size_t)b * N + idx[r];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) rel[q][d] = __fsub_rn(xyz[src[q] * 3 + d], new_xyz[(size_t)bj * 3 + d]);
+                    dv[q] = ld4(dy0 + r * C0 + c);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kSaUnroll; ++q) {
+                const long long r = r0 + q * stride;
+                if (r < rows) {
+                    const float g[4] = {dv[q].x, dv[q].y, dv[q].z, dv[q].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) acc[d][k] += g[k] * rel[q][d];
+                        if (dU) atomicAdd(dU + src[q] * C0 + c + k, g[k]);
+                    }
+                }
+            }
+        }
+    }
+    column_flush<3, false>(acc, lanes, rows_per_iter, rr < rows_per_iter, C0, nullptr, part);
+}
+
 inline int ew_grid(long long total) {
     long long g = (total + kEwThreads - 1) / kEwThreads;
     long long cap = (long long)kNumSMs * 8;
@@ -842,6 +949,28 @@ __global__ void marker_kernel(unsigned long long *stamps, int slot) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     stamps[slot] = t;
+}
+extern "C" int istnet_sa_gather_l0(int B, int N, int M, int ns, int C0, const float *xyz, const float *new_xyz, const int32_t *idx, const float *u,
+                                   const float *w0, int ldw, float *y0, float *stat_part, int *grid_out, void *stream) {
+    const long long rows = (long long)B * M * ns;
+    if (B <= 0 || N <= 0 || M <= 0 || ns <= 0 || C0 <= 0 || (C0 & 3) || C0 / 4 > kEwThreads || ldw < 3 || rows > 0x7fffffffLL) return ISTNET_ERR_BAD_ARG;
+    const int G = red_grid(rows, C0);  // <= 296: the size callers give the statistics scratch
+    sa_gather_l0_kernel<<<G, kEwThreads, 0, ST>>>(N, M, ns, C0, rows, xyz, new_xyz, idx, u, w0, ldw, y0, stat_part);
+    ISTNET_LAUNCH_CHECK();
+    if (grid_out) *grid_out = G;
+    return ISTNET_OK;
+}
+extern "C" int istnet_sa_scatter_l0(int B, int N, int M, int ns, int C0, const float *dy0, const float *xyz, const float *new_xyz,
+                                    const int32_t *idx, float *dU, float *part_ws, double *ws, void *stream) {
+    const long long rows = (long long)B * M * ns;
+    if (B <= 0 || N <= 0 || M <= 0 || ns <= 0 || C0 <= 0 || (C0 & 3) || C0 / 4 > kEwThreads || rows > 0x7fffffffLL) return ISTNET_ERR_BAD_ARG;
+    if (dU) ISTNET_CUDA_TRY(cudaMemsetAsync(dU, 0, sizeof(float) * (size_t)B * N * C0, ST));
+    const int G = red_grid(rows, C0);
+    sa_scatter_l0_kernel<<<G, kEwThreads, 0, ST>>>(N, M, ns, C0, rows, dy0, xyz, new_xyz, idx, dU, part_ws);
+    ISTNET_LAUNCH_CHECK();
+    bwd_finalize_kernel<<<ceil_div(C0, 32), 256, 0, ST>>>(part_ws, G, C0, ws);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
 }
 extern "C" int istnet_marker(unsigned long long *stamps, int slot, void *stream) {
     if (!stamps || slot < 0) return ISTNET_ERR_BAD_ARG;

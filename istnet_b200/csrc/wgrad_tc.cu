@@ -229,7 +229,8 @@ extern "C" int istnet_wgrad_ksplit(int B, int H, int W, int Cout, int Cin, int k
     int ks = capacity / base;
     if (ks > pix_tiles / 4) ks = (int)(pix_tiles / 4);
     if (ks < 1) ks = 1;
-    if (ks > 96) ks = 96;
+    const int cap = wg_env_int("ISTNET_WG_KSCAP", 148);
+    if (ks > cap) ks = cap;
     return ks;
 }
 

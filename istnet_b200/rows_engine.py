@@ -6,6 +6,9 @@ Replaces, for the reference: pytorch_utils.SharedMLP on (B,C,npoint,nsample) ten
 F.max_pool2d, pointnet2_modules.py:60-69), grouping_operation / three_interpolate on channel-first tensors, and the
 nn.Conv1d(k=1) stacks of ist_net.py:125-332.
 """
+import ctypes
+import os
+
 import torch
 
 from . import _C
@@ -108,7 +111,7 @@ class _SAScaleFn(torch.autograd.Function):
         ctx.units, ctx.saved, ctx.params = units, saved, params
         ctx.has_feats = feats is not None and feats.requires_grad
         ctx.shape = (xyz.shape[0], xyz.shape[1], new_xyz.shape[1], idx.shape[2], 0 if feats is None else feats.shape[2])
-        ctx.idx = idx
+        ctx.idx, ctx.xyz, ctx.new_xyz = idx, xyz, new_xyz
         return out
 
     @staticmethod
@@ -127,14 +130,82 @@ class _SAScaleFn(torch.autograd.Function):
         wsf = ws.float()
         grads[id(last.bn.weight)], grads[id(last.bn.bias)] = wsf[Cl : 2 * Cl], wsf[0:Cl]
         d = last.data_grads(rec, dy, True, grads)
-        d = _chain_backward(units[:-1], tape[:-1], d, grads, ctx.has_feats)
         d_feats = None
-        if ctx.has_feats:
-            d_feats = torch.empty(B, N, C, dtype=torch.float32, device=dz.device)
-            _C.call("group_rows_bwd", c_int(B), c_int(N), c_int(M), c_int(ns), c_int(C), ptr(d), ptr(ctx.idx), ptr(d_feats))
+        if tape[0].get("point_l0"):
+            d = _chain_backward(units[1:-1], tape[1:-1], d, grads, True)
+            d_feats = _sa_l0_backward(units[0], tape[0], d, ctx.xyz, ctx.new_xyz, ctx.idx, ctx.has_feats, grads)
+        else:
+            d = _chain_backward(units[:-1], tape[:-1], d, grads, ctx.has_feats)
+            if ctx.has_feats:
+                d_feats = torch.empty(B, N, C, dtype=torch.float32, device=dz.device)
+                _C.call("group_rows_bwd", c_int(B), c_int(N), c_int(M), c_int(ns), c_int(C), ptr(d), ptr(ctx.idx), ptr(d_feats))
         K.join_side_streams()
         ctx.saved = None
         return (None, None, None, None, None, d_feats) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
+
+
+# Layer 0 of a set-abstraction scale on the points instead of the grouped rows (csrc/elementwise.cu, sa_gather_l0_kernel);
+# ISTNET_SA_POINT_L0=0 keeps the round-1 dataflow (materialised grouped operand + grouped GEMM).
+SA_POINT_L0 = os.environ.get("ISTNET_SA_POINT_L0", "1") != "0"
+
+
+def _sa_l0_forward(u0, training, xyz, new_xyz, idx, feats, record):
+    """y0 = Wx (xyz_j - c_i) + Wf f_j for every grouped row, BN (batch statistics from the gather kernel's partials) + ReLU,
+    written as the operand planes of layer 1.  Returns (Act with planes, tape record)."""
+    B, N, _ = xyz.shape
+    M, ns = idx.shape[1], idx.shape[2]
+    C = 0 if feats is None else feats.shape[2]
+    rows, C0, dev = B * M * ns, u0.cout, xyz.device
+    fa = uf = wf = None
+    if C > 0:  # u = F Wf^T over the B*N points: 16..32x fewer rows than the grouped tensor
+        fa = Act(1, 1, B * N, C, None, K.empty_planes(1, 1, B * N, C, dev))
+        K.split(feats, B * N, C, fa.pl)
+        wf = u0.w.detach()[:, 3:, 0, 0].contiguous()
+        uf = torch.empty(1, 1, B * N, C0, dtype=torch.float32, device=dev)
+        K.conv_gemm(fa, K.prep_weight(wf), C0, 1, 1, out_f32=uf)
+    y0 = torch.empty(1, 1, rows, C0, dtype=torch.float32, device=dev)
+    part = torch.empty(2 * 296 * C0, dtype=torch.float32, device=dev)
+    grid = ctypes.c_int(0)
+    _C.call("sa_gather_l0", c_int(B), c_int(N), c_int(M), c_int(ns), c_int(C0), ptr(xyz), ptr(new_xyz), ptr(idx), K._p(uf), ptr(u0.w), c_int(3 + C),
+            ptr(y0), ptr(part), ctypes.byref(grid))
+    st = K.bn_state(u0.bn, y0, rows, C0, training, part, grid.value)
+    a = Act(1, 1, rows, C0, None, K.empty_planes(1, 1, rows, C0, dev))
+    K.bn_act_split(y0, rows, C0, 1, bn=st, act=ACT_RELU, out_pl=a.pl)
+    rec = {"point_l0": True, "bn": st}
+    if record:
+        rec.update({"y": y0, "z_hi": a.hi, "fa": fa, "wf": wf})
+    return a, rec
+
+
+def _sa_l0_backward(u0, rec, d, xyz, new_xyz, idx, need_dfeats, grads):
+    """d: FP32 gradient w.r.t. layer 0's output rows.  BN/ReLU backward on the rows, then ONE pass scatters dy0 to the
+    points (dU) and reduces dWx; the feature part of the weight gradient and the feature gradient are GEMMs over the
+    points.  Returns d_feats (B,N,C) or None."""
+    B, N, _ = xyz.shape
+    M, ns = idx.shape[1], idx.shape[2]
+    fa = rec["fa"]
+    C = 0 if fa is None else fa.C
+    rows, C0, dev = B * M * ns, u0.cout, d.device
+    dy0 = torch.empty(1, 1, rows, C0, dtype=torch.float32, device=dev)
+    ws = K.bn_act_bwd(d, None, rec["y"], rows, C0, 1, rec["bn"], ACT_RELU, None, rec["z_hi"], None, dy_f32=dy0)
+    wsf = ws.float()
+    grads[id(u0.bn.weight)], grads[id(u0.bn.bias)] = wsf[C0 : 2 * C0], wsf[0:C0]
+    dU = torch.empty(B * N, C0, dtype=torch.float32, device=dev) if C > 0 else None
+    part = torch.empty(_C.lib().istnet_reduce_ws_floats(c_ll(rows), C0, 3), dtype=torch.float32, device=dev)
+    wsx = torch.empty(3 * C0, dtype=torch.float64, device=dev)
+    _C.call("sa_scatter_l0", c_int(B), c_int(N), c_int(M), c_int(ns), c_int(C0), ptr(dy0), ptr(xyz), ptr(new_xyz), ptr(idx), K._p(dU), ptr(part), ptr(wsx))
+    gw = wsx.view(3, C0).t().float()
+    d_feats = None
+    if C > 0:
+        dupl = K.empty_planes(1, 1, B * N, C0, dev, nsplit=K.NSPLIT_BWD)
+        K.split(dU, B * N, C0, dupl)
+        gw = torch.cat([gw, K.conv_wgrad(dupl, C0, fa, 1, 1).view(C0, C)], 1)
+        if need_dfeats:
+            d_feats = torch.empty(B, N, C, dtype=torch.float32, device=dev)
+            K.conv_gemm(Act(1, 1, B * N, C0, None, dupl), K.prep_weight(rec["wf"], transpose=True, nsplit=dupl.shape[0]), C, 1, 1,
+                        out_f32=d_feats.view(1, 1, B * N, C))
+    grads[id(u0.w)] = gw.reshape(u0.w.shape)
+    return d_feats
 
 
 def sa_scale_forward(units, training, xyz, new_xyz, idx, feats, record):
@@ -143,11 +214,16 @@ def sa_scale_forward(units, training, xyz, new_xyz, idx, feats, record):
     C = 0 if feats is None else feats.shape[2]
     rows = B * M * ns
     dev = xyz.device
-    a = Act(1, 1, rows, 3 + C)
-    a.pl = K.empty_planes(1, 1, rows, 3 + C, dev)
-    _C.call("group_rows_split", c_int(B), c_int(N), c_int(M), c_int(ns), c_int(C), ptr(xyz), ptr(new_xyz), K._p(feats), ptr(idx), *K._pl_args(a.pl),
-            c_int(a.cs))
-    a, tape = _chain_forward(units[:-1], a, training, record, last_f32=False, last_pair=True)
+    if SA_POINT_L0 and len(units) >= 2 and units[0].cout % 4 == 0:
+        a, rec0 = _sa_l0_forward(units[0], training, xyz, new_xyz, idx, feats, record)
+        a, tape = _chain_forward(units[1:-1], a, training, record, last_f32=False, last_pair=True)
+        tape = [rec0] + tape
+    else:
+        a = Act(1, 1, rows, 3 + C)
+        a.pl = K.empty_planes(1, 1, rows, 3 + C, dev)
+        _C.call("group_rows_split", c_int(B), c_int(N), c_int(M), c_int(ns), c_int(C), ptr(xyz), ptr(new_xyz), K._p(feats), ptr(idx), *K._pl_args(a.pl),
+                c_int(a.cs))
+        a, tape = _chain_forward(units[:-1], a, training, record, last_f32=False, last_pair=True)
     last = units[-1]
     y, rec = last.forward(a, training, record, defer_act=True)
     tape.append(rec)

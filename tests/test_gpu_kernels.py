@@ -157,7 +157,7 @@ def test_sa_scale_and_interp_rows_match_reference_flow():
     d = make_batch(4, 512, 8, seed=3)
     xyz = (d["pts"] - d["pts"].mean(1, keepdim=True)).cuda().contiguous()
     g = torch.Generator(device="cuda").manual_seed(1)
-    feats = torch.randn(4, 512, 64, device="cuda", generator=g)
+    feats = torch.randn(4, 512, 64, device="cuda", generator=g).requires_grad_(True)
     idx_f = ext.furthest_point_sampling(xyz, 128)
     new_xyz = torch.gather(xyz, 1, idx_f.long()[..., None].expand(-1, -1, 3)).contiguous()
     idx = ext.ball_query(new_xyz, xyz, 0.04, 32)
@@ -167,10 +167,19 @@ def test_sa_scale_and_interp_rows_match_reference_flow():
     m64.load_state_dict(mlp.state_dict())
     gi = idx.long()
     gx = torch.gather(xyz.double()[:, None].expand(-1, 128, -1, -1), 2, gi[..., None].expand(-1, -1, -1, 3)) - new_xyz.double()[:, :, None]
-    gf = torch.gather(feats.double()[:, None].expand(-1, 128, -1, -1), 2, gi[..., None].expand(-1, -1, -1, 64))
+    f64 = feats.detach().double().requires_grad_(True)
+    gf = torch.gather(f64[:, None].expand(-1, 128, -1, -1), 2, gi[..., None].expand(-1, -1, -1, 64))
     grouped = torch.cat([gx, gf], -1).permute(0, 3, 1, 2)  # (B, 3+C, npoint, nsample)
     ref = F.max_pool2d(m64(grouped), kernel_size=[1, 32]).squeeze(-1).transpose(1, 2)
     assert rel_err(out, ref) < 1e-4
+    # backward: layer 0 is evaluated on the points (u = F Wf^T gathered per row + Wx (xyz_j - c_i)); its gradients (scatter to
+    # the points, point-level weight / feature GEMMs) must match autograd through the grouped reference flow
+    cot = torch.randn(out.shape, device="cuda", generator=g)
+    out.backward(cot)
+    ref.backward(cot.double())
+    assert rel_err(feats.grad, f64.grad) < 1e-4
+    for (n, p), p64 in zip(mlp.named_parameters(), m64.parameters()):
+        assert rel_err(p.grad, p64.grad) < 2e-4, n
     d2, i3 = ext.three_nn(xyz, new_xyz)
     w = torch.rand(4, 512, 3, device="cuda", generator=g)
     got = RE.interp_rows(out.detach().contiguous(), i3, w)
