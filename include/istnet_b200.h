@@ -119,10 +119,11 @@ int istnet_conv_wgrad(const void *dy_planes, long long dy_plane_stride, int dy_c
  * fixed order by a second tiny kernel: no atomics, deterministic). */
 int istnet_reduce_ws_floats(long long P, int C, int nacc); /* floats of partial-sum scratch for a per-channel reduction */
 int istnet_bn_stats(const float *y, long long P, int C, float *part_ws, float eps, float momentum, float *running_mean,
-                    float *running_var, float *mean, float *invstd, void *stream);
+                    float *running_var, float *mean, float *invstd, long long *num_batches_tracked, void *stream);
 
+/* num_batches_tracked (nullable): nn.BatchNorm2d's int64 step counter, incremented by the same launch */
 int istnet_bn_finalize(const float *part, int G, long long P, int C, float eps, float momentum, float *running_mean, float *running_var,
-                       float *mean, float *invstd, void *stream);
+                       float *mean, float *invstd, long long *num_batches_tracked, void *stream);
 
 /* z = noise[b,c] * act( bn(y) + bn_res(res) )  written as FP32 and/or as bf16 operand planes (channel stride cs, offset ch_off).
  * mean==NULL: no BN.  res==NULL: no residual; res_mean==NULL: raw residual.  act: 0 none, 1 ReLU, 2 PReLU(*prelu_a).
@@ -141,7 +142,8 @@ int istnet_bn_act_split(const float *y, long long P, int C, long long HW, const 
 int istnet_bn_act_bwd(const float *dz, const float *dz2, const float *y, long long P, int C, long long HW, const float *mean,
                       const float *invstd, const float *gamma, const float *beta, int act, const float *prelu_a, const void *z_hi,
                       int cs_z, const float *noise, int batch_stats, const uint8_t *argmax, int ns, float *part_ws, double *ws,
-                      void *dy_planes, long long plane_stride, int nsplit, int cs_dy, float *dy_f32, float *g_out, void *stream);
+                      void *dy_planes, long long plane_stride, int nsplit, int cs_dy, float *dy_f32, float *g_out, float *sum_g_f32,
+                      float *sum_gx_f32, void *stream);
 
 /* FP32 [P][C] (or NCHW with HW pixels per image when nchw != 0) -> bf16 operand planes [nsplit][P][cs] at channel offset ch_off */
 int istnet_split(const float *x, long long P, int C, long long HW, int nchw, void *planes, long long plane_stride, int nsplit, int cs,
@@ -173,6 +175,9 @@ int istnet_colsum_planes(const void *planes, long long plane_stride, int nsplit,
  * captured CUDA graph, so phase boundaries of the real (graph-replayed, multi-stream) step can be read back (tools/timeline.py);
  * the reference has no counterpart (its solver times whole iterations with time.time(), utils/solver.py:153). */
 int istnet_marker(unsigned long long *stamps, int slot, void *stream);
+/* istnet_prep_weight for transpose = 0 (planes_fwd) and transpose = 1 (planes_bwd) in one launch */
+int istnet_prep_weight_pair(const float *w, int Cout, int Cin, int kh, int kw, int im2col, void *planes_fwd, long long stride_fwd,
+                            int nsplit_fwd, int cs_fwd, void *planes_bwd, long long stride_bwd, int nsplit_bwd, int cs_bwd, void *stream);
 /* ws[c] = sum_p x[p][c] (double; bias gradients) */
 int istnet_colsum(const float *x, long long P, int C, double *ws, void *stream);
 

@@ -126,10 +126,12 @@ __global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const float *__res
 }
 
 __global__ void __launch_bounds__(256) bn_finalize_kernel(const float *__restrict__ part, int G, long long P, int C, float eps, float momentum,
-                                                          float *running_mean, float *running_var, float *mean, float *invstd) {
+                                                          float *running_mean, float *running_var, float *mean, float *invstd,
+                                                          long long *num_batches_tracked) {
     double t[2];
     sum_partials<2>(part, G, C, t);
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;  // nn.BatchNorm2d's counter, same launch
     if (threadIdx.x >= 32 || c >= C) return;
     double m = t[0] / (double)P;
     double var = t[1] / (double)P - m * m;
@@ -142,7 +144,8 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float *__restric
         running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
     }
 }
-__global__ void __launch_bounds__(256) bwd_finalize_kernel(const float *__restrict__ part, int G, int C, double *ws) {
+__global__ void __launch_bounds__(256) bwd_finalize_kernel(const float *__restrict__ part, int G, int C, double *ws, float *sum0_f32 = nullptr,
+                                                           float *sum1_f32 = nullptr) {
     double t[3];
     sum_partials<3>(part, G, C, t);
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -150,6 +153,8 @@ __global__ void __launch_bounds__(256) bwd_finalize_kernel(const float *__restri
     ws[c] = t[0];
     ws[C + c] = t[1];
     ws[2 * C + c] = t[2];
+    if (sum0_f32) sum0_f32[c] = (float)t[0];  // FP32 copies in their own tensors: the BatchNorm bias / weight gradients as autograd wants them
+    if (sum1_f32) sum1_f32[c] = (float)t[1];
 }
 
 // Per-thread channel constants: with lanes = C/4 dividing the CTA, a thread keeps the same 4 channels for every row it
@@ -438,8 +443,8 @@ __global__ void __launch_bounds__(kEwThreads) split_kernel(long long P, int C, c
 //   transpose = 0 (forward operand):        rows = co, cols = ci, tap = r*kw + s
 //   transpose = 1 (data-gradient operand):  rows = ci, cols = co, tap = flipped (kh-1-r, kw-1-s)
 //   im2col   = 1 (strided convs as 1x1 GEMM over patches): one tap, K index = (r*kw + s)*ci_total + ci
-__global__ void __launch_bounds__(kEwThreads) prep_weight_kernel(int co_n, int ci_n, int kh, int kw, const float *__restrict__ w, int transpose,
-                                                                 int im2col, __nv_bfloat16 *pl, long long pl_stride, int nsplit, int cs) {
+__device__ __forceinline__ void prep_weight_body(int co_n, int ci_n, int kh, int kw, const float *__restrict__ w, int transpose, int im2col,
+                                                 __nv_bfloat16 *pl, long long pl_stride, int nsplit, int cs) {
     const long long total = (long long)co_n * ci_n * kh * kw;
     const int taps = kh * kw;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -474,6 +479,18 @@ __global__ void __launch_bounds__(kEwThreads) prep_weight_kernel(int co_n, int c
         }
         store_planes1(pl + o, pl_stride, nsplit, v);
     }
+}
+__global__ void __launch_bounds__(kEwThreads) prep_weight_kernel(int co_n, int ci_n, int kh, int kw, const float *__restrict__ w, int transpose,
+                                                                 int im2col, __nv_bfloat16 *pl, long long pl_stride, int nsplit, int cs) {
+    prep_weight_body(co_n, ci_n, kh, kw, w, transpose, im2col, pl, pl_stride, nsplit, cs);
+}
+// forward operand and data-gradient operand of one weight in ONE launch (the training step needs both; the second is kept
+// on the tape until the backward pass)
+__global__ void __launch_bounds__(kEwThreads) prep_weight_pair_kernel(int co_n, int ci_n, int kh, int kw, const float *__restrict__ w, int im2col,
+                                                                      __nv_bfloat16 *pl_f, long long stride_f, int nsplit_f, int cs_f,
+                                                                      __nv_bfloat16 *pl_t, long long stride_t, int nsplit_t, int cs_t) {
+    prep_weight_body(co_n, ci_n, kh, kw, w, 0, im2col, pl_f, stride_f, nsplit_f, cs_f);
+    prep_weight_body(co_n, ci_n, kh, kw, w, 1, im2col, pl_t, stride_t, nsplit_t, cs_t);
 }
 __global__ void __launch_bounds__(kEwThreads) colsum_kernel(const float *__restrict__ x, long long P, int C, double *ws) {
     column_reduce<1, true>(P, C, ws, nullptr, [&](long long r, int c, float (*acc)[4]) {
@@ -842,21 +859,21 @@ inline BnP make_bn(const float *mean, const float *invstd, const float *gamma, c
 extern "C" int istnet_reduce_ws_floats(long long P, int C, int nacc) { return red_grid(P, C) * nacc * C; }
 
 extern "C" int istnet_bn_stats(const float *y, long long P, int C, float *part_ws, float eps, float momentum, float *running_mean,
-                               float *running_var, float *mean, float *invstd, void *stream) {
+                               float *running_var, float *mean, float *invstd, long long *num_batches_tracked, void *stream) {
     if (P <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
     const int G = red_grid(P, C);
     bn_stats_kernel<<<G, kEwThreads, 0, ST>>>(y, P, C, part_ws);
     ISTNET_LAUNCH_CHECK();
-    bn_finalize_kernel<<<ceil_div(C, 32), 256, 0, ST>>>(part_ws, G, P, C, eps, momentum, running_mean, running_var, mean, invstd);
+    bn_finalize_kernel<<<ceil_div(C, 32), 256, 0, ST>>>(part_ws, G, P, C, eps, momentum, running_mean, running_var, mean, invstd, num_batches_tracked);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
 
 // second stage of a BN-statistics reduction whose per-CTA partials [2][G][C] were produced elsewhere (the conv epilogue)
 extern "C" int istnet_bn_finalize(const float *part, int G, long long P, int C, float eps, float momentum, float *running_mean,
-                                  float *running_var, float *mean, float *invstd, void *stream) {
+                                  float *running_var, float *mean, float *invstd, long long *num_batches_tracked, void *stream) {
     if (G <= 0 || P <= 0 || C <= 0) return ISTNET_ERR_BAD_ARG;
-    bn_finalize_kernel<<<ceil_div(C, 32), 256, 0, ST>>>(part, G, P, C, eps, momentum, running_mean, running_var, mean, invstd);
+    bn_finalize_kernel<<<ceil_div(C, 32), 256, 0, ST>>>(part, G, P, C, eps, momentum, running_mean, running_var, mean, invstd, num_batches_tracked);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
@@ -881,7 +898,7 @@ extern "C" int istnet_bn_act_bwd(const float *dz, const float *dz2, const float 
                                  const float *invstd, const float *gamma, const float *beta, int act, const float *prelu_a,
                                  const void *z_hi, int cs_z, const float *noise, int batch_stats, const uint8_t *argmax, int ns,
                                  float *part_ws, double *ws /*3C*/, void *dy_planes, long long plane_stride, int nsplit, int cs_dy,
-                                 float *dy_f32, float *g_out, void *stream) {
+                                 float *dy_f32, float *g_out, float *sum_g_f32, float *sum_gx_f32, void *stream) {
     if (P <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
     if (act == 1 && !z_hi) return ISTNET_ERR_BAD_ARG;
     if (act == 3 && (!argmax || ns <= 0 || !mean || dz2)) return ISTNET_ERR_BAD_ARG;
@@ -894,7 +911,7 @@ extern "C" int istnet_bn_act_bwd(const float *dz, const float *dz2, const float 
     const int G = red_grid(P, C);
     bn_bwd_reduce_kernel<<<G, kEwThreads, 0, ST>>>(P, C, p, part_ws);
     ISTNET_LAUNCH_CHECK();
-    bwd_finalize_kernel<<<ceil_div(C, 32), 256, 0, ST>>>(part_ws, G, C, ws);
+    bwd_finalize_kernel<<<ceil_div(C, 32), 256, 0, ST>>>(part_ws, G, C, ws, sum_g_f32, sum_gx_f32);
     ISTNET_LAUNCH_CHECK();
     bn_bwd_apply_kernel<<<row_grid(P, C, kBwdUnroll), kEwThreads, 0, ST>>>(P, C, p, ws, (__nv_bfloat16 *)dy_planes, plane_stride, nsplit, cs_dy,
                                                                             dy_f32, g_out);
@@ -975,6 +992,15 @@ extern "C" int istnet_sa_scatter_l0(int B, int N, int M, int ns, int C0, const f
 extern "C" int istnet_marker(unsigned long long *stamps, int slot, void *stream) {
     if (!stamps || slot < 0) return ISTNET_ERR_BAD_ARG;
     marker_kernel<<<1, 1, 0, ST>>>(stamps, slot);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+extern "C" int istnet_prep_weight_pair(const float *w, int Cout, int Cin, int kh, int kw, int im2col, void *planes_fwd, long long stride_fwd,
+                                       int nsplit_fwd, int cs_fwd, void *planes_bwd, long long stride_bwd, int nsplit_bwd, int cs_bwd, void *stream) {
+    if (Cout <= 0 || Cin <= 0 || nsplit_fwd < 1 || nsplit_fwd > kMaxPlanes || nsplit_bwd < 1 || nsplit_bwd > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
+    prep_weight_pair_kernel<<<ew_grid((long long)Cout * Cin * kh * kw), kEwThreads, 0, ST>>>(Cout, Cin, kh, kw, w, im2col, (__nv_bfloat16 *)planes_fwd,
+                                                                                              stride_fwd, nsplit_fwd, cs_fwd, (__nv_bfloat16 *)planes_bwd,
+                                                                                              stride_bwd, nsplit_bwd, cs_bwd);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }

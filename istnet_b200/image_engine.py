@@ -112,9 +112,9 @@ def _head_backward(unit, rec, d_out, grads):
     C, Co, R = x.C, unit.cout, xg.W
     dys = K.empty_planes(1, 1, R, Co, dev, nsplit=K.NSPLIT_BWD)
     st_rows = K.BnState(st.mean, st.invstd, st.gamma, st.beta, batch=False)  # apply pass: dys = gamma*invstd*g (the sparse term)
-    ws = K.bn_act_bwd(d_out.view(1, 1, R, Co), None, yg, R, Co, 1, st_rows, ACT_PRELU, unit.prelu, None, None, dy_pl=dys)
+    ws, sg_f, sgx_f = K.bn_act_bwd(d_out.view(1, 1, R, Co), None, yg, R, Co, 1, st_rows, ACT_PRELU, unit.prelu, None, None, dy_pl=dys)
     sg, sgx = ws[0:Co], ws[Co : 2 * Co]
-    grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = sgx.float(), sg.float()
+    grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = sgx_f, sg_f
     grads[id(unit.prelu)] = ws[2 * Co : 3 * Co].sum().float().reshape(1)
     gw_s = K.conv_wgrad(dys, Co, Act(1, 1, R, C, None, xg.pl), 1, 1).view(Co, C)
     ds = torch.empty(1, 1, R, C, dtype=torch.float32, device=dev)
@@ -263,10 +263,9 @@ def backward(net, tape, d_out, u):
             _C.call("gather_bn_prelu_bwd", ptr(rf["y"]), c_int(B), c_ll(HW), c_int(128), c_int(N), ptr(choose), ptr(st.mean), ptr(st.invstd),
                     ptr(st.gamma), ptr(st.beta), ptr(unit.prelu), ptr(d_out), ptr(g), ptr(slope))
             dy = K.empty_planes(B, xin.H, xin.W, 128, dev, nsplit=K.NSPLIT_BWD)
-            ws = K.bn_act_bwd(g, None, rf["y"], rf["P"], 128, HW, st, ACT_NONE, None, None, None, dy_pl=dy)
-            wsf = ws.float()
-            grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = wsf[128:256], wsf[0:128]
-            grads[id(unit.b)] = torch.zeros_like(unit.b) if st.batch else (st.gamma * st.invstd * wsf[0:128]).detach()
+            ws, sg_f, sgx_f = K.bn_act_bwd(g, None, rf["y"], rf["P"], 128, HW, st, ACT_NONE, None, None, None, dy_pl=dy)
+            grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = sgx_f, sg_f
+            grads[id(unit.b)] = torch.zeros_like(unit.b) if st.batch else (st.gamma * st.invstd * sg_f).detach()
             grads[id(unit.prelu)] = slope.sum().float().reshape(1)
             dz = unit.data_grads(rf, dy, True, grads)
             dz2 = None
@@ -310,9 +309,8 @@ def backward(net, tape, d_out, u):
             _C.call("maxpool_relu_bwd", ptr(r0["y"]), c_int(B), c_int(H0), c_int(W0), c_int(64), ptr(st.mean), ptr(st.invstd), ptr(st.gamma),
                     ptr(st.beta), ptr(dz), K._p(dz2), ptr(argmax), ptr(g0))
             dy = K.empty_planes(B, H0, W0, 64, dev, nsplit=K.NSPLIT_BWD)
-            ws = K.bn_act_bwd(g0, None, r0["y"], r0["P"], 64, H0 * W0, st, ACT_NONE, None, None, None, dy_pl=dy)
-            wsf = ws.float()
-            grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = wsf[64:128], wsf[0:64]
+            _, sg_f, sgx_f = K.bn_act_bwd(g0, None, r0["y"], r0["P"], 64, H0 * W0, st, ACT_NONE, None, None, None, dy_pl=dy)
+            grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = sgx_f, sg_f
             unit.data_grads(r0, dy, False, grads)
     K.join_side_streams()
     if pending_wb is not None:

@@ -88,6 +88,24 @@ def prep_weight(w, transpose=False, nsplit=None, im2col=False):
     return pl
 
 
+def prep_weight_pair(w, im2col=False):
+    """Forward operand (NSPLIT planes) and data-gradient operand (NSPLIT_BWD planes, transposed / flipped) of one weight, one launch."""
+    if w.dim() == 2:
+        co, ci, kh, kw = w.shape[0], w.shape[1], 1, 1
+    elif w.dim() == 3:
+        co, ci, kh, kw = w.shape[0], w.shape[1], w.shape[2], 1
+    else:
+        co, ci, kh, kw = w.shape
+    taps = kh * kw
+    sf = (1, co, pad8(taps * ci)) if im2col else (taps, co, pad8(ci))
+    st = (1, taps * ci, pad8(co)) if im2col else (taps, ci, pad8(co))
+    pf = torch.empty(NSPLIT, *sf, dtype=torch.bfloat16, device=w.device)
+    pt = torch.empty(NSPLIT_BWD, *st, dtype=torch.bfloat16, device=w.device)
+    _C.call("prep_weight_pair", ptr(w), c_int(co), c_int(ci), c_int(kh), c_int(kw), c_int(1 if im2col else 0), *_pl_args(pf), c_int(sf[-1]),
+            *_pl_args(pt), c_int(st[-1]))
+    return pf, pt
+
+
 def pick_box(H, W):
     if H == 1:
         return 128, 1
@@ -203,14 +221,15 @@ def bn_state(bn, y, P, C, training, part=None, G=0):
         invstd = torch.empty(C, dtype=torch.float32, device=dev)
         mom = bn.momentum if bn.momentum is not None else 0.1
         track = bn.track_running_stats and bn.running_mean is not None
+        nbt = bn.num_batches_tracked if (track and bn.num_batches_tracked is not None and bn.num_batches_tracked.is_cuda) else None
         if part is not None:
             _C.call("bn_finalize", ptr(part), c_int(G), c_ll(P), c_int(C), c_float(bn.eps), c_float(mom), _p(bn.running_mean if track else None),
-                    _p(bn.running_var if track else None), ptr(mean), ptr(invstd))
+                    _p(bn.running_var if track else None), ptr(mean), ptr(invstd), _p(nbt))
         else:
             ws = torch.empty(_C.lib().istnet_reduce_ws_floats(c_ll(P), C, 2), dtype=torch.float32, device=dev)
             _C.call("bn_stats", ptr(y), c_ll(P), c_int(C), ptr(ws), c_float(bn.eps), c_float(mom), _p(bn.running_mean if track else None),
-                    _p(bn.running_var if track else None), ptr(mean), ptr(invstd))
-        if track:
+                    _p(bn.running_var if track else None), ptr(mean), ptr(invstd), _p(nbt))
+        if track and nbt is None and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
     else:
         return BnState(bn.running_mean, torch.rsqrt(bn.running_var + bn.eps), bn.weight, bn.bias, batch=False)
@@ -227,15 +246,18 @@ def bn_act_split(y, P, C, HW, bn=None, res=None, res_bn=None, act=0, prelu=None,
 
 
 def bn_act_bwd(dz, dz2, y, P, C, HW, bn, act, prelu, z_hi, noise, dy_pl=None, dy_f32=None, g_out=None, argmax=None, ns=0):
-    """Returns ws (3*C doubles): [sum g | sum g*xhat | PReLU slope partials]."""
+    """Returns (ws, sum_g, sum_gx): ws = 3*C doubles [sum g | sum g*xhat | PReLU slope partials]; sum_g / sum_gx are FP32 copies of
+    the first two thirds in tensors of their own (the BatchNorm bias / weight gradients: handed to autograd as they are)."""
     ws = torch.empty(3 * C, dtype=torch.float64, device=dz.device)
+    sg = torch.empty(C, dtype=torch.float32, device=dz.device)
+    sgx = torch.empty(C, dtype=torch.float32, device=dz.device)
     part = torch.empty(_C.lib().istnet_reduce_ws_floats(c_ll(P), C, 3), dtype=torch.float32, device=dz.device)
     _C.call(
         "bn_act_bwd", ptr(dz), _p(dz2), _p(y), c_ll(P), c_int(C), c_ll(HW), _p(bn.mean if bn else None), _p(bn.invstd if bn else None),
         _p(bn.gamma if bn else None), _p(bn.beta if bn else None), c_int(act), _p(prelu), _p(z_hi), c_int(z_hi.shape[-1] if z_hi is not None else 0),
-        _p(noise), c_int(1 if (bn is not None and bn.batch) else 0), _p(argmax), c_int(ns), ptr(part), ptr(ws), *_pl_args(dy_pl), c_int(dy_pl.shape[-1] if dy_pl is not None else 0), _p(dy_f32), _p(g_out),
+        _p(noise), c_int(1 if (bn is not None and bn.batch) else 0), _p(argmax), c_int(ns), ptr(part), ptr(ws), *_pl_args(dy_pl), c_int(dy_pl.shape[-1] if dy_pl is not None else 0), _p(dy_f32), _p(g_out), ptr(sg), ptr(sgx),
     )
-    return ws
+    return ws, sg, sgx
 
 
 def upsample2x(x_f32, B, H, W, C, out_pl):
@@ -290,11 +312,11 @@ class ConvUnit:
         if self.stride != 1 or x_f32_nchw is not None:
             src = x_f32_nchw if x_f32_nchw is not None else x.f32
             xin = im2col(src, x_f32_nchw is not None, x.B, x.H, x.W, x.C, self.k, self.stride, self.pad)
-            wp = prep_weight(self.w, im2col=True)  # [co, (r,s,c)] = the im2col K order
+            wp, wd = prep_weight_pair(self.w, im2col=True) if record else (prep_weight(self.w, im2col=True), None)  # [co, (r,s,c)] = the im2col K order
             kk = 1
         else:
             xin, kk = x, self.k
-            wp = prep_weight(self.w)
+            wp, wd = prep_weight_pair(self.w) if record else (prep_weight(self.w), None)
         B, H, W = xin.B, xin.H, xin.W
         P, C = B * H * W, self.cout
         if self.bn is None and self.act == ACT_RELU and noise is None and res is None and not defer_act:
@@ -309,7 +331,7 @@ class ConvUnit:
             rec = {"bn": None}
             if record:
                 rec.update({"xin": xin, "y": None, "noise": None, "kk": kk, "P": P, "HW": H * W, "in_shape": (x.B, x.H, x.W, x.C),
-                            "z_hi": out.hi})
+                            "z_hi": out.hi, "wd": wd})
             return out, rec
         y = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
         part = None
@@ -319,7 +341,7 @@ class ConvUnit:
         st = bn_state(self.bn, y, P, C, training, part, G) if self.bn is not None else None
         rec = {"bn": st}
         if record:
-            rec.update({"xin": xin, "y": y, "noise": noise, "kk": kk, "P": P, "HW": H * W, "in_shape": (x.B, x.H, x.W, x.C)})
+            rec.update({"xin": xin, "y": y, "noise": noise, "kk": kk, "P": P, "HW": H * W, "in_shape": (x.B, x.H, x.W, x.C), "wd": wd})
         if defer_act:
             return Act(B, H, W, C, y), rec
         if self.bn is None and self.act == ACT_NONE and noise is None and res is None:  # plain linear layer
@@ -358,24 +380,24 @@ class ConvUnit:
                 grads[id(self.b)] = d.reshape(P, C).sum(0)
             return self.data_grads(rec, dy, need_dx, grads), (d if g_out else None)
         g = torch.empty(B, H, W, C, dtype=torch.float32, device=dev) if g_out else None
-        ws = bn_act_bwd(dz, dz2, rec["y"], P, C, rec["HW"], rec["bn"], self.act, self.prelu, rec.get("z_hi"), rec["noise"], dy_pl=dy, g_out=g)
-        self.param_grads(rec, ws, grads)
+        sums = bn_act_bwd(dz, dz2, rec["y"], P, C, rec["HW"], rec["bn"], self.act, self.prelu, rec.get("z_hi"), rec["noise"], dy_pl=dy, g_out=g)
+        self.param_grads(rec, sums, grads)
         dx = self.data_grads(rec, dy, need_dx, grads)
         return dx, g
 
-    def param_grads(self, rec, ws, grads):
+    def param_grads(self, rec, sums, grads):
+        ws, sg, sgx = sums
         C = self.cout
-        wsf = ws.float()
         if self.bn is not None:
-            grads[id(self.bn.weight)] = wsf[C : 2 * C]
-            grads[id(self.bn.bias)] = wsf[0:C]
+            grads[id(self.bn.weight)] = sgx
+            grads[id(self.bn.bias)] = sg
             if self.b is not None:  # a bias feeding a train-mode BatchNorm has an identically zero gradient
                 if rec["bn"].batch:
                     grads[id(self.b)] = torch.zeros_like(self.b)
                 else:  # running statistics: d bias = sum_p dy = gamma*invstd*sum g
-                    grads[id(self.b)] = (rec["bn"].gamma * rec["bn"].invstd * wsf[0:C]).detach()
+                    grads[id(self.b)] = (rec["bn"].gamma * rec["bn"].invstd * sg).detach()
         elif self.b is not None:
-            grads[id(self.b)] = wsf[0:C]
+            grads[id(self.b)] = sg
         if self.act == ACT_PRELU:
             grads[id(self.prelu)] = ws[2 * C : 3 * C].sum().float().reshape(1)
 
@@ -401,12 +423,16 @@ class ConvUnit:
             return None
         dyA = Act(xin.B, xin.H, xin.W, C, None, dy)
         if kk != self.k or self.stride != 1:
-            wd = prep_weight(self.w, transpose=True, nsplit=dy.shape[0], im2col=True)
+            wd = rec.get("wd")
+            if wd is None or wd.shape[0] != dy.shape[0]:
+                wd = prep_weight(self.w, transpose=True, nsplit=dy.shape[0], im2col=True)
             dcol = torch.empty(xin.B, xin.H, xin.W, xin.C, dtype=torch.float32, device=dy.device)
             conv_gemm(dyA, wd, xin.C, 1, 1, out_f32=dcol)
             b, h, w, c = rec["in_shape"]
             return col2im(dcol, b, h, w, c, self.k, self.stride, self.pad)
-        wd = prep_weight(self.w, transpose=True, nsplit=dy.shape[0])
+        wd = rec.get("wd")
+        if wd is None or wd.shape[0] != dy.shape[0]:
+            wd = prep_weight(self.w, transpose=True, nsplit=dy.shape[0])
         dx = torch.empty(xin.B, xin.H, xin.W, xin.C, dtype=torch.float32, device=dy.device)
         conv_gemm(dyA, wd, xin.C, kk, kk, out_f32=dx)
         return dx

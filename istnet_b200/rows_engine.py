@@ -126,9 +126,8 @@ class _SAScaleFn(torch.autograd.Function):
         st = rec["bn"]
         dy = K.empty_planes(1, 1, G * ns, Cl, dz.device, nsplit=K.NSPLIT_BWD)
         # max-pool routing + ReLU mask + BN backward in one reduce / apply pair (no materialised [rows, C] selection tensor)
-        ws = K.bn_act_bwd(dz, None, rec["y"], G * ns, Cl, 1, st, K.ACT_RELU_MAXROWS, None, None, None, dy_pl=dy, argmax=argmax, ns=ns)
-        wsf = ws.float()
-        grads[id(last.bn.weight)], grads[id(last.bn.bias)] = wsf[Cl : 2 * Cl], wsf[0:Cl]
+        _, sg_f, sgx_f = K.bn_act_bwd(dz, None, rec["y"], G * ns, Cl, 1, st, K.ACT_RELU_MAXROWS, None, None, None, dy_pl=dy, argmax=argmax, ns=ns)
+        grads[id(last.bn.weight)], grads[id(last.bn.bias)] = sgx_f, sg_f
         d = last.data_grads(rec, dy, True, grads)
         d_feats = None
         if tape[0].get("point_l0"):
@@ -187,9 +186,8 @@ def _sa_l0_backward(u0, rec, d, xyz, new_xyz, idx, need_dfeats, grads):
     C = 0 if fa is None else fa.C
     rows, C0, dev = B * M * ns, u0.cout, d.device
     dy0 = torch.empty(1, 1, rows, C0, dtype=torch.float32, device=dev)
-    ws = K.bn_act_bwd(d, None, rec["y"], rows, C0, 1, rec["bn"], ACT_RELU, None, rec["z_hi"], None, dy_f32=dy0)
-    wsf = ws.float()
-    grads[id(u0.bn.weight)], grads[id(u0.bn.bias)] = wsf[C0 : 2 * C0], wsf[0:C0]
+    _, sg_f, sgx_f = K.bn_act_bwd(d, None, rec["y"], rows, C0, 1, rec["bn"], ACT_RELU, None, rec["z_hi"], None, dy_f32=dy0)
+    grads[id(u0.bn.weight)], grads[id(u0.bn.bias)] = sgx_f, sg_f
     dU = torch.empty(B * N, C0, dtype=torch.float32, device=dev) if C > 0 else None
     part = torch.empty(_C.lib().istnet_reduce_ws_floats(c_ll(rows), C0, 3), dtype=torch.float32, device=dev)
     wsx = torch.empty(3 * C0, dtype=torch.float64, device=dev)
