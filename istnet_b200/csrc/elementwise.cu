@@ -85,35 +85,39 @@ __device__ void column_reduce(long long P, int C, double *ws, float *part, F row
         }
     }
 }
-// tot[a*C + c] = sum_g part[(a*G + g)*C + c]  in double, fixed order: block = 32 channels x 8 partial-slices
+// tot[a*C + c] = sum_g part[(a*G + g)*C + c]  in double, fixed order: block = 32 channels x kFinSlices partial-slices.  The
+// kernel is pure latency (a few hundred KB out of L2), so every thread issues all its loads of all NACC quantities at once.
+constexpr int kFinSlices = 32;
+constexpr int kFinThreads = 32 * kFinSlices;
 template <int NACC>
 __device__ void sum_partials(const float *__restrict__ part, int G, int C, double (&out)[NACC]) {
-    __shared__ double sred[NACC][8][32];
+    __shared__ double sred[NACC][kFinSlices][32];
     const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + l;
+    double s[NACC];
 #pragma unroll
-    for (int a = 0; a < NACC; ++a) {
-        double s = 0.0;
-        if (c < C) {
-            const float *src = part + (size_t)a * G * C + c;
-            int g = w;
-            for (; g + 56 < G; g += 64) {  // 8 independent loads in flight per thread
-                float v[8];
+    for (int a = 0; a < NACC; ++a) s[a] = 0.0;
+    if (c < C) {
+        for (int g = w; g < G; g += 4 * kFinSlices) {
+            float v[NACC][4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(g + 8 * u) * C];
+            for (int a = 0; a < NACC; ++a)
 #pragma unroll
-                for (int u = 0; u < 8; ++u) s += (double)v[u];
-            }
-            for (; g < G; g += 8) s += (double)src[(size_t)g * C];
+                for (int u = 0; u < 4; ++u) v[a][u] = (g + u * kFinSlices < G) ? part[((size_t)a * G + g + u * kFinSlices) * C + c] : 0.f;
+#pragma unroll
+            for (int a = 0; a < NACC; ++a)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) s[a] += (double)v[a][u];
         }
-        sred[a][w][l] = s;
     }
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) sred[a][w][l] = s[a];
     __syncthreads();
 #pragma unroll
     for (int a = 0; a < NACC; ++a) {
-        double s = 0.0;
-        for (int q = 0; q < 8; ++q) s += sred[a][q][l];
-        out[a] = s;
+        double t = 0.0;
+        for (int q = 0; q < kFinSlices; ++q) t += sred[a][q][l];
+        out[a] = t;
     }
 }
 
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const float *__res
     });
 }
 
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float *__restrict__ part, int G, long long P, int C, float eps, float momentum,
+__global__ void __launch_bounds__(kFinThreads) bn_finalize_kernel(const float *__restrict__ part, int G, long long P, int C, float eps, float momentum,
                                                           float *running_mean, float *running_var, float *mean, float *invstd,
                                                           long long *num_batches_tracked) {
     double t[2];
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float *__restric
         running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
     }
 }
-__global__ void __launch_bounds__(256) bwd_finalize_kernel(const float *__restrict__ part, int G, int C, double *ws, float *sum0_f32 = nullptr,
+__global__ void __launch_bounds__(kFinThreads) bwd_finalize_kernel(const float *__restrict__ part, int G, int C, double *ws, float *sum0_f32 = nullptr,
                                                            float *sum1_f32 = nullptr) {
     double t[3];
     sum_partials<3>(part, G, C, t);
@@ -864,7 +868,7 @@ extern "C" int istnet_bn_stats(const float *y, long long P, int C, float *part_w
     const int G = red_grid(P, C);
     bn_stats_kernel<<<G, kEwThreads, 0, ST>>>(y, P, C, part_ws);
     ISTNET_LAUNCH_CHECK();
-    bn_finalize_kernel<<<ceil_div(C, 32), 256, 0, ST>>>(part_ws, G, P, C, eps, momentum, running_mean, running_var, mean, invstd, num_batches_tracked);
+    bn_finalize_kernel<<<ceil_div(C, 32), kFinThreads, 0, ST>>>(part_ws, G, P, C, eps, momentum, running_mean, running_var, mean, invstd, num_batches_tracked);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
@@ -873,7 +877,7 @@ extern "C" int istnet_bn_stats(const float *y, long long P, int C, float *part_w
 extern "C" int istnet_bn_finalize(const float *part, int G, long long P, int C, float eps, float momentum, float *running_mean,
                                   float *running_var, float *mean, float *invstd, long long *num_batches_tracked, void *stream) {
     if (G <= 0 || P <= 0 || C <= 0) return ISTNET_ERR_BAD_ARG;
-    bn_finalize_kernel<<<ceil_div(C, 32), 256, 0, ST>>>(part, G, P, C, eps, momentum, running_mean, running_var, mean, invstd, num_batches_tracked);
+    bn_finalize_kernel<<<ceil_div(C, 32), kFinThreads, 0, ST>>>(part, G, P, C, eps, momentum, running_mean, running_var, mean, invstd, num_batches_tracked);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
@@ -911,7 +915,7 @@ extern "C" int istnet_bn_act_bwd(const float *dz, const float *dz2, const float 
     const int G = red_grid(P, C);
     bn_bwd_reduce_kernel<<<G, kEwThreads, 0, ST>>>(P, C, p, part_ws);
     ISTNET_LAUNCH_CHECK();
-    bwd_finalize_kernel<<<ceil_div(C, 32), 256, 0, ST>>>(part_ws, G, C, ws, sum_g_f32, sum_gx_f32);
+    bwd_finalize_kernel<<<ceil_div(C, 32), kFinThreads, 0, ST>>>(part_ws, G, C, ws, sum_g_f32, sum_gx_f32);
     ISTNET_LAUNCH_CHECK();
     bn_bwd_apply_kernel<<<row_grid(P, C, kBwdUnroll), kEwThreads, 0, ST>>>(P, C, p, ws, (__nv_bfloat16 *)dy_planes, plane_stride, nsplit, cs_dy,
                                                                             dy_f32, g_out);
@@ -946,7 +950,7 @@ __global__ void __launch_bounds__(kEwThreads) colsum_planes_kernel(const __nv_bf
         }
     });
 }
-__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float *__restrict__ part, int G, int C, double *ws) {
+__global__ void __launch_bounds__(kFinThreads) colsum_finalize_kernel(const float *__restrict__ part, int G, int C, double *ws) {
     double t[1];
     sum_partials<1>(part, G, C, t);
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -958,7 +962,7 @@ extern "C" int istnet_colsum_planes(const void *planes, long long plane_stride, 
     const int G = red_grid(P, C);
     colsum_planes_kernel<<<G, kEwThreads, 0, ST>>>((const __nv_bfloat16 *)planes, plane_stride, nsplit, P, C, cs, part_ws);
     ISTNET_LAUNCH_CHECK();
-    colsum_finalize_kernel<<<ceil_div(C, 32), 256, 0, ST>>>(part_ws, G, C, ws);
+    colsum_finalize_kernel<<<ceil_div(C, 32), kFinThreads, 0, ST>>>(part_ws, G, C, ws);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
@@ -985,7 +989,7 @@ extern "C" int istnet_sa_scatter_l0(int B, int N, int M, int ns, int C0, const f
     const int G = red_grid(rows, C0);
     sa_scatter_l0_kernel<<<G, kEwThreads, 0, ST>>>(N, M, ns, C0, rows, dy0, xyz, new_xyz, idx, dU, part_ws);
     ISTNET_LAUNCH_CHECK();
-    bwd_finalize_kernel<<<ceil_div(C0, 32), 256, 0, ST>>>(part_ws, G, C0, ws);
+    bwd_finalize_kernel<<<ceil_div(C0, 32), kFinThreads, 0, ST>>>(part_ws, G, C0, ws);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }

@@ -165,25 +165,37 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
     }
 }
 
-// grad_w[co][ci][tap] = sum_split partial[split][tap][co][ci]   (fixed summation order)
+// grad_w[co][ci][tap] = sum_split partial[split][tap][co][ci]   (fixed summation order).  L = 1, 8 or 32 lanes share one
+// output element (lane q sums splits q, q+L, ...; the lanes are then combined by a fixed xor tree): small weight tensors
+// with many splits would otherwise leave one thread walking 100+ dependent-latency loads.
+template <int L>
 __global__ void wgrad_reduce_kernel(int ksplit, int taps, int Cout, int Cin, const float *__restrict__ partial, float *__restrict__ grad_w) {
     const long long total = (long long)taps * Cout * Cin;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ci = (int)(i % Cin);
-        const long long rest = i / Cin;
-        const int co = (int)(rest % Cout);
-        const int tap = (int)(rest / Cout);
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (total + 31) / 32 * 32 * L; t += nthreads) {  // whole warps stay in the loop
+        const long long i = t / L;
+        const int q = (int)(t % L);
         float acc = 0.f;
-        int sp = 0;
-        for (; sp + 8 <= ksplit; sp += 8) {  // 8 independent loads in flight, summed in a fixed order
-            float v[8];
+        if (i < total) {
+            int sp = q;
+            for (; sp + 7 * L < ksplit; sp += 8 * L) {  // 8 independent loads in flight, summed in a fixed order
+                float v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = partial[(size_t)(sp + u) * total + i];
+                for (int u = 0; u < 8; ++u) v[u] = partial[(size_t)(sp + u * L) * total + i];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) acc += v[u];
+                for (int u = 0; u < 8; ++u) acc += v[u];
+            }
+            for (; sp < ksplit; sp += L) acc += partial[(size_t)sp * total + i];
         }
-        for (; sp < ksplit; ++sp) acc += partial[(size_t)sp * total + i];
-        grad_w[((size_t)co * Cin + ci) * taps + tap] = acc;
+#pragma unroll
+        for (int off = L / 2; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (i < total && q == 0) {
+            const int ci = (int)(i % Cin);
+            const long long rest = i / Cin;
+            const int co = (int)(rest % Cout);
+            const int tap = (int)(rest / Cout);
+            grad_w[((size_t)co * Cin + ci) * taps + tap] = acc;
+        }
     }
 }
 
@@ -290,9 +302,12 @@ extern "C" int istnet_conv_wgrad(const void *dy_planes, long long dy_plane_strid
     wgrad_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(t_dy, t_x, p);
     ISTNET_LAUNCH_CHECK();
     const long long total = (long long)kh * kw * Cout * Cin;
-    int rgrid = (int)((total + 255) / 256);
+    const int L = (ksplit >= 32 && total <= 16384) ? 32 : (ksplit >= 8 && total <= 131072) ? 8 : 1;
+    int rgrid = (int)((total * L + 255) / 256);
     if (rgrid > kNumSMs * 8) rgrid = kNumSMs * 8;
-    wgrad_reduce_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(ksplit, kh * kw, Cout, Cin, partial_ws, grad_w);
+    if (L == 32) wgrad_reduce_kernel<32><<<rgrid, 256, 0, (cudaStream_t)stream>>>(ksplit, kh * kw, Cout, Cin, partial_ws, grad_w);
+    else if (L == 8) wgrad_reduce_kernel<8><<<rgrid, 256, 0, (cudaStream_t)stream>>>(ksplit, kh * kw, Cout, Cin, partial_ws, grad_w);
+    else wgrad_reduce_kernel<1><<<rgrid, 256, 0, (cudaStream_t)stream>>>(ksplit, kh * kw, Cout, Cin, partial_ws, grad_w);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
