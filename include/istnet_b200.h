@@ -93,11 +93,15 @@ int istnet_fps_chain(int b, int n, int nlevels, const int *npoint, const float *
  * ist_net.py:130-160).  wgt planes: bf16 [nsplit][kh*kw][Cout][wgt_cs].  Any of out_f32 / out_planes may be null.
  * (box_w, box_h): pixel tile; box_w*box_h must divide 128 (images: 8x8 -> 2 images per tile; row matrices: 128x1).
  * stat_part (optional, >= 2*296*Cout floats): the epilogue also accumulates the per-channel sum / sum of squares of the
- * output (train-mode BatchNorm statistics) per CTA; *grid_out receives the number of CTAs G, finish with istnet_bn_finalize. */
+ * output (train-mode BatchNorm statistics) per CTA; *grid_out receives the number of CTAs G, finish with istnet_bn_finalize.
+ * mask_hi (nullable, bf16 [B,H,W,mask_cs]): the output is zeroed where mask <= 0 before statistics / stores — used by the data
+ * gradient of a layer fed by a bias+ReLU layer (nn.Conv1d + nn.ReLU stacks, ist_net.py:130-160): the epilogue then produces that
+ * layer's dy operand planes and, through stat_part, its bias gradient (autograd's threshold_backward + sum in the reference). */
 int istnet_conv_gemm(const void *act_planes, long long act_plane_stride, int B, int H, int W, int Cin, int act_cs,
                      const void *wgt_planes, long long wgt_plane_stride, int Cout, int wgt_cs, int kh, int kw, int nsplit,
                      const float *bias, int relu, float *out_f32, int out_cs, void *out_planes, long long out_plane_stride,
-                     int nsplit_out, int split_cs, int box_w, int box_h, float *stat_part, int *grid_out, void *stream);
+                     int nsplit_out, int split_cs, int box_w, int box_h, float *stat_part, int *grid_out, const void *mask_hi, int mask_cs,
+                     void *stream);
 
 /* Weight gradient of the layer above (cuDNN wgrad in the reference):
  *   grad_w[co][ci][r][s] = sum_{b,h,w} dy[b,h,w,co] * x[b,h+r-kh/2,w+s-kw/2,ci]       (PyTorch weight layout, FP32)
@@ -178,6 +182,8 @@ int istnet_marker(unsigned long long *stamps, int slot, void *stream);
 /* istnet_prep_weight for transpose = 0 (planes_fwd) and transpose = 1 (planes_bwd) in one launch */
 int istnet_prep_weight_pair(const float *w, int Cout, int Cin, int kh, int kw, int im2col, void *planes_fwd, long long stride_fwd,
                             int nsplit_fwd, int cs_fwd, void *planes_bwd, long long stride_bwd, int nsplit_bwd, int cs_bwd, void *stream);
+/* out[c] = sum_g part[g*C + c]: column sums from the per-CTA partials of a statistics epilogue (first of its two quantities) */
+int istnet_colsum_finalize(const float *part, int G, int C, double *ws, float *out_f32, void *stream);
 /* ws[c] = sum_p x[p][c] (double; bias gradients) */
 int istnet_colsum(const float *x, long long P, int C, double *ws, void *stream);
 

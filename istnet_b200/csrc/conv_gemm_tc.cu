@@ -46,6 +46,8 @@ struct ConvGemmParams {
     int split_cs, nsplit_out;
     int nsplit;               // planes of the input operands
     float *stat_part;         // optional [gridDim.x][2][Cout]: per-CTA column sums / sums of squares of the output (BN statistics)
+    const __nv_bfloat16 *mask_hi;  // optional [B,H,W,mask_cs]: output element kept only where mask > 0 (ReLU backward of the layer below)
+    int mask_cs;
     uint32_t tmem_cols;
 };
 
@@ -213,6 +215,29 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
                 }
+                if (p.mask_hi != nullptr && row_ok) {
+                    // data gradient of a layer whose input is the ReLU output z of the layer below: g = dx * [z > 0]; the mask is
+                    // plane 0 of z as saved by the forward pass.  The statistics path below then yields sum(g) = that layer's
+                    // bias gradient and the plane stores its dy operand: no separate reduce / apply passes over dx.
+                    const __nv_bfloat16 *mrow = p.mask_hi + pix * p.mask_cs + n;
+                    if (valid == 32 && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0)) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            const uint4 m = __ldg(reinterpret_cast<const uint4 *>(mrow + i));
+                            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {  // bf16 > 0  <=>  sign clear and magnitude bits non-zero
+                                const uint32_t lo = mw[j] & 0xffffu, hi = mw[j] >> 16;
+                                if (!(lo != 0u && lo < 0x8000u)) f[i + 2 * j] = 0.f;
+                                if (!(hi != 0u && hi < 0x8000u)) f[i + 2 * j + 1] = 0.f;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < valid && !(__bfloat162float(mrow[i]) > 0.f)) f[i] = 0.f;
+                    }
+                }
                 if (p.stat_part) {
                     // BatchNorm statistics of this 32-row x 32-column block: butterfly transpose-reduce over the warp
                     // (31 shuffles per quantity), lane l ends with the column (c0 + l) totals and adds them to this lane
@@ -340,7 +365,8 @@ static int pick_bn(int cout, int nsplit, int block_k) {
 extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stride, int B, int H, int W, int Cin, int act_cs,
                                 const void *wgt_planes, long long wgt_plane_stride, int Cout, int wgt_cs, int kh, int kw, int nsplit,
                                 const float *bias, int relu, float *out_f32, int out_cs, void *out_planes, long long out_plane_stride,
-                                int nsplit_out, int split_cs, int box_w, int box_h, float *stat_part, int *grid_out, void *stream) {
+                                int nsplit_out, int split_cs, int box_w, int box_h, float *stat_part, int *grid_out, const void *mask_hi,
+                                int mask_cs, void *stream) {
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return ISTNET_ERR_BAD_ARG;
     if (nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
     if ((act_cs & 7) || (wgt_cs & 7) || act_cs < Cin || wgt_cs < Cin) return ISTNET_ERR_BAD_ARG;
@@ -360,6 +386,8 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     p.nsplit = nsplit;
     p.bias = bias; p.relu = relu;
     p.stat_part = stat_part;
+    p.mask_hi = (const __nv_bfloat16 *)mask_hi; p.mask_cs = mask_cs;
+    if (mask_hi && mask_cs < Cout) return ISTNET_ERR_BAD_ARG;
     p.out_f32 = out_f32; p.out_cs = out_cs;
     p.out_pl = (__nv_bfloat16 *)out_planes; p.out_pl_stride = out_plane_stride; p.split_cs = split_cs; p.nsplit_out = nsplit_out;
     p.n_tiles_n = ceil_div(Cout, p.BN);

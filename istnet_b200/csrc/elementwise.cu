@@ -950,11 +950,20 @@ __global__ void __launch_bounds__(kEwThreads) colsum_planes_kernel(const __nv_bf
         }
     });
 }
-__global__ void __launch_bounds__(kFinThreads) colsum_finalize_kernel(const float *__restrict__ part, int G, int C, double *ws) {
+__global__ void __launch_bounds__(kFinThreads) colsum_finalize_kernel(const float *__restrict__ part, int G, int C, double *ws, float *out_f32 = nullptr) {
     double t[1];
     sum_partials<1>(part, G, C, t);
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-    if (threadIdx.x < 32 && c < C) ws[c] = t[0];
+    if (threadIdx.x < 32 && c < C) {
+        if (ws) ws[c] = t[0];
+        if (out_f32) out_f32[c] = (float)t[0];
+    }
+}
+extern "C" int istnet_colsum_finalize(const float *part, int G, int C, double *ws, float *out_f32, void *stream) {
+    if (!part || G <= 0 || C <= 0) return ISTNET_ERR_BAD_ARG;
+    colsum_finalize_kernel<<<ceil_div(C, 32), kFinThreads, 0, ST>>>(part, G, C, ws, out_f32);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
 }
 extern "C" int istnet_colsum_planes(const void *planes, long long plane_stride, int nsplit, long long P, int C, int cs, float *part_ws,
                                     double *ws, void *stream) {

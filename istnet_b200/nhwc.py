@@ -115,6 +115,8 @@ def pick_box(H, W):
 
 
 FUSE_BN_STATS = os.environ.get("ISTNET_FUSE_BN_STATS", "1") != "0"
+# ReLU backward + bias gradient + operand split of a bias+ReLU layer inside the epilogue of the data-gradient GEMM above it
+FUSE_RELU_BWD = os.environ.get("ISTNET_FUSE_RELU_BWD", "1") != "0"
 WGRAD_SIDE_STREAM = os.environ.get("ISTNET_WGRAD_STREAM", "1") != "0"
 _SIDE = {}
 _PENDING_JOINS = []
@@ -166,7 +168,7 @@ def _timed(name, flops, nsplit, launch, desc=""):
     PROFILE.append((name, e0, e1, PROFILE_REPS, flops, nsplit, desc))
 
 
-def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl=None, stat_part=None):
+def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl=None, stat_part=None, mask_hi=None):
     """x: Act with operand planes; writes out_f32 [B,H,W,cout] and/or out_pl.  With stat_part (float buffer of
     >= 2*296*cout) the epilogue also leaves per-CTA BN-statistics partials there; returns the CTA count G."""
     bw, bh = pick_box(x.H, x.W)
@@ -175,7 +177,7 @@ def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl
         ptr(x.pl), c_ll(x.pl.stride(0)), c_int(x.B), c_int(x.H), c_int(x.W), c_int(x.C), c_int(x.cs), ptr(w_pl),
         c_ll(w_pl.stride(0)), c_int(cout), c_int(w_pl.shape[-1]), c_int(kh), c_int(kw), c_int(x.pl.shape[0]), _p(bias), c_int(1 if relu else 0),
         _p(out_f32), c_int(out_f32.shape[-1] if out_f32 is not None else 0), *_pl_args(out_pl), c_int(out_pl.shape[-1] if out_pl is not None else 0),
-        c_int(bw), c_int(bh), _p(stat_part), ctypes.byref(grid),
+        c_int(bw), c_int(bh), _p(stat_part), ctypes.byref(grid), _p(mask_hi), c_int(mask_hi.shape[-1] if mask_hi is not None else 0),
     )
     _timed("conv_gemm_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, x.pl.shape[0], lambda: _C.call("conv_gemm", *args),
            f"P={x.P} {x.H}x{x.W} cin={x.C} cout={cout} k={kh}")
@@ -369,6 +371,12 @@ class ConvUnit:
     # ---- backward
     def backward(self, rec, dz, dz2=None, need_dx=True, g_out=False, grads=None):
         """dz (+dz2): FP32 gradient w.r.t. the unit output.  Fills grads[param] and returns (dx FP32 or None, g or None)."""
+        dy, g = self.act_backward(rec, dz, dz2, g_out, grads)
+        return self.data_grads(rec, dy, need_dx, grads), g
+
+    def act_backward(self, rec, dz, dz2, g_out, grads):
+        """Activation / BatchNorm backward: FP32 gradient w.r.t. the unit output -> dy operand planes of the convolution's
+        backward GEMMs (+ the gradients of bias / BN / PReLU parameters).  Returns (dy planes, g or None)."""
         dev = dz.device
         xin, P, C = rec["xin"], rec["P"], self.cout
         B, H, W = xin.B, xin.H, xin.W
@@ -378,12 +386,16 @@ class ConvUnit:
             split(d.contiguous(), P, C, dy)
             if self.b is not None:
                 grads[id(self.b)] = d.reshape(P, C).sum(0)
-            return self.data_grads(rec, dy, need_dx, grads), (d if g_out else None)
+            return dy, (d if g_out else None)
         g = torch.empty(B, H, W, C, dtype=torch.float32, device=dev) if g_out else None
         sums = bn_act_bwd(dz, dz2, rec["y"], P, C, rec["HW"], rec["bn"], self.act, self.prelu, rec.get("z_hi"), rec["noise"], dy_pl=dy, g_out=g)
         self.param_grads(rec, sums, grads)
-        dx = self.data_grads(rec, dy, need_dx, grads)
-        return dx, g
+        return dy, g
+
+    def is_bias_relu(self, rec):
+        """Conv + bias + ReLU with nothing else (the nn.Conv1d / nn.ReLU stacks): its activation backward can ride in the
+        epilogue of the data-gradient GEMM of the layer above (conv_gemm mask_hi)."""
+        return self.bn is None and self.act == ACT_RELU and rec.get("noise") is None and rec.get("z_hi") is not None and rec.get("y") is None
 
     def param_grads(self, rec, sums, grads):
         ws, sg, sgx = sums
@@ -401,7 +413,10 @@ class ConvUnit:
         if self.act == ACT_PRELU:
             grads[id(self.prelu)] = ws[2 * C : 3 * C].sum().float().reshape(1)
 
-    def data_grads(self, rec, dy, need_dx, grads):
+    def data_grads(self, rec, dy, need_dx, grads, below=None):
+        """Weight gradient (side stream) and data gradient of the convolution.  below = (unit, rec) of the bias+ReLU layer that
+        produced this unit's input: the data-gradient GEMM then applies that layer's ReLU mask in its epilogue and returns
+        ITS dy operand planes (and fills its bias gradient) instead of the FP32 dx."""
         xin, kk, C = rec["xin"], rec["kk"], self.cout
         # weight gradient and data gradient are independent: wgrad goes to a side stream and overlaps the dgrad GEMM
         main = torch.cuda.current_stream()
@@ -433,6 +448,16 @@ class ConvUnit:
         wd = rec.get("wd")
         if wd is None or wd.shape[0] != dy.shape[0]:
             wd = prep_weight(self.w, transpose=True, nsplit=dy.shape[0])
+        if below is not None:
+            bu, brec = below
+            dyb = empty_planes(xin.B, xin.H, xin.W, xin.C, dy.device, nsplit=NSPLIT_BWD)
+            part = torch.empty(2 * 296 * xin.C, dtype=torch.float32, device=dy.device)
+            G = conv_gemm(dyA, wd, xin.C, kk, kk, out_pl=dyb, stat_part=part, mask_hi=brec["z_hi"])
+            if bu.b is not None:
+                gb = torch.empty(xin.C, dtype=torch.float32, device=dy.device)
+                _C.call("colsum_finalize", ptr(part), c_int(G), c_int(xin.C), NULL, ptr(gb))
+                grads[id(bu.b)] = gb
+            return dyb
         dx = torch.empty(xin.B, xin.H, xin.W, xin.C, dtype=torch.float32, device=dy.device)
         conv_gemm(dyA, wd, xin.C, kk, kk, out_f32=dx)
         return dx

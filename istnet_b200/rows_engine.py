@@ -55,8 +55,17 @@ def _chain_forward(units, a, training, record, last_f32=True, last_pair=False):
 
 
 def _chain_backward(units, tape, dz, grads, need_dx_first):
+    dy = None  # operand planes of unit i's dy when the layer above already produced them in its data-gradient epilogue
     for i in range(len(units) - 1, -1, -1):
-        dz, _ = units[i].backward(tape[i], dz, None, need_dx=(i > 0 or need_dx_first), grads=grads)
+        u, rec = units[i], tape[i]
+        if dy is None:
+            dy, _ = u.act_backward(rec, dz, None, False, grads)
+        fuse = (K.FUSE_RELU_BWD and i > 0 and rec["kk"] == u.k and u.stride == 1 and units[i - 1].is_bias_relu(tape[i - 1])
+                and tape[i - 1]["z_hi"].shape[-1] >= rec["xin"].C)
+        if fuse:
+            dy, dz = u.data_grads(rec, dy, True, grads, below=(units[i - 1], tape[i - 1])), None
+        else:
+            dz, dy = u.data_grads(rec, dy, i > 0 or need_dx_first, grads), None
     return dz
 
 
