@@ -25,7 +25,7 @@ import torch.distributed as dist  # noqa: E402
 LABELS = ("qo", "rotation_label", "translation_label", "size_label")
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's largest launch (up_1 conv, B=32) from one
 # `ncu --set full` capture (profiles/), bytes per launch; None until captured for the current kernel version
-ROOFLINE_TRAFFIC = 583.1e6  # profiles/r1_conv_up1_ns3_bk32.txt: 510.9 MB read + 72.2 MB written (algorithmic: 453 MB operand planes + 75.5 MB output)
+ROOFLINE_TRAFFIC = 573.7e6  # profiles/r1_conv_up1_after.txt: 511.1 MB read + 62.6 MB written (algorithmic: 453 MB operand planes + 75.5 MB output)
 MODEL_IN = ("rgb", "pts", "choose", "category_label", "qo")
 WORKLOADS = {
     "cfg1": dict(model="ist_net", batch=32, npts=1024, img=192, desc="ist_net_default.yaml train fwd+bwd, 32 x (1024 pts + 192x192 RGB) per GPU"),
@@ -246,7 +246,10 @@ def main():
 
         if world > 1:  # the first eager step built the flat gradient buckets; the graph writes into them, NCCL reduces them
             reducer.remove_hooks()
-        graphed = GraphedTrainStep(model, loss_fn, resident, MODEL_IN, LABELS, keep_grads=world > 1)
+        # N > 1: the graph ends with one multi-tensor copy of the step's gradients into the flat NCCL buckets
+        graphed = GraphedTrainStep(model, loss_fn, resident, MODEL_IN, LABELS, after_backward=reducer.gather_grads if world > 1 else None)
+        if world > 1:
+            reducer.bind_grads()
 
     def step(data):
         if graphed is None:

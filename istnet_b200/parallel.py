@@ -104,6 +104,35 @@ class GradAllReducer:
             h.wait()
             b["flat"].div_(self.world)
 
+    # -- CUDA-graph path: the captured step starts from grad=None, so autograd leaves every gradient in a tensor of the
+    # graph's private pool (no zero-fill, no accumulate kernels); ONE multi-tensor copy, captured as the graph's last node,
+    # packs them into the flat buckets that NCCL reduces after the replay
+    def _views(self):
+        for b in self.buckets:
+            off = 0
+            for p in b["params"]:
+                yield p, b["flat"][off : off + p.numel()].view_as(p)
+                off += p.numel()
+
+    def gather_grads(self):
+        """Copies every parameter's current `.grad` into its bucket slot (call inside the capture, after backward)."""
+        if self.buckets is None:
+            return
+        src, dst = [], []
+        for p, v in self._views():
+            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                src.append(p.grad)
+                dst.append(v)
+        if src:
+            torch._foreach_copy_(dst, src)
+
+    def bind_grads(self):
+        """Points every `.grad` at its bucket slot (after the capture: the optimizer then reads the all-reduced values)."""
+        if self.buckets is None:
+            return
+        for p, v in self._views():
+            p.grad = v
+
     def remove_hooks(self):
         for h in self._hooks:
             h.remove()

@@ -73,3 +73,30 @@ def test_bucketed_allreduce_matches_full_batch_gradient():
                 assert got is None
             else:
                 assert torch.allclose(p.grad, got, atol=1e-6), step
+
+
+def test_gather_and_bind_grads_pack_fresh_gradients_into_the_buckets():
+    """CUDA-graph path: gradients produced from grad=None are packed into the flat buckets by one multi-tensor copy."""
+    from istnet_b200.parallel import GradAllReducer
+
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+    unused = torch.nn.Parameter(torch.zeros(4))  # never receives a gradient: must stay out of the buckets
+    m.register_parameter("unused", unused)
+    red = GradAllReducer(m, bucket_mb=1e-4)
+    x = torch.randn(6, 5)
+    m(x).square().sum().backward()
+    red.finish()  # first step: discovers the used parameters and builds the buckets
+    assert red.num_buckets() >= 2 and unused.grad is None
+    for p in m.parameters():
+        p.grad = None
+    m(2 * x).square().sum().backward()  # fresh tensors, as autograd installs them inside the captured step
+    want = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    red.gather_grads()
+    red.bind_grads()
+    flat = torch.cat([b["flat"] for b in red.buckets])
+    assert flat.numel() == sum(v.numel() for v in want.values())
+    for n, p in m.named_parameters():
+        if n in want:
+            assert torch.equal(p.grad, want[n])
+            assert any(p.grad.data_ptr() >= b["flat"].data_ptr() and p.grad.data_ptr() < b["flat"].data_ptr() + 4 * b["flat"].numel() for b in red.buckets)
