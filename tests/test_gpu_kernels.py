@@ -185,3 +185,76 @@ def test_sa_scale_and_interp_rows_match_reference_flow():
     got = RE.interp_rows(out.detach().contiguous(), i3, w)
     want = sum(torch.gather(out.detach(), 1, i3[..., q].long()[..., None].expand(-1, -1, 64)) * w[..., q : q + 1] for q in range(3))
     assert rel_err(got, want) < 1e-6
+
+
+def test_head_from_input_moments_matches_dense_float64(K):
+    """image_engine._head_forward/_head_backward: 1x1 conv + train-mode BN + PReLU read only at the `choose`d pixels, with the BN
+    statistics taken from sum(x) and X^T X and the BN backward split into sparse rows + one affine 64->64 convolution, against the
+    dense float64 flow of the reference (modules.py:64-66, ist_net.py:42-45): outputs, running statistics, every gradient — 1e-4."""
+    import copy
+
+    from istnet_b200 import image_engine as IE
+    from istnet_b200.nhwc import ACT_PRELU, Act, ConvUnit
+
+    torch.manual_seed(5)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, H, W, C, Co, N = 3, 24, 24, 64, 128, 200
+    conv = torch.nn.Conv2d(C, Co, 1).cuda()
+    bn = torch.nn.BatchNorm2d(Co).cuda().train()
+    prelu = torch.nn.PReLU().cuda()
+    sign = (torch.arange(Co, device="cuda") % 2 * 2 - 1).float()
+    torch.nn.init.uniform_(bn.weight, 0.5, 1.0)
+    with torch.no_grad():
+        bn.bias.copy_(8.0 * sign)  # keep u away from the PReLU kink (see _unit_vs_torch)
+    bn.momentum = 0.3
+    x = (torch.randn(B, H, W, C, device="cuda", generator=g) * 0.7 + 0.4).relu()  # non-zero mean, like a PReLU output
+    choose = torch.randint(0, H * W, (B, N), device="cuda", generator=g)
+    choose[:, 1] = choose[:, 0]  # a pixel chosen twice: its gradient accumulates
+    cot = torch.randn(B, N, Co, device="cuda", generator=g)
+    # dense float64 reference
+    c64, b64, p64 = copy.deepcopy(conv).double(), copy.deepcopy(bn).double(), copy.deepcopy(prelu).double()
+    x64 = x.double().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    dense = p64(b64(c64(x64))).view(B, Co, H * W)
+    ref = torch.gather(dense, 2, choose[:, None, :].expand(-1, Co, -1)).transpose(1, 2)
+    ref.backward(cot.double())
+    # B200 path
+    unit = ConvUnit(conv.weight, conv.bias, bn, ACT_PRELU, prelu=prelu.weight, k=1)
+    xa = Act(B, H, W, C, None, K.empty_planes(B, H, W, C, "cuda"))
+    K.split(x.contiguous(), B * H * W, C, xa.pl)
+    out, rec = IE._head_forward(unit, xa, choose, True)
+    grads = {}
+    dx = IE._head_backward(unit, rec, cot.contiguous(), grads)
+    assert rel_err(out, ref) < 1e-4
+    assert rel_err(bn.running_mean, b64.running_mean) < 1e-4 and rel_err(bn.running_var, b64.running_var) < 1e-4
+    assert int(bn.num_batches_tracked) == 1
+    assert rel_err(dx, x64.grad.permute(0, 2, 3, 1)) < 1e-4
+    assert rel_err(grads[id(conv.weight)], c64.weight.grad) < 1e-4
+    assert rel_err(grads[id(bn.weight)], b64.weight.grad) < 1e-4 and rel_err(grads[id(bn.bias)], b64.bias.grad) < 1e-4
+    assert rel_err(grads[id(prelu.weight)], p64.weight.grad) < 1e-4
+    assert float(grads[id(conv.bias)].abs().max()) == 0.0 and float(c64.bias.grad.abs().max()) < 1e-9 * float(cot.abs().sum())
+
+
+def test_bias_relu_chain_backward_fused_into_dgrad_epilogue():
+    """nn.Conv1d(k=1)+ReLU stack (ist_net.py:130-160) on rows_engine.run_chain: the interior layers' ReLU backward, bias gradient and
+    dy operand split ride in the data-gradient GEMM epilogue above them (conv_gemm mask_hi).  Against float64 autograd: 1e-4."""
+    import copy
+
+    from istnet_b200 import nhwc, rows_engine as RE
+
+    assert nhwc.FUSE_RELU_BWD
+    torch.manual_seed(9)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    seq = torch.nn.Sequential(torch.nn.Conv1d(64, 384, 1), torch.nn.ReLU(), torch.nn.Conv1d(384, 256, 1), torch.nn.ReLU(),
+                              torch.nn.Conv1d(256, 18, 1)).cuda()
+    s64 = copy.deepcopy(seq).double()
+    x = torch.randn(1000, 64, device="cuda", generator=g).requires_grad_(True)
+    x64 = x.detach().double().requires_grad_(True)
+    out = RE.run_chain(RE.units_from_conv1d_seq(seq), x, True)
+    ref = s64(x64.t()[None]).squeeze(0).t()
+    assert rel_err(out, ref) < 1e-4
+    cot = torch.randn(out.shape, device="cuda", generator=g)
+    out.backward(cot)
+    ref.backward(cot.double())
+    assert rel_err(x.grad, x64.grad) < 1e-4
+    for (n, p), q in zip(seq.named_parameters(), s64.parameters()):
+        assert rel_err(p.grad, q.grad.float()) < 1e-4, n
