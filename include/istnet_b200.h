@@ -175,6 +175,16 @@ int istnet_sa_scatter_l0(int B, int N, int M, int ns, int C0, const float *dy0, 
  * head is only read at the `choose`d pixels (ist_net.py:42-45).  part_ws: istnet_reduce_ws_floats(P, C, 1) floats. */
 int istnet_colsum_planes(const void *planes, long long plane_stride, int nsplit, long long P, int C, int cs, float *part_ws, double *ws,
                          void *stream);
+/* PSP priors (PSPModule, modules.py:10-34) on their pooled maps.  The pyramid levels s0..s3 (0 = unused; the model uses 1,2,3,6) of an
+ * instance form one row block [cells = sum s^2][C], level k starting at row sum_{q<k} s_q^2, cell (i,j) at row i*s+j.
+ *   psp_pool      pooled[b,cell,:] = nn.AdaptiveAvgPool2d(s)(x)[b,:,i,j]        x: [B,H,W,C] channels-last (modules.py:17)
+ *   psp_prior     prior[b,h,w,:]   = sum_s F.interpolate(t_s, (H,W), 'bilinear', align_corners=False)[b,:,h,w]   (modules.py:30)
+ * and their adjoints (gather form, fixed summation order).  t is the level map AFTER both 1x1 convolutions (stage conv and the
+ * bottleneck's slice for that level): bilinear up-sampling commutes with a 1x1 convolution. */
+int istnet_psp_pool(const float *x, int B, int H, int W, int C, int s0, int s1, int s2, int s3, float *pooled, void *stream);
+int istnet_psp_pool_bwd(const float *dpooled, int B, int H, int W, int C, int s0, int s1, int s2, int s3, float *dx, void *stream);
+int istnet_psp_prior(const float *t, int B, int H, int W, int C, int s0, int s1, int s2, int s3, float *prior, void *stream);
+int istnet_psp_prior_bwd(const float *g, int B, int H, int W, int C, int s0, int s1, int s2, int s3, float *dt, void *stream);
 /* Timeline marker: one thread stores %globaltimer (ns) into stamps[slot] in stream order.  A node like any other inside a
  * captured CUDA graph, so phase boundaries of the real (graph-replayed, multi-stream) step can be read back (tools/timeline.py);
  * the reference has no counterpart (its solver times whole iterations with time.time(), utils/solver.py:153). */

@@ -513,20 +513,30 @@ __device__ __forceinline__ void up_src(int o, int in, int out, int &i0, int &i1,
     l1 = s - (float)i0;
     l0 = 1.f - l1;
 }
-__global__ void __launch_bounds__(kEwThreads) upsample2x_split_kernel(int B, int H, int W, int C, const float *__restrict__ x,
+// same arithmetic with the (host-computed, identical IEEE division) scale hoisted out of the per-element path
+__device__ __forceinline__ void up_src_s(int o, int in, float scale, int &i0, int &i1, float &l0, float &l1) {
+    const float s = scale * (float)o;
+    i0 = (int)s;
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    l1 = s - (float)i0;
+    l0 = 1.f - l1;
+}
+// All index arithmetic below is 32-bit (element counts < 2^31, checked by the launchers): a 64-bit div/mod chain per
+// element made these passes instruction-bound at a quarter of the HBM rate.
+__global__ void __launch_bounds__(kEwThreads) upsample2x_split_kernel(int B, int H, int W, int C, float sh, float sw, const float *__restrict__ x,
                                                                        __nv_bfloat16 *pl, long long pl_stride, int nsplit, int cs, float *out_f32) {
-    const int lanes = C >> 2, Ho = 2 * H, Wo = 2 * W;
-    const long long total = (long long)B * Ho * Wo * lanes;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned lanes = C >> 2, Ho = 2 * H, Wo = 2 * W;
+    const unsigned total = (unsigned)B * Ho * Wo * lanes;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int c = (int)(i % lanes) * 4;
-        long long r = i / lanes;
+        unsigned r = i / lanes;
         const int wo = (int)(r % Wo); r /= Wo;
         const int ho = (int)(r % Ho);
         const int b = (int)(r / Ho);
         int h0, h1, w0, w1;
         float hl0, hl1, wl0, wl1;
-        up_src(ho, H, Ho, h0, h1, hl0, hl1);
-        up_src(wo, W, Wo, w0, w1, wl0, wl1);
+        up_src_s(ho, H, sh, h0, h1, hl0, hl1);
+        up_src_s(wo, W, sw, w0, w1, wl0, wl1);
         const float *base = x + (size_t)b * H * W * C + c;
         float4 a = ld4(base + ((size_t)h0 * W + w0) * C), bq = ld4(base + ((size_t)h0 * W + w1) * C);
         float4 cq = ld4(base + ((size_t)h1 * W + w0) * C), d = ld4(base + ((size_t)h1 * W + w1) * C);
@@ -540,58 +550,97 @@ __global__ void __launch_bounds__(kEwThreads) upsample2x_split_kernel(int B, int
         if (out_f32) *reinterpret_cast<float4 *>(out_f32 + op * C + c) = o;
     }
 }
-// gather form of the adjoint: dx[b,h,w,:] = sum over the output pixels that read (h,w)
-__global__ void __launch_bounds__(kEwThreads) upsample2x_bwd_kernel(int B, int H, int W, int C, const float *__restrict__ dout, float *dx) {
-    const int lanes = C >> 2, Ho = 2 * H, Wo = 2 * W;
-    const long long total = (long long)B * H * W * lanes;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+// gather form of the adjoint: dx[b,h,w,:] = sum over the output pixels that read (h,w).  The per-axis weights of the 7
+// candidate outputs are computed once per element (7 + 7 evaluations instead of 49 x 2), the products in the same order.
+__global__ void __launch_bounds__(kEwThreads) upsample2x_bwd_kernel(int B, int H, int W, int C, float sh, float sw, const float *__restrict__ dout,
+                                                                     float *dx) {
+    const unsigned lanes = C >> 2;
+    const int Ho = 2 * H, Wo = 2 * W;
+    const unsigned total = (unsigned)B * H * W * lanes;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int c = (int)(i % lanes) * 4;
-        long long r = i / lanes;
-        const int w = (int)(r % W); r /= W;
-        const int h = (int)(r % H);
-        const int b = (int)(r / H);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        // candidate outputs: src in (h-1, h+1)  =>  o in ((h-1)*(Ho-1)/(H-1), (h+1)*(Ho-1)/(H-1)); scan a safe window
-        const int ho_lo = max(0, 2 * h - 3), ho_hi = min(Ho - 1, 2 * h + 3);
-        const int wo_lo = max(0, 2 * w - 3), wo_hi = min(Wo - 1, 2 * w + 3);
-        for (int ho = ho_lo; ho <= ho_hi; ++ho) {
-            int h0, h1; float hl0, hl1;
-            up_src(ho, H, Ho, h0, h1, hl0, hl1);
-            float wh = (h0 == h ? hl0 : 0.f) + (h1 == h ? hl1 : 0.f);
-            if (wh == 0.f) continue;
-            for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        unsigned r = i / lanes;
+        const int w = (int)(r % (unsigned)W); r /= (unsigned)W;
+        const int h = (int)(r % (unsigned)H);
+        const int b = (int)(r / (unsigned)H);
+        // candidate outputs: src in (h-1, h+1)  =>  o in ((h-1)*(Ho-1)/(H-1), (h+1)*(Ho-1)/(H-1)); a safe window of 7
+        float wh[7], ww[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int ho = 2 * h - 3 + k, wo = 2 * w - 3 + k;
+            wh[k] = ww[k] = 0.f;
+            if (ho >= 0 && ho <= Ho - 1) {
+                int h0, h1; float hl0, hl1;
+                up_src_s(ho, H, sh, h0, h1, hl0, hl1);
+                wh[k] = (h0 == h ? hl0 : 0.f) + (h1 == h ? hl1 : 0.f);
+            }
+            if (wo >= 0 && wo <= Wo - 1) {
                 int w0, w1; float wl0, wl1;
-                up_src(wo, W, Wo, w0, w1, wl0, wl1);
-                float ww = (w0 == w ? wl0 : 0.f) + (w1 == w ? wl1 : 0.f);
-                if (ww == 0.f) continue;
-                float4 d = ld4(dout + (((size_t)b * Ho + ho) * Wo + wo) * C + c);
-                const float k = wh * ww;
-                acc.x += k * d.x; acc.y += k * d.y; acc.z += k * d.z; acc.w += k * d.w;
+                up_src_s(wo, W, sw, w0, w1, wl0, wl1);
+                ww[k] = (w0 == w ? wl0 : 0.f) + (w1 == w ? wl1 : 0.f);
             }
         }
-        *reinterpret_cast<float4 *>(dx + i * 4) = acc;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            if (wh[k] == 0.f) continue;
+            const int ho = 2 * h - 3 + k;
+#pragma unroll
+            for (int l = 0; l < 7; ++l) {
+                if (ww[l] == 0.f) continue;
+                const int wo = 2 * w - 3 + l;
+                const float4 d = ld4(dout + (((size_t)b * Ho + ho) * Wo + wo) * C + c);
+                const float kk = wh[k] * ww[l];
+                acc.x += kk * d.x; acc.y += kk * d.y; acc.z += kk * d.z; acc.w += kk * d.w;
+            }
+        }
+        *reinterpret_cast<float4 *>(dx + (size_t)i * 4) = acc;
     }
 }
 
 // ------------------------------------------------------------------ im2col (strided convs) and its adjoint
 // out[b,ho,wo,(r*kw+s)*C + c] = x[b, ho*stride+r-pad, wo*stride+s-pad, c]   (zero outside); x NHWC or NCHW
+// One CTA per output pixel (grid-stride): a thread keeps the same patch columns k = tid, tid + 256, ... for every pixel, so
+// their (tap, channel) decomposition is hoisted out of the pixel loop and the pixel decomposition is uniform per CTA.
+constexpr int kIm2colMaxK = 3;  // K <= 768 columns take the hoisted path
 __global__ void __launch_bounds__(kEwThreads) im2col_split_kernel(int B, int H, int W, int C, int kh, int kw, int stride, int pad, int Ho,
                                                                    int Wo, const float *__restrict__ x, int nchw, __nv_bfloat16 *pl,
                                                                    long long pl_stride, int nsplit, int cs) {
     const int K = kh * kw * C;
-    const long long total = (long long)B * Ho * Wo * K;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(i % K);
-        long long r = i / K;
-        const int wo = (int)(r % Wo); r /= Wo;
-        const int ho = (int)(r % Ho);
-        const int b = (int)(r / Ho);
-        const int c = k % C, tap = k / C;
-        const int h = ho * stride + tap / kw - pad, w = wo * stride + tap % kw - pad;
-        float v = 0.f;
-        if (h >= 0 && h < H && w >= 0 && w < W) v = nchw ? x[(((size_t)b * C + c) * H + h) * W + w] : x[(((size_t)b * H + h) * W + w) * C + c];
-        const size_t o = (((size_t)b * Ho + ho) * Wo + wo) * cs + k;
-        store_planes1(pl + o, pl_stride, nsplit, v);
+    const unsigned rows = (unsigned)B * Ho * Wo;
+    int kc[kIm2colMaxK], kr[kIm2colMaxK], ks[kIm2colMaxK];
+#pragma unroll
+    for (int q = 0; q < kIm2colMaxK; ++q) {
+        const int k = threadIdx.x + q * kEwThreads;
+        const int tap = k / C;
+        kc[q] = k % C; kr[q] = tap / kw - pad; ks[q] = tap % kw - pad;
+    }
+    for (unsigned row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int wo = (int)(row % (unsigned)Wo);
+        const unsigned t = row / (unsigned)Wo;
+        const int ho = (int)(t % (unsigned)Ho), b = (int)(t / (unsigned)Ho);
+        const int hb = ho * stride, wb = wo * stride;
+        __nv_bfloat16 *orow = pl + (size_t)row * cs;
+        if (K <= kIm2colMaxK * kEwThreads) {
+#pragma unroll
+            for (int q = 0; q < kIm2colMaxK; ++q) {
+                const int k = threadIdx.x + q * kEwThreads;
+                if (k < K) {
+                    const int h = hb + kr[q], w = wb + ks[q], c = kc[q];
+                    float v = 0.f;
+                    if (h >= 0 && h < H && w >= 0 && w < W) v = nchw ? x[(((size_t)b * C + c) * H + h) * W + w] : x[(((size_t)b * H + h) * W + w) * C + c];
+                    store_planes1(orow + k, pl_stride, nsplit, v);
+                }
+            }
+        } else {
+            for (int k = threadIdx.x; k < K; k += kEwThreads) {
+                const int c = k % C, tap = k / C;
+                const int h = hb + tap / kw - pad, w = wb + tap % kw - pad;
+                float v = 0.f;
+                if (h >= 0 && h < H && w >= 0 && w < W) v = nchw ? x[(((size_t)b * C + c) * H + h) * W + w] : x[(((size_t)b * H + h) * W + w) * C + c];
+                store_planes1(orow + k, pl_stride, nsplit, v);
+            }
+        }
     }
 }
 // dx[b,h,w,c] (+)= sum over (r,s) with (h+pad-r) % stride == 0 ... of dcol[b,ho,wo,(r*kw+s)*C+c]
@@ -657,19 +706,20 @@ __global__ void __launch_bounds__(kEwThreads) bn_relu_maxpool_kernel(int B, int 
         *reinterpret_cast<uchar4 *>(argmax + op * C + c) = make_uchar4((uint8_t)bi[0], (uint8_t)bi[1], (uint8_t)bi[2], (uint8_t)bi[3]);
     }
 }
-// g[b,h,w,c] = relu'(bn(y)) * sum over pooled windows whose argmax is (h,w) of (dz1+dz2)
+// g[b,h,w,c] = relu'(bn(y)) * sum over pooled windows whose argmax is (h,w) of (dz1+dz2)      (4 channels per thread)
 __global__ void __launch_bounds__(kEwThreads) maxpool_relu_bwd_kernel(int B, int H, int W, int C, const float *__restrict__ y, BnP bn,
                                                                        const float *__restrict__ dz, const float *__restrict__ dz2,
                                                                        const uint8_t *__restrict__ argmax, float *g) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-    const long long total = (long long)B * H * W * C;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        long long r = i / C;
-        const int w = (int)(r % W); r /= W;
-        const int h = (int)(r % H);
-        const int b = (int)(r / H);
-        float acc = 0.f;
+    const unsigned lanes = C >> 2;
+    const unsigned total = (unsigned)B * H * W * lanes;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = (int)(i % lanes) * 4;
+        unsigned r = i / lanes;
+        const int w = (int)(r % (unsigned)W); r /= (unsigned)W;
+        const int h = (int)(r % (unsigned)H);
+        const int b = (int)(r / (unsigned)H);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
         for (int ho = max(0, (h - 1 + 1) / 2); ho <= min(Ho - 1, (h + 1) / 2); ++ho) {
             const int rr = h - (2 * ho - 1);
             if (rr < 0 || rr > 2) continue;
@@ -677,12 +727,19 @@ __global__ void __launch_bounds__(kEwThreads) maxpool_relu_bwd_kernel(int B, int
                 const int ss = w - (2 * wo - 1);
                 if (ss < 0 || ss > 2) continue;
                 const size_t op = (((size_t)b * Ho + ho) * Wo + wo) * C + c;
-                if (argmax[op] == rr * 3 + ss) acc += dz[op] + (dz2 ? dz2[op] : 0.f);
+                const uchar4 am = *reinterpret_cast<const uchar4 *>(argmax + op);
+                float4 d = ld4(dz + op);
+                if (dz2) { const float4 d2 = ld4(dz2 + op); d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w; }
+                const int sel = rr * 3 + ss;
+                if (am.x == sel) acc[0] += d.x;
+                if (am.y == sel) acc[1] += d.y;
+                if (am.z == sel) acc[2] += d.z;
+                if (am.w == sel) acc[3] += d.w;
             }
         }
-        float yv = y[i];
-        float u = bn.mean ? (yv - bn.mean[c]) * bn.invstd[c] * bn.gamma[c] + bn.beta[c] : yv;
-        g[i] = u > 0.f ? acc : 0.f;
+        const size_t ip = (size_t)i * 4;
+        const float4 u = bn4(ld4(y + ip), bn, c);
+        *reinterpret_cast<float4 *>(g + ip) = make_float4(u.x > 0.f ? acc[0] : 0.f, u.y > 0.f ? acc[1] : 0.f, u.z > 0.f ? acc[2] : 0.f, u.w > 0.f ? acc[3] : 0.f);
     }
 }
 
@@ -832,6 +889,143 @@ __global__ void __launch_bounds__(kEwThreads, 2) sa_scatter_l0_kernel(int N, int
     column_flush<3, false>(acc, lanes, rows_per_iter, rr < rows_per_iter, C0, nullptr, part);
 }
 
+// ------------------------------------------------------------------ PSP priors (modules.py:10-34) on their pooled maps
+// The four pyramid levels (sizes 1, 2, 3, 6) of one instance are kept as ONE row block [cells = 1+4+9+36][C]:
+//   psp_pool      : nn.AdaptiveAvgPool2d(s) for all sizes in one pass over the feature map (ATen bins: [floor(i*H/s), ceil((i+1)*H/s)) )
+//   psp_prior     : sum over the sizes of F.interpolate(t_s, (H,W), bilinear, align_corners=False), written once
+// and their adjoints.  Replaces 4 adaptive-pool + 3 up-sampling + 3 add launches (each a full pass over a 512- or 1024-channel
+// map, at 32-64 CTAs for the pools) and their autograd counterparts.
+struct PspSizes {
+    int n, cells;
+    int s[4], off[4];
+};
+__device__ __forceinline__ void psp_cell(const PspSizes &ps, int cell, int &q, int &i, int &j) {
+    q = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+        if (k < ps.n && cell >= ps.off[k]) q = k;
+    const int loc = cell - ps.off[q];
+    i = loc / ps.s[q];
+    j = loc % ps.s[q];
+}
+__device__ __forceinline__ int bin_lo(int i, int in, int s) { return (i * in) / s; }
+__device__ __forceinline__ int bin_hi(int i, int in, int s) { return ((i + 1) * in + s - 1) / s; }
+__global__ void __launch_bounds__(kEwThreads) psp_pool_kernel(int B, int H, int W, int C, PspSizes ps, const float *__restrict__ x, float *pooled) {
+    const unsigned lanes = C >> 2;
+    const unsigned total = (unsigned)B * ps.cells * lanes;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int c = (int)(t % lanes) * 4;
+        const unsigned r = t / lanes;
+        const int cell = (int)(r % (unsigned)ps.cells), b = (int)(r / (unsigned)ps.cells);
+        int q, i, j;
+        psp_cell(ps, cell, q, i, j);
+        const int h0 = bin_lo(i, H, ps.s[q]), h1 = bin_hi(i, H, ps.s[q]), w0 = bin_lo(j, W, ps.s[q]), w1 = bin_hi(j, W, ps.s[q]);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int h = h0; h < h1; ++h)
+            for (int w = w0; w < w1; ++w) {
+                const float4 v = ld4(x + (((size_t)b * H + h) * W + w) * C + c);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+        *reinterpret_cast<float4 *>(pooled + ((size_t)b * ps.cells + cell) * C + c) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    }
+}
+// dx[b,h,w,:] = sum over sizes and bins containing (h,w) of dpooled[b,cell,:] / |bin|
+__global__ void __launch_bounds__(kEwThreads) psp_pool_bwd_kernel(int B, int H, int W, int C, PspSizes ps, const float *__restrict__ dp, float *dx) {
+    const unsigned lanes = C >> 2;
+    const unsigned total = (unsigned)B * H * W * lanes;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int c = (int)(t % lanes) * 4;
+        unsigned r = t / lanes;
+        const int w = (int)(r % (unsigned)W); r /= (unsigned)W;
+        const int h = (int)(r % (unsigned)H), b = (int)(r / (unsigned)H);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < ps.n; ++q) {
+            const int sz = ps.s[q];
+            for (int i = max(0, (h * sz) / H - 1); i <= min(sz - 1, (h * sz) / H + 1); ++i) {
+                const int h0 = bin_lo(i, H, sz), h1 = bin_hi(i, H, sz);
+                if (h < h0 || h >= h1) continue;
+                for (int j = max(0, (w * sz) / W - 1); j <= min(sz - 1, (w * sz) / W + 1); ++j) {
+                    const int w0 = bin_lo(j, W, sz), w1 = bin_hi(j, W, sz);
+                    if (w < w0 || w >= w1) continue;
+                    const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+                    const float4 d = ld4(dp + ((size_t)b * ps.cells + ps.off[q] + i * sz + j) * C + c);
+                    acc.x += d.x * inv; acc.y += d.y * inv; acc.z += d.z * inv; acc.w += d.w * inv;
+                }
+            }
+        }
+        *reinterpret_cast<float4 *>(dx + (size_t)t * 4) = acc;
+    }
+}
+// ATen area_pixel_compute_source_index(align_corners=False): src = max(scale*(dst+0.5)-0.5, 0), scale = in/out
+__device__ __forceinline__ void up_src_half(int o, int in, float scale, int &i0, int &i1, float &l0, float &l1) {
+    float s = scale * ((float)o + 0.5f) - 0.5f;
+    s = s < 0.f ? 0.f : s;
+    i0 = (int)s;
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    l1 = s - (float)i0;
+    l0 = 1.f - l1;
+}
+__global__ void __launch_bounds__(kEwThreads) psp_prior_kernel(int B, int H, int W, int C, PspSizes ps, const float *__restrict__ t, float *prior) {
+    const unsigned lanes = C >> 2;
+    const unsigned total = (unsigned)B * H * W * lanes;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int c = (int)(e % lanes) * 4;
+        unsigned r = e / lanes;
+        const int w = (int)(r % (unsigned)W); r /= (unsigned)W;
+        const int h = (int)(r % (unsigned)H), b = (int)(r / (unsigned)H);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < ps.n; ++q) {
+            const int sz = ps.s[q];
+            const float *base = t + ((size_t)b * ps.cells + ps.off[q]) * C + c;
+            int h0, h1, w0, w1;
+            float hl0, hl1, wl0, wl1;
+            up_src_half(h, sz, (float)sz / (float)H, h0, h1, hl0, hl1);
+            up_src_half(w, sz, (float)sz / (float)W, w0, w1, wl0, wl1);
+            const float4 a = ld4(base + (size_t)(h0 * sz + w0) * C), bq = ld4(base + (size_t)(h0 * sz + w1) * C);
+            const float4 cq = ld4(base + (size_t)(h1 * sz + w0) * C), d = ld4(base + (size_t)(h1 * sz + w1) * C);
+            acc.x += hl0 * (wl0 * a.x + wl1 * bq.x) + hl1 * (wl0 * cq.x + wl1 * d.x);
+            acc.y += hl0 * (wl0 * a.y + wl1 * bq.y) + hl1 * (wl0 * cq.y + wl1 * d.y);
+            acc.z += hl0 * (wl0 * a.z + wl1 * bq.z) + hl1 * (wl0 * cq.z + wl1 * d.z);
+            acc.w += hl0 * (wl0 * a.w + wl1 * bq.w) + hl1 * (wl0 * cq.w + wl1 * d.w);
+        }
+        *reinterpret_cast<float4 *>(prior + (size_t)e * 4) = acc;
+    }
+}
+// dt[b,cell,:] = sum over the pixels that interpolate from the cell of weight * g[b,h,w,:]   (gather form, fixed order)
+__global__ void __launch_bounds__(kEwThreads) psp_prior_bwd_kernel(int B, int H, int W, int C, PspSizes ps, const float *__restrict__ g, float *dt) {
+    const unsigned lanes = C >> 2;
+    const unsigned total = (unsigned)B * ps.cells * lanes;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int c = (int)(e % lanes) * 4;
+        const unsigned r = e / lanes;
+        const int cell = (int)(r % (unsigned)ps.cells), b = (int)(r / (unsigned)ps.cells);
+        int q, i, j;
+        psp_cell(ps, cell, q, i, j);
+        const int sz = ps.s[q];
+        const float sh = (float)sz / (float)H, sw = (float)sz / (float)W;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int h = 0; h < H; ++h) {
+            int h0, h1; float hl0, hl1;
+            up_src_half(h, sz, sh, h0, h1, hl0, hl1);
+            const float wh = (h0 == i ? hl0 : 0.f) + (h1 == i ? hl1 : 0.f);
+            if (wh == 0.f) continue;
+            for (int w = 0; w < W; ++w) {
+                int w0, w1; float wl0, wl1;
+                up_src_half(w, sz, sw, w0, w1, wl0, wl1);
+                const float ww = (w0 == j ? wl0 : 0.f) + (w1 == j ? wl1 : 0.f);
+                if (ww == 0.f) continue;
+                const float4 d = ld4(g + (((size_t)b * H + h) * W + w) * C + c);
+                const float k = wh * ww;
+                acc.x += k * d.x; acc.y += k * d.y; acc.z += k * d.z; acc.w += k * d.w;
+            }
+        }
+        *reinterpret_cast<float4 *>(dt + ((size_t)b * ps.cells + cell) * C + c) = acc;
+    }
+}
+
+// ATen area_pixel_compute_scale(align_corners=True)
+inline float up_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
 inline int ew_grid(long long total) {
     long long g = (total + kEwThreads - 1) / kEwThreads;
     long long cap = (long long)kNumSMs * 8;
@@ -1002,6 +1196,51 @@ extern "C" int istnet_sa_scatter_l0(int B, int N, int M, int ns, int C0, const f
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
+static int make_psp_sizes(int s0, int s1, int s2, int s3, PspSizes &ps) {
+    const int v[4] = {s0, s1, s2, s3};
+    ps.n = 0; ps.cells = 0;
+    for (int k = 0; k < 4; ++k) {
+        ps.s[k] = 1; ps.off[k] = 0;
+    }
+    for (int k = 0; k < 4 && v[k] > 0; ++k) {
+        ps.s[k] = v[k]; ps.off[k] = ps.cells; ps.cells += v[k] * v[k]; ps.n = k + 1;
+    }
+    return ps.n;
+}
+#define PSP_ARGS_OK(B, H, W, C, ps) ((B) > 0 && (H) > 0 && (W) > 0 && (C) > 0 && !((C) & 3) && (ps).n > 0 && \
+                                      (long long)(B) * (H) * (W) * ((C) / 4) <= 0x7fffffffLL && (long long)(B) * (ps).cells * ((C) / 4) <= 0x7fffffffLL)
+extern "C" int istnet_psp_pool(const float *x, int B, int H, int W, int C, int s0, int s1, int s2, int s3, float *pooled, void *stream) {
+    PspSizes ps;
+    make_psp_sizes(s0, s1, s2, s3, ps);
+    if (!PSP_ARGS_OK(B, H, W, C, ps)) return ISTNET_ERR_BAD_ARG;
+    psp_pool_kernel<<<ew_grid((long long)B * ps.cells * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, ps, x, pooled);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+extern "C" int istnet_psp_pool_bwd(const float *dpooled, int B, int H, int W, int C, int s0, int s1, int s2, int s3, float *dx, void *stream) {
+    PspSizes ps;
+    make_psp_sizes(s0, s1, s2, s3, ps);
+    if (!PSP_ARGS_OK(B, H, W, C, ps)) return ISTNET_ERR_BAD_ARG;
+    psp_pool_bwd_kernel<<<ew_grid((long long)B * H * W * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, ps, dpooled, dx);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+extern "C" int istnet_psp_prior(const float *t, int B, int H, int W, int C, int s0, int s1, int s2, int s3, float *prior, void *stream) {
+    PspSizes ps;
+    make_psp_sizes(s0, s1, s2, s3, ps);
+    if (!PSP_ARGS_OK(B, H, W, C, ps)) return ISTNET_ERR_BAD_ARG;
+    psp_prior_kernel<<<ew_grid((long long)B * H * W * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, ps, t, prior);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+extern "C" int istnet_psp_prior_bwd(const float *g, int B, int H, int W, int C, int s0, int s1, int s2, int s3, float *dt, void *stream) {
+    PspSizes ps;
+    make_psp_sizes(s0, s1, s2, s3, ps);
+    if (!PSP_ARGS_OK(B, H, W, C, ps)) return ISTNET_ERR_BAD_ARG;
+    psp_prior_bwd_kernel<<<ew_grid((long long)B * ps.cells * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, ps, g, dt);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
 extern "C" int istnet_marker(unsigned long long *stamps, int slot, void *stream) {
     if (!stamps || slot < 0) return ISTNET_ERR_BAD_ARG;
     marker_kernel<<<1, 1, 0, ST>>>(stamps, slot);
@@ -1028,14 +1267,16 @@ extern "C" int istnet_colsum(const float *x, long long P, int C, double *ws, voi
 extern "C" int istnet_upsample2x_split(const float *x, int B, int H, int W, int C, void *planes, long long plane_stride, int nsplit, int cs,
                                        float *out_f32, void *stream) {
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
-    upsample2x_split_kernel<<<ew_grid((long long)B * 4 * H * W * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, x, (__nv_bfloat16 *)planes,
-                                                                                               plane_stride, nsplit, cs, out_f32);
+    if ((long long)B * 4 * H * W * (C / 4) > 0x7fffffffLL) return ISTNET_ERR_UNSUPPORTED;
+    upsample2x_split_kernel<<<ew_grid((long long)B * 4 * H * W * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, up_scale(H, 2 * H), up_scale(W, 2 * W), x,
+                                                                                               (__nv_bfloat16 *)planes, plane_stride, nsplit, cs, out_f32);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
 extern "C" int istnet_upsample2x_bwd(const float *dout, int B, int H, int W, int C, float *dx, void *stream) {
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
-    upsample2x_bwd_kernel<<<ew_grid((long long)B * H * W * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, dout, dx);
+    if ((long long)B * H * W * (C / 4) > 0x7fffffffLL) return ISTNET_ERR_UNSUPPORTED;
+    upsample2x_bwd_kernel<<<ew_grid((long long)B * H * W * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, up_scale(H, 2 * H), up_scale(W, 2 * W), dout, dx);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
@@ -1044,7 +1285,8 @@ extern "C" int istnet_im2col_split(const float *x, int nchw, int B, int H, int W
                                    long long plane_stride, int nsplit, int cs, void *stream) {
     const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
     if (B <= 0 || Ho <= 0 || Wo <= 0 || cs < kh * kw * C || nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
-    im2col_split_kernel<<<ew_grid((long long)B * Ho * Wo * kh * kw * C), kEwThreads, 0, ST>>>(B, H, W, C, kh, kw, stride, pad, Ho, Wo, x, nchw,
+    if ((long long)B * Ho * Wo > 0x7fffffffLL) return ISTNET_ERR_UNSUPPORTED;
+    im2col_split_kernel<<<ew_grid((long long)B * Ho * Wo * kEwThreads), kEwThreads, 0, ST>>>(B, H, W, C, kh, kw, stride, pad, Ho, Wo, x, nchw,
                                                                                              (__nv_bfloat16 *)planes, plane_stride, nsplit, cs);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
@@ -1070,8 +1312,8 @@ extern "C" int istnet_bn_relu_maxpool(const float *y, int B, int H, int W, int C
 }
 extern "C" int istnet_maxpool_relu_bwd(const float *y, int B, int H, int W, int C, const float *mean, const float *invstd, const float *gamma,
                                        const float *beta, const float *dz, const float *dz2, const uint8_t *argmax, float *g, void *stream) {
-    if (B <= 0) return ISTNET_ERR_BAD_ARG;
-    maxpool_relu_bwd_kernel<<<ew_grid((long long)B * H * W * C), kEwThreads, 0, ST>>>(B, H, W, C, y, make_bn(mean, invstd, gamma, beta), dz, dz2,
+    if (B <= 0 || (C & 3) || (long long)B * H * W * (C / 4) > 0x7fffffffLL) return ISTNET_ERR_BAD_ARG;
+    maxpool_relu_bwd_kernel<<<ew_grid((long long)B * H * W * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, y, make_bn(mean, invstd, gamma, beta), dz, dz2,
                                                                                      argmax, g);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;

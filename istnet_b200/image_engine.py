@@ -57,6 +57,54 @@ def _basic_block_fwd(u, pre, x, training, record, tape):
 DENSE_HEAD = os.environ.get("ISTNET_DENSE_HEAD", "0") == "1"
 
 
+# ISTNET_PSP_KERNELS=0: pooled levels / up-sampling of the priors through ATen (adaptive_avg_pool2d, upsample_bilinear2d)
+PSP_KERNELS = os.environ.get("ISTNET_PSP_KERNELS", "1") != "0"
+
+
+def _sz4(sizes):
+    return [c_int(v) for v in (list(sizes) + [0, 0, 0, 0])[:4]]
+
+
+class _PspPool(torch.autograd.Function):
+    """x [B,H,W,C] channels-last -> [B, sum s^2, C]: nn.AdaptiveAvgPool2d(s) for every pyramid level in one pass."""
+
+    @staticmethod
+    def forward(ctx, x, sizes):
+        x = x.contiguous()
+        B, H, W, C = x.shape
+        out = torch.empty(B, sum(v * v for v in sizes), C, dtype=torch.float32, device=x.device)
+        _C.call("psp_pool", ptr(x), c_int(B), c_int(H), c_int(W), c_int(C), *_sz4(sizes), ptr(out))
+        ctx.sizes, ctx.shape = sizes, (B, H, W, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        B, H, W, C = ctx.shape
+        dx = torch.empty(B, H, W, C, dtype=torch.float32, device=d.device)
+        _C.call("psp_pool_bwd", ptr(d.contiguous()), c_int(B), c_int(H), c_int(W), c_int(C), *_sz4(ctx.sizes), ptr(dx))
+        return dx, None
+
+
+class _PspPrior(torch.autograd.Function):
+    """t [B, sum s^2, C] -> [B,H,W,C]: sum over the levels of the bilinear (align_corners=False) up-sampling, one pass."""
+
+    @staticmethod
+    def forward(ctx, t, sizes, H, W):
+        t = t.contiguous()
+        B, _, C = t.shape
+        out = torch.empty(B, H, W, C, dtype=torch.float32, device=t.device)
+        _C.call("psp_prior", ptr(t), c_int(B), c_int(H), c_int(W), c_int(C), *_sz4(sizes), ptr(out))
+        ctx.sizes, ctx.shape = sizes, (B, H, W, C, t.shape[1])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, H, W, C, cells = ctx.shape
+        dt = torch.empty(B, cells, C, dtype=torch.float32, device=g.device)
+        _C.call("psp_prior_bwd", ptr(g.contiguous()), c_int(B), c_int(H), c_int(W), c_int(C), *_sz4(ctx.sizes), ptr(dt))
+        return dt, None, None, None
+
+
 def _head_forward(unit, x, choose, training):
     """modules.py:64-66 + ist_net.py:42-45: y = W x + b on every pixel, train-mode BatchNorm over all B*H*W pixels, PReLU,
     then only the `choose`d pixels are used.  y is affine in x, so its batch statistics follow from the first two moments
@@ -179,20 +227,34 @@ def forward(net, rgb, choose, training, record, u=None):
     wb = net.psp.bottleneck.weight  # [1024, 2560, 1, 1]: columns 512*i .. of stage i, the last 512 of feats (cat order)
     nst = len(net.psp.stages)
     cf = z.C
+    sizes = [int(st[0].output_size[0] if isinstance(st[0].output_size, (tuple, list)) else st[0].output_size) for st in net.psp.stages]
     with torch.enable_grad() if record else torch.no_grad():
-        leaf = z.f32.permute(0, 3, 1, 2).detach().requires_grad_(record)  # NCHW view of the channels-last tensor
-        prior = None
-        for i, stage in enumerate(net.psp.stages):
-            pooled = stage[0](leaf)  # AdaptiveAvgPool2d -> (B,512,s,s)
-            sz = pooled.shape[-1]
-            rows = pooled.permute(0, 2, 3, 1).reshape(-1, cf)
-            t = (rows @ stage[1].weight.view(cf, cf).t()) @ wb[:, i * cf : (i + 1) * cf, 0, 0].t()  # (B*s*s, 1024)
-            if sz == 1:
-                up = t.view(B, 1, 1, -1)  # a 1x1 map up-samples to a constant
-            else:
-                up = F.interpolate(t.view(B, sz, sz, -1).permute(0, 3, 1, 2), size=(Hf, Wf), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
-            prior = up if prior is None else prior + up
-        prior = prior.expand(B, Hf, Wf, wb.shape[0]).contiguous()
+        leaf = z.f32.detach().requires_grad_(record)  # [B,Hf,Wf,512] channels-last
+        if PSP_KERNELS and nst <= 4:
+            # all pooled levels in one pass ([B, 1+4+9+36, 512]), the two 1x1 convolutions as tiny matmuls per level, all
+            # up-samplings + their sum in one pass (csrc/elementwise.cu psp_*)
+            pooled = _PspPool.apply(leaf, sizes)
+            ts, off = [], 0
+            for i, stage in enumerate(net.psp.stages):
+                n = sizes[i] * sizes[i]
+                rows = pooled[:, off : off + n].reshape(-1, cf)
+                ts.append(((rows @ stage[1].weight.view(cf, cf).t()) @ wb[:, i * cf : (i + 1) * cf, 0, 0].t()).view(B, n, -1))
+                off += n
+            prior = _PspPrior.apply(torch.cat(ts, 1), sizes, Hf, Wf)
+        else:
+            nchw = leaf.permute(0, 3, 1, 2)
+            prior = None
+            for i, stage in enumerate(net.psp.stages):
+                pooled = stage[0](nchw)  # AdaptiveAvgPool2d -> (B,512,s,s)
+                sz = pooled.shape[-1]
+                rows = pooled.permute(0, 2, 3, 1).reshape(-1, cf)
+                t = (rows @ stage[1].weight.view(cf, cf).t()) @ wb[:, i * cf : (i + 1) * cf, 0, 0].t()  # (B*s*s, 1024)
+                if sz == 1:
+                    up = t.view(B, 1, 1, -1)  # a 1x1 map up-samples to a constant
+                else:
+                    up = F.interpolate(t.view(B, sz, sz, -1).permute(0, 3, 1, 2), size=(Hf, Wf), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+                prior = up if prior is None else prior + up
+            prior = prior.expand(B, Hf, Wf, wb.shape[0]).contiguous()
     noise = _draw_noise(net, B, training, dev)
     ub = ConvUnit(wb[:, nst * cf :].detach().contiguous(), net.psp.bottleneck.bias, None, ACT_RELU, k=1)
     p, rb = ub.forward(z, training, record, noise=noise[0], res=prior.detach(), want_f32=True, want_pair=False)
@@ -285,11 +347,11 @@ def backward(net, tape, d_out, u):
             wb = net.psp.bottleneck.weight
             gs = torch.autograd.grad(prior, [leaf, wb] + stage_w, g)
             grads[id(wb)] = gs[1]
-            pending_wb = (gs[1], len(stage_w) * leaf.shape[1], id(ub.w))  # + the GEMM's weight gradient (side stream): added after the join
+            pending_wb = (gs[1], len(stage_w) * leaf.shape[-1], id(ub.w))  # + the GEMM's weight gradient (side stream): added after the join
             for w_, g_ in zip(stage_w, gs[2:]):
                 grads[id(w_)] = g_
             dz = dxf
-            dz2 = gs[0].permute(0, 2, 3, 1).contiguous()
+            dz2 = gs[0].contiguous()  # leaf is channels-last: nothing to permute
         elif kind == "block":
             _, pre, r1, r2, rd = entry
             c1, c2, dn = u[pre + ".conv1"], u[pre + ".conv2"], u.get(pre + ".down")

@@ -258,3 +258,35 @@ def test_bias_relu_chain_backward_fused_into_dgrad_epilogue():
     assert rel_err(x.grad, x64.grad) < 1e-4
     for (n, p), q in zip(seq.named_parameters(), s64.parameters()):
         assert rel_err(p.grad, q.grad.float()) < 1e-4, n
+
+
+@pytest.mark.parametrize("B,H,W,C,Co", [(3, 24, 24, 64, 128), (2, 8, 8, 32, 64), (2, 7, 10, 16, 16)])
+def test_psp_pool_and_prior_kernels_match_aten(B, H, W, C, Co):
+    """psp_pool == nn.AdaptiveAvgPool2d(s) for s in (1,2,3,6) (incl. the overlapping bins of maps not divisible by s), psp_prior ==
+    sum of F.interpolate(bilinear, align_corners=False) of the level maps (modules.py:17,30), and both adjoints — vs float64 ATen."""
+    from istnet_b200.image_engine import _PspPool, _PspPrior
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    sizes = [1, 2, 3, 6]
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).requires_grad_(True)
+    x64 = x.detach().double().requires_grad_(True)
+    pooled = _PspPool.apply(x, sizes)
+    ref = torch.cat([F.adaptive_avg_pool2d(x64.permute(0, 3, 1, 2), s).permute(0, 2, 3, 1).reshape(B, s * s, C) for s in sizes], 1)
+    assert rel_err(pooled, ref) < 1e-6
+    cot = torch.randn(pooled.shape, device="cuda", generator=g)
+    pooled.backward(cot)
+    ref.backward(cot.double())
+    assert rel_err(x.grad, x64.grad) < 1e-6
+    t = torch.randn(B, sum(s * s for s in sizes), Co, device="cuda", generator=g).requires_grad_(True)
+    t64 = t.detach().double().requires_grad_(True)
+    prior = _PspPrior.apply(t, sizes, H, W)
+    off, want = 0, 0
+    for s in sizes:
+        m = t64[:, off : off + s * s].view(B, s, s, Co).permute(0, 3, 1, 2)
+        want = want + F.interpolate(m, size=(H, W), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+        off += s * s
+    assert rel_err(prior, want) < 1e-6
+    cot = torch.randn(prior.shape, device="cuda", generator=g)
+    prior.backward(cot)
+    want.backward(cot.double())
+    assert rel_err(t.grad, t64.grad) < 1e-6
