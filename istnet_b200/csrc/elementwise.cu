@@ -443,6 +443,18 @@ __global__ void __launch_bounds__(kEwThreads) split_kernel(long long P, int C, c
         store_planes1(pl + r * cs + ch_off + c, pl_stride, nsplit, v);
     }
 }
+// channels-last rows with C % 4 == 0 (every per-point MLP input, feature rows, gradient rows): float4 in, 8-byte plane stores,
+// 32-bit index arithmetic
+__global__ void __launch_bounds__(kEwThreads) split_rows4_kernel(unsigned P, int C, const float *__restrict__ x, __nv_bfloat16 *pl,
+                                                                 long long pl_stride, int nsplit, int cs, int ch_off) {
+    const unsigned lanes = C >> 2;
+    const unsigned total = P * lanes;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned r = i / lanes;
+        const int c = (int)(i - r * lanes) * 4;
+        store_planes4(pl + (size_t)r * cs + ch_off + c, pl_stride, nsplit, ld4(x + (size_t)i * 4));
+    }
+}
 // PyTorch weight [co][ci][kh][kw] -> operand planes [nsplit][tap][rows][cs]:
 //   transpose = 0 (forward operand):        rows = co, cols = ci, tap = r*kw + s
 //   transpose = 1 (data-gradient operand):  rows = ci, cols = co, tap = flipped (kh-1-r, kw-1-s)
@@ -1120,7 +1132,11 @@ extern "C" int istnet_bn_act_bwd(const float *dz, const float *dz2, const float 
 extern "C" int istnet_split(const float *x, long long P, int C, long long HW, int nchw, void *planes, long long plane_stride, int nsplit,
                             int cs, int ch_off, void *stream) {
     if (P <= 0 || C <= 0 || nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
-    split_kernel<<<ew_grid(P * C), kEwThreads, 0, ST>>>(P, C, x, HW > 0 ? HW : 1, nchw, (__nv_bfloat16 *)planes, plane_stride, nsplit, cs, ch_off);
+    if (!nchw && (C & 3) == 0 && (cs & 3) == 0 && (ch_off & 3) == 0 && (plane_stride & 3) == 0 && P * (C / 4) <= 0x7fffffffLL &&
+        (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(planes) & 7) == 0)
+        split_rows4_kernel<<<ew_grid(P * (C / 4)), kEwThreads, 0, ST>>>((unsigned)P, C, x, (__nv_bfloat16 *)planes, plane_stride, nsplit, cs, ch_off);
+    else
+        split_kernel<<<ew_grid(P * C), kEwThreads, 0, ST>>>(P, C, x, HW > 0 ? HW : 1, nchw, (__nv_bfloat16 *)planes, plane_stride, nsplit, cs, ch_off);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
@@ -1137,12 +1153,39 @@ extern "C" int istnet_prep_weight(const float *w, int Cout, int Cin, int kh, int
 // column sums of a tensor that only exists as operand planes: part[g*C + c] = sum over CTA g's rows of (p0 + p1 + ...)[r][c]
 __global__ void __launch_bounds__(kEwThreads) colsum_planes_kernel(const __nv_bfloat16 *__restrict__ pl, long long pl_stride, int nsplit, long long P,
                                                                    int C, int cs, float *part) {
-    column_reduce<1, false>(P, C, nullptr, part, [&](long long r, int c, float (*acc)[4]) {
-        for (int i = 0; i < nsplit; ++i) {
-            const float4 v = bf4_to_f4(pl + (size_t)i * pl_stride + r * cs + c);
-            acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
+    const int lanes = C >> 2;
+    if (lanes > kEwThreads) {
+        column_reduce<1, false>(P, C, nullptr, part, [&](long long r, int c, float (*acc)[4]) {
+            for (int i = 0; i < nsplit; ++i) {
+                const float4 v = bf4_to_f4(pl + (size_t)i * pl_stride + r * cs + c);
+                acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
+            }
+        });
+        return;
+    }
+    float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+    const int rows_per_iter = kEwThreads / lanes;
+    const int c = (threadIdx.x % lanes) * 4, rr = threadIdx.x / lanes;
+    if (rr < rows_per_iter) {
+        const long long stride = (long long)gridDim.x * rows_per_iter;
+        for (long long r0 = (long long)blockIdx.x * rows_per_iter + rr; r0 < P; r0 += stride * 4) {
+            uint2 raw[4][kMaxPlanes];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < kMaxPlanes; ++i)
+                    if (i < nsplit && r0 + u * stride < P) raw[u][i] = *reinterpret_cast<const uint2 *>(pl + (size_t)i * pl_stride + (r0 + u * stride) * cs + c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < kMaxPlanes; ++i)
+                    if (i < nsplit && r0 + u * stride < P) {
+                        acc[0][0] += __uint_as_float(raw[u][i].x << 16); acc[0][1] += __uint_as_float(raw[u][i].x & 0xffff0000u);
+                        acc[0][2] += __uint_as_float(raw[u][i].y << 16); acc[0][3] += __uint_as_float(raw[u][i].y & 0xffff0000u);
+                    }
         }
-    });
+    }
+    column_flush<1, false>(acc, lanes, rows_per_iter, rr < rows_per_iter, C, nullptr, part);
 }
 __global__ void __launch_bounds__(kFinThreads) colsum_finalize_kernel(const float *__restrict__ part, int G, int C, double *ws, float *out_f32 = nullptr) {
     double t[1];

@@ -120,9 +120,9 @@ def _mlp(seq, x_rows, training=False):
 
 
 def _with_global(x_rows, b, n):
-    """cat([f, mean_over_points(f).expand]) of ist_net.py:172-173,257-258,325-326 on rows"""
+    """[f, mean_over_points(f).expand] of ist_net.py:172-173,257-258,325-326 on rows (the concatenation happens in the operand split)"""
     f = x_rows.view(b, n, -1)
-    return torch.cat([f, f.mean(1, keepdim=True).expand_as(f)], 2).reshape(b * n, -1)
+    return [x_rows, f.mean(1, keepdim=True).expand_as(f).reshape(b * n, -1)]
 
 
 class _PoseHeads(nn.Module):
@@ -150,7 +150,7 @@ class LightEstimator(_PoseHeads):
     def forward(self, pts, rgb_local, pts_local):
         b, n, _ = pts.shape
         e = _mlp(self.pts_mlp, _rows(pts))
-        return self._tail(torch.cat([_rows(rgb_local), e, _rows(pts_local)], dim=1), b, n)
+        return self._tail([_rows(rgb_local), e, _rows(pts_local)], b, n)
 
 
 class HeavyEstimator(_PoseHeads):
@@ -168,7 +168,7 @@ class HeavyEstimator(_PoseHeads):
         b, n, _ = pts.shape
         e1 = _mlp(self.pts_mlp1, _rows(pts))
         e2 = _mlp(self.pts_mlp2, _rows(pts_w))
-        return self._tail(torch.cat([_rows(rgb_local), e1, _rows(pts_local), e2, _rows(pts_w_local)], dim=1), b, n)
+        return self._tail([_rows(rgb_local), e1, _rows(pts_local), e2, _rows(pts_w_local)], b, n)
 
 
 class FeatureDeformer(nn.Module):
@@ -185,7 +185,7 @@ class FeatureDeformer(nn.Module):
     def forward(self, pts, rgb_local, pts_local, cls):
         b, n, _ = pts.shape
         e = _mlp(self.pts_mlp1, _rows(pts))
-        x = _mlp(self.deform_mlp1, torch.cat([e, _rows(pts_local), _rows(rgb_local)], dim=1))
+        x = _mlp(self.deform_mlp1, [e, _rows(pts_local), _rows(rgb_local)])
         x = _mlp(self.deform_mlp2, _with_global(x, b, n))
         q = _mlp(self.pred_nocs, x).view(b, n, self.nclass, 3)
         # ist_net.py:178-181: view(-1,3,N) + index_select(cls + nclass*b) == pick the class's 3 channels per instance

@@ -110,10 +110,11 @@ class PointnetFPModule(nn.Module):
         """unknown (B,n,3), known (B,m,3), unknown_rows (B,n,C1) or None, known_rows (B,m,C2) -> (B,n,mlp[-1])"""
         idx, weight = PF.three_nn_weights(unknown, known)
         x = RE.interp_rows(known_rows, idx, weight)
-        if unknown_rows is not None:
-            x = torch.cat([x, unknown_rows], dim=2)
-        B, n, C = x.shape
-        return RE.run_chain(RE.units_from_shared_mlp(self.mlp), x.reshape(B * n, C), self.training).view(B, n, -1)
+        B, n, _ = x.shape
+        srcs = [x.reshape(B * n, -1)]
+        if unknown_rows is not None:  # torch.cat([interpolated, skip], dim=1) of pointnet2_modules.py:196-199 happens in the operand split
+            srcs.append(unknown_rows.reshape(B * n, -1))
+        return RE.run_chain(RE.units_from_shared_mlp(self.mlp), srcs, self.training).view(B, n, -1)
 
     def forward(self, unknown, known, unknow_feats, known_feats):
         ur = unknow_feats.transpose(1, 2).contiguous() if unknow_feats is not None else None

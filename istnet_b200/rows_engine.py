@@ -69,44 +69,56 @@ def _chain_backward(units, tape, dz, grads, need_dx_first):
     return dz
 
 
+def _split_sources(srcs, dev):
+    """[rows, c_i] FP32 tensors -> ONE operand-plane buffer [NSPLIT,1,1,rows,pad8(sum c_i)]: the channel concatenation of the
+    reference (torch.cat at ist_net.py:168,172,255,323 ...) happens inside the split pass, no FP32 concat tensor is written."""
+    rows = srcs[0].shape[0]
+    cin = sum(t.shape[1] for t in srcs)
+    a = Act(1, 1, rows, cin, srcs[0] if len(srcs) == 1 else None)
+    a.pl = K.empty_planes(1, 1, rows, cin, dev)
+    off = 0
+    for t in srcs:
+        K.split(t, rows, t.shape[1], a.pl, ch_off=off)
+        off += t.shape[1]
+    return a
+
+
 class _ChainFn(torch.autograd.Function):
-    """x [rows, Cin] FP32 -> [rows, Cout] FP32 through a list of ConvUnits."""
+    """x_1 .. x_n [rows, c_i] FP32 (concatenated along the channels) -> [rows, Cout] FP32 through a list of ConvUnits."""
 
     @staticmethod
-    def forward(ctx, units, training, x, *params):
-        rows, cin = x.shape
-        a = Act(1, 1, rows, cin, x)
-        a.pl = K.empty_planes(1, 1, rows, cin, x.device)
-        K.split(x, rows, cin, a.pl)
-        out, tape = _chain_forward(units, a, training, True)
-        ctx.units, ctx.tape, ctx.params, ctx.need_dx = units, tape, params, x.requires_grad
-        return out.f32.view(rows, -1)
+    def forward(ctx, units, training, nsrc, *tensors):
+        srcs, params = tensors[:nsrc], tensors[nsrc:]
+        out, tape = _chain_forward(units, _split_sources(srcs, srcs[0].device), training, True)
+        ctx.units, ctx.tape, ctx.params = units, tape, params
+        ctx.widths = [t.shape[1] for t in srcs]
+        ctx.need = [t.requires_grad for t in srcs]
+        return out.f32.view(srcs[0].shape[0], -1)
 
     @staticmethod
     def backward(ctx, dz):
         grads = {}
         trace.mark(f"chain bwd> rows={dz.shape[0]} cout={dz.shape[1]}")
-        dx = _chain_backward(ctx.units, ctx.tape, dz.contiguous().view(1, 1, dz.shape[0], dz.shape[1]), grads, ctx.need_dx)
+        dx = _chain_backward(ctx.units, ctx.tape, dz.contiguous().view(1, 1, dz.shape[0], dz.shape[1]), grads, any(ctx.need))
         K.join_side_streams()
         trace.mark("chain bwd<")
         ctx.tape = None
-        return (None, None, dx.view(dx.shape[2], dx.shape[3]) if dx is not None else None) + tuple(
-            grads.get(id(p)) if p.requires_grad else None for p in ctx.params
-        )
+        dsrc, off = [], 0
+        for w, need in zip(ctx.widths, ctx.need):
+            dsrc.append(dx.view(dx.shape[2], dx.shape[3])[:, off : off + w] if (need and dx is not None) else None)
+            off += w
+        return (None, None, None) + tuple(dsrc) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
 
 
 def run_chain(units, x, training):
-    """Differentiable chain of 1x1-conv units on a row matrix x [rows, Cin] (contiguous FP32)."""
-    x = x.contiguous()
+    """Differentiable chain of 1x1-conv units on a row matrix x [rows, Cin] (contiguous FP32), or on the channel
+    concatenation of a list of such matrices."""
+    srcs = [t.contiguous() for t in (x if isinstance(x, (list, tuple)) else (x,))]
     params = _unit_params(units)
-    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
-        return _ChainFn.apply(units, training, x, *params)
-    rows, cin = x.shape
-    a = Act(1, 1, rows, cin, x)
-    a.pl = K.empty_planes(1, 1, rows, cin, x.device)
-    K.split(x, rows, cin, a.pl)
-    out, _ = _chain_forward(units, a, training, False)
-    return out.f32.view(rows, -1)
+    if torch.is_grad_enabled() and (any(t.requires_grad for t in srcs) or any(p.requires_grad for p in params)):
+        return _ChainFn.apply(units, training, len(srcs), *srcs, *params)
+    out, _ = _chain_forward(units, _split_sources(srcs, srcs[0].device), training, False)
+    return out.f32.view(srcs[0].shape[0], -1)
 
 
 # ------------------------------------------------------------------------------------------ set abstraction scale
