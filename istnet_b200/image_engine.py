@@ -19,21 +19,42 @@ from ._C import c_int, c_ll, ptr
 from .nhwc import ACT_NONE, ACT_PRELU, ACT_RELU, Act, ConvUnit
 
 
+def _parse_ns_map(text):
+    out = {}
+    for item in text.split(","):
+        if "=" in item:
+            k, v = item.split("=")
+            out[k.strip()] = int(v)
+    return out
+
+
+# Forward operand planes per layer group of the image branch ("prefix=planes,..." matched against the unit names of _units);
+# 3 everywhere unless DESIGN.md section 2 documents a measured 2-plane choice
+NS_MAP = _parse_ns_map(os.environ.get("ISTNET_NSPLIT_MAP", "up_=2,layer4=2"))
+
+
+def _ns(name):
+    for k, v in NS_MAP.items():
+        if name.startswith(k):
+            return v
+    return None
+
+
 def _units(net):
     """ConvUnit views of every conv of Modified_PSPNet, keyed like the state dict.  Rebuilt per call (cheap) so that
     module replicas (DataParallel) and re-materialised parameters are always the ones used."""
     f = net.feats
-    u = {"conv1": ConvUnit(f.conv1.weight, None, f.bn1, ACT_RELU, k=7, stride=2, pad=3)}
+    u = {"conv1": ConvUnit(f.conv1.weight, None, f.bn1, ACT_RELU, k=7, stride=2, pad=3, nsplit=_ns("conv1"))}
     for li in (1, 2, 3, 4):
         for bi, blk in enumerate(getattr(f, f"layer{li}")):
             pre = f"layer{li}.{bi}"
-            u[pre + ".conv1"] = ConvUnit(blk.conv1.weight, None, blk.bn1, ACT_RELU, k=3, stride=blk.stride)
-            u[pre + ".conv2"] = ConvUnit(blk.conv2.weight, None, blk.bn2, ACT_RELU, k=3)
+            u[pre + ".conv1"] = ConvUnit(blk.conv1.weight, None, blk.bn1, ACT_RELU, k=3, stride=blk.stride, nsplit=_ns(pre))
+            u[pre + ".conv2"] = ConvUnit(blk.conv2.weight, None, blk.bn2, ACT_RELU, k=3, nsplit=_ns(pre))
             if blk.downsample is not None:
-                u[pre + ".down"] = ConvUnit(blk.downsample[0].weight, None, blk.downsample[1], ACT_NONE, k=1, stride=blk.stride, pad=0)
+                u[pre + ".down"] = ConvUnit(blk.downsample[0].weight, None, blk.downsample[1], ACT_NONE, k=1, stride=blk.stride, pad=0, nsplit=_ns(pre))
     for name in ("up_1", "up_2", "up_3"):
         seq = getattr(net, name).conv
-        u[name] = ConvUnit(seq[1].weight, seq[1].bias, seq[2], ACT_PRELU, prelu=seq[3].weight, k=3)
+        u[name] = ConvUnit(seq[1].weight, seq[1].bias, seq[2], ACT_PRELU, prelu=seq[3].weight, k=3, nsplit=_ns(name))
     u["final"] = ConvUnit(net.final[0].weight, net.final[0].bias, net.final[1], ACT_PRELU, prelu=net.final[2].weight, k=1)
     return u
 
@@ -256,7 +277,7 @@ def forward(net, rgb, choose, training, record, u=None):
                 prior = up if prior is None else prior + up
             prior = prior.expand(B, Hf, Wf, wb.shape[0]).contiguous()
     noise = _draw_noise(net, B, training, dev)
-    ub = ConvUnit(wb[:, nst * cf :].detach().contiguous(), net.psp.bottleneck.bias, None, ACT_RELU, k=1)
+    ub = ConvUnit(wb[:, nst * cf :].detach().contiguous(), net.psp.bottleneck.bias, None, ACT_RELU, k=1, nsplit=_ns("bottleneck"))
     p, rb = ub.forward(z, training, record, noise=noise[0], res=prior.detach(), want_f32=True, want_pair=False)
     if record:
         tape.append(("psp", rb, leaf, prior, ub))

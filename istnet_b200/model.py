@@ -114,9 +114,13 @@ def _rows(x_bnc):
     return x_bnc.reshape(b * n, c)
 
 
+# Operand planes of the pose heads' per-point MLPs (BatchNorm-free Conv1d+ReLU stacks, <= 10 layers deep): see DESIGN.md section 2
+HEADS_NSPLIT = int(os.environ.get("ISTNET_NSPLIT_HEADS", "2"))
+
+
 def _mlp(seq, x_rows, training=False):
     """nn.Sequential of Conv1d(k=1)(+ReLU) applied to a row matrix on the tcgen05 GEMM chain (rows_engine)."""
-    return RE.run_chain(RE.units_from_conv1d_seq(seq), x_rows, training)
+    return RE.run_chain(RE.units_from_conv1d_seq(seq, nsplit=min(HEADS_NSPLIT, RE.K.NSPLIT)), x_rows, training)
 
 
 def _with_global(x_rows, b, n):

@@ -88,8 +88,8 @@ def prep_weight(w, transpose=False, nsplit=None, im2col=False):
     return pl
 
 
-def prep_weight_pair(w, im2col=False):
-    """Forward operand (NSPLIT planes) and data-gradient operand (NSPLIT_BWD planes, transposed / flipped) of one weight, one launch."""
+def prep_weight_pair(w, im2col=False, nsplit=None):
+    """Forward operand (nsplit planes) and data-gradient operand (NSPLIT_BWD planes, transposed / flipped) of one weight, one launch."""
     if w.dim() == 2:
         co, ci, kh, kw = w.shape[0], w.shape[1], 1, 1
     elif w.dim() == 3:
@@ -99,8 +99,8 @@ def prep_weight_pair(w, im2col=False):
     taps = kh * kw
     sf = (1, co, pad8(taps * ci)) if im2col else (taps, co, pad8(ci))
     st = (1, taps * ci, pad8(co)) if im2col else (taps, ci, pad8(co))
-    pf = torch.empty(NSPLIT, *sf, dtype=torch.bfloat16, device=w.device)
-    pt = torch.empty(NSPLIT_BWD, *st, dtype=torch.bfloat16, device=w.device)
+    pf = torch.empty(nsplit or NSPLIT, *sf, dtype=torch.bfloat16, device=w.device)
+    pt = torch.empty(min(nsplit or NSPLIT, NSPLIT_BWD), *st, dtype=torch.bfloat16, device=w.device)
     _C.call("prep_weight_pair", ptr(w), c_int(co), c_int(ci), c_int(kh), c_int(kw), c_int(1 if im2col else 0), *_pl_args(pf), c_int(sf[-1]),
             *_pl_args(pt), c_int(st[-1]))
     return pf, pt
@@ -172,14 +172,15 @@ def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl
     """x: Act with operand planes; writes out_f32 [B,H,W,cout] and/or out_pl.  With stat_part (float buffer of
     >= 2*296*cout) the epilogue also leaves per-CTA BN-statistics partials there; returns the CTA count G."""
     bw, bh = pick_box(x.H, x.W)
+    ns = min(x.pl.shape[0], w_pl.shape[0])  # planes are nested: the first n planes of an operand are its n-plane representation
     grid = ctypes.c_int(0)
     args = (
         ptr(x.pl), c_ll(x.pl.stride(0)), c_int(x.B), c_int(x.H), c_int(x.W), c_int(x.C), c_int(x.cs), ptr(w_pl),
-        c_ll(w_pl.stride(0)), c_int(cout), c_int(w_pl.shape[-1]), c_int(kh), c_int(kw), c_int(x.pl.shape[0]), _p(bias), c_int(1 if relu else 0),
+        c_ll(w_pl.stride(0)), c_int(cout), c_int(w_pl.shape[-1]), c_int(kh), c_int(kw), c_int(ns), _p(bias), c_int(1 if relu else 0),
         _p(out_f32), c_int(out_f32.shape[-1] if out_f32 is not None else 0), *_pl_args(out_pl), c_int(out_pl.shape[-1] if out_pl is not None else 0),
         c_int(bw), c_int(bh), _p(stat_part), ctypes.byref(grid), _p(mask_hi), c_int(mask_hi.shape[-1] if mask_hi is not None else 0),
     )
-    _timed("conv_gemm_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, x.pl.shape[0], lambda: _C.call("conv_gemm", *args),
+    _timed("conv_gemm_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, ns, lambda: _C.call("conv_gemm", *args),
            f"P={x.P} {x.H}x{x.W} cin={x.C} cout={cout} k={kh}")
     return grid.value
 
@@ -299,8 +300,10 @@ class ConvUnit:
     stride-1 "same" convolutions run as implicit GEMM on the activation pair; strided ones (conv1, layer2.0) go through
     im2col (the patch matrix is then the GEMM's A operand and the wgrad's B operand)."""
 
-    def __init__(self, conv_w, conv_b, bn, act, prelu=None, k=1, stride=1, pad=None):
+    def __init__(self, conv_w, conv_b, bn, act, prelu=None, k=1, stride=1, pad=None, nsplit=None, nsplit_out=None):
         self.w, self.b, self.bn, self.act, self.prelu = conv_w, conv_b, bn, act, prelu
+        self.ns = min(nsplit or NSPLIT, NSPLIT)          # operand planes of this unit's forward contraction (input and weight)
+        self.ns_out = min(nsplit_out or NSPLIT, NSPLIT)  # planes written for the consumer of this unit's output
         self.k, self.stride = k, stride
         self.pad = k // 2 if pad is None else pad
         self.cout = conv_w.shape[0]
@@ -314,11 +317,11 @@ class ConvUnit:
         if self.stride != 1 or x_f32_nchw is not None:
             src = x_f32_nchw if x_f32_nchw is not None else x.f32
             xin = im2col(src, x_f32_nchw is not None, x.B, x.H, x.W, x.C, self.k, self.stride, self.pad)
-            wp, wd = prep_weight_pair(self.w, im2col=True) if record else (prep_weight(self.w, im2col=True), None)  # [co, (r,s,c)] = the im2col K order
+            wp, wd = prep_weight_pair(self.w, im2col=True, nsplit=self.ns) if record else (prep_weight(self.w, im2col=True, nsplit=self.ns), None)  # [co, (r,s,c)] = the im2col K order
             kk = 1
         else:
             xin, kk = x, self.k
-            wp, wd = prep_weight_pair(self.w) if record else (prep_weight(self.w), None)
+            wp, wd = prep_weight_pair(self.w, nsplit=self.ns) if record else (prep_weight(self.w, nsplit=self.ns), None)
         B, H, W = xin.B, xin.H, xin.W
         P, C = B * H * W, self.cout
         if self.bn is None and self.act == ACT_RELU and noise is None and res is None and not defer_act:
@@ -328,7 +331,7 @@ class ConvUnit:
             if want_f32:
                 out.f32 = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
             if want_pair or record:
-                out.pl = empty_planes(B, H, W, C, dev)
+                out.pl = empty_planes(B, H, W, C, dev, nsplit=self.ns_out)
             conv_gemm(xin, wp, C, kk, kk, bias=self.b, relu=True, out_f32=out.f32, out_pl=out.pl)
             rec = {"bn": None}
             if record:
@@ -349,7 +352,7 @@ class ConvUnit:
         if self.bn is None and self.act == ACT_NONE and noise is None and res is None:  # plain linear layer
             out = Act(B, H, W, C, y)
             if want_pair:
-                out.pl = empty_planes(B, H, W, C, dev)
+                out.pl = empty_planes(B, H, W, C, dev, nsplit=self.ns_out)
                 split(y, P, C, out.pl)
             if record:
                 rec["y"] = None
@@ -358,7 +361,7 @@ class ConvUnit:
         if want_f32:
             out.f32 = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
         if want_pair:
-            out.pl = empty_planes(B, H, W, C, dev)
+            out.pl = empty_planes(B, H, W, C, dev, nsplit=self.ns_out)
         elif record and self.act == ACT_RELU:
             out.pl = empty_planes(B, H, W, C, dev, nsplit=1)  # plane 0 only: the ReLU mask of the backward pass
         bn_act_split(y, P, C, H * W, bn=st, res=res, res_bn=res_bn, act=self.act, prelu=self.prelu, noise=noise, out_f32=out.f32, out_pl=out.pl)

@@ -18,19 +18,22 @@ from ._C import c_int, c_ll, ptr
 from .nhwc import ACT_NONE, ACT_RELU, Act, ConvUnit
 
 
+PN_NSPLIT = int(os.environ.get("ISTNET_NSPLIT_PN", "3"))  # forward operand planes of the PointNet++ SharedMLP GEMMs
+
+
 def units_from_shared_mlp(mlp):
     """pytorch_utils.SharedMLP (conv1x1 no bias -> BN2d -> ReLU) * n  ->  [ConvUnit]"""
-    return [ConvUnit(layer.conv.weight, None, layer.normlayer.bn, ACT_RELU, k=1) for layer in mlp]
+    return [ConvUnit(layer.conv.weight, None, layer.normlayer.bn, ACT_RELU, k=1, nsplit=PN_NSPLIT) for layer in mlp]
 
 
-def units_from_conv1d_seq(seq):
+def units_from_conv1d_seq(seq, nsplit=None):
     """nn.Sequential of Conv1d(k=1) [+ ReLU] pairs -> [ConvUnit] (bias, optional ReLU)"""
     mods = [m for m in seq if not isinstance(m, torch.nn.AdaptiveAvgPool1d)]
     units = []
     for i, m in enumerate(mods):
         if isinstance(m, torch.nn.Conv1d):
             relu = i + 1 < len(mods) and isinstance(mods[i + 1], torch.nn.ReLU)
-            units.append(ConvUnit(m.weight, m.bias, None, ACT_RELU if relu else ACT_NONE, k=1))
+            units.append(ConvUnit(m.weight, m.bias, None, ACT_RELU if relu else ACT_NONE, k=1, nsplit=nsplit, nsplit_out=nsplit))
     return units
 
 
@@ -69,13 +72,13 @@ def _chain_backward(units, tape, dz, grads, need_dx_first):
     return dz
 
 
-def _split_sources(srcs, dev):
+def _split_sources(srcs, dev, nsplit=None):
     """[rows, c_i] FP32 tensors -> ONE operand-plane buffer [NSPLIT,1,1,rows,pad8(sum c_i)]: the channel concatenation of the
     reference (torch.cat at ist_net.py:168,172,255,323 ...) happens inside the split pass, no FP32 concat tensor is written."""
     rows = srcs[0].shape[0]
     cin = sum(t.shape[1] for t in srcs)
     a = Act(1, 1, rows, cin, srcs[0] if len(srcs) == 1 else None)
-    a.pl = K.empty_planes(1, 1, rows, cin, dev)
+    a.pl = K.empty_planes(1, 1, rows, cin, dev, nsplit=nsplit)
     off = 0
     for t in srcs:
         K.split(t, rows, t.shape[1], a.pl, ch_off=off)
@@ -89,7 +92,7 @@ class _ChainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, units, training, nsrc, *tensors):
         srcs, params = tensors[:nsrc], tensors[nsrc:]
-        out, tape = _chain_forward(units, _split_sources(srcs, srcs[0].device), training, True)
+        out, tape = _chain_forward(units, _split_sources(srcs, srcs[0].device, units[0].ns), training, True)
         ctx.units, ctx.tape, ctx.params = units, tape, params
         ctx.widths = [t.shape[1] for t in srcs]
         ctx.need = [t.requires_grad for t in srcs]
@@ -117,7 +120,7 @@ def run_chain(units, x, training):
     params = _unit_params(units)
     if torch.is_grad_enabled() and (any(t.requires_grad for t in srcs) or any(p.requires_grad for p in params)):
         return _ChainFn.apply(units, training, len(srcs), *srcs, *params)
-    out, _ = _chain_forward(units, _split_sources(srcs, srcs[0].device), training, False)
+    out, _ = _chain_forward(units, _split_sources(srcs, srcs[0].device, units[0].ns), training, False)
     return out.f32.view(srcs[0].shape[0], -1)
 
 
