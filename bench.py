@@ -172,8 +172,8 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = max(1, min(4, wl["batch"]))
-    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+    sample = max(1, min(8, wl["batch"]))  # bounded sample of the workload: ~10 s of host work at ~6.5 inst/s
+    steps, warmup = min(args.steps, 6), min(args.warmup, 1)
     rate, cores = cpu_reference_rate(wl, sample, steps, warmup)
     line = {
         "impl": "reference", "metric": "instances/sec", "value": rate, "unit": "instances/s", "n_gpus": args.gpus,
@@ -359,9 +359,9 @@ def main():
                                         "gflop_per_instance": gflop}},
         }
         if not args.no_cpu_baseline and world == 1:
-            rate, cores = cpu_reference_rate(wl, 2, 2, 1)
+            rate, cores = cpu_reference_rate(wl, 4, 3, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "instances/s", "cores": cores, "kind": "port",
-                                    "sample": "2 timed steps of fwd+loss+bwd on a batch of 2 (same shapes), oracle port on host threads"}
+                                    "sample": "3 timed steps of fwd+loss+bwd on a batch of 4 (same shapes), oracle port on host threads"}
             try:
                 g = gpu_reference_rate(wl, dev)
             except Exception as e:  # context only: never fail the bench on it

@@ -889,11 +889,10 @@ __global__ void __launch_bounds__(kEwThreads, 2) sa_scatter_l0_kernel(int N, int
                 if (r < rows) {
                     const float g[4] = {dv[q].x, dv[q].y, dv[q].z, dv[q].w};
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < 4; ++k)
 #pragma unroll
                         for (int d = 0; d < 3; ++d) acc[d][k] += g[k] * rel[q][d];
-                        if (dU) atomicAdd(dU + src[q] * C0 + c + k, g[k]);
-                    }
+                    if (dU) atomicAdd(reinterpret_cast<float4 *>(dU + src[q] * C0 + c), dv[q]);  // one 16-byte reduction (red.global.add.v4.f32)
                 }
             }
         }

@@ -31,6 +31,7 @@ PRIORITY_MODE = os.environ.get("ISTNET_PRIO", "image")
 # autograd (which replays nodes newest-first and makes a consumer stream wait for everything already enqueued on the
 # producer stream) starts the enhancers' backward passes right after the loss instead of behind the main path's backward
 HEADS_MAIN_FIRST = os.environ.get("ISTNET_HEADS_MAIN_FIRST", "1") != "0"
+MAIN_PATH_HIGH_PRIORITY = os.environ.get("ISTNET_MAIN_HI", "1") == "1"
 
 
 class _Branches:
@@ -261,19 +262,23 @@ class IST_Net(nn.Module):
         br.join()
         # the three pose heads are independent of each other: camera-space enhancer and world-space enhancer on the side
         # streams, implicit space transformation -> main estimator on the main stream
-        br2 = _Branches(pts.device, 2)  # the side streams' wait on the main stream is taken here, before the main path is enqueued
+        br2 = _Branches(pts.device, 3)  # the side streams' wait on the main stream is taken here, before the main path is enqueued
 
         def _main_path():
             pw, pwl = ph("implicit_transform", lambda: self.implicit_transform(rgb_local, pts_local, pts, c, cls))
             return (pw, pwl) + tuple(ph("main_estimator", lambda: self.main_estimator(pts, pw, rgb_local, pts_local, pwl)))
 
+        # MAIN_PATH_HIGH_PRIORITY: the chain implicit transformation -> main estimator (forward) and its backward gate the image
+        # branch's backward, the longest chain of the step; on the high-priority stream (idle between the image branch's forward
+        # and backward) it is not slowed down by the two enhancer heads running beside it
+        run_main = (lambda: br2.run(2, _main_path)) if (MAIN_PATH_HIGH_PRIORITY and self.training) else _main_path
         if HEADS_MAIN_FIRST:
-            pts_w, pts_w_local, r, t, s = _main_path()
+            pts_w, pts_w_local, r, t, s = run_main()
         if self.training:
             r_c, t_c, s_c = br2.run(0, lambda: ph("cam_enhancer", lambda: self.cam_enhancer(pts, rgb_local, pts_local)))
             r_w, t_w, s_w, pts_w_local_gt = br2.run(1, lambda: ph("world_enhancer", lambda: self.world_enhancer(pts, inputs["qo"], rgb_local, pts_local, gt_feats)))
         if not HEADS_MAIN_FIRST:
-            pts_w, pts_w_local, r, t, s = _main_path()
+            pts_w, pts_w_local, r, t, s = run_main()
         br2.join()
         trace.mark("forward joined")
         end_points["pred_qo"] = pts_w
