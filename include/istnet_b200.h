@@ -96,12 +96,15 @@ int istnet_fps_chain(int b, int n, int nlevels, const int *npoint, const float *
  * output (train-mode BatchNorm statistics) per CTA; *grid_out receives the number of CTAs G, finish with istnet_bn_finalize.
  * mask_hi (nullable, bf16 [B,H,W,mask_cs]): the output is zeroed where mask <= 0 before statistics / stores — used by the data
  * gradient of a layer fed by a bias+ReLU layer (nn.Conv1d + nn.ReLU stacks, ist_net.py:130-160): the epilogue then produces that
- * layer's dy operand planes and, through stat_part, its bias gradient (autograd's threshold_backward + sum in the reference). */
+ * layer's dy operand planes and, through stat_part, its bias gradient (autograd's threshold_backward + sum in the reference).
+ * stat_y (nullable, FP32 [B,H,W,stat_y_cs], needs stat_part): the second statistic becomes sum(out * stat_y) instead of sum(out^2) —
+ * with mask_hi this is the reduction of the BatchNorm backward of a conv+BN+ReLU layer below (finish with
+ * istnet_bn_bwd_finalize_gy + istnet_bn_bwd_apply). */
 int istnet_conv_gemm(const void *act_planes, long long act_plane_stride, int B, int H, int W, int Cin, int act_cs,
                      const void *wgt_planes, long long wgt_plane_stride, int Cout, int wgt_cs, int kh, int kw, int nsplit,
                      const float *bias, int relu, float *out_f32, int out_cs, void *out_planes, long long out_plane_stride,
                      int nsplit_out, int split_cs, int box_w, int box_h, float *stat_part, int *grid_out, const void *mask_hi, int mask_cs,
-                     void *stream);
+                     const float *stat_y, int stat_y_cs, void *stream);
 
 /* Weight gradient of the layer above (cuDNN wgrad in the reference):
  *   grad_w[co][ci][r][s] = sum_{b,h,w} dy[b,h,w,co] * x[b,h+r-kh/2,w+s-kw/2,ci]       (PyTorch weight layout, FP32)
@@ -148,6 +151,15 @@ int istnet_bn_act_bwd(const float *dz, const float *dz2, const float *y, long lo
                       int cs_z, const float *noise, int batch_stats, const uint8_t *argmax, int ns, float *part_ws, double *ws,
                       void *dy_planes, long long plane_stride, int nsplit, int cs_dy, float *dy_f32, float *g_out, float *sum_g_f32,
                       float *sum_gx_f32, void *stream);
+
+/* BatchNorm backward of a conv+BN+ReLU layer whose reduction rode in the data-gradient GEMM above it (istnet_conv_gemm with mask_hi and
+ * stat_y): finalize_gy turns the per-CTA partials [sum g | sum g*y] into ws = [sum g | sum g*xhat | 0] (+ FP32 copies = the BN bias /
+ * weight gradients); bn_bwd_apply is the apply pass of istnet_bn_act_bwd alone (dz = the masked gradient g written by that GEMM). */
+int istnet_bn_bwd_finalize_gy(const float *part, int G, int C, const float *mean, const float *invstd, double *ws, float *sum_g_f32,
+                              float *sum_gx_f32, void *stream);
+int istnet_bn_bwd_apply(const float *dz, const float *y, long long P, int C, const float *mean, const float *invstd, const float *gamma,
+                        const float *beta, int act, const void *z_hi, int cs_z, const double *ws, void *dy_planes, long long plane_stride,
+                        int nsplit, int cs_dy, float *dy_f32, void *stream);
 
 /* FP32 [P][C] (or NCHW with HW pixels per image when nchw != 0) -> bf16 operand planes [nsplit][P][cs] at channel offset ch_off */
 int istnet_split(const float *x, long long P, int C, long long HW, int nchw, void *planes, long long plane_stride, int nsplit, int cs,

@@ -48,6 +48,8 @@ struct ConvGemmParams {
     float *stat_part;         // optional [gridDim.x][2][Cout]: per-CTA column sums / sums of squares of the output (BN statistics)
     const __nv_bfloat16 *mask_hi;  // optional [B,H,W,mask_cs]: output element kept only where mask > 0 (ReLU backward of the layer below)
     int mask_cs;
+    const float *stat_y;      // optional [B,H,W,stat_y_cs]: second statistic = sum(out * stat_y) instead of sum(out^2) (BN backward)
+    int stat_y_cs;
     uint32_t tmem_cols;
 };
 
@@ -246,6 +248,22 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     float a[32], q2[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) { a[i] = row_ok ? f[i] : 0.f; q2[i] = a[i] * a[i]; }
+                    if (p.stat_y != nullptr) {
+                        // BatchNorm backward of the layer below (whose pre-BN output is stat_y): with the ReLU mask applied above,
+                        // the two statistics are sum(g) and sum(g*y); sum(g*xhat) = invstd * (sum(g*y) - mean * sum(g)) follows
+                        // in the finalize kernel, so the separate reduce pass over (dz, y, mask) is not needed
+                        const float *yrow = p.stat_y + pix * p.stat_y_cs + n;
+                        if (row_ok && valid == 32 && ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                const float4 yv = __ldg(reinterpret_cast<const float4 *>(yrow + i));
+                                q2[i] = a[i] * yv.x; q2[i + 1] = a[i + 1] * yv.y; q2[i + 2] = a[i + 2] * yv.z; q2[i + 3] = a[i + 3] * yv.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) q2[i] = (row_ok && i < valid) ? a[i] * __ldg(yrow + i) : 0.f;
+                        }
+                    }
 #pragma unroll
                     for (int half = 16; half >= 1; half >>= 1) {
                         const bool up = (lane & half) != 0;
@@ -366,7 +384,7 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
                                 const void *wgt_planes, long long wgt_plane_stride, int Cout, int wgt_cs, int kh, int kw, int nsplit,
                                 const float *bias, int relu, float *out_f32, int out_cs, void *out_planes, long long out_plane_stride,
                                 int nsplit_out, int split_cs, int box_w, int box_h, float *stat_part, int *grid_out, const void *mask_hi,
-                                int mask_cs, void *stream) {
+                                int mask_cs, const float *stat_y, int stat_y_cs, void *stream) {
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return ISTNET_ERR_BAD_ARG;
     if (nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
     if ((act_cs & 7) || (wgt_cs & 7) || act_cs < Cin || wgt_cs < Cin) return ISTNET_ERR_BAD_ARG;
@@ -387,6 +405,8 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     p.bias = bias; p.relu = relu;
     p.stat_part = stat_part;
     p.mask_hi = (const __nv_bfloat16 *)mask_hi; p.mask_cs = mask_cs;
+    p.stat_y = stat_y; p.stat_y_cs = stat_y_cs;
+    if (stat_y && (!stat_part || stat_y_cs < Cout)) return ISTNET_ERR_BAD_ARG;
     if (mask_hi && mask_cs < Cout) return ISTNET_ERR_BAD_ARG;
     p.out_f32 = out_f32; p.out_cs = out_cs;
     p.out_pl = (__nv_bfloat16 *)out_planes; p.out_pl_stride = out_plane_stride; p.split_cs = split_cs; p.nsplit_out = nsplit_out;

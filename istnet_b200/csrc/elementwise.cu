@@ -1128,6 +1128,41 @@ extern "C" int istnet_bn_act_bwd(const float *dz, const float *dz2, const float 
     return ISTNET_OK;
 }
 
+// BN-backward sums from the statistics epilogue of the data-gradient GEMM above (conv_gemm stat_y): part = [sum g | sum g*y] per CTA
+__global__ void __launch_bounds__(kFinThreads) bwd_finalize_gy_kernel(const float *__restrict__ part, int G, int C, const float *__restrict__ mean,
+                                                                      const float *__restrict__ invstd, double *ws, float *sum_g_f32,
+                                                                      float *sum_gx_f32) {
+    double t[2];
+    sum_partials<2>(part, G, C, t);
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    if (threadIdx.x >= 32 || c >= C) return;
+    const double sgx = (double)invstd[c] * (t[1] - (double)mean[c] * t[0]);  // sum g*xhat, xhat = (y - mean)*invstd
+    ws[c] = t[0];
+    ws[C + c] = sgx;
+    ws[2 * C + c] = 0.0;
+    if (sum_g_f32) sum_g_f32[c] = (float)t[0];
+    if (sum_gx_f32) sum_gx_f32[c] = (float)sgx;
+}
+extern "C" int istnet_bn_bwd_finalize_gy(const float *part, int G, int C, const float *mean, const float *invstd, double *ws, float *sum_g_f32,
+                                         float *sum_gx_f32, void *stream) {
+    if (!part || G <= 0 || C <= 0 || !mean || !invstd || !ws) return ISTNET_ERR_BAD_ARG;
+    bwd_finalize_gy_kernel<<<ceil_div(C, 32), kFinThreads, 0, ST>>>(part, G, C, mean, invstd, ws, sum_g_f32, sum_gx_f32);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+// apply pass of istnet_bn_act_bwd alone, for sums (ws) produced elsewhere
+extern "C" int istnet_bn_bwd_apply(const float *dz, const float *y, long long P, int C, const float *mean, const float *invstd, const float *gamma,
+                                   const float *beta, int act, const void *z_hi, int cs_z, const double *ws, void *dy_planes,
+                                   long long plane_stride, int nsplit, int cs_dy, float *dy_f32, void *stream) {
+    if (P <= 0 || P > 0x7fffffffLL || C <= 0 || (C & 3) || !mean || !ws || (act != 0 && act != 1) || (act == 1 && !z_hi)) return ISTNET_ERR_BAD_ARG;
+    ActBwdP p{};
+    p.dz = dz; p.y = y; p.bn = make_bn(mean, invstd, gamma, beta);
+    p.act = act; p.z_hi = (const __nv_bfloat16 *)z_hi; p.cs_z = cs_z; p.HW = 1; p.batch_stats = 1;
+    bn_bwd_apply_kernel<<<row_grid(P, C, kBwdUnroll), kEwThreads, 0, ST>>>(P, C, p, ws, (__nv_bfloat16 *)dy_planes, plane_stride, nsplit, cs_dy, dy_f32,
+                                                                            nullptr);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
 extern "C" int istnet_split(const float *x, long long P, int C, long long HW, int nchw, void *planes, long long plane_stride, int nsplit,
                             int cs, int ch_off, void *stream) {
     if (P <= 0 || C <= 0 || nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;

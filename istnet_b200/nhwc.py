@@ -117,6 +117,8 @@ def pick_box(H, W):
 FUSE_BN_STATS = os.environ.get("ISTNET_FUSE_BN_STATS", "1") != "0"
 # ReLU backward + bias gradient + operand split of a bias+ReLU layer inside the epilogue of the data-gradient GEMM above it
 FUSE_RELU_BWD = os.environ.get("ISTNET_FUSE_RELU_BWD", "1") != "0"
+# conv+BN+ReLU layer below: ReLU mask and the BatchNorm-backward reduction (sum g, sum g*y) in that epilogue; only the apply pass remains
+FUSE_BN_BWD = os.environ.get("ISTNET_FUSE_BN_BWD", "0") != "0"  # measured: no gain (1133 vs 1136 inst/s), see DESIGN.md section 9
 WGRAD_SIDE_STREAM = os.environ.get("ISTNET_WGRAD_STREAM", "1") != "0"
 _SIDE = {}
 _PENDING_JOINS = []
@@ -168,7 +170,7 @@ def _timed(name, flops, nsplit, launch, desc=""):
     PROFILE.append((name, e0, e1, PROFILE_REPS, flops, nsplit, desc))
 
 
-def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl=None, stat_part=None, mask_hi=None):
+def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl=None, stat_part=None, mask_hi=None, stat_y=None):
     """x: Act with operand planes; writes out_f32 [B,H,W,cout] and/or out_pl.  With stat_part (float buffer of
     >= 2*296*cout) the epilogue also leaves per-CTA BN-statistics partials there; returns the CTA count G."""
     bw, bh = pick_box(x.H, x.W)
@@ -179,6 +181,7 @@ def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl
         c_ll(w_pl.stride(0)), c_int(cout), c_int(w_pl.shape[-1]), c_int(kh), c_int(kw), c_int(ns), _p(bias), c_int(1 if relu else 0),
         _p(out_f32), c_int(out_f32.shape[-1] if out_f32 is not None else 0), *_pl_args(out_pl), c_int(out_pl.shape[-1] if out_pl is not None else 0),
         c_int(bw), c_int(bh), _p(stat_part), ctypes.byref(grid), _p(mask_hi), c_int(mask_hi.shape[-1] if mask_hi is not None else 0),
+        _p(stat_y), c_int(stat_y.shape[-1] if stat_y is not None else 0),
     )
     _timed("conv_gemm_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, ns, lambda: _C.call("conv_gemm", *args),
            f"P={x.P} {x.H}x{x.W} cin={x.C} cout={cout} k={kh}")
@@ -346,7 +349,8 @@ class ConvUnit:
         st = bn_state(self.bn, y, P, C, training, part, G) if self.bn is not None else None
         rec = {"bn": st}
         if record:
-            rec.update({"xin": xin, "y": y, "noise": noise, "kk": kk, "P": P, "HW": H * W, "in_shape": (x.B, x.H, x.W, x.C), "wd": wd})
+            rec.update({"xin": xin, "y": y, "noise": noise, "kk": kk, "P": P, "HW": H * W, "in_shape": (x.B, x.H, x.W, x.C), "wd": wd,
+                        "has_res": res is not None})
         if defer_act:
             return Act(B, H, W, C, y), rec
         if self.bn is None and self.act == ACT_NONE and noise is None and res is None:  # plain linear layer
@@ -416,7 +420,14 @@ class ConvUnit:
         if self.act == ACT_PRELU:
             grads[id(self.prelu)] = ws[2 * C : 3 * C].sum().float().reshape(1)
 
-    def data_grads(self, rec, dy, need_dx, grads, below=None):
+    def is_bn_relu(self, rec):
+        """Conv + train-mode BatchNorm + ReLU, no residual / Dropout2d: its BN-backward reduction can ride in the epilogue of the
+        data-gradient GEMM of the layer above (conv_gemm mask_hi + stat_y)."""
+        st = rec.get("bn")
+        return (self.bn is not None and st is not None and st.batch and self.act == ACT_RELU and rec.get("noise") is None and not rec.get("has_res")
+                and rec.get("z_hi") is not None and rec.get("y") is not None)
+
+    def data_grads(self, rec, dy, need_dx, grads, below=None, below_f32=False):
         """Weight gradient (side stream) and data gradient of the convolution.  below = (unit, rec) of the bias+ReLU layer that
         produced this unit's input: the data-gradient GEMM then applies that layer's ReLU mask in its epilogue and returns
         ITS dy operand planes (and fills its bias gradient) instead of the FP32 dx."""
@@ -451,6 +462,26 @@ class ConvUnit:
         wd = rec.get("wd")
         if wd is None or wd.shape[0] != dy.shape[0]:
             wd = prep_weight(self.w, transpose=True, nsplit=dy.shape[0])
+        if below is not None and below[0].bn is not None:
+            # conv+BN+ReLU below: g = dx*mask (FP32) and the partials of sum g, sum g*y come out of this GEMM; finalize; apply pass
+            bu, brec = below
+            st, Cb, dev = brec["bn"], xin.C, dy.device
+            g = torch.empty(xin.B, xin.H, xin.W, Cb, dtype=torch.float32, device=dev)
+            part = torch.empty(2 * 296 * Cb, dtype=torch.float32, device=dev)
+            G = conv_gemm(dyA, wd, Cb, kk, kk, out_f32=g, stat_part=part, mask_hi=brec["z_hi"], stat_y=brec["y"])
+            ws = torch.empty(3 * Cb, dtype=torch.float64, device=dev)
+            sg = torch.empty(Cb, dtype=torch.float32, device=dev)
+            sgx = torch.empty(Cb, dtype=torch.float32, device=dev)
+            _C.call("bn_bwd_finalize_gy", ptr(part), c_int(G), c_int(Cb), ptr(st.mean), ptr(st.invstd), ptr(ws), ptr(sg), ptr(sgx))
+            grads[id(bu.bn.weight)], grads[id(bu.bn.bias)] = sgx, sg
+            if bu.b is not None:
+                grads[id(bu.b)] = torch.zeros_like(bu.b)
+            dyb = None if below_f32 else empty_planes(xin.B, xin.H, xin.W, Cb, dev, nsplit=NSPLIT_BWD)
+            dyf = torch.empty_like(g) if below_f32 else None
+            zh = brec["z_hi"]
+            _C.call("bn_bwd_apply", ptr(g), ptr(brec["y"]), c_ll(xin.P), c_int(Cb), ptr(st.mean), ptr(st.invstd), ptr(st.gamma), ptr(st.beta), c_int(1),
+                    ptr(zh), c_int(zh.shape[-1]), ptr(ws), *_pl_args(dyb), c_int(dyb.shape[-1] if dyb is not None else 0), _p(dyf))
+            return dyf if below_f32 else dyb
         if below is not None:
             bu, brec = below
             dyb = empty_planes(xin.B, xin.H, xin.W, xin.C, dy.device, nsplit=NSPLIT_BWD)

@@ -57,16 +57,25 @@ def _chain_forward(units, a, training, record, last_f32=True, last_pair=False):
     return a, tape
 
 
-def _chain_backward(units, tape, dz, grads, need_dx_first):
-    dy = None  # operand planes of unit i's dy when the layer above already produced them in its data-gradient epilogue
+def _fusable_below(u, rec):
+    return (K.FUSE_RELU_BWD and u.is_bias_relu(rec)) or (K.FUSE_BN_BWD and u.is_bn_relu(rec))
+
+
+def _chain_backward(units, tape, dz, grads, need_dx_first, dy_first=None, below_first=None):
+    """Backward through a chain of units.  dz: FP32 gradient w.r.t. the chain output (or dy_first: the top unit's dy operand
+    planes, already made).  Wherever the layer below is bias+ReLU or BN+ReLU its activation backward rides in the epilogue of
+    the data-gradient GEMM above it.  below_first = (unit, rec) of such a layer feeding units[0] from outside the chain: the
+    return value is then that layer's FP32 dy instead of the gradient w.r.t. the chain input."""
+    dy = dy_first  # operand planes of unit i's dy when the layer above already produced them in its data-gradient epilogue
     for i in range(len(units) - 1, -1, -1):
         u, rec = units[i], tape[i]
         if dy is None:
             dy, _ = u.act_backward(rec, dz, None, False, grads)
-        fuse = (K.FUSE_RELU_BWD and i > 0 and rec["kk"] == u.k and u.stride == 1 and units[i - 1].is_bias_relu(tape[i - 1])
-                and tape[i - 1]["z_hi"].shape[-1] >= rec["xin"].C)
-        if fuse:
+        plain = rec["kk"] == u.k and u.stride == 1
+        if i > 0 and plain and _fusable_below(units[i - 1], tape[i - 1]) and tape[i - 1]["z_hi"].shape[-1] >= rec["xin"].C:
             dy, dz = u.data_grads(rec, dy, True, grads, below=(units[i - 1], tape[i - 1])), None
+        elif i == 0 and below_first is not None and plain:
+            return u.data_grads(rec, dy, True, grads, below=below_first, below_f32=True)
         else:
             dz, dy = u.data_grads(rec, dy, i > 0 or need_dx_first, grads), None
     return dz
@@ -152,12 +161,15 @@ class _SAScaleFn(torch.autograd.Function):
         # max-pool routing + ReLU mask + BN backward in one reduce / apply pair (no materialised [rows, C] selection tensor)
         _, sg_f, sgx_f = K.bn_act_bwd(dz, None, rec["y"], G * ns, Cl, 1, st, K.ACT_RELU_MAXROWS, None, None, None, dy_pl=dy, argmax=argmax, ns=ns)
         grads[id(last.bn.weight)], grads[id(last.bn.bias)] = sgx_f, sg_f
-        d = last.data_grads(rec, dy, True, grads)
         d_feats = None
         if tape[0].get("point_l0"):
-            d = _chain_backward(units[1:-1], tape[1:-1], d, grads, True)
-            d_feats = _sa_l0_backward(units[0], tape[0], d, ctx.xyz, ctx.new_xyz, ctx.idx, ctx.has_feats, grads)
+            # layers 1.. (the last one's dy is made above): every BN+ReLU layer's reduction rides in the data-gradient GEMM above it,
+            # down to layer 0, whose FP32 dy comes out of layer 1's data-gradient GEMM + apply pass
+            fuse0 = K.FUSE_BN_BWD and units[0].is_bn_relu(tape[0])
+            d = _chain_backward(units[1:], tape[1:], None, grads, True, dy_first=dy, below_first=(units[0], tape[0]) if fuse0 else None)
+            d_feats = _sa_l0_backward(units[0], tape[0], d, ctx.xyz, ctx.new_xyz, ctx.idx, ctx.has_feats, grads, have_dy0=fuse0)
         else:
+            d = last.data_grads(rec, dy, True, grads)
             d = _chain_backward(units[:-1], tape[:-1], d, grads, ctx.has_feats)
             if ctx.has_feats:
                 d_feats = torch.empty(B, N, C, dtype=torch.float32, device=dz.device)
@@ -200,7 +212,7 @@ def _sa_l0_forward(u0, training, xyz, new_xyz, idx, feats, record):
     return a, rec
 
 
-def _sa_l0_backward(u0, rec, d, xyz, new_xyz, idx, need_dfeats, grads):
+def _sa_l0_backward(u0, rec, d, xyz, new_xyz, idx, need_dfeats, grads, have_dy0=False):
     """d: FP32 gradient w.r.t. layer 0's output rows.  BN/ReLU backward on the rows, then ONE pass scatters dy0 to the
     points (dU) and reduces dWx; the feature part of the weight gradient and the feature gradient are GEMMs over the
     points.  Returns d_feats (B,N,C) or None."""
@@ -209,9 +221,12 @@ def _sa_l0_backward(u0, rec, d, xyz, new_xyz, idx, need_dfeats, grads):
     fa = rec["fa"]
     C = 0 if fa is None else fa.C
     rows, C0, dev = B * M * ns, u0.cout, d.device
-    dy0 = torch.empty(1, 1, rows, C0, dtype=torch.float32, device=dev)
-    _, sg_f, sgx_f = K.bn_act_bwd(d, None, rec["y"], rows, C0, 1, rec["bn"], ACT_RELU, None, rec["z_hi"], None, dy_f32=dy0)
-    grads[id(u0.bn.weight)], grads[id(u0.bn.bias)] = sgx_f, sg_f
+    if have_dy0:  # d already is dy0 (BN/ReLU backward fused into layer 1's data-gradient GEMM, BN gradients set there)
+        dy0 = d
+    else:
+        dy0 = torch.empty(1, 1, rows, C0, dtype=torch.float32, device=dev)
+        _, sg_f, sgx_f = K.bn_act_bwd(d, None, rec["y"], rows, C0, 1, rec["bn"], ACT_RELU, None, rec["z_hi"], None, dy_f32=dy0)
+        grads[id(u0.bn.weight)], grads[id(u0.bn.bias)] = sgx_f, sg_f
     dU = torch.empty(B * N, C0, dtype=torch.float32, device=dev) if C > 0 else None
     part = torch.empty(_C.lib().istnet_reduce_ws_floats(c_ll(rows), C0, 3), dtype=torch.float32, device=dev)
     wsx = torch.empty(3 * C0, dtype=torch.float64, device=dev)
