@@ -2,10 +2,11 @@
 executed channels-last on the B200 kernels with an explicit tape and a hand-written backward.
 
 Forward dataflow (train): rgb -> im2col -> conv1 GEMM -> [BN+ReLU+MaxPool fused] -> 8 BasicBlocks (each conv is an
-implicit-GEMM tcgen05 kernel; BN statistics, BN-apply + residual + ReLU + operand split are one pass each) -> PSP priors
-(tiny pooled maps, torch) + concat -> bottleneck GEMM -> [ReLU + Dropout2d scale] -> 3 x [bilinear x2 fused with the
-operand split -> conv3x3 GEMM -> BN + PReLU (+Dropout2d scale)] -> final 1x1 GEMM -> BN + PReLU evaluated only at the
-`choose`d pixels, directly in the reference's (B,128,N) layout (ist_net.py:41-45).
+implicit-GEMM tcgen05 kernel; BN statistics in its epilogue, BN-apply + residual + ReLU + operand split one pass) -> PSP:
+pyramid pooling in one pass, both 1x1 convolutions on the <= 36-pixel level maps, one pass for all up-samplings + their sum,
+which enters the K = 512 bottleneck GEMM's activation pass as a residual -> [ReLU + Dropout2d scale] -> 3 x [bilinear x2
+fused with the operand split -> conv3x3 GEMM -> BN + PReLU (+Dropout2d scale)] -> head: BN statistics of the final 1x1
+convolution from the moments of its input, convolution + BN + PReLU only on the `choose`d rows (ist_net.py:41-45).
 """
 import os
 

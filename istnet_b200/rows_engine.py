@@ -1,6 +1,7 @@
 """Point-set layers ("rows": one row per point, channels contiguous) on the B200 kernels: chains of 1x1 convolutions
 (SharedMLP conv+BN+ReLU, Conv1d+bias+ReLU) as tcgen05 GEMMs with fused BN / activation passes and hand-written
-backward; the set-abstraction scale (group -> 3-layer MLP -> max over neighbours) and the three-NN interpolation.
+backward; the set-abstraction scale (layer 0 on the points + gather, layers 1-2 on the grouped rows, max over neighbours)
+and the three-NN interpolation.
 
 Replaces, for the reference: pytorch_utils.SharedMLP on (B,C,npoint,nsample) tensors (cuDNN 1x1 convs + BN + ReLU +
 F.max_pool2d, pointnet2_modules.py:60-69), grouping_operation / three_interpolate on channel-first tensors, and the
