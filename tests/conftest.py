@@ -51,3 +51,16 @@ def fixed_dropout_noise(seed):
         return torch.empty(b, c, 1, 1).bernoulli_(1 - p, generator=g).div_(1 - p)
 
     return fn
+
+
+def perturb_batchnorm(model, seed):
+    """Deterministic non-trivial BatchNorm running statistics / affine parameters (eval-mode goldens would otherwise see
+    mean 0, var 1, gamma 1, beta 0 everywhere).  Used by the golden generator and by the tests on the same module tree."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.copy_(0.1 * torch.randn(mod.num_features, generator=g))
+                mod.running_var.copy_(0.5 + torch.rand(mod.num_features, generator=g))
+                mod.weight.copy_(0.5 + torch.rand(mod.num_features, generator=g))
+                mod.bias.copy_(0.1 * torch.randn(mod.num_features, generator=g))

@@ -36,6 +36,23 @@ def test_cfg0_eval_forward_matches_reference_golden():
         assert rel_err(v, z["out_" + k]) < TOL, (k, rel_err(v, z["out_" + k]))
 
 
+def test_cfg4_dense_cloud_eval_forward_matches_reference_golden():
+    """4096-point crop (BASELINE.json configs[4] shape): FPS over 4096 points, SA1 on 512 x {16,32} neighbours of a 4x denser
+    surface, FP0 and every per-point MLP on 4096 rows; eval forward with non-trivial BatchNorm statistics vs the reference."""
+    from conftest import perturb_batchnorm
+
+    z = load_golden("cfg4_eval.npz")
+    torch.manual_seed(1)
+    m = M.IST_Net(6, False)
+    perturb_batchnorm(m, seed=41)
+    assert abs(sd_checksum(m.state_dict()) - float(z["sd_checksum"])) < 1e-6 * float(z["sd_checksum"])
+    m = m.cuda().eval()
+    with torch.no_grad():
+        ep = m(cuda_inputs(golden_inputs(z)))
+    for k, v in ep.items():
+        assert rel_err(v, z["out_" + k]) < TOL, (k, rel_err(v, z["out_" + k]))
+
+
 def _train_step(m, inp, loss_mod, noise_seed, momentum=None):
     psp = (m.rgb_cam_extractor if hasattr(m, "rgb_cam_extractor") else m.rgb_extractor).model
     psp.dropout_noise_fn = fixed_dropout_noise(noise_seed)

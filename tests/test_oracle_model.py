@@ -33,6 +33,21 @@ def test_port_reproduces_cfg0_golden():
         assert rel_err(v, z["out_" + k]) < 1e-6, k
 
 
+def test_port_reproduces_cfg4_dense_cloud_golden():
+    """4096-point crop (BASELINE.json configs[4] shape), eval forward with non-trivial BatchNorm statistics: port == reference."""
+    from conftest import perturb_batchnorm
+
+    z = load_golden("cfg4_eval.npz")
+    torch.manual_seed(1)
+    m = M.IST_Net(6, False)
+    perturb_batchnorm(m, seed=41)
+    assert abs(sd_checksum(m.state_dict()) - float(z["sd_checksum"])) < 1e-6 * float(z["sd_checksum"])
+    with torch.no_grad():
+        ep = port.ist_net_forward(_sd(m), golden_inputs(z), training=False)
+    for k, v in ep.items():
+        assert rel_err(v, z["out_" + k]) < 1e-6, k
+
+
 def test_port_reproduces_train_golden():
     z = load_golden("train_b4.npz")
     torch.manual_seed(1)
