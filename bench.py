@@ -25,7 +25,7 @@ import torch.distributed as dist  # noqa: E402
 LABELS = ("qo", "rotation_label", "translation_label", "size_label")
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's largest launch (up_1 conv, B=32) from one
 # `ncu --set full` capture (profiles/), bytes per launch; None until captured for the current kernel version
-ROOFLINE_TRAFFIC = 573.7e6  # profiles/r1_conv_up1_after.txt: 511.1 MB read + 62.6 MB written (algorithmic: 453 MB operand planes + 75.5 MB output)
+ROOFLINE_TRAFFIC = 398.0e6  # profiles/r1_conv_up1_ns2.txt (up_1 forward as it runs now, 2 operand planes): 337.0 MB read + 61.0 MB written (algorithmic: 302 MB operand planes + 75.5 MB output)
 MODEL_IN = ("rgb", "pts", "choose", "category_label", "qo")
 WORKLOADS = {
     "cfg1": dict(model="ist_net", batch=32, npts=1024, img=192, desc="ist_net_default.yaml train fwd+bwd, 32 x (1024 pts + 192x192 RGB) per GPU"),
@@ -352,7 +352,7 @@ def main():
                          "avg_launch_ms": dom["ms"] / dom["n"], "algorithmic_gflop_per_launch": dom["flop"] / dom["n"] / 1e9,
                          "executed_mma_tflops": dom["mma_flop"] / (dom["ms"] * 1e-3) / 1e12,
                          "peak_source": f"bf16 dense burst (kernel timed alone), {pk_src}",
-                         "note": "achieved counts one multiply-add per reference MAC; the tensor pipe executes 6x (forward, 3 bf16 planes) / 3x (backward) that for FP32-level accuracy",
+                         "note": "achieved counts one multiply-add per reference MAC; the tensor pipe executes 6x (3 bf16 operand planes: PointNet++ and lower ResNet layers) or 3x (2 planes: up_1..3, layer4, pose heads, every backward GEMM) that for FP32-level accuracy (DESIGN.md section 2)",
                          "wgrad_tc_kernel": {"achieved": kstat["wgrad_tc_kernel"]["flop"] / (kstat["wgrad_tc_kernel"]["ms"] * 1e-3) / 1e12,
                                              "launches_per_step": kstat["wgrad_tc_kernel"]["n"]},
                          "whole_step": {"achieved": step_tflops, "frac_of_sustained_peak": step_tflops / pk["bf16_tflops_sustained"],
