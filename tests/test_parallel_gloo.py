@@ -100,3 +100,54 @@ def test_gather_and_bind_grads_pack_fresh_gradients_into_the_buckets():
         if n in want:
             assert torch.equal(p.grad, want[n])
             assert any(p.grad.data_ptr() >= b["flat"].data_ptr() and p.grad.data_ptr() < b["flat"].data_ptr() + 4 * b["flat"].numel() for b in red.buckets)
+
+
+def _worker_graph_path(rank, world, port, ret):
+    """The N > 1 CUDA-graph flow of bench.py without a graph: first step eager (discovers the buckets), hooks removed, then every
+    step starts from grad=None, ends with gather_grads() (the captured multi-tensor copy) + reduce_all(), bind_grads() once."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from istnet_b200.parallel import GradAllReducer, broadcast_module
+
+    torch.manual_seed(200 + rank)
+    m = Toy()
+    broadcast_module(m)
+    red = GradAllReducer(m, bucket_mb=0.0002)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(3, 8, 8, generator=g)
+    red.zero_grad()
+    m(x[0, rank * 4 : (rank + 1) * 4]).pow(2).mean().backward()
+    red.finish()
+    red.remove_hooks()
+    out = []
+    for step in (1, 2):
+        for p in m.parameters():
+            p.grad = None
+        m(x[step, rank * 4 : (rank + 1) * 4]).pow(2).mean().backward()
+        red.gather_grads()
+        red.reduce_all()
+        red.bind_grads()
+        out.append([p.grad.clone() if p.grad is not None else None for p in m.parameters()])
+    if rank == 0:
+        ret["grads"] = out
+        ret["state"] = {k: v.clone() for k, v in m.state_dict().items()}
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_graph_path_gather_reduce_bind_matches_full_batch_gradient():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_graph_path, args=(2, _free_port(), ret), nprocs=2, join=True)
+    ref = Toy()
+    ref.load_state_dict(ret["state"])
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(3, 8, 8, generator=g)
+    for i, step in enumerate((1, 2)):
+        ref.zero_grad(set_to_none=True)
+        ref(x[step]).pow(2).mean().backward()
+        for (n, p), got in zip(ref.named_parameters(), ret["grads"][i]):
+            if p.grad is None:
+                assert got is None, n
+            else:
+                assert torch.allclose(p.grad, got, atol=1e-6), (step, n)
