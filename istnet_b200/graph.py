@@ -31,6 +31,8 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._eager()
+        # the gradient tensors autograd installed during the capture: graph-pool memory that every replay rewrites
+        self._grads = [(p, p.grad) for p in model.parameters() if p.grad is not None]
 
     def _eager(self):
         # keep_grads: accumulate into the existing (flat-bucket) tensors, zeroed by the graph itself.  Otherwise the step
@@ -59,4 +61,8 @@ class GraphedTrainStep:
         if batch is not None:
             self.load(batch)
         self.graph.replay()
+        if self.after_backward is None and not self.keep_grads:
+            for p, g in self._grads:  # an optimizer.zero_grad(set_to_none=True) between steps must not detach the step's output
+                if p.grad is None:
+                    p.grad = g
         return self.loss
