@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--no-optimizer", action="store_true", help="time forward + loss + backward (+ all-reduce) without the Adam step")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.config])
     if args.batch:
@@ -206,7 +207,7 @@ def main():
         return run_reference(args, wl)
 
     from istnet_b200 import _C
-    from istnet_b200.parallel import GradAllReducer, broadcast_module
+    from istnet_b200.parallel import DataParallelStep, FlatAdam, GradAllReducer, broadcast_module
     from istnet_b200.synth import flops_per_instance, make_batch
 
     assert torch.cuda.is_available(), "bench.py (own arm) needs a GPU; there is no CPU fallback"
@@ -227,6 +228,8 @@ def main():
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
+    opt = None  # built after the first step (the flat buckets come from the parameters that received a gradient)
+
     def eager_step(data):
         reducer.zero_grad()
         ep = model({k: data[k] for k in MODEL_IN})
@@ -234,30 +237,33 @@ def main():
         loss = loss_fn(ep)
         loss.backward()
         reducer.finish()
+        if opt is not None:
+            opt.step()
         return loss
 
-    # one eager step first: counts the kernel launches of a step (the graph replays exactly these) and warms everything up
-    l_probe = _C.LAUNCHES
+    # one eager step first: discovers the gradient buckets and warms everything up
     eager_step(resident)
+    if not args.no_optimizer:
+        # the reference's optimizer (utils/solver.py:41-46: Adam, default betas/eps, CyclicLR from base_lr 1e-5) on the flat buckets
+        opt = FlatAdam(reducer, lr=1e-5, weight_decay=0.0)
+    l_probe = _C.LAUNCHES
+    eager_step(resident)  # counts the kernel launches of a step (the graph replays exactly these)
     launches_per_step = _C.LAUNCHES - l_probe
     graphed = None
+    nccl_in_graph = os.environ.get("ISTNET_GRAPH_NCCL", "1") != "0"
     if not args.eager:
         from istnet_b200.graph import GraphedTrainStep
 
-        if world > 1:  # the first eager step built the flat gradient buckets; the graph writes into them, NCCL reduces them
-            reducer.remove_hooks()
-        # N > 1: the graph ends with one multi-tensor copy of the step's gradients into the flat NCCL buckets
-        graphed = GraphedTrainStep(model, loss_fn, resident, MODEL_IN, LABELS, after_backward=reducer.gather_grads if world > 1 else None)
-        if world > 1:
-            reducer.bind_grads()
+        # the captured step = forward + loss + backward + per-bucket gradient packing / NCCL all-reduce (communication stream,
+        # first bucket behind the image branch's backward) + Adam on the flat buckets
+        dp = DataParallelStep(reducer, opt, nccl_in_graph=nccl_in_graph)
+        graphed = GraphedTrainStep(model, loss_fn, resident, MODEL_IN, LABELS, before_forward=dp.before, after_backward=dp.after,
+                                   before_replay=dp.before_replay, after_replay=dp.after_replay)
 
     def step(data):
         if graphed is None:
             return eager_step(data)
-        loss = graphed()
-        if world > 1:
-            reducer.reduce_all()
-        return loss
+        return graphed()
 
     def barrier():
         if world > 1:
@@ -307,12 +313,10 @@ def main():
 
     nhwc.PROFILE = []
     model_mod.USE_SIDE_STREAMS, nhwc.WGRAD_SIDE_STREAM = False, False  # time each kernel alone on its launching stream
-    if world > 1 and graphed is not None:  # hooks were removed for the graph path: plain forward+backward is enough here
-        ep_ = model({k: resident[k] for k in MODEL_IN})
-        ep_.update({k: resident[k] for k in LABELS})
-        loss_fn(ep_).backward()
-    else:
-        eager_step(resident)
+    reducer.zero_grad()
+    ep_ = model({k: resident[k] for k in MODEL_IN})
+    ep_.update({k: resident[k] for k in LABELS})
+    loss_fn(ep_).backward()
     torch.cuda.synchronize()
     prof, nhwc.PROFILE = nhwc.PROFILE, None
     kstat = {}
@@ -341,7 +345,11 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: {wl['desc']}", "per_gpu_batch": B, "global_batch": B * world,
-                       "parallelism": f"dp{world}", "launch": "eager" if graphed is None else "cuda-graph (whole step)", "l2": "per-step activation working set (>1 GB) exceeds the 126 MB L2; no explicit flush"},
+                       "parallelism": f"dp{world}", "launch": "eager" if graphed is None else "cuda-graph (whole step)",
+                       "step": "forward + SupervisedLoss + backward" + (" + NCCL gradient all-reduce" if world > 1 else "") +
+                               ("" if opt is None else " + Adam (flat buckets, utils/solver.py:41-46)") +
+                               ((" [all inside the graph]" if nccl_in_graph or world == 1 else " [all-reduce + Adam after the replay]") if graphed is not None else ""),
+                       "l2": "per-step activation working set (>1 GB) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "instances/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,

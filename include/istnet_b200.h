@@ -78,6 +78,36 @@ int istnet_three_interpolate_grad(int b, int c, int n, int m, const float *grad_
 int istnet_fps_chain(int b, int n, int nlevels, const int *npoint, const float *xyz, int32_t *const *idx_out, float *const *xyz_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * 2b. In-kernel completion of per-channel reductions ("last CTA finishes": csrc/ticket.cuh)
+ *
+ * Kernels that leave per-CTA partial sums (BatchNorm statistics in a GEMM epilogue, BatchNorm-backward sums, bias gradients)
+ * finish the reduction themselves when given this descriptor: the last CTA to arrive sums the partials in a fixed order (no
+ * floating-point atomics, bitwise reproducible) and applies the epilogue of `kind`.  Replaces the separate finalize launches
+ * (nn.BatchNorm2d's statistics kernels in the reference: resnet.py:129, modules.py:43,65, pytorch_utils.py:53-71).
+ * `tickets` points at ISTNET_FIN_TICKETS zero-initialised uint32 counters that are zero again when the kernel exits (graph
+ * replays need no memset); the partial-sum scratch given to the kernel must hold ISTNET_FIN_ROWS rows per quantity.
+ * `momentum` is a DEVICE scalar read when the kernel runs, so a BNMomentumScheduler update (utils/scheduler.py:277-303) takes
+ * effect on a replayed CUDA graph; a negative value selects nn.BatchNorm2d(momentum=None)'s cumulative average.
+ * ---------------------------------------------------------------------------------------------------- */
+#define ISTNET_FIN_NONE 0
+#define ISTNET_FIN_BN_STATS 1 /* partials {sum, sum^2} -> mean, invstd, running stats, num_batches_tracked */
+#define ISTNET_FIN_COLSUM 2   /* partials {sum} -> sum_f64 / sum_f32 [C] */
+#define ISTNET_FIN_BN_BWD 3   /* partials {sum g, sum g*xhat, slope} -> sum_f64 [3C], sum_f32 = sum g, sum2_f32 = sum g*xhat */
+#define ISTNET_FIN_TICKETS 20
+#define ISTNET_FIN_ROWS (296 + 19)
+typedef struct istnet_fin {
+    int kind;
+    unsigned *tickets;
+    long long P;
+    float eps;
+    const float *momentum;
+    float *running_mean, *running_var, *mean, *invstd;
+    long long *num_batches_tracked;
+    double *sum_f64;
+    float *sum_f32, *sum2_f32;
+} istnet_fin;
+
+/* ------------------------------------------------------------------------------------------------------
  * 3. Dense contractions on tcgen05 tensor cores (image branch model/resnet.py + model/modules.py:10-81,
  *    per-point MLPs model/ist_net.py:125-332, SharedMLP 1x1 convolutions pytorch_utils.py:25-206)
  *
@@ -92,8 +122,10 @@ int istnet_fps_chain(int b, int n, int nlevels, const int *npoint, const float *
  * (replaces nn.Conv2d / nn.Conv1d(k=1) / nn.Linear call sites: resnet.py:34-35, modules.py:17-25,41-44,64-66,
  * ist_net.py:130-160).  wgt planes: bf16 [nsplit][kh*kw][Cout][wgt_cs].  Any of out_f32 / out_planes may be null.
  * (box_w, box_h): pixel tile; box_w*box_h must divide 128 (images: 8x8 -> 2 images per tile; row matrices: 128x1).
- * stat_part (optional, >= 2*296*Cout floats): the epilogue also accumulates the per-channel sum / sum of squares of the
- * output (train-mode BatchNorm statistics) per CTA; *grid_out receives the number of CTAs G, finish with istnet_bn_finalize.
+ * stat_part (optional, >= 2*ISTNET_FIN_ROWS*Cout floats): the epilogue also accumulates the per-channel sum / sum of squares of the
+ * output (train-mode BatchNorm statistics) per CTA; *grid_out receives the number of CTAs G.  With `fin` (nullable; kinds
+ * ISTNET_FIN_BN_STATS, ISTNET_FIN_COLSUM) the kernel's last CTA finishes the reduction itself; otherwise finish with
+ * istnet_bn_finalize / istnet_colsum_finalize.
  * mask_hi (nullable, bf16 [B,H,W,mask_cs]): the output is zeroed where mask <= 0 before statistics / stores — used by the data
  * gradient of a layer fed by a bias+ReLU layer (nn.Conv1d + nn.ReLU stacks, ist_net.py:130-160): the epilogue then produces that
  * layer's dy operand planes and, through stat_part, its bias gradient (autograd's threshold_backward + sum in the reference).
@@ -104,7 +136,7 @@ int istnet_conv_gemm(const void *act_planes, long long act_plane_stride, int B, 
                      const void *wgt_planes, long long wgt_plane_stride, int Cout, int wgt_cs, int kh, int kw, int nsplit,
                      const float *bias, int relu, float *out_f32, int out_cs, void *out_planes, long long out_plane_stride,
                      int nsplit_out, int split_cs, int box_w, int box_h, float *stat_part, int *grid_out, const void *mask_hi, int mask_cs,
-                     const float *stat_y, int stat_y_cs, void *stream);
+                     const float *stat_y, int stat_y_cs, const istnet_fin *fin, void *stream);
 
 /* Weight gradient of the layer above (cuDNN wgrad in the reference):
  *   grad_w[co][ci][r][s] = sum_{b,h,w} dy[b,h,w,co] * x[b,h+r-kh/2,w+s-kw/2,ci]       (PyTorch weight layout, FP32)
@@ -124,9 +156,11 @@ int istnet_conv_wgrad(const void *dy_planes, long long dy_plane_stride, int dy_c
  * 1/sqrt(biased var + eps) over P rows; running stats updated in place with `momentum` (unbiased variance) when the
  * pointers are non-null.  part_ws: istnet_reduce_ws_floats(P, C, 2) floats of scratch (per-CTA partial sums, summed in a
  * fixed order by a second tiny kernel: no atomics, deterministic). */
-int istnet_reduce_ws_floats(long long P, int C, int nacc); /* floats of partial-sum scratch for a per-channel reduction */
+int istnet_reduce_ws_floats(long long P, int C, int nacc); /* floats of partial-sum scratch for a per-channel reduction (both ticket levels) */
 int istnet_bn_stats(const float *y, long long P, int C, float *part_ws, float eps, float momentum, float *running_mean,
                     float *running_var, float *mean, float *invstd, long long *num_batches_tracked, void *stream);
+/* same, one launch: the reduction kernel's last CTA finishes (fin->kind = ISTNET_FIN_BN_STATS; part_ws as above) */
+int istnet_bn_stats_fin(const float *y, long long P, int C, float *part_ws, const istnet_fin *fin, void *stream);
 
 /* num_batches_tracked (nullable): nn.BatchNorm2d's int64 step counter, incremented by the same launch */
 int istnet_bn_finalize(const float *part, int G, long long P, int C, float eps, float momentum, float *running_mean, float *running_var,
@@ -144,13 +178,14 @@ int istnet_bn_act_split(const float *y, long long P, int C, long long HW, const 
  * slope partials;  dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))  (batch_stats=1; gamma*invstd*g with running
  * statistics, batch_stats=0; g without BN) written as bf16 operand planes and/or FP32;
  * g_out (optional) receives g (the residual branch's gradient).  ReLU masks come from plane 0 (z_hi) of the saved forward output.
+ * tickets (nullable, ISTNET_FIN_TICKETS zeroed counters): the reduce kernel's last CTA finishes the sums (two launches instead of three).
  * act = 3: BN + ReLU + max over `ns` consecutive rows (the last SharedMLP layer of a set-abstraction scale): dz is [P/ns][C]
  * and is routed to the arg-max row of each group (argmax from istnet_bn_relu_maxrows). */
 int istnet_bn_act_bwd(const float *dz, const float *dz2, const float *y, long long P, int C, long long HW, const float *mean,
                       const float *invstd, const float *gamma, const float *beta, int act, const float *prelu_a, const void *z_hi,
                       int cs_z, const float *noise, int batch_stats, const uint8_t *argmax, int ns, float *part_ws, double *ws,
                       void *dy_planes, long long plane_stride, int nsplit, int cs_dy, float *dy_f32, float *g_out, float *sum_g_f32,
-                      float *sum_gx_f32, void *stream);
+                      float *sum_gx_f32, unsigned *tickets, void *stream);
 
 /* BatchNorm backward of a conv+BN+ReLU layer whose reduction rode in the data-gradient GEMM above it (istnet_conv_gemm with mask_hi and
  * stat_y): finalize_gy turns the per-CTA partials [sum g | sum g*y] into ws = [sum g | sum g*xhat | 0] (+ FP32 copies = the BN bias /
@@ -175,12 +210,13 @@ int istnet_prep_weight(const float *w, int Cout, int Cin, int kh, int kw, int tr
  * Replaces group_points + the grouped 1x1 convolution; also leaves the train-mode BatchNorm statistics partials of y0 in
  * stat_part (>= 2*296*C0 floats, layout of istnet_bn_finalize; *grid_out = number of partial rows G). */
 int istnet_sa_gather_l0(int B, int N, int M, int ns, int C0, const float *xyz, const float *new_xyz, const int32_t *idx, const float *u,
-                        const float *w0, int ldw, float *y0, float *stat_part, int *grid_out, void *stream);
+                        const float *w0, int ldw, float *y0, float *stat_part, int *grid_out, const istnet_fin *fin, void *stream);
 /* Backward of istnet_sa_gather_l0: dU[b, idx, :] += dy0[row, :] (zeroed here; float atomics like group_points_grad,
  * group_points_gpu.cu:48-69; may be null) and ws[d*C0 + c] = sum_rows dy0[row, c] * (xyz_j - c_i)[d] (double, fixed summation
- * order; ws holds 3*C0).  part_ws: istnet_reduce_ws_floats(rows, C0, 3) floats. */
+ * order; ws holds 3*C0).  part_ws: istnet_reduce_ws_floats(rows, C0, 3) floats.  tickets (nullable): ISTNET_FIN_TICKETS zeroed
+ * counters -> the kernel's last CTA finishes the dWx sums (no finalize launch). */
 int istnet_sa_scatter_l0(int B, int N, int M, int ns, int C0, const float *dy0, const float *xyz, const float *new_xyz, const int32_t *idx,
-                         float *dU, float *part_ws, double *ws, void *stream);
+                         float *dU, float *part_ws, double *ws, unsigned *tickets, void *stream);
 /* ws[c] = sum_p sum_i planes[i][p][c] (double): column sums of a tensor held only as bf16 operand planes.  With the Gram matrix
  * X^T X (istnet_conv_wgrad of the planes against themselves) this gives the train-mode BatchNorm statistics of the head's 1x1
  * convolution (modules.py:64-66: Conv2d(64,128,1) -> BatchNorm2d -> PReLU) without materialising its 192x192x128 output: the
@@ -254,6 +290,20 @@ int istnet_interp_rows(int B, int m, int n, int C, const float *feats, const int
                        int out_off, void *stream);
 int istnet_interp_rows_bwd(int B, int m, int n, int C, const float *dout, int d_ld, int d_off, const int32_t *idx, const float *weight,
                            float *d_feats, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * 6. Optimizer step of the training loop (utils/solver.py:41-46,98-99: torch.optim.Adam + CyclicLR)
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* torch.optim.Adam (amsgrad=False) over one FLAT bucket of n parameters (n % 4 == 0, 16-byte aligned buffers):
+ *   g = grad*grad_scale + weight_decay*p;  m += (g-m)(1-beta1);  v = beta2 v + (1-beta2) g^2;
+ *   p -= lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps),  t = *step_dev + 1.
+ * lr_dev and step_dev are DEVICE scalars (CyclicLR rewrites the learning rate every iteration, solver.py:88-89), so the step can
+ * live inside a captured CUDA graph; grad_scale = 1/world_size turns the all-reduced gradient SUM into the mean.
+ * istnet_adam_tick increments *step_dev once per optimizer step (after the last bucket). */
+int istnet_adam_flat(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, const float *lr_dev, float beta1,
+                     float beta2, float eps, float weight_decay, float grad_scale, const long long *step_dev, void *stream);
+int istnet_adam_tick(long long *step_dev, void *stream);
 
 #ifdef __cplusplus
 }

@@ -62,6 +62,39 @@ def req_i(t, name, ndim=None):
     _require(t, torch.int32, name, ndim)
 
 
+class Fin(ctypes.Structure):
+    """include/istnet_b200.h `istnet_fin`: in-kernel completion of a per-channel reduction by the producer's last CTA."""
+
+    _fields_ = [
+        ("kind", ctypes.c_int), ("tickets", ctypes.c_void_p), ("P", ctypes.c_longlong), ("eps", ctypes.c_float),
+        ("momentum", ctypes.c_void_p), ("running_mean", ctypes.c_void_p), ("running_var", ctypes.c_void_p), ("mean", ctypes.c_void_p),
+        ("invstd", ctypes.c_void_p), ("num_batches_tracked", ctypes.c_void_p), ("sum_f64", ctypes.c_void_p), ("sum_f32", ctypes.c_void_p),
+        ("sum2_f32", ctypes.c_void_p),
+    ]
+
+
+FIN_BN_STATS, FIN_COLSUM, FIN_BN_BWD = 1, 2, 3
+FIN_TICKETS, FIN_ROWS = 20, 296 + 19  # ISTNET_FIN_TICKETS / ISTNET_FIN_ROWS
+_TICKET_SLOTS = 8192
+_ticket_arena = {}
+
+
+def tickets(dev):
+    """Pointer to FIN_TICKETS zeroed uint32 counters for one reduction.  The counters are self-resetting (zero again when the
+    kernel exits), so the arena is handed out round-robin: a slot is reused only thousands of launches later, and a
+    captured CUDA graph keeps replaying on the slots it was captured with."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    a = _ticket_arena.get(key)
+    if a is None:
+        a = _ticket_arena[key] = [torch.zeros(_TICKET_SLOTS * FIN_TICKETS, dtype=torch.int32, device=dev), 0]
+    a[1] = (a[1] + 1) % _TICKET_SLOTS
+    return c_void_p(a[0].data_ptr() + 4 * FIN_TICKETS * a[1])
+
+
+def _vp(t):
+    return t.data_ptr() if t is not None else None
+
+
 LAUNCHES = 0  # number of C-ABI calls made by this process (each enqueues >= 1 kernel); bench.py reports it
 
 

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include "tc_common.cuh"
+#include "ticket.cuh"
 
 namespace {
 
@@ -51,6 +52,7 @@ struct ConvGemmParams {
     const float *stat_y;      // optional [B,H,W,stat_y_cs]: second statistic = sum(out * stat_y) instead of sum(out^2) (BN backward)
     int stat_y_cs;
     uint32_t tmem_cols;
+    FinP fin;                 // optional: the last CTA finishes the statistics reduction (ticket.cuh)
 };
 
 __global__ void __launch_bounds__(kThreadsWide, 1)
@@ -326,6 +328,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                               s_stat[(3 * 2 + a) * p.Cout + c];
             p.stat_part[((size_t)a * gridDim.x + blockIdx.x) * p.Cout + c] = tot;
         }
+    if (p.stat_part && p.fin.kind != 0) {
+        // the last CTA of the grid turns the partials into the BatchNorm statistics (or the bias gradient) — no finalize launch
+        if (p.fin.kind == 2) ticket_finish<1>(p.fin, p.stat_part, (int)gridDim.x, p.Cout);
+        else ticket_finish<2>(p.fin, p.stat_part, (int)gridDim.x, p.Cout);
+    }
     if (warp == 2) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, p.tmem_cols);
@@ -369,7 +376,7 @@ static int env_int(const char *name, int dflt) {
 // cycles = the full 128 B/clk); with 3 operand planes a 64-wide K block would leave a single 144 KB stage, so K = 32
 // (SWIZZLE_64B rows) is used there: 72 KB stages, 3 in flight.
 static int pick_block_k(int cout, int nsplit) {
-    const int force = env_int("ISTNET_BK", 0);
+    static const int force = env_int("ISTNET_BK", 0);  // tuning knobs are read once per process, not per launch
     if (force == 32 || force == 64) return force;
     return nsplit >= 3 ? 32 : 64;
 }
@@ -384,7 +391,7 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
                                 const void *wgt_planes, long long wgt_plane_stride, int Cout, int wgt_cs, int kh, int kw, int nsplit,
                                 const float *bias, int relu, float *out_f32, int out_cs, void *out_planes, long long out_plane_stride,
                                 int nsplit_out, int split_cs, int box_w, int box_h, float *stat_part, int *grid_out, const void *mask_hi,
-                                int mask_cs, const float *stat_y, int stat_y_cs, void *stream) {
+                                int mask_cs, const float *stat_y, int stat_y_cs, const istnet_fin *fin, void *stream) {
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return ISTNET_ERR_BAD_ARG;
     if (nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
     if ((act_cs & 7) || (wgt_cs & 7) || act_cs < Cin || wgt_cs < Cin) return ISTNET_ERR_BAD_ARG;
@@ -408,6 +415,8 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     p.stat_y = stat_y; p.stat_y_cs = stat_y_cs;
     if (stat_y && (!stat_part || stat_y_cs < Cout)) return ISTNET_ERR_BAD_ARG;
     if (mask_hi && mask_cs < Cout) return ISTNET_ERR_BAD_ARG;
+    if (fin && fin->kind != ISTNET_FIN_NONE && (!stat_part || stat_y || fin->kind == ISTNET_FIN_BN_BWD)) return ISTNET_ERR_BAD_ARG;
+    if (!make_fin(fin, stat_part, 2, Cout, p.fin)) return ISTNET_ERR_BAD_ARG;
     p.out_f32 = out_f32; p.out_cs = out_cs;
     p.out_pl = (__nv_bfloat16 *)out_planes; p.out_pl_stride = out_plane_stride; p.split_cs = split_cs; p.nsplit_out = nsplit_out;
     p.n_tiles_n = ceil_div(Cout, p.BN);
@@ -422,7 +431,8 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     // (measured on up_3, 64->64 3x3 @192^2: 1.52 ms -> 0.88 ms; profiles/r1_conv_small_tiles.txt).
     const long long n_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b * ceil_div(Cout, p.BN);
     int budget_kb = (p.BN <= 128 && n_tiles >= 2 * kNumSMs) ? 110 : 225;
-    budget_kb = env_int("ISTNET_CG_SMEM_KB", budget_kb);
+    static const int budget_override = env_int("ISTNET_CG_SMEM_KB", 0);
+    if (budget_override > 0) budget_kb = budget_override;
     const int stat_bytes = stat_part ? 8 * Cout * (int)sizeof(float) : 0;
     int max_stages = (budget_kb * 1024 - 1024 - 256 - stat_bytes) / stage_bytes;
     if (max_stages < 1) max_stages = 1;
@@ -460,7 +470,8 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     if (grid_x > n_tiles) grid_x = n_tiles;
     if (grid_out) *grid_out = (int)grid_x;
     int threads = ctas_per_sm >= 2 ? kThreads : kThreadsWide;
-    threads = env_int("ISTNET_CG_THREADS", threads);
+    static const int threads_override = env_int("ISTNET_CG_THREADS", 0);
+    if (threads_override > 0) threads = threads_override;
     conv_gemm_tc_kernel<<<(unsigned)grid_x, threads, smem, (cudaStream_t)stream>>>(ta, tb, p);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;

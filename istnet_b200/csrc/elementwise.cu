@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "ticket.cuh"
 
 namespace {
 
@@ -121,12 +122,13 @@ __device__ void sum_partials(const float *__restrict__ part, int G, int C, doubl
     }
 }
 
-__global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const float *__restrict__ y, long long P, int C, float *part) {
+__global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const float *__restrict__ y, long long P, int C, float *part, FinP fin) {
     column_reduce<2, false>(P, C, nullptr, part, [&](long long r, int c, float (*acc)[4]) {
         float4 v = ld4(y + r * C + c);
         acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
         acc[1][0] += v.x * v.x; acc[1][1] += v.y * v.y; acc[1][2] += v.z * v.z; acc[1][3] += v.w * v.w;
     });
+    ticket_finish<2>(fin, part, (int)gridDim.x, C);
 }
 
 __global__ void __launch_bounds__(kFinThreads) bn_finalize_kernel(const float *__restrict__ part, int G, long long P, int C, float eps, float momentum,
@@ -328,7 +330,7 @@ __device__ __forceinline__ void act_bwd4(const ActBwdP &p, long long r, int c, i
 }
 constexpr int kBwdUnroll = 4;  // rows in flight per thread: 4 x (2..3) independent 16-byte loads
 // ws[0:C] = sum g, ws[C:2C] = sum g*xhat, ws[2C:3C] = PReLU slope partial
-__global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_reduce_kernel(long long P, int C, ActBwdP p, float *part) {
+__global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_reduce_kernel(long long P, int C, ActBwdP p, float *part, FinP fin) {
     const float a = (p.act == 2) ? *p.prelu_a : 0.f;
     const int lanes = C >> 2;
     if (lanes > kEwThreads) {  // very wide rows: generic path
@@ -339,6 +341,7 @@ __global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_reduce_kernel(long long 
             acc[1][0] += g.x * xh.x; acc[1][1] += g.y * xh.y; acc[1][2] += g.z * xh.z; acc[1][3] += g.w * xh.w;
             acc[2][0] += ex.x; acc[2][1] += ex.y; acc[2][2] += ex.z; acc[2][3] += ex.w;
         });
+        ticket_finish<3>(fin, part, (int)gridDim.x, C);
         return;
     }
     float acc[3][4];
@@ -367,6 +370,7 @@ __global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_reduce_kernel(long long 
         }
     }
     column_flush<3, false>(acc, lanes, rows_per_iter, rr < rows_per_iter, C, nullptr, part);
+    ticket_finish<3>(fin, part, (int)gridDim.x, C);  // the last CTA writes ws / the BatchNorm parameter gradients: no finalize launch
 }
 // dy = gamma*invstd*(g - sum_g/P - xhat*sum_gx/P)  (BN)   or   dy = g   (no BN);  dy -> bf16 pair (+ optional FP32 copies)
 __device__ __forceinline__ void bwd_apply_store(const ActBwdP &p, const Chan4 &ch, float a, const RowIn &in, const float (&mg)[4],
@@ -805,7 +809,7 @@ constexpr int kSaUnroll = 4;
 __global__ void __launch_bounds__(kEwThreads, 2) sa_gather_l0_kernel(int N, int M, int ns, int C0, long long rows, const float *__restrict__ xyz,
                                                                      const float *__restrict__ new_xyz, const int32_t *__restrict__ idx,
                                                                      const float *__restrict__ u, const float *__restrict__ w0, int ldw,
-                                                                     float *__restrict__ y0, float *part) {
+                                                                     float *__restrict__ y0, float *part, FinP fin) {
     const int lanes = C0 >> 2;  // <= kEwThreads (launcher)
     const int rows_per_iter = kEwThreads / lanes;
     const int cv = threadIdx.x % lanes, rr = threadIdx.x / lanes;
@@ -852,12 +856,13 @@ __global__ void __launch_bounds__(kEwThreads, 2) sa_gather_l0_kernel(int N, int 
         }
     }
     column_flush<2, false>(acc, lanes, rows_per_iter, rr < rows_per_iter, C0, nullptr, part);
+    ticket_finish<2>(fin, part, (int)gridDim.x, C0);
 }
 // Backward of the above for one scale: dU[j, :] += dy0[(i,k), :] (float atomics, as group_points_grad in the reference) and
 // the per-CTA partials of dWx[c][d] = sum_rows dy0[row, c] * (xyz_j - c_i)[d]  (part[(d*G + g)*C0 + c], summed in fixed order).
 __global__ void __launch_bounds__(kEwThreads, 2) sa_scatter_l0_kernel(int N, int M, int ns, int C0, long long rows, const float *__restrict__ dy0,
                                                                       const float *__restrict__ xyz, const float *__restrict__ new_xyz,
-                                                                      const int32_t *__restrict__ idx, float *dU, float *part) {
+                                                                      const int32_t *__restrict__ idx, float *dU, float *part, FinP fin) {
     const int lanes = C0 >> 2;
     const int rows_per_iter = kEwThreads / lanes;
     const int cv = threadIdx.x % lanes, rr = threadIdx.x / lanes;
@@ -898,6 +903,7 @@ __global__ void __launch_bounds__(kEwThreads, 2) sa_scatter_l0_kernel(int N, int
         }
     }
     column_flush<3, false>(acc, lanes, rows_per_iter, rr < rows_per_iter, C0, nullptr, part);
+    ticket_finish<3>(fin, part, (int)gridDim.x, C0);
 }
 
 // ------------------------------------------------------------------ PSP priors (modules.py:10-34) on their pooled maps
@@ -1065,15 +1071,24 @@ inline BnP make_bn(const float *mean, const float *invstd, const float *gamma, c
 
 #define ST ((cudaStream_t)stream)
 
-extern "C" int istnet_reduce_ws_floats(long long P, int C, int nacc) { return red_grid(P, C) * nacc * C; }
+// partial rows of both ticket levels (ticket.cuh): [nacc][kMaxPartialRows][C] per-CTA partials + [nacc][kMaxTicketGroups][C] group sums
+extern "C" int istnet_reduce_ws_floats(long long P, int C, int nacc) { (void)P; return ISTNET_FIN_ROWS * nacc * C; }
 
 extern "C" int istnet_bn_stats(const float *y, long long P, int C, float *part_ws, float eps, float momentum, float *running_mean,
                                float *running_var, float *mean, float *invstd, long long *num_batches_tracked, void *stream) {
     if (P <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
     const int G = red_grid(P, C);
-    bn_stats_kernel<<<G, kEwThreads, 0, ST>>>(y, P, C, part_ws);
+    bn_stats_kernel<<<G, kEwThreads, 0, ST>>>(y, P, C, part_ws, FinP{});
     ISTNET_LAUNCH_CHECK();
     bn_finalize_kernel<<<ceil_div(C, 32), kFinThreads, 0, ST>>>(part_ws, G, P, C, eps, momentum, running_mean, running_var, mean, invstd, num_batches_tracked);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+extern "C" int istnet_bn_stats_fin(const float *y, long long P, int C, float *part_ws, const istnet_fin *fin, void *stream) {
+    if (P <= 0 || C <= 0 || (C & 3) || !fin || fin->kind != ISTNET_FIN_BN_STATS) return ISTNET_ERR_BAD_ARG;
+    FinP f;
+    if (!make_fin(fin, part_ws, 2, C, f)) return ISTNET_ERR_BAD_ARG;
+    bn_stats_kernel<<<red_grid(P, C), kEwThreads, 0, ST>>>(y, P, C, part_ws, f);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
@@ -1107,7 +1122,7 @@ extern "C" int istnet_bn_act_bwd(const float *dz, const float *dz2, const float 
                                  const float *invstd, const float *gamma, const float *beta, int act, const float *prelu_a,
                                  const void *z_hi, int cs_z, const float *noise, int batch_stats, const uint8_t *argmax, int ns,
                                  float *part_ws, double *ws /*3C*/, void *dy_planes, long long plane_stride, int nsplit, int cs_dy,
-                                 float *dy_f32, float *g_out, float *sum_g_f32, float *sum_gx_f32, void *stream) {
+                                 float *dy_f32, float *g_out, float *sum_g_f32, float *sum_gx_f32, unsigned *tickets, void *stream) {
     if (P <= 0 || C <= 0 || (C & 3)) return ISTNET_ERR_BAD_ARG;
     if (act == 1 && !z_hi) return ISTNET_ERR_BAD_ARG;
     if (act == 3 && (!argmax || ns <= 0 || !mean || dz2)) return ISTNET_ERR_BAD_ARG;
@@ -1118,10 +1133,18 @@ extern "C" int istnet_bn_act_bwd(const float *dz, const float *dz2, const float 
     p.batch_stats = batch_stats;
     p.argmax = argmax; p.ns = ns;
     const int G = red_grid(P, C);
-    bn_bwd_reduce_kernel<<<G, kEwThreads, 0, ST>>>(P, C, p, part_ws);
+    FinP f{};
+    if (tickets) {  // the reduce kernel's last CTA finishes the sums itself (ticket.cuh)
+        istnet_fin h{};
+        h.kind = ISTNET_FIN_BN_BWD; h.tickets = tickets; h.sum_f64 = ws; h.sum_f32 = sum_g_f32; h.sum2_f32 = sum_gx_f32;
+        if (!make_fin(&h, part_ws, 3, C, f)) return ISTNET_ERR_BAD_ARG;
+    }
+    bn_bwd_reduce_kernel<<<G, kEwThreads, 0, ST>>>(P, C, p, part_ws, f);
     ISTNET_LAUNCH_CHECK();
-    bwd_finalize_kernel<<<ceil_div(C, 32), kFinThreads, 0, ST>>>(part_ws, G, C, ws, sum_g_f32, sum_gx_f32);
-    ISTNET_LAUNCH_CHECK();
+    if (!tickets) {
+        bwd_finalize_kernel<<<ceil_div(C, 32), kFinThreads, 0, ST>>>(part_ws, G, C, ws, sum_g_f32, sum_gx_f32);
+        ISTNET_LAUNCH_CHECK();
+    }
     bn_bwd_apply_kernel<<<row_grid(P, C, kBwdUnroll), kEwThreads, 0, ST>>>(P, C, p, ws, (__nv_bfloat16 *)dy_planes, plane_stride, nsplit, cs_dy,
                                                                             dy_f32, g_out);
     ISTNET_LAUNCH_CHECK();
@@ -1252,25 +1275,35 @@ __global__ void marker_kernel(unsigned long long *stamps, int slot) {
     stamps[slot] = t;
 }
 extern "C" int istnet_sa_gather_l0(int B, int N, int M, int ns, int C0, const float *xyz, const float *new_xyz, const int32_t *idx, const float *u,
-                                   const float *w0, int ldw, float *y0, float *stat_part, int *grid_out, void *stream) {
+                                   const float *w0, int ldw, float *y0, float *stat_part, int *grid_out, const istnet_fin *fin, void *stream) {
     const long long rows = (long long)B * M * ns;
     if (B <= 0 || N <= 0 || M <= 0 || ns <= 0 || C0 <= 0 || (C0 & 3) || C0 / 4 > kEwThreads || ldw < 3 || rows > 0x7fffffffLL) return ISTNET_ERR_BAD_ARG;
     const int G = red_grid(rows, C0);  // <= 296: the size callers give the statistics scratch
-    sa_gather_l0_kernel<<<G, kEwThreads, 0, ST>>>(N, M, ns, C0, rows, xyz, new_xyz, idx, u, w0, ldw, y0, stat_part);
+    FinP f;
+    if ((fin && fin->kind != ISTNET_FIN_NONE && fin->kind != ISTNET_FIN_BN_STATS) || !make_fin(fin, stat_part, 2, C0, f)) return ISTNET_ERR_BAD_ARG;
+    sa_gather_l0_kernel<<<G, kEwThreads, 0, ST>>>(N, M, ns, C0, rows, xyz, new_xyz, idx, u, w0, ldw, y0, stat_part, f);
     ISTNET_LAUNCH_CHECK();
     if (grid_out) *grid_out = G;
     return ISTNET_OK;
 }
 extern "C" int istnet_sa_scatter_l0(int B, int N, int M, int ns, int C0, const float *dy0, const float *xyz, const float *new_xyz,
-                                    const int32_t *idx, float *dU, float *part_ws, double *ws, void *stream) {
+                                    const int32_t *idx, float *dU, float *part_ws, double *ws, unsigned *tickets, void *stream) {
     const long long rows = (long long)B * M * ns;
     if (B <= 0 || N <= 0 || M <= 0 || ns <= 0 || C0 <= 0 || (C0 & 3) || C0 / 4 > kEwThreads || rows > 0x7fffffffLL) return ISTNET_ERR_BAD_ARG;
     if (dU) ISTNET_CUDA_TRY(cudaMemsetAsync(dU, 0, sizeof(float) * (size_t)B * N * C0, ST));
     const int G = red_grid(rows, C0);
-    sa_scatter_l0_kernel<<<G, kEwThreads, 0, ST>>>(N, M, ns, C0, rows, dy0, xyz, new_xyz, idx, dU, part_ws);
+    FinP f{};
+    if (tickets) {
+        istnet_fin h{};
+        h.kind = ISTNET_FIN_BN_BWD; h.tickets = tickets; h.sum_f64 = ws;
+        if (!make_fin(&h, part_ws, 3, C0, f)) return ISTNET_ERR_BAD_ARG;
+    }
+    sa_scatter_l0_kernel<<<G, kEwThreads, 0, ST>>>(N, M, ns, C0, rows, dy0, xyz, new_xyz, idx, dU, part_ws, f);
     ISTNET_LAUNCH_CHECK();
-    bwd_finalize_kernel<<<ceil_div(C0, 32), kFinThreads, 0, ST>>>(part_ws, G, C0, ws);
-    ISTNET_LAUNCH_CHECK();
+    if (!tickets) {
+        bwd_finalize_kernel<<<ceil_div(C0, 32), kFinThreads, 0, ST>>>(part_ws, G, C0, ws);
+        ISTNET_LAUNCH_CHECK();
+    }
     return ISTNET_OK;
 }
 static int make_psp_sizes(int s0, int s1, int s2, int s3, PspSizes &ps) {

@@ -153,7 +153,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
                     *reinterpret_cast<float4 *>(o + i) =
                         make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
             } else {
-                for (int i = 0; i < valid; ++i) o[i] = __uint_as_float(v[i]);
+#pragma unroll
+                for (int i = 0; i < 32; ++i)  // predicated, fully unrolled: a dynamic index would put v[] in local memory
+                    if (i < valid) o[i] = __uint_as_float(v[i]);
             }
         }
         tc::tc_fence_before();
@@ -206,13 +208,13 @@ static int wg_env_int(const char *name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 static int wgrad_pick_pix() {
-    const int f = wg_env_int("ISTNET_WG_PIX", 0);
+    static const int f = wg_env_int("ISTNET_WG_PIX", 0);  // knobs are read once per process
     return (f == 32 || f == 64) ? f : 64;
 }
 static int wgrad_pick_bn(int cin, int nsplit) {
     int bn = (cin + 63) / 64 * 64;
     int cap = nsplit >= 3 ? 128 : 256;  // keep >= 2 pipeline stages
-    const int f = wg_env_int("ISTNET_WG_BN", 0);
+    static const int f = wg_env_int("ISTNET_WG_BN", 0);
     if (f == 64 || f == 128 || f == 256) cap = f;
     return bn > cap ? cap : bn;
 }
@@ -220,7 +222,8 @@ static int wgrad_pick_bn(int cin, int nsplit) {
 // Shared-memory budget per CTA: wide tiles run one deep-ring CTA per SM; narrow multi-tap tiles (small channel counts)
 // are bound by L2->SM delivery / latency and do better with several shallow CTAs per SM (measured).
 static int wgrad_budget_kb(int bn, int taps) {
-    return wg_env_int("ISTNET_WG_SMEM_KB", (bn <= 128 && taps > 1) ? 60 : 225);
+    static const int f = wg_env_int("ISTNET_WG_SMEM_KB", 0);
+    return f > 0 ? f : ((bn <= 128 && taps > 1) ? 60 : 225);
 }
 static int wgrad_stage_bytes(int bn, int nsplit, int pix) { return nsplit * (2 + bn / 64) * pix * 64 * 2; }
 
@@ -241,7 +244,7 @@ extern "C" int istnet_wgrad_ksplit(int B, int H, int W, int Cout, int Cin, int k
     int ks = capacity / base;
     if (ks > pix_tiles / 4) ks = (int)(pix_tiles / 4);
     if (ks < 1) ks = 1;
-    const int cap = wg_env_int("ISTNET_WG_KSCAP", 148);
+    static const int cap = wg_env_int("ISTNET_WG_KSCAP", 148);
     if (ks > cap) ks = cap;
     return ks;
 }

@@ -151,7 +151,15 @@ class ModifiedResnet(nn.Module):
         self.model = Modified_PSPNet()
 
     def forward(self, x):
-        """Dense (B,128,H,W) feature map through PyTorch library ops — API compatibility only; the hot path is gather()."""
+        """Dense (B,128,H,W) feature map (modules.py:239-241).  On CUDA it runs on the B200 kernels, forward only (the training
+        path is gather(): IST_Net reads the map only at the `choose`d pixels); CPU tensors take the plain-torch modules, which
+        exist for state-dict / API compatibility and are not part of the product path."""
+        if x.is_cuda:
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                raise RuntimeError("istnet_b200: ModifiedResnet.forward is forward-only on CUDA; use gather()/gather_rows() for training")
+            from .image_engine import dense_map
+
+            return dense_map(self.model, x)
         return self.model(x)
 
     def gather(self, rgb, choose):

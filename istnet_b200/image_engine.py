@@ -156,10 +156,13 @@ def _head_forward(unit, x, choose, training):
             var = ((W64 @ cov) * W64).sum(1).clamp_min_(0.0)
             invstd = torch.rsqrt(var + bn.eps)
             if bn.track_running_stats and bn.running_mean is not None:
-                mom = bn.momentum if bn.momentum is not None else 0.1
+                bn.num_batches_tracked += 1
+                # momentum as a device scalar (nhwc.momentum_ptr): a scheduler update reaches a replayed CUDA graph;
+                # momentum=None is nn.BatchNorm2d's cumulative average 1 / num_batches_tracked
+                mom = K.momentum_tensor(bn, dev).double()
+                mom = torch.where(mom < 0, 1.0 / bn.num_batches_tracked.double(), mom)
                 bn.running_mean.copy_(((1.0 - mom) * bn.running_mean.double() + mom * mean).float())
                 bn.running_var.copy_(((1.0 - mom) * bn.running_var.double() + mom * var * (P / max(P - 1, 1))).float())
-                bn.num_batches_tracked += 1
         st = K.BnState(mean.float(), invstd.float(), bn.weight, bn.bias, batch=True)
         rec.update({"sx": sx, "S": S})
     else:
@@ -294,6 +297,9 @@ def forward(net, rgb, choose, training, record, u=None):
         if record:
             tape.append(("up", name, ru))
     trace.mark("image: ups done")
+    if choose is None:  # dense feature map (ModifiedResnet.forward): the head on every pixel, no tape
+        out, _ = u["final"].forward(p, training, False, want_f32=True, want_pair=False)
+        return out.f32, None
     # ---- head: final 1x1 conv + BN + PReLU, evaluated only at the `choose`d pixels (see _head_forward)
     if DENSE_HEAD:
         yf, rf = u["final"].forward(p, training, True, defer_act=True)
@@ -428,3 +434,11 @@ def image_branch(net, rgb, choose):
         return _ImageBranchFn.apply(net, rgb, choose, *params)
     out, _ = forward(net, rgb, choose, net.training, False)
     return out
+
+
+def dense_map(net, rgb):
+    """Modified_PSPNet.forward (modules.py:69-81) on the B200 kernels: (B,3,H,W) -> (B,128,H,W).  Forward only: the training path
+    never needs the dense map (IST_Net reads it at the `choose`d pixels, ist_net.py:42-45)."""
+    with torch.no_grad():
+        out, _ = forward(net, rgb, None, net.training, False)
+    return out.permute(0, 3, 1, 2).contiguous()

@@ -160,6 +160,18 @@ PROFILE_REPS = 3
 
 def _timed(name, flops, nsplit, launch, desc=""):
     launch()
+    _timed_only(name, flops, nsplit, launch, desc)
+
+
+def _scratch_fin(fin):
+    """Copy of a BatchNorm-statistics descriptor whose outputs go to scratch (no running-statistics / counter update)."""
+    rep = _C.Fin.from_buffer_copy(fin)
+    if fin.kind == _C.FIN_BN_STATS:
+        rep.running_mean = rep.running_var = rep.num_batches_tracked = None
+    return rep
+
+
+def _timed_only(name, flops, nsplit, launch, desc=""):
     if PROFILE is None:
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -170,9 +182,10 @@ def _timed(name, flops, nsplit, launch, desc=""):
     PROFILE.append((name, e0, e1, PROFILE_REPS, flops, nsplit, desc))
 
 
-def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl=None, stat_part=None, mask_hi=None, stat_y=None):
+def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl=None, stat_part=None, mask_hi=None, stat_y=None, fin=None):
     """x: Act with operand planes; writes out_f32 [B,H,W,cout] and/or out_pl.  With stat_part (float buffer of
-    >= 2*296*cout) the epilogue also leaves per-CTA BN-statistics partials there; returns the CTA count G."""
+    >= 2*FIN_ROWS*cout) the epilogue also leaves per-CTA BN-statistics partials there; with `fin` (a _C.Fin) the kernel's last
+    CTA finishes that reduction itself (BatchNorm statistics / bias gradient), no finalize launch.  Returns the CTA count G."""
     bw, bh = pick_box(x.H, x.W)
     ns = min(x.pl.shape[0], w_pl.shape[0])  # planes are nested: the first n planes of an operand are its n-plane representation
     grid = ctypes.c_int(0)
@@ -183,8 +196,13 @@ def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl
         c_int(bw), c_int(bh), _p(stat_part), ctypes.byref(grid), _p(mask_hi), c_int(mask_hi.shape[-1] if mask_hi is not None else 0),
         _p(stat_y), c_int(stat_y.shape[-1] if stat_y is not None else 0),
     )
-    _timed("conv_gemm_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, ns, lambda: _C.call("conv_gemm", *args),
-           f"P={x.P} {x.H}x{x.W} cin={x.C} cout={cout} k={kh}")
+    fin_ref = ctypes.byref(fin) if fin is not None else NULL
+    _C.call("conv_gemm", *args, fin_ref)
+    if PROFILE is not None:  # timed repeats must not update running statistics again: same kernel, statistics into scratch outputs
+        rep = _scratch_fin(fin) if fin is not None else None
+        rep_ref = ctypes.byref(rep) if rep is not None else NULL
+        _timed_only("conv_gemm_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, ns, lambda: _C.call("conv_gemm", *args, rep_ref),
+                    f"P={x.P} {x.H}x{x.W} cin={x.C} cout={cout} k={kh}")
     return grid.value
 
 
@@ -218,28 +236,114 @@ def bn_uses_batch_stats(bn, training):
     return bn is not None and training and bn.training  # each BatchNorm module's own flag decides, as in nn.BatchNorm2d.forward
 
 
-def bn_state(bn, y, P, C, training, part=None, G=0):
-    """Reads momentum / eps / running stats from the nn.BatchNorm2d at call time (BNMomentumScheduler, scheduler.py:277-303).
-    `part`/`G`: per-CTA statistics partials already produced by the convolution's epilogue (else a reduction pass over y)."""
-    dev = y.device
-    if bn_uses_batch_stats(bn, training):
-        mean = torch.empty(C, dtype=torch.float32, device=dev)
-        invstd = torch.empty(C, dtype=torch.float32, device=dev)
-        mom = bn.momentum if bn.momentum is not None else 0.1
-        track = bn.track_running_stats and bn.running_mean is not None
-        nbt = bn.num_batches_tracked if (track and bn.num_batches_tracked is not None and bn.num_batches_tracked.is_cuda) else None
-        if part is not None:
-            _C.call("bn_finalize", ptr(part), c_int(G), c_ll(P), c_int(C), c_float(bn.eps), c_float(mom), _p(bn.running_mean if track else None),
-                    _p(bn.running_var if track else None), ptr(mean), ptr(invstd), _p(nbt))
-        else:
-            ws = torch.empty(_C.lib().istnet_reduce_ws_floats(c_ll(P), C, 2), dtype=torch.float32, device=dev)
-            _C.call("bn_stats", ptr(y), c_ll(P), c_int(C), ptr(ws), c_float(bn.eps), c_float(mom), _p(bn.running_mean if track else None),
-                    _p(bn.running_var if track else None), ptr(mean), ptr(invstd), _p(nbt))
-        if track and nbt is None and bn.num_batches_tracked is not None:
+# ---- BatchNorm momentum as DEVICE scalars.  The reference rewrites `bn.momentum` on every BatchNorm module each iteration
+# (BNMomentumScheduler, utils/scheduler.py:277-303, utils/solver.py:48-49,91-92).  A kernel argument passed by value would be
+# frozen into a captured CUDA graph, so the statistics kernels read momentum from a per-device table instead: every
+# nn.BatchNorm2d gets a slot, `momentum_ptr` keeps the slot equal to the module's current Python value (eager path) and
+# `refresh_momentum` does the same for a set of modules with one host->device copy before a graph replay.
+# momentum=None (cumulative moving average) is stored as -1 and resolved on the device from num_batches_tracked.
+_MOM_SLOTS = 4096
+_mom_tables = {}
+
+
+class _MomTable:
+    def __init__(self, dev):
+        self.dev = torch.full((_MOM_SLOTS,), 0.1, dtype=torch.float32, device=dev)
+        self.host = torch.full((_MOM_SLOTS,), 0.1, dtype=torch.float32).pin_memory()
+        self.mirror = [None] * _MOM_SLOTS  # Python copy of what the device holds (no tensor op on the per-call path)
+        self.used = 0
+
+
+def _mom_value(bn):
+    return -1.0 if bn.momentum is None else float(bn.momentum)
+
+
+def _mom_slot(bn, dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    tab = _mom_tables.get(key)
+    if tab is None:
+        tab = _mom_tables[key] = _MomTable(dev)
+    slot = getattr(bn, "_istnet_mom_slot", None)
+    if slot is None or slot[0] != key:
+        if tab.used >= _MOM_SLOTS:
+            raise RuntimeError("istnet_b200: more than %d BatchNorm modules on one device" % _MOM_SLOTS)
+        slot = (key, tab.used)
+        tab.used += 1
+        object.__setattr__(bn, "_istnet_mom_slot", slot)
+    return tab, slot[1]
+
+
+def momentum_ptr(bn, dev):
+    """Device address of this module's momentum scalar, brought up to date with `bn.momentum`."""
+    tab, i = _mom_slot(bn, dev)
+    v = _mom_value(bn)
+    if tab.mirror[i] != v:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("istnet_b200: a BatchNorm momentum changed while a CUDA graph was being captured; "
+                               "run one eager step (or refresh_momentum) with the new value first")
+        tab.mirror[i] = v
+        tab.host[i] = v
+        tab.dev[i : i + 1].fill_(v)
+    return c_void_p(tab.dev.data_ptr() + 4 * i)
+
+
+def momentum_tensor(bn, dev):
+    """The same scalar as a 0-dim tensor view (for the few statistics updates still written in torch)."""
+    momentum_ptr(bn, dev)
+    tab, i = _mom_slot(bn, dev)
+    return tab.dev[i]
+
+
+def refresh_momentum(bn_modules, dev):
+    """Makes the device scalars of `bn_modules` equal to their current `.momentum` (one pinned host->device copy if any
+    changed).  GraphedTrainStep calls this before every replay, so a scheduler update is honoured by the captured step."""
+    tab, dirty = None, False
+    for bn in bn_modules:
+        tab, i = _mom_slot(bn, dev)
+        v = _mom_value(bn)
+        if tab.mirror[i] != v:
+            tab.mirror[i] = v
+            tab.host[i] = v
+            dirty = True
+    if dirty:
+        tab.dev.copy_(tab.host, non_blocking=True)
+    return dirty
+
+
+def bn_begin(bn, C, training, P, dev):
+    """State of one BatchNorm call: reads eps / running statistics / training from the nn.BatchNorm2d at call time.
+    Train mode: returns (BnState with fresh mean / invstd tensors, _C.Fin) — the descriptor goes to the kernel that produces
+    the statistics partials (conv_gemm epilogue, sa_gather_l0, bn_stats), whose last CTA fills mean / invstd and updates the
+    running statistics (momentum from the device table) and num_batches_tracked.  Eval mode: (running-statistics state, None)."""
+    if not bn_uses_batch_stats(bn, training):
+        return BnState(bn.running_mean, torch.rsqrt(bn.running_var + bn.eps), bn.weight, bn.bias, batch=False), None
+    mean = torch.empty(C, dtype=torch.float32, device=dev)
+    invstd = torch.empty(C, dtype=torch.float32, device=dev)
+    track = bn.track_running_stats and bn.running_mean is not None
+    nbt = bn.num_batches_tracked if (track and bn.num_batches_tracked is not None) else None
+    fin = _C.Fin()
+    fin.kind, fin.tickets, fin.P, fin.eps = _C.FIN_BN_STATS, _C.tickets(dev).value, P, bn.eps
+    fin.mean, fin.invstd = mean.data_ptr(), invstd.data_ptr()
+    if track:
+        fin.momentum = momentum_ptr(bn, dev).value
+        fin.running_mean, fin.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+        if nbt is not None and nbt.is_cuda:
+            fin.num_batches_tracked = nbt.data_ptr()
+        elif nbt is not None:
+            if bn.momentum is None:
+                raise RuntimeError("istnet_b200: momentum=None needs num_batches_tracked on the device")
             bn.num_batches_tracked += 1
-    else:
-        return BnState(bn.running_mean, torch.rsqrt(bn.running_var + bn.eps), bn.weight, bn.bias, batch=False)
-    return BnState(mean, invstd, bn.weight, bn.bias, batch=True)
+    return BnState(mean, invstd, bn.weight, bn.bias, batch=True), fin
+
+
+def stat_scratch(C, dev, nacc=2):
+    """Partial-sum scratch of a statistics epilogue (both ticket levels, csrc/ticket.cuh)."""
+    return torch.empty(nacc * _C.FIN_ROWS * C, dtype=torch.float32, device=dev)
+
+
+def bn_stats(y, P, C, fin):
+    """Train-mode statistics of an existing FP32 tensor (one launch; used when the producing GEMM did not carry them)."""
+    _C.call("bn_stats_fin", ptr(y), c_ll(P), c_int(C), ptr(stat_scratch(C, y.device)), ctypes.byref(fin))
 
 
 def bn_act_split(y, P, C, HW, bn=None, res=None, res_bn=None, act=0, prelu=None, noise=None, out_f32=None, out_pl=None, ch_off=0):
@@ -262,6 +366,7 @@ def bn_act_bwd(dz, dz2, y, P, C, HW, bn, act, prelu, z_hi, noise, dy_pl=None, dy
         "bn_act_bwd", ptr(dz), _p(dz2), _p(y), c_ll(P), c_int(C), c_ll(HW), _p(bn.mean if bn else None), _p(bn.invstd if bn else None),
         _p(bn.gamma if bn else None), _p(bn.beta if bn else None), c_int(act), _p(prelu), _p(z_hi), c_int(z_hi.shape[-1] if z_hi is not None else 0),
         _p(noise), c_int(1 if (bn is not None and bn.batch) else 0), _p(argmax), c_int(ns), ptr(part), ptr(ws), *_pl_args(dy_pl), c_int(dy_pl.shape[-1] if dy_pl is not None else 0), _p(dy_f32), _p(g_out), ptr(sg), ptr(sgx),
+        _C.tickets(dz.device),
     )
     return ws, sg, sgx
 
@@ -342,11 +447,13 @@ class ConvUnit:
                             "z_hi": out.hi, "wd": wd})
             return out, rec
         y = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
-        part = None
-        if FUSE_BN_STATS and bn_uses_batch_stats(self.bn, training):
-            part = torch.empty(2 * 296 * C, dtype=torch.float32, device=dev)  # per-CTA partials from the GEMM epilogue
-        G = conv_gemm(xin, wp, C, kk, kk, bias=self.b, out_f32=y, stat_part=part)
-        st = bn_state(self.bn, y, P, C, training, part, G) if self.bn is not None else None
+        st, fin = bn_begin(self.bn, C, training, P, dev) if self.bn is not None else (None, None)
+        if fin is not None and FUSE_BN_STATS:  # statistics in the GEMM epilogue, finished by its last CTA
+            conv_gemm(xin, wp, C, kk, kk, bias=self.b, out_f32=y, stat_part=stat_scratch(C, dev), fin=fin)
+        else:
+            conv_gemm(xin, wp, C, kk, kk, bias=self.b, out_f32=y)
+            if fin is not None:
+                bn_stats(y, P, C, fin)
         rec = {"bn": st}
         if record:
             rec.update({"xin": xin, "y": y, "noise": noise, "kk": kk, "P": P, "HW": H * W, "in_shape": (x.B, x.H, x.W, x.C), "wd": wd,
@@ -467,7 +574,7 @@ class ConvUnit:
             bu, brec = below
             st, Cb, dev = brec["bn"], xin.C, dy.device
             g = torch.empty(xin.B, xin.H, xin.W, Cb, dtype=torch.float32, device=dev)
-            part = torch.empty(2 * 296 * Cb, dtype=torch.float32, device=dev)
+            part = stat_scratch(Cb, dev)
             G = conv_gemm(dyA, wd, Cb, kk, kk, out_f32=g, stat_part=part, mask_hi=brec["z_hi"], stat_y=brec["y"])
             ws = torch.empty(3 * Cb, dtype=torch.float64, device=dev)
             sg = torch.empty(Cb, dtype=torch.float32, device=dev)
@@ -485,12 +592,14 @@ class ConvUnit:
         if below is not None:
             bu, brec = below
             dyb = empty_planes(xin.B, xin.H, xin.W, xin.C, dy.device, nsplit=NSPLIT_BWD)
-            part = torch.empty(2 * 296 * xin.C, dtype=torch.float32, device=dy.device)
-            G = conv_gemm(dyA, wd, xin.C, kk, kk, out_pl=dyb, stat_part=part, mask_hi=brec["z_hi"])
-            if bu.b is not None:
+            if bu.b is not None:  # bias gradient = column sums of the masked dx: statistics epilogue, finished by the GEMM's last CTA
                 gb = torch.empty(xin.C, dtype=torch.float32, device=dy.device)
-                _C.call("colsum_finalize", ptr(part), c_int(G), c_int(xin.C), NULL, ptr(gb))
+                fin = _C.Fin()
+                fin.kind, fin.tickets, fin.sum_f32 = _C.FIN_COLSUM, _C.tickets(dy.device).value, gb.data_ptr()
+                conv_gemm(dyA, wd, xin.C, kk, kk, out_pl=dyb, stat_part=stat_scratch(xin.C, dy.device), mask_hi=brec["z_hi"], fin=fin)
                 grads[id(bu.b)] = gb
+            else:
+                conv_gemm(dyA, wd, xin.C, kk, kk, out_pl=dyb, mask_hi=brec["z_hi"])
             return dyb
         dx = torch.empty(xin.B, xin.H, xin.W, xin.C, dtype=torch.float32, device=dy.device)
         conv_gemm(dyA, wd, xin.C, kk, kk, out_f32=dx)

@@ -200,11 +200,10 @@ def _sa_l0_forward(u0, training, xyz, new_xyz, idx, feats, record):
         uf = torch.empty(1, 1, B * N, C0, dtype=torch.float32, device=dev)
         K.conv_gemm(fa, K.prep_weight(wf), C0, 1, 1, out_f32=uf)
     y0 = torch.empty(1, 1, rows, C0, dtype=torch.float32, device=dev)
-    part = torch.empty(2 * 296 * C0, dtype=torch.float32, device=dev)
+    st, fin = K.bn_begin(u0.bn, C0, training, rows, dev)  # train mode: the gather kernel's last CTA finishes the statistics
     grid = ctypes.c_int(0)
     _C.call("sa_gather_l0", c_int(B), c_int(N), c_int(M), c_int(ns), c_int(C0), ptr(xyz), ptr(new_xyz), ptr(idx), K._p(uf), ptr(u0.w), c_int(3 + C),
-            ptr(y0), ptr(part), ctypes.byref(grid))
-    st = K.bn_state(u0.bn, y0, rows, C0, training, part, grid.value)
+            ptr(y0), ptr(K.stat_scratch(C0, dev)), ctypes.byref(grid), ctypes.byref(fin) if fin is not None else K.NULL)
     a = Act(1, 1, rows, C0, None, K.empty_planes(1, 1, rows, C0, dev))
     K.bn_act_split(y0, rows, C0, 1, bn=st, act=ACT_RELU, out_pl=a.pl)
     rec = {"point_l0": True, "bn": st}
@@ -231,7 +230,8 @@ def _sa_l0_backward(u0, rec, d, xyz, new_xyz, idx, need_dfeats, grads, have_dy0=
     dU = torch.empty(B * N, C0, dtype=torch.float32, device=dev) if C > 0 else None
     part = torch.empty(_C.lib().istnet_reduce_ws_floats(c_ll(rows), C0, 3), dtype=torch.float32, device=dev)
     wsx = torch.empty(3 * C0, dtype=torch.float64, device=dev)
-    _C.call("sa_scatter_l0", c_int(B), c_int(N), c_int(M), c_int(ns), c_int(C0), ptr(dy0), ptr(xyz), ptr(new_xyz), ptr(idx), K._p(dU), ptr(part), ptr(wsx))
+    _C.call("sa_scatter_l0", c_int(B), c_int(N), c_int(M), c_int(ns), c_int(C0), ptr(dy0), ptr(xyz), ptr(new_xyz), ptr(idx), K._p(dU), ptr(part), ptr(wsx),
+            _C.tickets(dev))
     gw = wsx.view(3, C0).t().float()
     d_feats = None
     if C > 0:
