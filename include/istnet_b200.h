@@ -292,6 +292,55 @@ int istnet_interp_rows_bwd(int B, int m, int n, int C, const float *dout, int d_
                            float *d_feats, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * 5b. Fused set-abstraction level (csrc/sa_fused.cu) — PointnetSAModuleMSG.forward (pointnet2_modules.py:29-73) for one level
+ *     with its two (radius, nsample) scales in ONE launch per pass: ball query (ball_query_gpu.cu:14-49, bit-exact) + grouping
+ *     (pointnet2_utils.py:335-367) + SharedMLP 3 x [1x1 conv, train-mode BatchNorm, ReLU] (pytorch_utils.py:25-206) + max over
+ *     nsample (pointnet2_modules.py:66-68), nothing grouped written to memory.  Supported widths: istnet_sa_level_supported.
+ *     xyz [B,N,3], new_xyz [B,M,3] (M % 8 == 0), u [B*N][ldu] = F Wf^T of both scales (scale s at column s*C0; null when the level
+ *     has no input features), nsample in {16, 32}.
+ *     forward pass p (0, 1, 2) ends with the statistics of layer p: scales[s].part (2*ISTNET_FIN_ROWS*C_p floats) + scales[s].fin
+ *     (ISTNET_FIN_BN_STATS; null part: running statistics, nothing reduced); bn_* of the layers below must be valid.  query != 0:
+ *     the pass runs the ball query and writes scales[s].idx, otherwise it reads it.  Pass 2 also writes ysel / asel [B*M][C2]:
+ *     the max (gamma2 >= 0) or min (gamma2 < 0) of the pre-BatchNorm layer-2 output over the neighbours and its first position;
+ *     istnet_sa_level_final then gives out[bj][s*C2 + c] = relu(bn2(ysel)) — equal to max_k relu(bn2(y_k)) because relu(bn(.)) is
+ *     monotone per channel.
+ *     backward stage -1: sums of layer 2 from (dz, ysel) -> fin (ISTNET_FIN_BN_BWD, part 3*ISTNET_FIN_ROWS*C2);  stage 0: needs ws2,
+ *     writes g1 [rows][C1], sums of layer 1 -> fin, dW2 -> dw [C2][ld_dw];  stage 1: needs ws1, g1; writes g0, sums of layer 0 -> fin,
+ *     dW1 -> dw;  stage 2: needs ws0, g0; dU[point][s*C0 + c] += dy0 (zeroed here; float atomics like group_points_grad,
+ *     group_points_gpu.cu:48-69), dWx -> dw[c*ld_dw + 0..2].  part_w: ISTNET_FIN_ROWS * (rows*cols of that weight) floats, tickets_w:
+ *     ISTNET_FIN_TICKETS zeroed counters.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct istnet_sa_scale {
+    float radius;
+    int nsample;
+    int32_t *idx;
+    const float *w0; int ldw0;
+    const float *w1, *w2;
+    const float *bn_mean[3], *bn_invstd[3], *bn_gamma[3], *bn_beta[3];
+    float *part;
+    const istnet_fin *fin;
+    float *ysel;
+    uint8_t *asel;
+    const float *dz; int ld_dz, off_dz;
+    const double *ws2, *ws1, *ws0;
+    float *g1, *g0;
+    float *part_w;
+    unsigned *tickets_w;
+    float *dw; int ld_dw;
+} istnet_sa_scale;
+int istnet_sa_level_supported(int C0, int C1, int C2);
+int istnet_sa_level_forward(int B, int N, int M, int C0, int C1, int C2, const float *xyz, const float *new_xyz, const float *u, int ldu,
+                            const istnet_sa_scale *scales, int pass, int query, void *stream);
+int istnet_sa_level_final(int B, int M, int C2, const istnet_sa_scale *scales, float *out, int ld_out, void *stream);
+int istnet_sa_level_backward(int B, int N, int M, int C0, int C1, int C2, const float *xyz, const float *new_xyz, const float *u, int ldu,
+                             float *dU, const istnet_sa_scale *scales, int stage, void *stream);
+/* u[r][s*C0 + c] = sum_k F[r][k] * w0_s[c][3 + k] over the R = B*N points (the feature part of layer 0, both scales), and its
+ * backward: dF = dU Wf, dWf -> dw0_s[c][3 + k] (fixed-order ticket reduction; part_w: ISTNET_FIN_ROWS*2*C0*K floats) */
+int istnet_sa_u(int R, int K, int C0, const float *F, const float *w0a, const float *w0b, int ldw0, float *u, void *stream);
+int istnet_sa_u_bwd(int R, int K, int C0, const float *F, const float *dU, const float *w0a, const float *w0b, int ldw0, float *dF,
+                    float *part_w, unsigned *tickets_w, float *dw0a, float *dw0b, int ld_dw, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * 6. Optimizer step of the training loop (utils/solver.py:41-46,98-99: torch.optim.Adam + CyclicLR)
  * ---------------------------------------------------------------------------------------------------- */
 

@@ -31,14 +31,15 @@ struct FinP {
     float *sum2_f32;     // kind 3: sum g*xhat (nullable)
 };
 
-// All threads of the CTA call this after the CTA's partial row part[(a*G + blockIdx.x)*C + c] is written.  Returns true (for
-// every thread) in exactly one CTA of the grid — the last one to finish — after part2[(a*G2 + g2)*C + c], g2 < G2 =
-// ceil(G / kTicketGroup), holds the group sums of all CTAs.
+// All threads of the CTA call this after the CTA's partial row part[(a*G + cta)*C + c] is written (cta = this CTA's index among
+// the G CTAs that share the reduction: blockIdx.x for a whole grid, or an offset into it when one launch carries several
+// independent reductions).  Returns true (for every thread) in exactly one of the G CTAs — the last one to finish — after
+// part2[(a*G2 + g2)*C + c], g2 < G2 = ceil(G / kTicketGroup), holds the group sums of all CTAs.
 template <int NACC>
-__device__ bool ticket_reduce(const float *part, int G, int C, unsigned *tickets, float *part2) {
+__device__ bool ticket_reduce(const float *part, int cta, int G, int C, unsigned *tickets, float *part2) {
     __shared__ int s_last;
     const int G2 = (G + kTicketGroup - 1) / kTicketGroup;
-    const int grp = blockIdx.x / kTicketGroup;
+    const int grp = cta / kTicketGroup;
     const int g0 = grp * kTicketGroup;
     const int gsz = min(kTicketGroup, G - g0);
     __threadfence();
@@ -101,9 +102,9 @@ __device__ __forceinline__ void bn_fin_channel(const FinP &f, int c, double sum,
 // The complete tail of a producer whose partials are laid out part[(a*G + cta)*C + c].  kind 1 expects a = {sum, sum of
 // squares}; kind 2 a = {sum}; kind 3 a = {sum g, sum g*xhat, slope}.  Call with all threads of every CTA.
 template <int NACC>
-__device__ void ticket_finish(const FinP &f, const float *part, int G, int C) {
+__device__ void ticket_finish(const FinP &f, const float *part, int G, int C, int cta = -1) {
     if (f.kind == 0 || f.tickets == nullptr) return;
-    if (!ticket_reduce<NACC>(part, G, C, f.tickets, f.part2)) return;
+    if (!ticket_reduce<NACC>(part, cta < 0 ? (int)blockIdx.x : cta, G, C, f.tickets, f.part2)) return;
     __shared__ long long s_nold;
     if (threadIdx.x == 0) s_nold = (f.kind == 1 && f.num_batches_tracked) ? *f.num_batches_tracked : 0;
     __syncthreads();

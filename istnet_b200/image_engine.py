@@ -75,6 +75,52 @@ def _basic_block_fwd(u, pre, x, training, record, tape):
     return out
 
 
+def _basic_block_bwd(u, entry, dz, dz2, grads):
+    """Backward of _basic_block_fwd.  dz (+dz2): gradient(s) w.r.t. the block output; returns the two gradient streams w.r.t. the
+    block input (main path, identity / downsample path) — the block below adds them inside its own activation backward."""
+    _, pre, r1, r2, rd = entry
+    c1, c2, dn = u[pre + ".conv1"], u[pre + ".conv2"], u.get(pre + ".down")
+    dmid, g = c2.backward(r2, dz, dz2, need_dx=True, g_out=True, grads=grads)
+    dx1, _ = c1.backward(r1, dmid, None, need_dx=True, grads=grads)
+    if dn is not None:
+        dxd, _ = dn.backward(rd, g, None, need_dx=True, grads=grads)
+        return dx1, dxd
+    return dx1, g
+
+
+def _stem_fwd(u, rgb, training, record, tape):
+    """conv1 7x7/2 (im2col GEMM) + BN + ReLU + MaxPool(3,2,1) (resnet.py:182-186): rgb (B,3,H,W) NCHW -> Act [B,H/4,W/4,64]"""
+    dev = rgb.device
+    B, _, H, W = rgb.shape
+    x0 = Act(B, H, W, 3)
+    y0, r0 = u["conv1"].forward(x0, training, True, x_f32_nchw=rgb, defer_act=True)
+    st0 = r0["bn"]
+    Hp, Wp = (y0.H - 1) // 2 + 1, (y0.W - 1) // 2 + 1
+    z = Act(B, Hp, Wp, 64, torch.empty(B, Hp, Wp, 64, dtype=torch.float32, device=dev))
+    z.pl = K.empty_planes(B, Hp, Wp, 64, dev)
+    argmax = torch.empty(B, Hp, Wp, 64, dtype=torch.uint8, device=dev)
+    _C.call("bn_relu_maxpool", ptr(y0.f32), c_int(B), c_int(y0.H), c_int(y0.W), c_int(64), ptr(st0.mean), ptr(st0.invstd), ptr(st0.gamma),
+            ptr(st0.beta), ptr(z.f32), *K._pl_args(z.pl), c_int(z.cs), ptr(argmax))
+    if record:
+        tape.append(("stem", r0, argmax, (y0.H, y0.W)))
+    return z
+
+
+def _stem_bwd(u, entry, dz, dz2, grads):
+    _, r0, argmax, (H0, W0) = entry
+    unit = u["conv1"]
+    st = r0["bn"]
+    B = r0["xin"].B
+    dev = dz.device
+    g0 = torch.empty(B, H0, W0, 64, dtype=torch.float32, device=dev)
+    _C.call("maxpool_relu_bwd", ptr(r0["y"]), c_int(B), c_int(H0), c_int(W0), c_int(64), ptr(st.mean), ptr(st.invstd), ptr(st.gamma),
+            ptr(st.beta), ptr(dz), K._p(dz2), ptr(argmax), ptr(g0))
+    dy = K.empty_planes(B, H0, W0, 64, dev, nsplit=K.NSPLIT_BWD)
+    _, sg_f, sgx_f = K.bn_act_bwd(g0, None, r0["y"], r0["P"], 64, H0 * W0, st, ACT_NONE, None, None, None, dy_pl=dy)
+    grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = sgx_f, sg_f
+    unit.data_grads(r0, dy, False, grads)
+
+
 # ISTNET_DENSE_HEAD=1 keeps the round-1 head (dense 192x192x128 convolution output, statistics over it, dense BN backward)
 DENSE_HEAD = os.environ.get("ISTNET_DENSE_HEAD", "0") == "1"
 
@@ -224,18 +270,7 @@ def forward(net, rgb, choose, training, record, u=None):
     B, _, H, W = rgb.shape
     tape = []
     rgb = rgb.contiguous()
-    # ---- stem: conv1 7x7/2 (im2col GEMM) + BN + ReLU + MaxPool(3,2,1)
-    x0 = Act(B, H, W, 3)
-    y0, r0 = u["conv1"].forward(x0, training, True, x_f32_nchw=rgb, defer_act=True)
-    st0 = r0["bn"]
-    Hp, Wp = (y0.H - 1) // 2 + 1, (y0.W - 1) // 2 + 1
-    z = Act(B, Hp, Wp, 64, torch.empty(B, Hp, Wp, 64, dtype=torch.float32, device=dev))
-    z.pl = K.empty_planes(B, Hp, Wp, 64, dev)
-    argmax = torch.empty(B, Hp, Wp, 64, dtype=torch.uint8, device=dev)
-    _C.call("bn_relu_maxpool", ptr(y0.f32), c_int(B), c_int(y0.H), c_int(y0.W), c_int(64), ptr(st0.mean), ptr(st0.invstd), ptr(st0.gamma),
-            ptr(st0.beta), ptr(z.f32), *K._pl_args(z.pl), c_int(z.cs), ptr(argmax))
-    if record:
-        tape.append(("stem", r0, argmax, (y0.H, y0.W)))
+    z = _stem_fwd(u, rgb, training, record, tape)
     trace.mark("image: stem done")
     # ---- layer1..4
     for li in (1, 2, 3, 4):
@@ -381,27 +416,9 @@ def backward(net, tape, d_out, u):
             dz = dxf
             dz2 = gs[0].contiguous()  # leaf is channels-last: nothing to permute
         elif kind == "block":
-            _, pre, r1, r2, rd = entry
-            c1, c2, dn = u[pre + ".conv1"], u[pre + ".conv2"], u.get(pre + ".down")
-            dmid, g = c2.backward(r2, dz, dz2, need_dx=True, g_out=True, grads=grads)
-            dx1, _ = c1.backward(r1, dmid, None, need_dx=True, grads=grads)
-            if dn is not None:
-                dxd, _ = dn.backward(rd, g, None, need_dx=True, grads=grads)
-                dz, dz2 = dx1, dxd
-            else:
-                dz, dz2 = dx1, g
+            dz, dz2 = _basic_block_bwd(u, entry, dz, dz2, grads)
         elif kind == "stem":
-            _, r0, argmax, (H0, W0) = entry
-            unit = u["conv1"]
-            st = r0["bn"]
-            B = r0["xin"].B
-            g0 = torch.empty(B, H0, W0, 64, dtype=torch.float32, device=dev)
-            _C.call("maxpool_relu_bwd", ptr(r0["y"]), c_int(B), c_int(H0), c_int(W0), c_int(64), ptr(st.mean), ptr(st.invstd), ptr(st.gamma),
-                    ptr(st.beta), ptr(dz), K._p(dz2), ptr(argmax), ptr(g0))
-            dy = K.empty_planes(B, H0, W0, 64, dev, nsplit=K.NSPLIT_BWD)
-            _, sg_f, sgx_f = K.bn_act_bwd(g0, None, r0["y"], r0["P"], 64, H0 * W0, st, ACT_NONE, None, None, None, dy_pl=dy)
-            grads[id(unit.bn.weight)], grads[id(unit.bn.bias)] = sgx_f, sg_f
-            unit.data_grads(r0, dy, False, grads)
+            _stem_bwd(u, entry, dz, dz2, grads)
     K.join_side_streams()
     if pending_wb is not None:
         gwb, col0, key = pending_wb

@@ -14,6 +14,7 @@ import torch.nn.functional as F
 from . import ext
 from . import functional as PF
 from . import rows_engine as RE
+from . import sa_fused as SF
 
 
 class _NormLayer(nn.Sequential):
@@ -86,6 +87,12 @@ class PointnetSAModuleMSG(nn.Module):
             with torch.no_grad():
                 _, cent = ext.fps_chain(xyz, (self.npoint,))
             new_xyz = cent[0]
+        if SF.supported(self, xyz, new_xyz, feats_rows):
+            bn0 = self.mlps[0][0].normlayer.bn
+            needs_grad = torch.is_grad_enabled() and ((feats_rows is not None and feats_rows.requires_grad) or any(p.requires_grad for p in self.parameters()))
+            if RE.K.bn_uses_batch_stats(bn0, self.training) or not needs_grad:
+                # both scales, ball query + grouping + SharedMLP + max in one launch per pass (csrc/sa_fused.cu)
+                return new_xyz, SF.sa_level(self, xyz, new_xyz, feats_rows)
         outs = []
         for grouper, mlp in zip(self.groupers, self.mlps):
             idx = PF.ball_query(grouper.radius, grouper.nsample, xyz, new_xyz)

@@ -76,7 +76,9 @@ def _unit_vs_torch(K, B, H, W, cin, cout, k, stride, bn, act, bias, noise, seed)
     if bnm is not None:
         torch.nn.init.uniform_(bnm.weight, 0.5, 1.0)
         with torch.no_grad():
-            bnm.bias.copy_(8.0 * sign if act != 0 else 0.3 * torch.randn(cout, device="cuda"))
+            # ReLU (act 1): +-3 keeps a realistic share of masked elements per channel while making a rounding-level sign flip of
+            # a pre-activation (which would change single gradient elements by O(1)) vanishingly unlikely
+            bnm.bias.copy_(8.0 * sign if act == 2 else (3.0 * sign if act == 1 else 0.3 * torch.randn(cout, device="cuda")))
         bnm.momentum = 0.7
     elif bias and act != 0:
         with torch.no_grad():
@@ -123,6 +125,8 @@ def _unit_vs_torch(K, B, H, W, cin, cout, k, stride, bn, act, bias, noise, seed)
     dict(B=2, H=1, W=2048, cin=320, cout=256, k=1, stride=1, bn=False, act=2, bias=True, noise=False),  # per-point layer
     dict(B=4, H=16, W=16, cin=64, cout=128, k=3, stride=2, bn=True, act=0, bias=False, noise=False),   # strided (im2col) conv
     dict(B=4, H=16, W=16, cin=64, cout=128, k=1, stride=2, bn=True, act=0, bias=False, noise=False),   # strided downsample
+    dict(B=4, H=16, W=16, cin=64, cout=128, k=3, stride=1, bn=True, act=1, bias=False, noise=False),   # conv + BN(train) + ReLU (every ResNet / SharedMLP layer)
+    dict(B=2, H=1, W=4096, cin=128, cout=128, k=1, stride=1, bn=True, act=1, bias=False, noise=False),  # SharedMLP layer on rows
 ])
 def test_conv_bn_act_unit_forward_backward(K, cfg):
     """conv (+bias) -> BatchNorm(train) -> PReLU -> Dropout2d scale, forward and hand-written backward, vs float64 autograd.
@@ -290,3 +294,133 @@ def test_psp_pool_and_prior_kernels_match_aten(B, H, W, C, Co):
     prior.backward(cot)
     want.backward(cot.double())
     assert rel_err(t.grad, t64.grad) < 1e-6
+
+
+def _block_units(blk, pre):
+    from istnet_b200.nhwc import ACT_NONE, ACT_RELU, ConvUnit
+
+    u = {pre + ".conv1": ConvUnit(blk.conv1.weight, None, blk.bn1, ACT_RELU, k=3, stride=blk.stride),
+         pre + ".conv2": ConvUnit(blk.conv2.weight, None, blk.bn2, ACT_RELU, k=3)}
+    if blk.downsample is not None:
+        u[pre + ".down"] = ConvUnit(blk.downsample[0].weight, None, blk.downsample[1], ACT_NONE, k=1, stride=blk.stride, pad=0)
+    return u
+
+
+@pytest.mark.parametrize("cin,cout,stride", [(64, 64, 1), (64, 128, 2), (128, 256, 1)])
+def test_basic_block_residual_forward_backward_vs_float64(K, cin, cout, stride):
+    """resnet.py:50-66 BasicBlock in train mode — conv+BN+ReLU, conv+BN, residual (identity, or 1x1 conv + BN downsample incl. the
+    stride-2 variant of layer2.0), ReLU — forward, both gradient streams into the block input and every parameter gradient
+    against float64 autograd: 1e-4.  Covers the `res` / `res_bn` / second-gradient-stream (`dz2`) paths of the fused passes."""
+    import copy
+
+    from istnet_b200 import image_engine as IE
+    from istnet_b200.image import BasicBlock
+    from istnet_b200.nhwc import Act
+
+    torch.manual_seed(3)
+    g = torch.Generator(device="cuda").manual_seed(17)
+    down = None
+    if stride != 1 or cin != cout:
+        down = torch.nn.Sequential(torch.nn.Conv2d(cin, cout, 1, stride=stride, bias=False), torch.nn.BatchNorm2d(cout))
+    blk = BasicBlock(cin, cout, stride=stride, downsample=down).cuda().train()
+    sign = (torch.arange(cout, device="cuda") % 2 * 2 - 1).float()
+    with torch.no_grad():
+        for bn in [m for m in blk.modules() if isinstance(m, torch.nn.BatchNorm2d)]:
+            torch.nn.init.uniform_(bn.weight, 0.5, 1.0)
+            bn.momentum = 0.6
+        blk.bn1.bias.copy_(3.0 * sign)
+        blk.bn2.bias.copy_(4.0 * sign)
+    B, H, W = 4, 16, 16
+    x = torch.randn(B, cin, H, W, device="cuda", generator=g)
+    b64 = copy.deepcopy(blk).double()
+    x64 = x.double().requires_grad_(True)
+    z64 = b64(x64)
+    dz = torch.randn(z64.shape, device="cuda", dtype=torch.float64, generator=g)
+    z64.backward(dz)
+    u = _block_units(blk, "b")
+    xin = Act(B, H, W, cin, x.permute(0, 2, 3, 1).contiguous())
+    xin.pl = K.empty_planes(B, H, W, cin, "cuda")
+    K.split(xin.f32, B * H * W, cin, xin.pl)
+    tape = []
+    out = IE._basic_block_fwd(u, "b", xin, True, True, tape)
+    grads = {}
+    d1, d2 = IE._basic_block_bwd(u, tape[0], dz.float().permute(0, 2, 3, 1).contiguous(), None, grads)
+    K.join_side_streams()
+    assert rel_err(out.f32, z64.detach().permute(0, 2, 3, 1)) < 1e-4
+    assert rel_err(out.pl.float().sum(0)[..., :cout], z64.detach().permute(0, 2, 3, 1)) < 1e-4
+    assert rel_err(d1 + d2, x64.grad.permute(0, 2, 3, 1)) < 1e-4, rel_err(d1 + d2, x64.grad.permute(0, 2, 3, 1))
+    for (n, p), (_, p64) in zip(blk.named_parameters(), b64.named_parameters()):
+        e = rel_err(grads[id(p)].reshape(p64.grad.shape), p64.grad)
+        assert e < 1e-4, (n, e)
+    for (n, b), (_, b_64) in zip(blk.named_buffers(), b64.named_buffers()):
+        assert rel_err(b.double(), b_64.double()) < 1e-4, n
+
+
+def test_stem_conv7x7_bn_relu_maxpool_forward_backward_vs_float64(K):
+    """resnet.py:182-186: conv1 7x7/2 (im2col GEMM from the NCHW image) + BN(train) + ReLU + MaxPool(3,2,1), and the backward
+    through max-pool / ReLU / BN into the 7x7 weight gradient (col2im is not needed: the image receives no gradient)."""
+    import copy
+
+    from istnet_b200 import image_engine as IE
+    from istnet_b200.nhwc import ACT_RELU, ConvUnit
+
+    torch.manual_seed(5)
+    g = torch.Generator(device="cuda").manual_seed(19)
+    conv = torch.nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False).cuda()
+    bn = torch.nn.BatchNorm2d(64).cuda().train()
+    with torch.no_grad():
+        torch.nn.init.uniform_(bn.weight, 0.5, 1.0)
+        bn.bias.copy_(0.5 * torch.randn(64, device="cuda", generator=g))
+    B, H, W = 3, 64, 64
+    rgb = torch.randn(B, 3, H, W, device="cuda", generator=g)
+    c64, b64 = copy.deepcopy(conv).double(), copy.deepcopy(bn).double()
+    z64 = F.max_pool2d(F.relu(b64(c64(rgb.double()))), 3, 2, 1)
+    dz = torch.randn(z64.shape, device="cuda", dtype=torch.float64, generator=g)
+    z64.backward(dz)
+    u = {"conv1": ConvUnit(conv.weight, None, bn, ACT_RELU, k=7, stride=2, pad=3)}
+    tape = []
+    z = IE._stem_fwd(u, rgb, True, True, tape)
+    grads = {}
+    IE._stem_bwd(u, tape[0], dz.float().permute(0, 2, 3, 1).contiguous(), None, grads)
+    K.join_side_streams()
+    assert rel_err(z.f32, z64.detach().permute(0, 2, 3, 1)) < 1e-4
+    assert rel_err(grads[id(conv.weight)], c64.weight.grad) < 1e-4, rel_err(grads[id(conv.weight)], c64.weight.grad)
+    assert rel_err(grads[id(bn.weight)], b64.weight.grad) < 1e-4
+    assert rel_err(grads[id(bn.bias)], b64.bias.grad) < 1e-4
+    assert rel_err(bn.running_var.double(), b64.running_var) < 1e-4
+
+
+def test_im2col_col2im_are_adjoint_and_match_unfold(K):
+    """7x7/2 and 3x3/2 patch extraction (im2col_split) against F.unfold, and col2im against its autograd adjoint (fold)."""
+    g = torch.Generator(device="cuda").manual_seed(23)
+    for (C, k, stride, pad, H) in ((3, 7, 2, 3, 32), (64, 3, 2, 1, 16)):
+        B = 2
+        x = torch.randn(B, C, H, H, device="cuda", generator=g, dtype=torch.float64).requires_grad_(True)
+        cols = F.unfold(x, k, padding=pad, stride=stride)  # (B, C*k*k, L), channel-major (c, r, s)
+        Ho = (H + 2 * pad - k) // stride + 1
+        ref = cols.view(B, C, k * k, Ho, Ho).permute(0, 3, 4, 2, 1).reshape(B, Ho, Ho, k * k * C)  # our K order: (r, s, c)
+        a = K.im2col(x.detach().float().permute(0, 2, 3, 1).contiguous(), False, B, H, H, C, k, stride, pad)
+        assert rel_err(a.pl.float().sum(0)[..., : k * k * C], ref.detach()) < 1e-6
+        d = torch.randn(ref.shape, device="cuda", generator=g, dtype=torch.float64)
+        ref.backward(d)
+        dx = K.col2im(d.float().contiguous(), B, H, H, C, k, stride, pad)
+        assert rel_err(dx, x.grad.permute(0, 2, 3, 1)) < 1e-6
+
+
+def test_interp_rows_backward_vs_float64():
+    """three_interpolate_grad on rows (interpolate_gpu.cu:121-148): d_feats[b, idx[b,j,q], :] += dout[b,j,:] * w[b,j,q]."""
+    from istnet_b200 import rows_engine as RE
+
+    g = torch.Generator(device="cuda").manual_seed(29)
+    B, m, n, C = 3, 64, 200, 96
+    feats = torch.randn(B, m, C, device="cuda", generator=g).requires_grad_(True)
+    idx = torch.randint(0, m, (B, n, 3), device="cuda", generator=g, dtype=torch.int32)
+    w = torch.rand(B, n, 3, device="cuda", generator=g)
+    out = RE.interp_rows(feats, idx, w)
+    cot = torch.randn(out.shape, device="cuda", generator=g)
+    out.backward(cot)
+    f64 = feats.detach().double().requires_grad_(True)
+    ref = sum(torch.gather(f64, 1, idx[..., q].long()[..., None].expand(-1, -1, C)) * w.double()[..., q : q + 1] for q in range(3))
+    ref.backward(cot.double())
+    assert rel_err(out, ref) < 1e-6
+    assert rel_err(feats.grad, f64.grad) < 1e-5
