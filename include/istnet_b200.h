@@ -290,6 +290,14 @@ int istnet_interp_rows(int B, int m, int n, int C, const float *feats, const int
                        int out_off, void *stream);
 int istnet_interp_rows_bwd(int B, int m, int n, int C, const float *dout, int d_ld, int d_off, const int32_t *idx, const float *weight,
                            float *d_feats, void *stream);
+/* three_nn (bindings.cpp:15) + the interpolation weights of PointnetFPModule.forward (pointnet2_utils.py:142 sqrt; pointnet2_modules.py:
+ * 186-188 recip = 1/(dist + 1e-8), weight = recip / sum(recip)) in one launch; dist2 may be null */
+int istnet_three_nn_weights(int b, int n, int m, const float *unknown, const float *known, float *dist2, int32_t *idx, float *weight,
+                            void *stream);
+/* operand planes of the first FP-layer GEMM: row (b,j) = [three_interpolate(feats [B][m][C2]) | skip [B][n][C1]] (the torch.cat of
+ * pointnet2_modules.py:196-199 happens in the split; C1 may be 0) */
+int istnet_interp_concat_split(int B, int m, int n, int C2, int C1, const float *feats, const int32_t *idx, const float *weight,
+                               const float *skip, void *planes, long long plane_stride, int nsplit, int cs, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * 5b. Fused set-abstraction level (csrc/sa_fused.cu) — PointnetSAModuleMSG.forward (pointnet2_modules.py:29-73) for one level

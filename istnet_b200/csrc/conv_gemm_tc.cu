@@ -460,8 +460,17 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
         int e = istnet_make_tmap_bf16(&tb, wgt_planes, 4, dims, str, box, kBlockK * 2);
         if (e) return e;
     }
-    ISTNET_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    int ctas_per_sm = (int)((227 * 1024) / smem);
+    // dynamic + static shared memory share the 227 KB per-CTA limit (the ticket tail of the statistics epilogue keeps a few
+    // bytes of static shared memory)
+    static int static_smem = -1;
+    if (static_smem < 0) {
+        cudaFuncAttributes fa;
+        ISTNET_CUDA_TRY(cudaFuncGetAttributes(&fa, conv_gemm_tc_kernel));
+        static_smem = (int)fa.sharedSizeBytes;
+    }
+    if (smem + (size_t)static_smem > 227 * 1024) return ISTNET_ERR_UNSUPPORTED;
+    ISTNET_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - static_smem));
+    int ctas_per_sm = (int)((227 * 1024) / (smem + static_smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     if (ctas_per_sm > 512 / (int)p.tmem_cols) ctas_per_sm = 512 / (int)p.tmem_cols;  // tensor memory: 512 columns per SM
     if (ctas_per_sm < 1) ctas_per_sm = 1;

@@ -343,7 +343,7 @@ constexpr int kNnThreads = 128;
 // grid = (ceil(n/128), b); dynamic smem = m*3 floats.  One thread per unknown point, broadcast reads of `known`.
 __global__ void __launch_bounds__(kNnThreads)
 three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__restrict__ known, float *__restrict__ dist2,
-                int32_t *__restrict__ idx) {
+                int32_t *__restrict__ idx, float *__restrict__ weight) {
     extern __shared__ float nn_known[];
     const int bi = blockIdx.y;
     const float *src = known + (size_t)bi * m * 3;
@@ -369,8 +369,17 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__
         }
     }
     size_t o = ((size_t)bi * n + j) * 3;
-    dist2[o + 0] = b1; dist2[o + 1] = b2; dist2[o + 2] = b3;
+    if (dist2) { dist2[o + 0] = b1; dist2[o + 1] = b2; dist2[o + 2] = b3; }
     idx[o + 0] = i1; idx[o + 1] = i2; idx[o + 2] = i3;
+    if (weight) {
+        // PointnetFPModule.forward (pointnet2_modules.py:185-188) on top of pointnet2_utils.py:142: dist = sqrt(dist2);
+        // recip = 1 / (dist + 1e-8); weight = recip / sum(recip) — the same IEEE FP32 operations torch issues, in one place
+        const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b1), 1e-8f));
+        const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b2), 1e-8f));
+        const float r3 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b3), 1e-8f));
+        const float norm = __fadd_rn(__fadd_rn(r1, r2), r3);
+        weight[o + 0] = __fdiv_rn(r1, norm); weight[o + 1] = __fdiv_rn(r2, norm); weight[o + 2] = __fdiv_rn(r3, norm);
+    }
 }
 
 // out[(bi*c + l)*n + j] = fma(p[i3], w3, fma(p[i1], w1, p[i2]*w2)) (the reference's SASS contraction),  p = points + (bi*c + l)*m
@@ -410,7 +419,22 @@ extern "C" int istnet_three_nn(int b, int n, int m, const float *unknown, const 
     if (smem > 48 * 1024)
         ISTNET_CUDA_TRY(cudaFuncSetAttribute(three_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(n, kNnThreads), b);
-    three_nn_kernel<<<grid, kNnThreads, smem, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx);
+    three_nn_kernel<<<grid, kNnThreads, smem, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx, nullptr);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+// three_nn + the inverse-distance interpolation weights of PointnetFPModule.forward in ONE launch (the reference: three_nn kernel +
+// sqrt, add, reciprocal, sum, div as five ATen launches).  dist2 may be null.
+extern "C" int istnet_three_nn_weights(int b, int n, int m, const float *unknown, const float *known, float *dist2, int32_t *idx, float *weight,
+                                       void *stream) {
+    if (b <= 0 || n <= 0) return ISTNET_OK;
+    if (m < 0 || !weight) return ISTNET_ERR_BAD_ARG;
+    size_t smem = (size_t)m * 3 * sizeof(float);
+    if (smem > 200 * 1024) return ISTNET_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024)
+        ISTNET_CUDA_TRY(cudaFuncSetAttribute(three_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(n, kNnThreads), b);
+    three_nn_kernel<<<grid, kNnThreads, smem, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx, weight);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }

@@ -103,6 +103,36 @@ __global__ void __launch_bounds__(kThreads) interp_rows_kernel(int B, int m, int
                                                    __fmaf_rn(f[(long long)idx[o] * C], w[o], __fmul_rn(f[(long long)idx[o + 1] * C], w[o + 1])));
     }
 }
+// Operand planes of the first FP-layer GEMM in one pass: row (b,j) = [ three_interpolate(known feats)[0:C2] | skip feats[0:C1] ]
+// (torch.cat([interpolated, unknow_feats], dim=1), pointnet2_modules.py:190-199) — replaces interp_rows + two split passes.
+__global__ void __launch_bounds__(kThreads) interp_concat_split_kernel(int B, int m, int n, int C2, int C1, const float *__restrict__ feats,
+                                                                        const int32_t *__restrict__ idx, const float *__restrict__ w,
+                                                                        const float *__restrict__ skip, __nv_bfloat16 *pl, long long pl_stride,
+                                                                        int nsplit, int cs) {
+    const int lanes = (C2 + C1) >> 2;
+    const long long total = (long long)B * n * lanes;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % lanes) * 4;
+        const long long bj = i / lanes;
+        float4 v;
+        if (c < C2) {
+            const int b = (int)(bj / n);
+            const float *f = feats + (long long)b * m * C2 + c;
+            const long long o = bj * 3;
+            const float4 p1 = *reinterpret_cast<const float4 *>(f + (long long)idx[o] * C2);
+            const float4 p2 = *reinterpret_cast<const float4 *>(f + (long long)idx[o + 1] * C2);
+            const float4 p3 = *reinterpret_cast<const float4 *>(f + (long long)idx[o + 2] * C2);
+            const float w1 = w[o], w2 = w[o + 1], w3 = w[o + 2];
+            v.x = __fmaf_rn(p3.x, w3, __fmaf_rn(p1.x, w1, __fmul_rn(p2.x, w2)));
+            v.y = __fmaf_rn(p3.y, w3, __fmaf_rn(p1.y, w1, __fmul_rn(p2.y, w2)));
+            v.z = __fmaf_rn(p3.z, w3, __fmaf_rn(p1.z, w1, __fmul_rn(p2.z, w2)));
+            v.w = __fmaf_rn(p3.w, w3, __fmaf_rn(p1.w, w1, __fmul_rn(p2.w, w2)));
+        } else {
+            v = *reinterpret_cast<const float4 *>(skip + bj * C1 + (c - C2));
+        }
+        store_planes4(pl + bj * cs + c, pl_stride, nsplit, v);
+    }
+}
 // d_feats[b, idx[b,j,q], c] += dout[b, j, off + c] * w_q   (d_feats pre-zeroed)
 __global__ void __launch_bounds__(kThreads) interp_rows_bwd_kernel(int B, int m, int n, int C, const float *__restrict__ dout, int d_ld, int d_off,
                                                                     const int32_t *__restrict__ idx, const float *__restrict__ w, float *d_feats) {
@@ -164,6 +194,15 @@ extern "C" int istnet_interp_rows_bwd(int B, int m, int n, int C, const float *d
     if (B <= 0 || n <= 0 || C <= 0) return ISTNET_ERR_BAD_ARG;
     ISTNET_CUDA_TRY(cudaMemsetAsync(d_feats, 0, sizeof(float) * (size_t)B * m * C, ST));
     interp_rows_bwd_kernel<<<grid1d((long long)B * n * C), kThreads, 0, ST>>>(B, m, n, C, dout, d_ld, d_off, idx, weight, d_feats);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+extern "C" int istnet_interp_concat_split(int B, int m, int n, int C2, int C1, const float *feats, const int32_t *idx, const float *weight,
+                                          const float *skip, void *planes, long long plane_stride, int nsplit, int cs, void *stream) {
+    if (B <= 0 || n <= 0 || C2 <= 0 || (C2 & 3) || (C1 & 3) || C1 < 0 || (C1 > 0 && !skip) || cs < C2 + C1 || (cs & 3) || nsplit < 1 || nsplit > kMaxPlanes)
+        return ISTNET_ERR_BAD_ARG;
+    interp_concat_split_kernel<<<grid1d((long long)B * n * ((C2 + C1) / 4)), kThreads, 0, ST>>>(B, m, n, C2, C1, feats, idx, weight, skip,
+                                                                                              (__nv_bfloat16 *)planes, plane_stride, nsplit, cs);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }

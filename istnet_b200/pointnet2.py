@@ -115,6 +115,9 @@ class PointnetFPModule(nn.Module):
 
     def forward_rows(self, unknown, known, unknown_rows, known_rows):
         """unknown (B,n,3), known (B,m,3), unknown_rows (B,n,C1) or None, known_rows (B,m,C2) -> (B,n,mlp[-1])"""
+        out = RE.fp_level(RE.units_from_shared_mlp(self.mlp), self.training, unknown, known, known_rows, unknown_rows)
+        if out is not None:
+            return out
         idx, weight = PF.three_nn_weights(unknown, known)
         x = RE.interp_rows(known_rows, idx, weight)
         B, n, _ = x.shape

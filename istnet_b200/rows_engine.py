@@ -310,3 +310,67 @@ class _InterpRowsFn(torch.autograd.Function):
 def interp_rows(feats, idx, weight):
     """three_interpolate on channels-last features: feats (B,m,C), idx/weight (B,n,3) -> (B,n,C)"""
     return _InterpRowsFn.apply(feats.contiguous(), idx, weight)
+
+
+# ------------------------------------------------------------------------------------------ feature-propagation level
+class _FPLevelFn(torch.autograd.Function):
+    """PointnetFPModule.forward (pointnet2_modules.py:164-209) on rows: three_nn + interpolation weights (one launch), three_interpolate
+    + torch.cat([interpolated, skip]) + operand split (one launch), SharedMLP chain.  Round 1 issued three_nn, five ATen launches
+    for the weights, interp_rows, two split passes and two .contiguous() copies for the same work."""
+
+    @staticmethod
+    def forward(ctx, units, training, unknown, known, known_rows, skip_rows, *params):
+        B, n, _ = unknown.shape
+        m, C2 = known.shape[1], known_rows.shape[2]
+        C1 = 0 if skip_rows is None else skip_rows.shape[2]
+        dev = unknown.device
+        idx = torch.empty(B, n, 3, dtype=torch.int32, device=dev)
+        w = torch.empty(B, n, 3, dtype=torch.float32, device=dev)
+        _C.call("three_nn_weights", c_int(B), c_int(n), c_int(m), ptr(unknown), ptr(known), K.NULL, ptr(idx), ptr(w))
+        a = Act(1, 1, B * n, C2 + C1)
+        a.pl = K.empty_planes(1, 1, B * n, C2 + C1, dev, nsplit=units[0].ns)
+        _C.call("interp_concat_split", c_int(B), c_int(m), c_int(n), c_int(C2), c_int(C1), ptr(known_rows), ptr(idx), ptr(w), K._p(skip_rows),
+                *K._pl_args(a.pl), c_int(a.cs))
+        out, tape = _chain_forward(units, a, training, not isinstance(ctx, _NoCtx))
+        ctx.units, ctx.tape, ctx.params = units, tape, params
+        ctx.idx, ctx.w, ctx.dims = idx, w, (B, m, n, C2, C1)
+        ctx.need = (known_rows.requires_grad, skip_rows is not None and skip_rows.requires_grad)
+        return out.f32.view(B, n, -1)
+
+    @staticmethod
+    def backward(ctx, dz):
+        B, m, n, C2, C1 = ctx.dims
+        grads = {}
+        trace.mark(f"fp bwd> rows={B * n} cout={dz.shape[-1]}")
+        dz = dz.contiguous()
+        dx = _chain_backward(ctx.units, ctx.tape, dz.view(1, 1, B * n, dz.shape[-1]), grads, any(ctx.need))
+        K.join_side_streams()
+        d_known = d_skip = None
+        if ctx.need[0]:
+            d_known = torch.empty(B, m, C2, dtype=torch.float32, device=dz.device)
+            _C.call("interp_rows_bwd", c_int(B), c_int(m), c_int(n), c_int(C2), ptr(dx), c_int(C2 + C1), c_int(0), ptr(ctx.idx), ptr(ctx.w), ptr(d_known))
+        if ctx.need[1]:
+            d_skip = dx.view(B, n, C2 + C1)[:, :, C2:]
+        trace.mark("fp bwd<")
+        ctx.tape = None
+        return (None, None, None, None, d_known, d_skip) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
+
+
+def fp_level(units, training, unknown, known, known_rows, skip_rows):
+    """unknown (B,n,3), known (B,m,3), known_rows (B,m,C2), skip_rows (B,n,C1) or None -> (B,n,Cout)"""
+    params = _unit_params(units)
+    known_rows = known_rows.contiguous()
+    if skip_rows is not None:
+        skip_rows = skip_rows.contiguous()
+    C2, C1 = known_rows.shape[2], 0 if skip_rows is None else skip_rows.shape[2]
+    if (C2 % 4) or (C1 % 4):
+        return None  # caller falls back to the unfused flow
+    tensors = (known_rows, skip_rows) if skip_rows is not None else (known_rows,)
+    if torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or any(p.requires_grad for p in params)):
+        return _FPLevelFn.apply(units, training, unknown.contiguous(), known.contiguous(), known_rows, skip_rows, *params)
+    with torch.no_grad():
+        return _FPLevelFn.forward(_NoCtx(), units, training, unknown.contiguous(), known.contiguous(), known_rows, skip_rows, *params)
+
+
+class _NoCtx:
+    """Stand-in for an autograd ctx when a Function's forward is used without recording."""

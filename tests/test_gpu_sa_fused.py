@@ -21,10 +21,10 @@ def _level(cin, widths, radii, npoint, seed, negative_gamma):
     with torch.no_grad():
         for m in sa.modules():
             if isinstance(m, torch.nn.BatchNorm2d):
-                m.weight.copy_(0.5 + torch.rand(m.num_features, generator=g))
+                m.weight.copy_((0.5 + torch.rand(m.num_features, generator=g)).to(m.weight.device))
                 if negative_gamma:  # exercises the min-selection branch: relu(bn(.)) is decreasing in y for gamma < 0
-                    m.weight.mul_(torch.where(torch.rand(m.num_features, generator=g) < 0.4, -1.0, 1.0))
-                m.bias.copy_(0.2 * torch.randn(m.num_features, generator=g))
+                    m.weight.mul_(torch.where(torch.rand(m.num_features, generator=g) < 0.4, -1.0, 1.0).to(m.weight.device))
+                m.bias.copy_((0.2 * torch.randn(m.num_features, generator=g)).to(m.weight.device))
                 m.momentum = 0.37
     return sa
 
