@@ -93,8 +93,8 @@ int istnet_fps_chain(int b, int n, int nlevels, const int *npoint, const float *
 #define ISTNET_FIN_BN_STATS 1 /* partials {sum, sum^2} -> mean, invstd, running stats, num_batches_tracked */
 #define ISTNET_FIN_COLSUM 2   /* partials {sum} -> sum_f64 / sum_f32 [C] */
 #define ISTNET_FIN_BN_BWD 3   /* partials {sum g, sum g*xhat, slope} -> sum_f64 [3C], sum_f32 = sum g, sum2_f32 = sum g*xhat */
-#define ISTNET_FIN_TICKETS 20
-#define ISTNET_FIN_ROWS (296 + 19)
+#define ISTNET_FIN_TICKETS 38
+#define ISTNET_FIN_ROWS (592 + 37)
 typedef struct istnet_fin {
     int kind;
     unsigned *tickets;
@@ -343,10 +343,11 @@ int istnet_sa_level_final(int B, int M, int C2, const istnet_sa_scale *scales, f
 int istnet_sa_level_backward(int B, int N, int M, int C0, int C1, int C2, const float *xyz, const float *new_xyz, const float *u, int ldu,
                              float *dU, const istnet_sa_scale *scales, int stage, void *stream);
 /* u[r][s*C0 + c] = sum_k F[r][k] * w0_s[c][3 + k] over the R = B*N points (the feature part of layer 0, both scales), and its
- * backward: dF = dU Wf, dWf -> dw0_s[c][3 + k] (fixed-order ticket reduction; part_w: ISTNET_FIN_ROWS*2*C0*K floats) */
+ * backward: dF = dU Wf, dWf -> dwf [2*C0][K] (rows of scale 0 first; fixed-order reduction of the per-CTA partials in part_w:
+ * ISTNET_FIN_ROWS*2*C0*K floats) */
 int istnet_sa_u(int R, int K, int C0, const float *F, const float *w0a, const float *w0b, int ldw0, float *u, void *stream);
 int istnet_sa_u_bwd(int R, int K, int C0, const float *F, const float *dU, const float *w0a, const float *w0b, int ldw0, float *dF,
-                    float *part_w, unsigned *tickets_w, float *dw0a, float *dw0b, int ld_dw, void *stream);
+                    float *part_w, float *dwf, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * 6. Optimizer step of the training loop (utils/solver.py:41-46,98-99: torch.optim.Adam + CyclicLR)

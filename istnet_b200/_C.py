@@ -74,7 +74,7 @@ class Fin(ctypes.Structure):
 
 
 FIN_BN_STATS, FIN_COLSUM, FIN_BN_BWD = 1, 2, 3
-FIN_TICKETS, FIN_ROWS = 20, 296 + 19  # ISTNET_FIN_TICKETS / ISTNET_FIN_ROWS
+FIN_TICKETS, FIN_ROWS = 38, 592 + 37  # ISTNET_FIN_TICKETS / ISTNET_FIN_ROWS
 _TICKET_SLOTS = 8192
 _ticket_arena = {}
 

@@ -416,7 +416,9 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     if (stat_y && (!stat_part || stat_y_cs < Cout)) return ISTNET_ERR_BAD_ARG;
     if (mask_hi && mask_cs < Cout) return ISTNET_ERR_BAD_ARG;
     if (fin && fin->kind != ISTNET_FIN_NONE && (!stat_part || stat_y || fin->kind == ISTNET_FIN_BN_BWD)) return ISTNET_ERR_BAD_ARG;
-    if (!make_fin(fin, stat_part, 2, Cout, p.fin)) return ISTNET_ERR_BAD_ARG;
+    FinP fin_p;
+    if (!make_fin(fin, stat_part, 2, Cout, fin_p)) return ISTNET_ERR_BAD_ARG;
+    p.fin = fin_in_kernel(Cout) ? fin_p : FinP{};  // wide reductions: channel-parallel finalize launch below instead of the in-kernel tail
     p.out_f32 = out_f32; p.out_cs = out_cs;
     p.out_pl = (__nv_bfloat16 *)out_planes; p.out_pl_stride = out_plane_stride; p.split_cs = split_cs; p.nsplit_out = nsplit_out;
     p.n_tiles_n = ceil_div(Cout, p.BN);
@@ -483,5 +485,7 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     if (threads_override > 0) threads = threads_override;
     conv_gemm_tc_kernel<<<(unsigned)grid_x, threads, smem, (cudaStream_t)stream>>>(ta, tb, p);
     ISTNET_LAUNCH_CHECK();
+    if (fin_p.kind != 0 && !fin_in_kernel(Cout))
+        return istnet_fin_finalize_launch(stat_part, (int)grid_x, Cout, fin_p.kind == ISTNET_FIN_COLSUM ? 1 : 2, fin_p, (cudaStream_t)stream);
     return ISTNET_OK;
 }

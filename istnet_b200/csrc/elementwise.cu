@@ -163,6 +163,41 @@ __global__ void __launch_bounds__(kFinThreads) bwd_finalize_kernel(const float *
     if (sum1_f32) sum1_f32[c] = (float)t[1];
 }
 
+// Channel-parallel finish of a reduction described by a FinP (ticket.cuh) from per-CTA partials part[(a*G + g)*C + c]: one CTA per
+// 32 channels, 32 partial-slices each — used instead of the in-kernel ticket tail when the reduction is wide (C > kTicketMaxC).
+template <int NACC>
+__global__ void __launch_bounds__(kFinThreads) fin_finalize_kernel(const float *__restrict__ part, int G, int C, FinP f) {
+    __shared__ long long s_nold;
+    if (threadIdx.x == 0) s_nold = (f.kind == 1 && f.num_batches_tracked) ? *f.num_batches_tracked : 0;
+    double t[NACC];
+    sum_partials<NACC>(part, G, C, t);  // contains a __syncthreads: s_nold is visible afterwards
+    const long long n_old = s_nold;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    if (threadIdx.x < 32 && c < C) {
+        if (f.kind == 1) {
+            bn_fin_channel(f, c, t[0], t[NACC >= 2 ? 1 : 0], n_old);
+        } else if (f.kind == 2) {
+            if (f.sum_f64) f.sum_f64[c] = t[0];
+            if (f.sum_f32) f.sum_f32[c] = (float)t[0];
+        } else {
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) {
+                if (f.sum_f64) f.sum_f64[(size_t)a * C + c] = t[a];
+                if (a == 0 && f.sum_f32) f.sum_f32[c] = (float)t[a];
+                if (a == 1 && f.sum2_f32) f.sum2_f32[c] = (float)t[a];
+            }
+        }
+    }
+    // nn.BatchNorm2d's step counter: incremented by the LAST block, i.e. after every block has read the old value
+    if (f.kind == 1 && f.num_batches_tracked) {
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(&f.tickets[0], 1u) == gridDim.x - 1) {
+            f.tickets[0] = 0u;
+            *f.num_batches_tracked = n_old + 1;
+        }
+    }
+}
+
 // Per-thread channel constants: with lanes = C/4 dividing the CTA, a thread keeps the same 4 channels for every row it
 // visits, so the BatchNorm parameters live in registers and the row loop contains no division.
 struct Chan4 {
@@ -1071,6 +1106,18 @@ inline BnP make_bn(const float *mean, const float *invstd, const float *gamma, c
 
 #define ST ((cudaStream_t)stream)
 
+int istnet_fin_finalize_launch(const float *part, int G, int C, int nacc, const FinP &f, cudaStream_t st) {
+    if (f.kind == 0) return ISTNET_OK;
+    if (!part || G <= 0 || C <= 0) return ISTNET_ERR_BAD_ARG;
+    const int grid = ceil_div(C, 32);
+    if (nacc == 1) fin_finalize_kernel<1><<<grid, kFinThreads, 0, st>>>(part, G, C, f);
+    else if (nacc == 2) fin_finalize_kernel<2><<<grid, kFinThreads, 0, st>>>(part, G, C, f);
+    else if (nacc == 3) fin_finalize_kernel<3><<<grid, kFinThreads, 0, st>>>(part, G, C, f);
+    else return ISTNET_ERR_BAD_ARG;
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+
 // partial rows of both ticket levels (ticket.cuh): [nacc][kMaxPartialRows][C] per-CTA partials + [nacc][kMaxTicketGroups][C] group sums
 extern "C" int istnet_reduce_ws_floats(long long P, int C, int nacc) { (void)P; return ISTNET_FIN_ROWS * nacc * C; }
 
@@ -1088,8 +1135,10 @@ extern "C" int istnet_bn_stats_fin(const float *y, long long P, int C, float *pa
     if (P <= 0 || C <= 0 || (C & 3) || !fin || fin->kind != ISTNET_FIN_BN_STATS) return ISTNET_ERR_BAD_ARG;
     FinP f;
     if (!make_fin(fin, part_ws, 2, C, f)) return ISTNET_ERR_BAD_ARG;
-    bn_stats_kernel<<<red_grid(P, C), kEwThreads, 0, ST>>>(y, P, C, part_ws, f);
+    const int G = red_grid(P, C);
+    bn_stats_kernel<<<G, kEwThreads, 0, ST>>>(y, P, C, part_ws, fin_in_kernel(C) ? f : FinP{});
     ISTNET_LAUNCH_CHECK();
+    if (!fin_in_kernel(C)) return istnet_fin_finalize_launch(part_ws, G, C, 2, f, ST);
     return ISTNET_OK;
 }
 
@@ -1139,8 +1188,12 @@ extern "C" int istnet_bn_act_bwd(const float *dz, const float *dz2, const float 
         h.kind = ISTNET_FIN_BN_BWD; h.tickets = tickets; h.sum_f64 = ws; h.sum_f32 = sum_g_f32; h.sum2_f32 = sum_gx_f32;
         if (!make_fin(&h, part_ws, 3, C, f)) return ISTNET_ERR_BAD_ARG;
     }
-    bn_bwd_reduce_kernel<<<G, kEwThreads, 0, ST>>>(P, C, p, part_ws, f);
+    bn_bwd_reduce_kernel<<<G, kEwThreads, 0, ST>>>(P, C, p, part_ws, fin_in_kernel(C) ? f : FinP{});
     ISTNET_LAUNCH_CHECK();
+    if (tickets && !fin_in_kernel(C)) {
+        int e = istnet_fin_finalize_launch(part_ws, G, C, 3, f, ST);
+        if (e) return e;
+    }
     if (!tickets) {
         bwd_finalize_kernel<<<ceil_div(C, 32), kFinThreads, 0, ST>>>(part_ws, G, C, ws, sum_g_f32, sum_gx_f32);
         ISTNET_LAUNCH_CHECK();
@@ -1281,8 +1334,12 @@ extern "C" int istnet_sa_gather_l0(int B, int N, int M, int ns, int C0, const fl
     const int G = red_grid(rows, C0);  // <= 296: the size callers give the statistics scratch
     FinP f;
     if ((fin && fin->kind != ISTNET_FIN_NONE && fin->kind != ISTNET_FIN_BN_STATS) || !make_fin(fin, stat_part, 2, C0, f)) return ISTNET_ERR_BAD_ARG;
-    sa_gather_l0_kernel<<<G, kEwThreads, 0, ST>>>(N, M, ns, C0, rows, xyz, new_xyz, idx, u, w0, ldw, y0, stat_part, f);
+    sa_gather_l0_kernel<<<G, kEwThreads, 0, ST>>>(N, M, ns, C0, rows, xyz, new_xyz, idx, u, w0, ldw, y0, stat_part, fin_in_kernel(C0) ? f : FinP{});
     ISTNET_LAUNCH_CHECK();
+    if (!fin_in_kernel(C0)) {
+        int e = istnet_fin_finalize_launch(stat_part, G, C0, 2, f, ST);
+        if (e) return e;
+    }
     if (grid_out) *grid_out = G;
     return ISTNET_OK;
 }
@@ -1298,8 +1355,12 @@ extern "C" int istnet_sa_scatter_l0(int B, int N, int M, int ns, int C0, const f
         h.kind = ISTNET_FIN_BN_BWD; h.tickets = tickets; h.sum_f64 = ws;
         if (!make_fin(&h, part_ws, 3, C0, f)) return ISTNET_ERR_BAD_ARG;
     }
-    sa_scatter_l0_kernel<<<G, kEwThreads, 0, ST>>>(N, M, ns, C0, rows, dy0, xyz, new_xyz, idx, dU, part_ws, f);
+    sa_scatter_l0_kernel<<<G, kEwThreads, 0, ST>>>(N, M, ns, C0, rows, dy0, xyz, new_xyz, idx, dU, part_ws, fin_in_kernel(C0) ? f : FinP{});
     ISTNET_LAUNCH_CHECK();
+    if (tickets && !fin_in_kernel(C0)) {
+        int e = istnet_fin_finalize_launch(part_ws, G, C0, 3, f, ST);
+        if (e) return e;
+    }
     if (!tickets) {
         bwd_finalize_kernel<<<ceil_div(C0, 32), kFinThreads, 0, ST>>>(part_ws, G, C0, ws);
         ISTNET_LAUNCH_CHECK();
@@ -1449,3 +1510,10 @@ extern "C" int istnet_gather_bn_prelu_bwd(const float *y, int B, long long HW, i
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
+
+#ifdef ISTNET_TICKET_DEBUG
+// debug build only (-DISTNET_TICKET_DEBUG): %globaltimer stamps of the ticket tail of the last reduction kernel of THIS file
+extern "C" int istnet_ticket_debug(unsigned long long *out8) {
+    return (int)cudaMemcpyFromSymbol(out8, g_ticket_dbg, sizeof(unsigned long long) * 8);
+}
+#endif

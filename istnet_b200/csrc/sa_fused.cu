@@ -18,9 +18,12 @@
 // gradients per CTA in registers (fixed-order ticket reduction, no float atomics except the scatter to the points that the
 // reference also performs with atomics, group_points_gpu.cu:48-69).
 //
-// Mapping: one lane = one output channel, one warp = one neighbourhood (forward) or a block of rows (backward); the weight row
-// of the lane lives in registers, the rows of the current tile are broadcast from shared memory (LDS.128, same address for
-// all lanes), so BatchNorm statistics and the max over neighbours are lane-local running values: no shuffles, no atomics.
+// Mapping: one lane = one output channel; a warp works alone on 16-row tiles (one neighbourhood of 16, or half of one of 32) held in
+// its own shared-memory slots: the weight row of the lane lives in registers, the rows of the tile are broadcast from shared
+// memory (LDS.128, same address for all lanes), so BatchNorm statistics and the max over neighbours are lane-local running
+// values — no shuffles, no atomics — and there is no block-wide barrier before the final flush: the 12-16 warps of an SM drift
+// apart and hide each other's gather / shared-memory latencies (the first version synchronised the CTA per 128-256-row tile and
+// was latency-bound: profiles/r2_sa_fused_v1_launches.txt).  The forward pass scans the cloud ONCE per centroid for both radii.
 #include "common.cuh"
 #include "ticket.cuh"
 
@@ -85,125 +88,7 @@ __device__ __forceinline__ float row_dot(const float *__restrict__ z, const floa
     return __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
 }
 
-struct TileCtx {
-    int s;         // scale
-    int cta, G;    // this CTA among the scale's CTAs
-    int ns, T;     // neighbours per centroid, rows per tile
-    int t_begin, t_end;
-};
-template <int GT>
-__device__ __forceinline__ TileCtx tile_ctx(const SaLevelP &p) {
-    TileCtx c;
-    c.s = ((int)blockIdx.x >= p.sc[1].cta0 && p.sc[1].ncta > 0) ? 1 : 0;
-    const SaScale &sc = p.sc[c.s];
-    c.cta = (int)blockIdx.x - sc.cta0;
-    c.G = sc.ncta;
-    c.ns = sc.ns;
-    c.T = GT * sc.ns;
-    const int n_tiles = p.B * p.M / GT;
-    const int per = (n_tiles + c.G - 1) / c.G;
-    c.t_begin = min(n_tiles, c.cta * per);
-    c.t_end = min(n_tiles, c.t_begin + per);
-    return c;
-}
-
-// Shared-memory carve-up (floats unless noted); every region 16-byte aligned.
-template <int C0, int C1, int C2, int GT>
-struct Smem {
-    static constexpr int T = GT * kMaxNs;
-    float *cloud;   // [N*3]            (query pass only)
-    int *idx;       // [T]
-    int *src;       // [T]   global point row b*N + idx
-    float *rel;     // [T][4]
-    float *z0;      // [T][C0]
-    float *y1;      // [T][C1]  (backward A/B)
-    float *z1;      // [T][C1]
-    float *d2;      // [T][C2]  (backward A: dy2;  backward B reuses it for dy1 [T][C1])
-    float *red;     // [kWarps][3][64] cross-warp combine
-    __device__ Smem(float *base, int N, bool query, bool bwd) {
-        float *q = base;
-        cloud = q; q += query ? ((N * 3 + 3) & ~3) : 0;
-        idx = reinterpret_cast<int *>(q); q += T;
-        src = reinterpret_cast<int *>(q); q += T;
-        rel = q; q += T * 4;
-        z0 = q; q += T * C0;
-        z1 = q; q += T * C1;
-        y1 = q; q += bwd ? T * C1 : 0;
-        d2 = q; q += bwd ? T * C2 : 0;
-        red = q;
-    }
-    static size_t bytes(int N, bool query, bool bwd) {
-        size_t f = (query ? ((N * 3 + 3) & ~3) : 0) + 2 * T + 4 * T + (size_t)T * C0 + (size_t)T * C1 + (bwd ? (size_t)T * C1 + (size_t)T * C2 : 0) +
-                   kWarps * 3 * 64;
-        return f * sizeof(float);
-    }
-};
-
-// rows of the tile: ball query (or reload of idx), relative coordinates, point rows.  tile = GT consecutive centroids of one instance.
-template <int GT, bool QUERY>
-__device__ __forceinline__ void tile_rows(const SaLevelP &p, const SaScale &sc, int tile, int &cur_b, float *cloud, int *idx_s, int *src_s, float *rel_s) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ns = sc.ns, T = GT * ns;
-    const int bj0 = tile * GT;   // first flattened centroid index b*M + j
-    const int b = bj0 / p.M;
-    if (QUERY) {
-        if (b != cur_b) {  // uniform over the CTA
-            __syncthreads();
-            const float *srcp = p.xyz + (size_t)b * p.N * 3;
-            for (int i = threadIdx.x; i < p.N * 3; i += kThreads) cloud[i] = srcp[i];
-            cur_b = b;
-        }
-        __syncthreads();
-        const float r2 = __fmul_rn(sc.radius, sc.radius);  // ball_query_gpu.cu:27
-        const unsigned lt_mask = (1u << lane) - 1u;
-        for (int g = warp; g < GT; g += kWarps) {
-            const float *q = p.new_xyz + (size_t)(bj0 + g) * 3;
-            const float cx = q[0], cy = q[1], cz = q[2];
-            int32_t *out = sc.idx + (size_t)(bj0 + g) * ns;
-            int *outs = idx_s + g * ns;
-            int cnt = 0, first = 0;
-            for (int base = 0; base < p.N && cnt < ns; base += 32) {
-                const int k = base + lane;
-                bool hit = false;
-                if (k < p.N) {
-                    const float d2 = sqdist_ref(__fsub_rn(cx, cloud[k * 3 + 0]), __fsub_rn(cy, cloud[k * 3 + 1]), __fsub_rn(cz, cloud[k * 3 + 2]));
-                    hit = d2 < r2;
-                }
-                const unsigned mask = __ballot_sync(0xffffffffu, hit);
-                if (mask) {
-                    if (cnt == 0) first = base + __ffs(mask) - 1;
-                    const int pos = cnt + __popc(mask & lt_mask);
-                    if (hit && pos < ns) { out[pos] = k; outs[pos] = k; }
-                    cnt += __popc(mask);
-                }
-            }
-            if (cnt > ns) cnt = ns;
-            // tail: the reference pre-fills the row with the first hit (ball_query_gpu.cu:39-43); no hit => zeros
-            for (int l = cnt + lane; l < ns; l += 32) { out[l] = first; outs[l] = first; }
-        }
-    } else {
-        __syncthreads();  // the previous tile's readers are done with the tile buffers
-        for (int t = threadIdx.x; t < T; t += kThreads) idx_s[t] = sc.idx[(size_t)bj0 * ns + t];
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < T; t += kThreads) {
-        const int g = t / ns;
-        const int src = b * p.N + idx_s[t];
-        src_s[t] = src;
-        const float *x = p.xyz + (size_t)src * 3, *c = p.new_xyz + (size_t)(bj0 + g) * 3;
-        rel_s[t * 4 + 0] = __fsub_rn(x[0], c[0]);
-        rel_s[t * 4 + 1] = __fsub_rn(x[1], c[1]);
-        rel_s[t * 4 + 2] = __fsub_rn(x[2], c[2]);
-    }
-    __syncthreads();
-}
-
-// y0 of one row for the lane's channel: same FMA chain as sa_gather_l0_kernel (elementwise.cu)
-__device__ __forceinline__ float y0_row(const SaLevelP &p, int s_off, int src, const float *rel, const float (&wx)[3]) {
-    const float uv = p.u ? __ldg(p.u + (size_t)src * p.ldu + s_off) : 0.f;
-    return __fmaf_rn(wx[0], rel[0], __fmaf_rn(wx[1], rel[1], __fmaf_rn(wx[2], rel[2], uv)));
-}
-
+// ---- per-lane BatchNorm parameters
 struct LaneBn {
     float m, s, g, b;
 };
@@ -212,109 +97,253 @@ __device__ __forceinline__ LaneBn lane_bn(const SaBn &bn, int c, bool ok) {
     if (ok && bn.mean) { r.m = bn.mean[c]; r.s = bn.invstd[c]; r.g = bn.gamma[c]; r.b = bn.beta[c]; }
     return r;
 }
+template <int K>
+__device__ __forceinline__ void load_row(float (&w)[K], const float *src, int stride, bool ok) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) w[k] = ok ? __ldg(src + (size_t)k * stride) : 0.f;
+}
+// Weight matrix W[CO][CI] (row-major, global) -> shared memory TRANSPOSED wT[ci*CO + co]: lane co then reads its row with
+// consecutive-bank (conflict-free) loads.  Loading a row per lane straight from global memory touches 32 cache lines per
+// instruction; repeated per 16-row tile that made the first warp-autonomous version L1-bound (profiles/r2_sa_fused_v2_launches.txt).
+template <int CO, int CI>
+__device__ __forceinline__ void stage_weight_t(float *wT, const float *__restrict__ w) {
+    for (int i = threadIdx.x; i < CO * CI; i += blockDim.x) {
+        const int co = i / CI, ci = i - co * CI;
+        wT[ci * CO + co] = __ldg(w + i);
+    }
+}
+template <int K>
+__device__ __forceinline__ void load_row_t(float (&w)[K], const float *wT, int CO, int co, bool ok) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) w[k] = ok ? wT[k * CO + co] : 0.f;
+}
+// y0 of one row for the lane's channel: same FMA chain as sa_gather_l0_kernel (elementwise.cu)
+__device__ __forceinline__ float y0_val(float uv, const float *rel, const float (&wx)[3]) {
+    return __fmaf_rn(wx[0], rel[0], __fmaf_rn(wx[1], rel[1], __fmaf_rn(wx[2], rel[2], uv)));
+}
 
-// cross-warp combine of per-lane partial sums: warp w, quantity a, lane -> red[(w*3 + a)*64 + slot]; then fixed-order sum over
-// the warps that own channel c and one partial row per CTA.
-template <int NACC>
-__device__ __forceinline__ void flush_lane_sums(float *red, const float (&acc)[NACC], int slot, bool ok, int C, int nslices, float *part, int cta, int G) {
-    // slot = channel index this lane owns; warps with the same (warp % nslices) own the same channels
-    const int warp = threadIdx.x >> 5;
+constexpr int kTileRows = 16;  // rows a warp works on at a time: one neighbourhood of 16, or half of one of 32
+
+// The 16 rows [l0, l0 + 16) of neighbourhood bj: point rows and relative coordinates into the warp's shared-memory slots.
+// `cloud` is the instance's point cloud in shared memory ([k*3 + d]: a stride of 3 words is conflict-free, while the same
+// access pattern on global memory costs 12 sectors per load and made the ball query L1-bound).
+__device__ __forceinline__ void tile_geometry(const SaLevelP &p, const float *cloud, int b, int bj, const int *idx16, int *src_s, float *rel_s) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    if (lane < kTileRows) {
+        const int k = idx16[lane];
+        src_s[lane] = b * p.N + k;
+        const float *c = p.new_xyz + (size_t)bj * 3;
+        rel_s[lane * 4 + 0] = __fsub_rn(cloud[k * 3 + 0], __ldg(c + 0));
+        rel_s[lane * 4 + 1] = __fsub_rn(cloud[k * 3 + 1], __ldg(c + 1));
+        rel_s[lane * 4 + 2] = __fsub_rn(cloud[k * 3 + 2], __ldg(c + 2));
+    }
+    __syncwarp();
+}
+// all threads of the CTA: instance b's cloud -> shared memory (barriers on both sides)
+__device__ __forceinline__ void stage_cloud(const SaLevelP &p, int b, float *cloud) {
+    __syncthreads();
+    const float *src = p.xyz + (size_t)b * p.N * 3;
+    for (int i = threadIdx.x; i < p.N * 3; i += blockDim.x) cloud[i] = __ldg(src + i);
+    __syncthreads();
+}
+// layer 0 of the 16 rows for the lane's channel: y[r] (the u gathers of all rows are issued before the first use)
+__device__ __forceinline__ void tile_y0(const SaLevelP &p, int s_off, bool ok, const int *src_s, const float *rel_s, const float (&wx)[3], float (&y)[kTileRows]) {
+    float uv[kTileRows];
+#pragma unroll
+    for (int r = 0; r < kTileRows; ++r) uv[r] = (ok && p.u) ? __ldg(p.u + (size_t)src_s[r] * p.ldu + s_off) : 0.f;
+#pragma unroll
+    for (int r = 0; r < kTileRows; ++r) y[r] = y0_val(uv[r], rel_s + r * 4, wx);
+}
+
+// Sum of per-lane partials over the CTA's warps (fixed order) into this CTA's partial row: lane l of every warp holds quantity a of
+// channel q*32 + l in acc[q][a].  red: >= nwarps * NACC * NQ * 32 floats of shared memory.
+template <int NACC, int NQ>
+__device__ __forceinline__ void flush_sums(float *red, const float (&acc)[NQ][NACC], int C, float *part, int cta, int G) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     __syncthreads();
 #pragma unroll
-    for (int a = 0; a < NACC; ++a) red[(warp * 3 + a) * 64 + (threadIdx.x & 31)] = ok ? acc[a] : 0.f;
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) red[((warp * NACC + a) * NQ + q) * 32 + lane] = acc[q][a];
     __syncthreads();
-    for (int i = threadIdx.x; i < NACC * C; i += kThreads) {
+    for (int i = threadIdx.x; i < NACC * C; i += blockDim.x) {
         const int a = i / C, c = i - a * C;
-        const int sl = c >> 5, ln = c & 31;
         float t = 0.f;
-        for (int w = sl; w < kWarps; w += nslices) t += red[(w * 3 + a) * 64 + ln];
+        for (int w = 0; w < nwarps; ++w) t += red[((w * NACC + a) * NQ + (c >> 5)) * 32 + (c & 31)];
         part[((size_t)a * G + cta) * C + c] = t;
     }
-    (void)slot;
 }
 
 // ------------------------------------------------------------------------------------------------ forward
 // PASS 0: layer-0 statistics;  PASS 1: layer-1 statistics;  PASS 2: layer-2 statistics + selection.  QUERY: run the ball query.
-template <int C0, int C1, int C2, int GT, int PASS, bool QUERY>
-__global__ void __launch_bounds__(kThreads, 2) sa_fwd_kernel(const SaLevelP p) {
-    extern __shared__ __align__(16) float sa_smem[];
-    Smem<C0, C1, C2, GT> sm(sa_smem, p.N, QUERY, false);
-    const TileCtx tc = tile_ctx<GT>(p);
-    const SaScale &sc = p.sc[tc.s];
+// Warp-autonomous: a warp takes one centroid, scans the cloud ONCE for both radii, then runs the two neighbourhoods (16 and 32
+// rows) through the layers in 16-row tiles held in its own shared-memory slots.  No block-wide barrier until the final flush of
+// the statistics, so the warps of an SM drift apart and hide each other's gather / shared-memory latencies.
+constexpr int kFwdThreads = 256;
+template <int C0, int C1, int C2, int PASS, bool QUERY>
+__global__ void __launch_bounds__(kFwdThreads, 2) sa_fwd_kernel(const SaLevelP p) {
+    static_assert(C0 <= 32 && C1 <= 32 && C2 % 32 == 0 && C2 <= 64, "fused set abstraction: narrow levels only");
+    constexpr int NW = kFwdThreads / 32;
+    constexpr int NS2 = C2 / 32;
+    constexpr int WF = 48 + 16 + 64 + kTileRows * C0 + kTileRows * C1;  // floats of shared memory per warp
+    constexpr int WT = C0 * C1 + C1 * C2;                                // transposed weights of one scale
+    extern __shared__ __align__(16) float smem_dyn[];
+    float *wts = smem_dyn;              // [2][WT]
+    float *smem = smem_dyn + 2 * WT;    // [NW][WF] + red
+    float *cloud = smem + NW * WF + NW * 2 * NS2 * 32;  // [N*3]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ns = tc.ns;
-    static_assert(C0 <= 32 && C1 <= 32 && C2 % 32 == 0 && C2 <= 64 && GT == kWarps, "fused set abstraction: narrow levels only");
-    constexpr int NS2 = C2 / 32;  // channel slices of layer 2
-    // lane-resident weights / BatchNorm parameters
+    if (PASS >= 1) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            stage_weight_t<C1, C0>(wts + s * WT, p.sc[s].w1);
+            if (PASS >= 2) stage_weight_t<C2, C1>(wts + s * WT + C0 * C1, p.sc[s].w2);
+        }
+        __syncthreads();
+    }
+    float *ws = smem + warp * WF;
+    int *idx_s = reinterpret_cast<int *>(ws);        // [48]: scale 0 rows 0..15, scale 1 rows 16..47
+    int *src_s = reinterpret_cast<int *>(ws + 48);   // [16]
+    float *rel_s = ws + 64;                          // [16][4]
+    float *z0 = ws + 128;                            // [16][C0]
+    float *z1 = z0 + kTileRows * C0;                 // [16][C1]
+    float *red = smem + NW * WF;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int BM = p.B * p.M;
+    const int per = (BM + G - 1) / G;
+    const int j_begin = min(BM, cta * per), j_end = min(BM, j_begin + per);
     const bool ok0 = lane < C0, ok1 = lane < C1;
-    float wx[3] = {0.f, 0.f, 0.f};
-    if (ok0) { wx[0] = sc.w0[(size_t)lane * sc.ldw0]; wx[1] = sc.w0[(size_t)lane * sc.ldw0 + 1]; wx[2] = sc.w0[(size_t)lane * sc.ldw0 + 2]; }
-    const LaneBn b0 = lane_bn(sc.bn0, lane, ok0 && PASS >= 1);
-    float w1[C0];
+    const float r2a = __fmul_rn(p.sc[0].radius, p.sc[0].radius), r2b = __fmul_rn(p.sc[1].radius, p.sc[1].radius);  // ball_query_gpu.cu:27
+    const unsigned lt_mask = (1u << lane) - 1u;
+    float acc[2][NS2][2];  // [scale][slice][sum, sum of squares] of the pass's layer for the lane's channel(s)
 #pragma unroll
-    for (int k = 0; k < C0; ++k) w1[k] = (PASS >= 1 && ok1) ? sc.w1[(size_t)lane * C0 + k] : 0.f;
-    const LaneBn b1 = lane_bn(sc.bn1, lane, ok1 && PASS >= 2);
-    const int c2 = (warp % NS2) * 32 + lane;  // layer-2 channel of this lane
-    float w2[C1];
+    for (int s = 0; s < 2; ++s)
 #pragma unroll
-    for (int k = 0; k < C1; ++k) w2[k] = (PASS >= 2) ? sc.w2[(size_t)c2 * C1 + k] : 0.f;
-    const bool pick_max = (PASS >= 2 && sc.bn2.gamma) ? (sc.bn2.gamma[c2] >= 0.f) : true;
-    float acc[2] = {0.f, 0.f};  // sum, sum of squares of the pass's layer for the lane's channel
-    int cur_b = -1;
-    for (int tile = tc.t_begin; tile < tc.t_end; ++tile) {
-        tile_rows<GT, QUERY>(p, sc, tile, cur_b, sm.cloud, sm.idx, sm.src, sm.rel);
-        const int bj0 = tile * GT;
-        // ---- layer 0: warp = neighbourhood, lane = channel
-        {
-            const int r0 = warp * ns;
-            if (ok0) {
-                for (int l = 0; l < ns; ++l) {
-                    const float y = y0_row(p, tc.s * C0 + lane, sm.src[r0 + l], sm.rel + (r0 + l) * 4, wx);
-                    if (PASS == 0) { acc[0] += y; acc[1] += y * y; }
-                    else sm.z0[(r0 + l) * C0 + lane] = fmaxf(bn_apply(y, b0.m, b0.s, b0.g, b0.b), 0.f);
+        for (int q = 0; q < NS2; ++q) acc[s][q][0] = acc[s][q][1] = 0.f;
+
+    for (int seg = j_begin; seg < j_end;) {  // the CTA's centroids, one instance at a time (its cloud staged in shared memory)
+    const int b = seg / p.M;
+    const int seg_end = min(j_end, (b + 1) * p.M);
+    stage_cloud(p, b, cloud);
+    for (int bj = seg + warp; bj < seg_end; bj += NW) {
+        __syncwarp();
+        if (QUERY) {
+            const float *q = p.new_xyz + (size_t)bj * 3;
+            const float cx = __ldg(q), cy = __ldg(q + 1), cz = __ldg(q + 2);
+            int32_t *out0 = p.sc[0].idx + (size_t)bj * 16, *out1 = p.sc[1].idx + (size_t)bj * 32;
+            int cnt0 = 0, cnt1 = 0, first0 = 0, first1 = 0;
+            for (int base = 0; base < p.N && (cnt0 < 16 || cnt1 < 32); base += 32) {
+                const int k = base + lane;
+                bool h0 = false, h1 = false;
+                if (k < p.N) {
+                    const float d2 = sqdist_ref(__fsub_rn(cx, cloud[k * 3 + 0]), __fsub_rn(cy, cloud[k * 3 + 1]), __fsub_rn(cz, cloud[k * 3 + 2]));
+                    h0 = d2 < r2a;
+                    h1 = d2 < r2b;
+                }
+                const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+                if (cnt0 < 16 && m0) {  // the reference stops looking once nsample hits are stored (ball_query_gpu.cu:34-46)
+                    if (cnt0 == 0) first0 = base + __ffs(m0) - 1;
+                    const int pos = cnt0 + __popc(m0 & lt_mask);
+                    if (h0 && pos < 16) { out0[pos] = k; idx_s[pos] = k; }
+                    cnt0 += __popc(m0);
+                }
+                if (cnt1 < 32 && m1) {
+                    if (cnt1 == 0) first1 = base + __ffs(m1) - 1;
+                    const int pos = cnt1 + __popc(m1 & lt_mask);
+                    if (h1 && pos < 32) { out1[pos] = k; idx_s[16 + pos] = k; }
+                    cnt1 += __popc(m1);
                 }
             }
+            // tail: the reference pre-fills the row with the first hit (ball_query_gpu.cu:39-43); no hit => zeros
+            for (int l = min(cnt0, 16) + lane; l < 16; l += 32) { out0[l] = first0; idx_s[l] = first0; }
+            for (int l = min(cnt1, 32) + lane; l < 32; l += 32) { out1[l] = first1; idx_s[16 + l] = first1; }
+        } else {
+            if (lane < 16) idx_s[lane] = p.sc[0].idx[(size_t)bj * 16 + lane];
+            idx_s[16 + lane] = p.sc[1].idx[(size_t)bj * 32 + lane];
         }
-        if (PASS == 0) continue;
-        __syncwarp();  // layer 1 of this warp reads only the rows this warp wrote
-        {
-            const int r0 = warp * ns;
-            if (ok1) {
-                for (int l = 0; l < ns; ++l) {
-                    const float y = row_dot<C0>(sm.z0 + (r0 + l) * C0, w1);
-                    if (PASS == 1) { acc[0] += y; acc[1] += y * y; }
-                    else sm.z1[(r0 + l) * C1 + lane] = fmaxf(bn_apply(y, b1.m, b1.s, b1.g, b1.b), 0.f);
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const SaScale &sc = p.sc[s];
+            float wx[3] = {0.f, 0.f, 0.f};
+            if (ok0) { wx[0] = __ldg(sc.w0 + (size_t)lane * sc.ldw0); wx[1] = __ldg(sc.w0 + (size_t)lane * sc.ldw0 + 1); wx[2] = __ldg(sc.w0 + (size_t)lane * sc.ldw0 + 2); }
+            const LaneBn b0 = lane_bn(sc.bn0, lane, ok0 && PASS >= 1);
+            const LaneBn b1 = lane_bn(sc.bn1, lane, ok1 && PASS >= 2);
+            float best[NS2];
+            int bi[NS2];
+#pragma unroll
+            for (int q = 0; q < NS2; ++q) { best[q] = 0.f; bi[q] = 0; }
+            for (int h = 0; h <= s; ++h) {  // scale 0: one 16-row tile; scale 1: two
+                tile_geometry(p, cloud, b, bj, idx_s + s * 16 + h * kTileRows, src_s, rel_s);
+                {
+                    float y[kTileRows];
+                    tile_y0(p, s * C0 + lane, ok0, src_s, rel_s, wx, y);
+                    if (ok0) {
+#pragma unroll
+                        for (int r = 0; r < kTileRows; ++r) {
+                            if (PASS == 0) { acc[s][0][0] += y[r]; acc[s][0][1] += y[r] * y[r]; }
+                            else z0[r * C0 + lane] = fmaxf(bn_apply(y[r], b0.m, b0.s, b0.g, b0.b), 0.f);
+                        }
+                    }
+                }
+                if (PASS == 0) continue;
+                __syncwarp();
+                {
+                    float w1[C0];
+                    load_row_t<C0>(w1, wts + s * WT, C1, lane, ok1);
+                    if (ok1) {
+#pragma unroll 4
+                        for (int r = 0; r < kTileRows; ++r) {
+                            const float y = row_dot<C0>(z0 + r * C0, w1);
+                            if (PASS == 1) { acc[s][0][0] += y; acc[s][0][1] += y * y; }
+                            else z1[r * C1 + lane] = fmaxf(bn_apply(y, b1.m, b1.s, b1.g, b1.b), 0.f);
+                        }
+                    }
+                }
+                if (PASS == 1) continue;
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < NS2; ++q) {
+                    const int c2 = q * 32 + lane;
+                    float w2[C1];
+                    load_row_t<C1>(w2, wts + s * WT + C0 * C1, C2, c2, true);
+                    const bool pick_max = __ldg(sc.bn2.gamma + c2) >= 0.f;
+#pragma unroll 4
+                    for (int r = 0; r < kTileRows; ++r) {
+                        const float y = row_dot<C1>(z1 + r * C1, w2);
+                        acc[s][q][0] += y; acc[s][q][1] += y * y;
+                        const int l = h * kTileRows + r;
+                        const bool take = (l == 0) || (pick_max ? (y > best[q]) : (y < best[q]));  // strict: the first extreme wins (max_pool2d)
+                        if (take) { best[q] = y; bi[q] = l; }
+                    }
                 }
             }
-        }
-        if (PASS == 1) continue;
-        __syncthreads();  // with two channel slices a warp reads neighbourhoods written by other warps
-        for (int g = warp / NS2; g < GT; g += kWarps / NS2) {
-            const int r0 = g * ns;
-            float best = 0.f;
-            int bi = 0;
-            for (int l = 0; l < ns; ++l) {
-                const float y = row_dot<C1>(sm.z1 + (r0 + l) * C1, w2);
-                acc[0] += y; acc[1] += y * y;
-                const bool take = (l == 0) || (pick_max ? (y > best) : (y < best));  // strict: the first extreme wins (max_pool2d)
-                if (take) { best = y; bi = l; }
+            if (PASS == 2) {
+#pragma unroll
+                for (int q = 0; q < NS2; ++q) {
+                    sc.ysel[(size_t)bj * C2 + q * 32 + lane] = best[q];
+                    sc.asel[(size_t)bj * C2 + q * 32 + lane] = (uint8_t)bi[q];
+                }
             }
-            sc.ysel[(size_t)(bj0 + g) * C2 + c2] = best;
-            sc.asel[(size_t)(bj0 + g) * C2 + c2] = (uint8_t)bi;
         }
     }
-    if (sc.part == nullptr) return;  // running statistics (eval): nothing to reduce
+    seg = seg_end;
+    }
     constexpr int CS = PASS == 0 ? C0 : (PASS == 1 ? C1 : C2);
-    constexpr int NSL = PASS == 2 ? NS2 : 1;
-    flush_lane_sums<2>(sm.red, acc, 0, PASS == 0 ? ok0 : (PASS == 1 ? ok1 : true), CS, NSL, sc.part, tc.cta, tc.G);
-    ticket_finish<2>(sc.fin, sc.part, tc.G, CS, tc.cta);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const SaScale &sc = p.sc[s];
+        if (sc.part == nullptr) continue;  // running statistics (eval): nothing to reduce
+        flush_sums<2, NS2>(red, acc[s], CS, sc.part, cta, G);
+        ticket_finish<2>(sc.fin, sc.part, G, CS, cta);
+    }
 }
 
 // out[bj][off + c] = relu(bn2(ysel[bj][c])) for both scales
 template <int C2>
-__global__ void __launch_bounds__(kThreads) sa_final_kernel(int BM, SaScale s0, SaScale s1, float *out, int ld_out) {
+__global__ void __launch_bounds__(256) sa_final_kernel(int BM, SaScale s0, SaScale s1, float *out, int ld_out) {
     const int total = BM * 2 * C2;
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int c = i % (2 * C2), bj = i / (2 * C2);
         const SaScale &sc = c < C2 ? s0 : s1;
         const int cc = c < C2 ? c : c - C2;
@@ -324,131 +353,153 @@ __global__ void __launch_bounds__(kThreads) sa_final_kernel(int BM, SaScale s0, 
 }
 
 // ------------------------------------------------------------------------------------------------ backward
+// The CTAs of a backward launch are split between the two scales (cta0 / ncta) because the weight-gradient accumulators of a
+// scale live in registers for the whole kernel.
+struct BwdCtx {
+    int s, cta, G;
+};
+__device__ __forceinline__ BwdCtx bwd_ctx(const SaLevelP &p) {
+    BwdCtx c;
+    c.s = ((int)blockIdx.x >= p.sc[1].cta0 && p.sc[1].ncta > 0) ? 1 : 0;
+    c.cta = (int)blockIdx.x - p.sc[c.s].cta0;
+    c.G = p.sc[c.s].ncta;
+    return c;
+}
 // pre: BatchNorm-backward sums of layer 2.  The gradient of the max over the neighbours is non-zero on one row per (centroid,
 // channel), so sum g and sum g*xhat run over [B*M, C2] values only: g = dz * [bn2(ysel) > 0], xhat = (ysel - mean) * invstd.
 template <int C2>
-__global__ void __launch_bounds__(kThreads, 2) sa_bwd_pre_kernel(const SaLevelP p) {
-    __shared__ float red[kWarps * 3 * 64];
-    const int s = ((int)blockIdx.x >= p.sc[1].cta0 && p.sc[1].ncta > 0) ? 1 : 0;
-    const SaScale &sc = p.sc[s];
-    const int cta = (int)blockIdx.x - sc.cta0, G = sc.ncta;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256, 2) sa_bwd_pre_kernel(const SaLevelP p) {
     constexpr int NS2 = C2 / 32;
-    const int c = (warp % NS2) * 32 + lane;
-    const LaneBn b2 = lane_bn(sc.bn2, c, true);
-    float acc[3] = {0.f, 0.f, 0.f};
+    __shared__ float red[8 * 3 * NS2 * 32];
+    const BwdCtx bc = bwd_ctx(p);
+    const SaScale &sc = p.sc[bc.s];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc[NS2][3];
+    LaneBn b2[NS2];
+#pragma unroll
+    for (int q = 0; q < NS2; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = 0.f; b2[q] = lane_bn(sc.bn2, q * 32 + lane, true); }
     const int BM = p.B * p.M;
-    for (int bj = cta * (kWarps / NS2) + warp / NS2; bj < BM; bj += G * (kWarps / NS2)) {
-        const float y = sc.ysel[(size_t)bj * C2 + c];
-        const float xh = __fmul_rn(__fsub_rn(y, b2.m), b2.s);
-        const float u = __fmaf_rn(xh, b2.g, b2.b);
-        const float g = u > 0.f ? sc.dz[(size_t)bj * sc.ld_dz + sc.off_dz + c] : 0.f;
-        acc[0] += g;
-        acc[1] += g * xh;
+    for (int bj = bc.cta * 8 + warp; bj < BM; bj += bc.G * 8) {
+#pragma unroll
+        for (int q = 0; q < NS2; ++q) {
+            const int c = q * 32 + lane;
+            const float y = sc.ysel[(size_t)bj * C2 + c];
+            const float xh = __fmul_rn(__fsub_rn(y, b2[q].m), b2[q].s);
+            const float u = __fmaf_rn(xh, b2[q].g, b2[q].b);
+            const float g = u > 0.f ? sc.dz[(size_t)bj * sc.ld_dz + sc.off_dz + c] : 0.f;
+            acc[q][0] += g;
+            acc[q][1] += g * xh;
+        }
     }
-    flush_lane_sums<3>(red, acc, 0, true, C2, NS2, sc.part, cta, G);
-    ticket_finish<3>(sc.fin, sc.part, G, C2, cta);
+    flush_sums<3, NS2>(red, acc, C2, sc.part, bc.cta, bc.G);
+    ticket_finish<3>(sc.fin, sc.part, bc.G, C2, bc.cta);
 }
 
 // Weight-gradient accumulators of one warp (lane = input channel ci < CI, one register per output channel co < CO) are combined
-// across the CTA's warps in a fixed order and written as this CTA's partial row; the scale's last CTA sums the rows (two-level
-// ticket reduction) into dw[co*ld + ci].
+// across the CTA's warps in a fixed order and written as this CTA's partial row part[cta][co*CI + ci]; the launcher then sums the
+// rows with the channel-parallel finalize kernel (a CO*CI-wide reduction is too long for a one-CTA tail).
 template <int CO, int CI>
-__device__ void flush_weight_grad(float *scratch /* >= kWarps*CO*CI floats of shared memory */, const float (&aw)[CO], bool ok, float *part, unsigned *tickets,
-                                  int cta, int G, float *dw, int ld) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ void flush_weight_grad(float *scratch /* >= nwarps*CO*CI floats of shared memory */, const float (&aw)[CO], bool ok, float *part, int cta) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    constexpr int CW = CO * CI;
     __syncthreads();
     if (ok) {
 #pragma unroll
-        for (int co = 0; co < CO; ++co) scratch[((size_t)warp * CO + co) * CI + lane] = aw[co];
+        for (int co = 0; co < CO; ++co) scratch[(size_t)warp * CW + co * CI + lane] = aw[co];
     }
     __syncthreads();
-    constexpr int CW = CO * CI;
-    for (int i = threadIdx.x; i < CW; i += kThreads) {
+    for (int i = threadIdx.x; i < CW; i += blockDim.x) {
         float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) t += scratch[(size_t)w * CW + i];
+        for (int w = 0; w < nwarps; ++w) t += scratch[(size_t)w * CW + i];
         part[(size_t)cta * CW + i] = t;
-    }
-    float *part2 = part + (size_t)kMaxPartialRows * CW;
-    if (!ticket_reduce<1>(part, cta, G, CW, tickets, part2)) return;
-    for (int i = threadIdx.x; i < CW; i += kThreads) {
-        const int co = i / CI, ci = i - co * CI;
-        dw[(size_t)co * ld + ci] = (float)ticket_total(part2, G, CW, 0, i);
     }
 }
 
 // STAGE 0 ("A"): layer 2: dy2 = BN-backward of the max-routed gradient; g1 = (dy2 W2) * [z1 > 0] -> sc.g1, sums of layer 1, dW2.
 // STAGE 1 ("B"): layer 1: dy1 from g1; g0 = (dy1 W1) * [z0 > 0] -> sc.g0, sums of layer 0, dW1.
 // STAGE 2 ("C"): layer 0: dy0 from g0; dU[point] += dy0 (atomics, as group_points_grad), dWx.
-// Weight rows / columns are (re)loaded from global memory (L1-resident, <= 8 KB) at the start of the phase that uses them, so that
-// only the weight-gradient accumulators live in registers across a tile.
-template <int K>
-__device__ __forceinline__ void load_row(float (&w)[K], const float *src, int stride, bool ok) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) w[k] = ok ? __ldg(src + (size_t)k * stride) : 0.f;
-}
-template <int C0, int C1, int C2, int GT, int STAGE>
-__global__ void __launch_bounds__(kThreads, (C2 <= 32 ? 2 : 1)) sa_bwd_kernel(const SaLevelP p) {
-    extern __shared__ __align__(16) float sa_smem[];
-    Smem<C0, C1, C2, GT> sm(sa_smem, p.N, false, true);
-    const TileCtx tc = tile_ctx<GT>(p);
-    const SaScale &sc = p.sc[tc.s];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ns = tc.ns, T = tc.T;
-    const double invP = 1.0 / ((double)p.B * p.M * ns);
-    static_assert(C0 <= C1 && C1 <= 32 && C2 % 32 == 0 && C2 <= 64 && (GT * 16) % kWarps == 0, "fused set abstraction: narrow levels only");
+// Warp-autonomous 16-row tiles like the forward pass.  Weight rows / columns are (re)loaded from global memory (L1-resident,
+// <= 8 KB) at the start of the phase that uses them, so that only the weight-gradient accumulators live in registers for the
+// whole kernel.
+constexpr int kBwdThreads = 128;
+template <int C0, int C1, int C2, int STAGE>
+__global__ void __launch_bounds__(kBwdThreads, 3) sa_bwd_kernel(const SaLevelP p) {
+    static_assert(C0 <= C1 && C1 <= 32 && C2 % 32 == 0 && C2 <= 64, "fused set abstraction: narrow levels only");
+    constexpr int NW = kBwdThreads / 32;
     constexpr int NS2 = C2 / 32;
+    constexpr int WF = 16 + 64 + kTileRows * (C0 + 2 * C1 + C2);  // floats of shared memory per warp
+    constexpr int CWMAX = C2 * C1;
+    constexpr int SF = (NW * WF > NW * CWMAX ? NW * WF : NW * CWMAX);
+    constexpr int WT = C0 * C1 + C1 * C2;  // transposed weights of this CTA's scale
+    extern __shared__ __align__(16) float smem_dyn[];
+    float *w1T = smem_dyn, *w2T = smem_dyn + C0 * C1;
+    float *smem = smem_dyn + WT;  // [SF] tiles / weight-gradient scratch + red
+    float *cloud = smem + SF + NW * 3 * 32;  // [N*3]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *ws = smem + warp * WF;
+    int *src_s = reinterpret_cast<int *>(ws);  // [16]
+    float *rel_s = ws + 16;                    // [16][4]
+    float *z0 = ws + 80;                       // [16][C0]
+    float *y1 = z0 + kTileRows * C0;           // [16][C1]  (stage 1: y0 parked here)
+    float *z1 = y1 + kTileRows * C1;           // [16][C1]
+    float *d2 = z1 + kTileRows * C1;           // [16][C2]  (stage 1: dy1 [16][C1])
+    float *red = smem + SF;
+    const BwdCtx bc = bwd_ctx(p);
+    const SaScale &sc = p.sc[bc.s];
+    const int ns = sc.ns, tiles_per_group = ns / kTileRows;
+    const int n_tiles = p.B * p.M * tiles_per_group;
+    const int per = (n_tiles + bc.G - 1) / bc.G;
+    const int t_begin = min(n_tiles, bc.cta * per), t_end = min(n_tiles, t_begin + per);
+    const double invP = 1.0 / ((double)p.B * p.M * ns);
     const bool ok0 = lane < C0, ok1 = lane < C1;
     float wx[3] = {0.f, 0.f, 0.f};
     if (ok0) { wx[0] = sc.w0[(size_t)lane * sc.ldw0]; wx[1] = sc.w0[(size_t)lane * sc.ldw0 + 1]; wx[2] = sc.w0[(size_t)lane * sc.ldw0 + 2]; }
     const LaneBn b0 = lane_bn(sc.bn0, lane, ok0);
     const LaneBn b1 = lane_bn(sc.bn1, lane, ok1);
-    const int rows_w = T / kWarps;  // rows of the tile owned by this warp in the row-parallel phases
-    const int rw0 = warp * rows_w;
-    int cur_b = -1;
+    if (STAGE <= 1) {
+        stage_weight_t<C1, C0>(w1T, sc.w1);
+        if (STAGE == 0) stage_weight_t<C2, C1>(w2T, sc.w2);
+        __syncthreads();
+    }
 
     if (STAGE == 2) {
         // ---------------- layer 0: BatchNorm backward, scatter to the points, dWx
         const float mg = ok0 ? (float)(sc.ws0[lane] * invP) : 0.f, mgx = ok0 ? (float)(sc.ws0[C0 + lane] * invP) : 0.f;
-        float aw[3] = {0.f, 0.f, 0.f};
-        for (int tile = tc.t_begin; tile < tc.t_end; ++tile) {
-            tile_rows<GT, false>(p, sc, tile, cur_b, sm.cloud, sm.idx, sm.src, sm.rel);
-            const size_t row0 = (size_t)tile * T;
+        float aw[1][3] = {{0.f, 0.f, 0.f}};
+        for (int seg = t_begin; seg < t_end;) {  // the CTA's tiles, one instance at a time (its cloud staged in shared memory)
+        const int b = seg / (p.M * tiles_per_group);
+        const int seg_end = min(t_end, (b + 1) * p.M * tiles_per_group);
+        stage_cloud(p, b, cloud);
+        for (int tile = seg + warp; tile < seg_end; tile += NW) {
+            const int bj = tile / tiles_per_group, l0 = (tile - bj * tiles_per_group) * kTileRows;
+            const size_t row0 = (size_t)bj * ns + l0;
+            __syncwarp();
+            if (lane < kTileRows) d2[lane] = __int_as_float(sc.idx[row0 + lane]);
+            tile_geometry(p, cloud, b, bj, reinterpret_cast<const int *>(d2), src_s, rel_s);
+            float y[kTileRows], g[kTileRows];
+            tile_y0(p, bc.s * C0 + lane, ok0, src_s, rel_s, wx, y);
+#pragma unroll
+            for (int r = 0; r < kTileRows; ++r) g[r] = ok0 ? __ldg(sc.g0 + (row0 + r) * C0 + lane) : 0.f;
             if (ok0) {
-                for (int r = rw0; r < rw0 + rows_w; ++r) {
-                    const float *rel = sm.rel + r * 4;
-                    const int src = sm.src[r];
-                    const float y = y0_row(p, tc.s * C0 + lane, src, rel, wx);
-                    const float xh = __fmul_rn(__fsub_rn(y, b0.m), b0.s);
-                    const float g = sc.g0[(row0 + r) * C0 + lane];
-                    const float dy = b0.g * b0.s * (g - mg - xh * mgx);
-                    aw[0] += dy * rel[0]; aw[1] += dy * rel[1]; aw[2] += dy * rel[2];
-                    if (p.dU) atomicAdd(p.dU + (size_t)src * p.ldu + tc.s * C0 + lane, dy);
+#pragma unroll
+                for (int r = 0; r < kTileRows; ++r) {
+                    const float xh = __fmul_rn(__fsub_rn(y[r], b0.m), b0.s);
+                    const float dy = b0.g * b0.s * (g[r] - mg - xh * mgx);
+                    aw[0][0] += dy * rel_s[r * 4 + 0]; aw[0][1] += dy * rel_s[r * 4 + 1]; aw[0][2] += dy * rel_s[r * 4 + 2];
+                    if (p.dU) atomicAdd(p.dU + (size_t)src_s[r] * p.ldu + bc.s * C0 + lane, dy);
                 }
             }
         }
-        // dWx[c][d]: lane = c, 3 values -> dw[c*ld + d]
-        float *scratch = sm.z0;
-        __syncthreads();
-        if (ok0) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) scratch[(warp * 3 + d) * 32 + lane] = aw[d];
+        seg = seg_end;
         }
-        __syncthreads();
-        constexpr int CW = 3 * C0;
-        for (int i = threadIdx.x; i < CW; i += kThreads) {
-            const int c = i / 3, d = i - c * 3;
-            float t = 0.f;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) t += scratch[(w * 3 + d) * 32 + c];
-            sc.part_w[(size_t)tc.cta * CW + i] = t;
-        }
+        // dWx[c][d] -> dw[c*ld + d]: per-CTA partial laid out [d][c] (quantity d, channel c), finished by the scale's last CTA
+        constexpr int CW = 3 * 32;
         float *part2 = sc.part_w + (size_t)kMaxPartialRows * CW;
-        if (!ticket_reduce<1>(sc.part_w, tc.cta, tc.G, CW, sc.tickets_w, part2)) return;
-        for (int i = threadIdx.x; i < CW; i += kThreads) {
+        flush_sums<3, 1>(red, aw, 32, sc.part_w, bc.cta, bc.G);  // part_w[(d*G + cta)*32 + c]
+        if (!ticket_reduce<3>(sc.part_w, bc.cta, bc.G, 32, sc.tickets_w, part2)) return;
+        for (int i = threadIdx.x; i < 3 * C0; i += blockDim.x) {
             const int c = i / 3, d = i - c * 3;
-            sc.dw[(size_t)c * sc.ld_dw + d] = (float)ticket_total(part2, tc.G, CW, 0, i);
+            sc.dw[(size_t)c * sc.ld_dw + d] = (float)ticket_total(part2, bc.G, 32, d, c);
         }
         return;
     }
@@ -456,31 +507,46 @@ __global__ void __launch_bounds__(kThreads, (C2 <= 32 ? 2 : 1)) sa_bwd_kernel(co
     if (STAGE == 1) {
         // ---------------- layer 1: dy1 from the stored g1; dz0 = dy1 W1; g0; sums of layer 0; dW1
         const float mg1 = ok1 ? (float)(sc.ws1[lane] * invP) : 0.f, mgx1 = ok1 ? (float)(sc.ws1[C1 + lane] * invP) : 0.f;
-        float acc[3] = {0.f, 0.f, 0.f};
+        float acc[1][3] = {{0.f, 0.f, 0.f}};
         float aw[C1];  // dW1[c1][c0] for the lane's c0
 #pragma unroll
         for (int k = 0; k < C1; ++k) aw[k] = 0.f;
-        float *dy1 = sm.d2;  // [T][C1]
-        for (int tile = tc.t_begin; tile < tc.t_end; ++tile) {
-            tile_rows<GT, false>(p, sc, tile, cur_b, sm.cloud, sm.idx, sm.src, sm.rel);
-            const size_t row0 = (size_t)tile * T;
-            if (ok0) {
-                for (int r = rw0; r < rw0 + rows_w; ++r) {
-                    const float y = y0_row(p, tc.s * C0 + lane, sm.src[r], sm.rel + r * 4, wx);
-                    sm.y1[r * C0 + lane] = y;  // y0 parked in the (otherwise unused) y1 buffer: [T][C0] <= [T][C1] floats... see host check C0 <= C1
-                    sm.z0[r * C0 + lane] = fmaxf(bn_apply(y, b0.m, b0.s, b0.g, b0.b), 0.f);
+        float *dy1 = d2;   // [16][C1]
+        float *y0s = y1;   // [16][C0]
+        for (int seg = t_begin; seg < t_end;) {  // the CTA's tiles, one instance at a time (its cloud staged in shared memory)
+        const int b = seg / (p.M * tiles_per_group);
+        const int seg_end = min(t_end, (b + 1) * p.M * tiles_per_group);
+        stage_cloud(p, b, cloud);
+        for (int tile = seg + warp; tile < seg_end; tile += NW) {
+            const int bj = tile / tiles_per_group, l0 = (tile - bj * tiles_per_group) * kTileRows;
+            const size_t row0 = (size_t)bj * ns + l0;
+            __syncwarp();
+            if (lane < kTileRows) z1[lane] = __int_as_float(sc.idx[row0 + lane]);
+            tile_geometry(p, cloud, b, bj, reinterpret_cast<const int *>(z1), src_s, rel_s);
+            {
+                float y[kTileRows];
+                tile_y0(p, bc.s * C0 + lane, ok0, src_s, rel_s, wx, y);
+                if (ok0) {
+#pragma unroll
+                    for (int r = 0; r < kTileRows; ++r) {
+                        y0s[r * C0 + lane] = y[r];
+                        z0[r * C0 + lane] = fmaxf(bn_apply(y[r], b0.m, b0.s, b0.g, b0.b), 0.f);
+                    }
                 }
             }
             __syncwarp();
             {
                 float w1[C0];  // row of W1 for the lane's output channel c1
-                load_row<C0>(w1, sc.w1 + (size_t)lane * C0, 1, ok1);
+                load_row_t<C0>(w1, w1T, C1, lane, ok1);
+                float g[kTileRows];
+#pragma unroll
+                for (int r = 0; r < kTileRows; ++r) g[r] = ok1 ? __ldg(sc.g1 + (row0 + r) * C1 + lane) : 0.f;
                 if (ok1) {
-                    for (int r = rw0; r < rw0 + rows_w; ++r) {
-                        const float y = row_dot<C0>(sm.z0 + r * C0, w1);
+#pragma unroll 4
+                    for (int r = 0; r < kTileRows; ++r) {
+                        const float y = row_dot<C0>(z0 + r * C0, w1);
                         const float xh = __fmul_rn(__fsub_rn(y, b1.m), b1.s);
-                        const float g = sc.g1[(row0 + r) * C1 + lane];
-                        dy1[r * C1 + lane] = b1.g * b1.s * (g - mg1 - xh * mgx1);
+                        dy1[r * C1 + lane] = b1.g * b1.s * (g[r] - mg1 - xh * mgx1);
                     }
                 }
             }
@@ -489,13 +555,14 @@ __global__ void __launch_bounds__(kThreads, (C2 <= 32 ? 2 : 1)) sa_bwd_kernel(co
                 float w1c[C1];  // column of W1 for the lane's input channel c0: dz0[c0] = sum_c1 dy1[c1] * W1[c1][c0]
                 load_row<C1>(w1c, sc.w1 + lane, C0, ok0);
                 if (ok0) {
-                    for (int r = rw0; r < rw0 + rows_w; ++r) {
+#pragma unroll 2
+                    for (int r = 0; r < kTileRows; ++r) {
                         const float dz0 = row_dot<C1>(dy1 + r * C1, w1c);
-                        const float z = sm.z0[r * C0 + lane];
+                        const float z = z0[r * C0 + lane];
                         const float g = z > 0.f ? dz0 : 0.f;
                         sc.g0[(row0 + r) * C0 + lane] = g;
-                        const float xh = __fmul_rn(__fsub_rn(sm.y1[r * C0 + lane], b0.m), b0.s);
-                        acc[0] += g; acc[1] += g * xh;
+                        const float xh = __fmul_rn(__fsub_rn(y0s[r * C0 + lane], b0.m), b0.s);
+                        acc[0][0] += g; acc[0][1] += g * xh;
 #pragma unroll
                         for (int k = 0; k < C1; k += 4) {  // dW1[:, c0] += dy1[r, :] * z0[r, c0]
                             const float4 v = *reinterpret_cast<const float4 *>(dy1 + r * C1 + k);
@@ -506,86 +573,111 @@ __global__ void __launch_bounds__(kThreads, (C2 <= 32 ? 2 : 1)) sa_bwd_kernel(co
                 }
             }
         }
-        flush_lane_sums<3>(sm.red, acc, 0, ok0, C0, 1, sc.part, tc.cta, tc.G);
-        ticket_finish<3>(sc.fin, sc.part, tc.G, C0, tc.cta);
-        flush_weight_grad<C1, C0>(sm.z0, aw, ok0, sc.part_w, sc.tickets_w, tc.cta, tc.G, sc.dw, sc.ld_dw);
+        seg = seg_end;
+        }
+        flush_sums<3, 1>(red, acc, C0, sc.part, bc.cta, bc.G);
+        ticket_finish<3>(sc.fin, sc.part, bc.G, C0, bc.cta);
+        flush_weight_grad<C1, C0>(smem, aw, ok0, sc.part_w, bc.cta);
         return;
     }
 
     // ---------------- STAGE 0: layer 2
     {
-        float acc[3] = {0.f, 0.f, 0.f};
+        float acc[1][3] = {{0.f, 0.f, 0.f}};
         float aw[C2];  // dW2[c2][c1] for the lane's c1
 #pragma unroll
         for (int k = 0; k < C2; ++k) aw[k] = 0.f;
-        // phase 3 (dy2) splits the tile by (channel slice, row block): warp -> slice q3, rows [r3, r3 + rows3)
-        const int q3 = warp % NS2, rows3 = T / (kWarps / NS2), r3 = (warp / NS2) * rows3;
-        const int c3 = q3 * 32 + lane;
-        const LaneBn b2 = lane_bn(sc.bn2, c3, true);
-        const float mg2 = (float)(sc.ws2[c3] * invP), mgx2 = (float)(sc.ws2[C2 + c3] * invP);
-        for (int tile = tc.t_begin; tile < tc.t_end; ++tile) {
-            tile_rows<GT, false>(p, sc, tile, cur_b, sm.cloud, sm.idx, sm.src, sm.rel);
-            const size_t row0 = (size_t)tile * T;
-            const int bj0 = tile * GT;
-            if (ok0) {
-                for (int r = rw0; r < rw0 + rows_w; ++r) {
-                    const float y = y0_row(p, tc.s * C0 + lane, sm.src[r], sm.rel + r * 4, wx);
-                    sm.z0[r * C0 + lane] = fmaxf(bn_apply(y, b0.m, b0.s, b0.g, b0.b), 0.f);
+        for (int seg = t_begin; seg < t_end;) {  // the CTA's tiles, one instance at a time (its cloud staged in shared memory)
+        const int b = seg / (p.M * tiles_per_group);
+        const int seg_end = min(t_end, (b + 1) * p.M * tiles_per_group);
+        stage_cloud(p, b, cloud);
+        for (int tile = seg + warp; tile < seg_end; tile += NW) {
+            const int bj = tile / tiles_per_group, l0 = (tile - bj * tiles_per_group) * kTileRows;
+            const size_t row0 = (size_t)bj * ns + l0;
+            __syncwarp();
+            if (lane < kTileRows) z1[lane] = __int_as_float(sc.idx[row0 + lane]);
+            tile_geometry(p, cloud, b, bj, reinterpret_cast<const int *>(z1), src_s, rel_s);
+            {
+                float y[kTileRows];
+                tile_y0(p, bc.s * C0 + lane, ok0, src_s, rel_s, wx, y);
+                if (ok0) {
+#pragma unroll
+                    for (int r = 0; r < kTileRows; ++r) z0[r * C0 + lane] = fmaxf(bn_apply(y[r], b0.m, b0.s, b0.g, b0.b), 0.f);
                 }
             }
             __syncwarp();
             {
                 float w1[C0];
-                load_row<C0>(w1, sc.w1 + (size_t)lane * C0, 1, ok1);
+                load_row_t<C0>(w1, w1T, C1, lane, ok1);
                 if (ok1) {
-                    for (int r = rw0; r < rw0 + rows_w; ++r) {
-                        const float y = row_dot<C0>(sm.z0 + r * C0, w1);
-                        sm.y1[r * C1 + lane] = y;
-                        sm.z1[r * C1 + lane] = fmaxf(bn_apply(y, b1.m, b1.s, b1.g, b1.b), 0.f);
+#pragma unroll 4
+                    for (int r = 0; r < kTileRows; ++r) {
+                        const float y = row_dot<C0>(z0 + r * C0, w1);
+                        y1[r * C1 + lane] = y;
+                        z1[r * C1 + lane] = fmaxf(bn_apply(y, b1.m, b1.s, b1.g, b1.b), 0.f);
                     }
                 }
             }
-            __syncthreads();
-            {
-                float w2[C1];  // row of W2 for the lane's layer-2 channel c3
-                load_row<C1>(w2, sc.w2 + (size_t)c3 * C1, 1, true);
-                for (int r = r3; r < r3 + rows3; ++r) {
-                    const int g = r / ns, l = r - g * ns;
-                    const float y = row_dot<C1>(sm.z1 + r * C1, w2);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < NS2; ++q) {
+                const int c2 = q * 32 + lane;
+                float w2[C1];  // row of W2 for the lane's layer-2 channel
+                load_row_t<C1>(w2, w2T, C2, c2, true);
+                const LaneBn b2 = lane_bn(sc.bn2, c2, true);
+                const float mg2 = (float)(sc.ws2[c2] * invP), mgx2 = (float)(sc.ws2[C2 + c2] * invP);
+                const int lsel = (int)sc.asel[(size_t)bj * C2 + c2] - l0;  // row of this tile that holds the selected neighbour (if any)
+                const float dzv = __ldg(sc.dz + (size_t)bj * sc.ld_dz + sc.off_dz + c2);
+#pragma unroll 4
+                for (int r = 0; r < kTileRows; ++r) {
+                    const float y = row_dot<C1>(z1 + r * C1, w2);
                     const float xh = __fmul_rn(__fsub_rn(y, b2.m), b2.s);
                     float gg = 0.f;
-                    if (sc.asel[(size_t)(bj0 + g) * C2 + c3] == l) {
-                        const float u = __fmaf_rn(xh, b2.g, b2.b);
-                        if (u > 0.f) gg = sc.dz[(size_t)(bj0 + g) * sc.ld_dz + sc.off_dz + c3];
-                    }
-                    sm.d2[r * C2 + c3] = b2.g * b2.s * (gg - mg2 - xh * mgx2);
+                    if (r == lsel && __fmaf_rn(xh, b2.g, b2.b) > 0.f) gg = dzv;
+                    d2[r * C2 + c2] = b2.g * b2.s * (gg - mg2 - xh * mgx2);
                 }
             }
-            __syncthreads();
+            __syncwarp();
             {
-                float w2c[C2];  // column of W2 for the lane's layer-1 channel c1: dz1[c1] = sum_c2 dy2[c2] * W2[c2][c1]
-                load_row<C2>(w2c, sc.w2 + lane, C1, ok1);
-                if (ok1) {
-                    for (int r = rw0; r < rw0 + rows_w; ++r) {
-                        const float dz1 = row_dot<C2>(sm.d2 + r * C2, w2c);
-                        const float z = sm.z1[r * C1 + lane];
-                        const float g = z > 0.f ? dz1 : 0.f;
-                        sc.g1[(row0 + r) * C1 + lane] = g;
-                        const float xh = __fmul_rn(__fsub_rn(sm.y1[r * C1 + lane], b1.m), b1.s);
-                        acc[0] += g; acc[1] += g * xh;
+                // dz1[c1] = sum_c2 dy2[c2] * W2[c2][c1] for the lane's layer-1 channel c1, 32 layer-2 channels at a time (one 32-entry
+                // block of W2's column c1 in registers), together with dW2[c2][c1] += dy2[r][c2] * z1[r][c1]
+                float *dz1 = z0;  // [16][C1]: the z0 tile is dead after the layer-1 recompute (C0 == C1 on the supported levels)
+                static_assert(C0 == C1, "dz1 partial sums reuse the z0 tile");
 #pragma unroll
-                        for (int k = 0; k < C2; k += 4) {  // dW2[:, c1] += dy2[r, :] * z1[r, c1]
-                            const float4 v = *reinterpret_cast<const float4 *>(sm.d2 + r * C2 + k);
-                            aw[k] = __fmaf_rn(v.x, z, aw[k]); aw[k + 1] = __fmaf_rn(v.y, z, aw[k + 1]);
-                            aw[k + 2] = __fmaf_rn(v.z, z, aw[k + 2]); aw[k + 3] = __fmaf_rn(v.w, z, aw[k + 3]);
+                for (int hq = 0; hq < NS2; ++hq) {
+                    float w2c[32];
+                    load_row<32>(w2c, sc.w2 + (size_t)(hq * 32) * C1 + lane, C1, ok1);
+                    if (ok1) {
+#pragma unroll 2
+                        for (int r = 0; r < kTileRows; ++r) {
+                            const float part = row_dot<32>(d2 + r * C2 + hq * 32, w2c);
+                            dz1[r * C1 + lane] = hq == 0 ? part : dz1[r * C1 + lane] + part;
+                            const float z = z1[r * C1 + lane];
+#pragma unroll
+                            for (int k = 0; k < 32; k += 4) {
+                                const float4 v = *reinterpret_cast<const float4 *>(d2 + r * C2 + hq * 32 + k);
+                                aw[hq * 32 + k] = __fmaf_rn(v.x, z, aw[hq * 32 + k]); aw[hq * 32 + k + 1] = __fmaf_rn(v.y, z, aw[hq * 32 + k + 1]);
+                                aw[hq * 32 + k + 2] = __fmaf_rn(v.z, z, aw[hq * 32 + k + 2]); aw[hq * 32 + k + 3] = __fmaf_rn(v.w, z, aw[hq * 32 + k + 3]);
+                            }
                         }
+                    }
+                }
+                if (ok1) {
+#pragma unroll
+                    for (int r = 0; r < kTileRows; ++r) {
+                        const float g = z1[r * C1 + lane] > 0.f ? dz1[r * C1 + lane] : 0.f;
+                        sc.g1[(row0 + r) * C1 + lane] = g;
+                        const float xh = __fmul_rn(__fsub_rn(y1[r * C1 + lane], b1.m), b1.s);
+                        acc[0][0] += g; acc[0][1] += g * xh;
                     }
                 }
             }
         }
-        flush_lane_sums<3>(sm.red, acc, 0, ok1, C1, 1, sc.part, tc.cta, tc.G);
-        ticket_finish<3>(sc.fin, sc.part, tc.G, C1, tc.cta);
-        flush_weight_grad<C2, C1>(sm.z0, aw, ok1, sc.part_w, sc.tickets_w, tc.cta, tc.G, sc.dw, sc.ld_dw);
+        seg = seg_end;
+        }
+        flush_sums<3, 1>(red, acc, C1, sc.part, bc.cta, bc.G);
+        ticket_finish<3>(sc.fin, sc.part, bc.G, C1, bc.cta);
+        flush_weight_grad<C2, C1>(smem, aw, ok1, sc.part_w, bc.cta);
     }
 }
 
@@ -630,8 +722,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_u_kernel(int R, const float *_
 // one column block of Wf and one block of accumulators live in registers.
 template <int K, int C0>
 __global__ void __launch_bounds__(kThreads, 1) sa_u_bwd_kernel(int R, const float *__restrict__ F, const float *__restrict__ dU, const float *w0a,
-                                                                const float *w0b, int ldw0, float *dF, float *part_w, unsigned *tickets_w, float *dwa,
-                                                                float *dwb, int ld_dw) {
+                                                                const float *w0b, int ldw0, float *dF, float *part_w) {
     extern __shared__ __align__(16) float ub_smem[];
     constexpr int CO = 2 * C0;
     constexpr int NK = K / 32;
@@ -682,13 +773,6 @@ __global__ void __launch_bounds__(kThreads, 1) sa_u_bwd_kernel(int R, const floa
             part_w[(size_t)blockIdx.x * CW + j * K + q * 32 + kk] = t;
         }
     }
-    float *part2 = part_w + (size_t)kMaxPartialRows * CW;
-    if (!ticket_reduce<1>(part_w, (int)blockIdx.x, (int)gridDim.x, CW, tickets_w, part2)) return;
-    for (int i = threadIdx.x; i < CW; i += kThreads) {
-        const int j = i / K, k = i - j * K;
-        float *dst = j < C0 ? dwa + (size_t)j * ld_dw + 3 + k : dwb + (size_t)(j - C0) * ld_dw + 3 + k;
-        *dst = (float)ticket_total(part2, (int)gridDim.x, CW, 0, i);
-    }
 }
 
 }  // namespace
@@ -711,22 +795,25 @@ static bool fill_scale(const istnet_sa_scale &h, int C0, int C1, int C2, int nac
     (void)C0; (void)C1; (void)C2;
     return h.nsample == 16 || h.nsample == 32;
 }
+// the kernels assume scale 0 = 16 neighbours, scale 1 = 32 (PointNet2MSG, modules.py:253,266)
+static bool scales_ok(const SaLevelP &p) { return p.sc[0].ns == 16 && p.sc[1].ns == 32; }
 static bool fill_level(int B, int N, int M, const float *xyz, const float *new_xyz, const float *u, int ldu, float *dU, SaLevelP &p) {
-    if (B <= 0 || N <= 0 || M <= 0 || (M % kWarps) != 0 || !xyz || !new_xyz) return false;
-    if ((long long)B * M * kMaxNs > 0x7fffffffLL || (size_t)N * 12 > 96 * 1024) return false;
+    if (B <= 0 || N <= 0 || M <= 0 || !xyz || !new_xyz) return false;
+    if ((long long)B * M * kMaxNs > 0x7fffffffLL || (long long)B * N > 0x7fffffffLL / 4 || N > 8192) return false;  // cloud in shared memory: <= 96 KB
     p = SaLevelP{};
     p.B = B; p.N = N; p.M = M; p.xyz = xyz; p.new_xyz = new_xyz; p.u = u; p.ldu = ldu; p.dU = dU;
     return true;
 }
-// CTAs of one launch shared between the two scales in proportion to their rows (16 : 32 neighbours)
-static void split_ctas(SaLevelP &p, int total) {
-    const int n_tiles = p.B * p.M / kWarps;
+// CTAs of a backward launch shared between the two scales in proportion to their rows (16 : 32 neighbours)
+static void split_ctas(SaLevelP &p, int total, int rows_per_unit) {
     const int w0 = p.sc[0].ns, w1 = p.sc[1].ns;
     int g0 = total * w0 / (w0 + w1);
     if (g0 < 1) g0 = 1;
     int g1 = total - g0;
-    if (g0 > n_tiles) g0 = n_tiles;
-    if (g1 > n_tiles) g1 = n_tiles;
+    if (g1 < 1) g1 = 1;
+    const long long u0 = (long long)p.B * p.M * w0 / rows_per_unit, u1 = (long long)p.B * p.M * w1 / rows_per_unit;
+    if (g0 > u0) g0 = (int)(u0 < 1 ? 1 : u0);
+    if (g1 > u1) g1 = (int)(u1 < 1 ? 1 : u1);
     if (g0 > kMaxPartialRows) g0 = kMaxPartialRows;
     if (g1 > kMaxPartialRows) g1 = kMaxPartialRows;
     p.sc[0].cta0 = 0; p.sc[0].ncta = g0;
@@ -735,15 +822,17 @@ static void split_ctas(SaLevelP &p, int total) {
 
 template <int C0, int C1, int C2>
 static int launch_fwd(SaLevelP &p, int pass, int query, cudaStream_t st) {
-    constexpr int GT = kWarps;
-    const size_t smem = Smem<C0, C1, C2, GT>::bytes(p.N, query != 0, false);
-    const int per_sm = smem * 2 <= 220 * 1024 ? 2 : 1;
-    split_ctas(p, kNumSMs * per_sm);
-    const int grid = p.sc[0].ncta + p.sc[1].ncta;
-#define SA_FWD(PASS, Q)                                                                                                             \
-    do {                                                                                                                            \
-        ISTNET_CUDA_TRY(cudaFuncSetAttribute(sa_fwd_kernel<C0, C1, C2, GT, PASS, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        sa_fwd_kernel<C0, C1, C2, GT, PASS, Q><<<grid, kThreads, smem, st>>>(p);                                                    \
+    // warp-autonomous forward: one grid for both scales, every CTA's partial row belongs to both reductions
+    int grid = kNumSMs * 2;
+    const int units = (p.B * p.M + 7) / 8;  // at least one centroid per warp
+    if (grid > units) grid = units;
+    if (grid > kMaxPartialRows) grid = kMaxPartialRows;
+    constexpr int NW = kFwdThreads / 32, NS2 = C2 / 32;
+    const size_t smem = sizeof(float) * (2 * (C0 * C1 + C1 * C2) + NW * (48 + 16 + 64 + kTileRows * C0 + kTileRows * C1) + NW * 2 * NS2 * 32 + ((p.N * 3 + 3) & ~3));
+#define SA_FWD(PASS, Q)                                                                                                          \
+    do {                                                                                                                         \
+        ISTNET_CUDA_TRY(cudaFuncSetAttribute(sa_fwd_kernel<C0, C1, C2, PASS, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        sa_fwd_kernel<C0, C1, C2, PASS, Q><<<grid, kFwdThreads, smem, st>>>(p);                                                   \
     } while (0)
     if (pass == 0 && query) SA_FWD(0, true);
     else if (pass == 0) SA_FWD(0, false);
@@ -757,21 +846,22 @@ static int launch_fwd(SaLevelP &p, int pass, int query, cudaStream_t st) {
 }
 template <int C0, int C1, int C2>
 static int launch_bwd(SaLevelP &p, int stage, cudaStream_t st) {
-    constexpr int GT = kWarps;
     if (stage < 0) {
-        split_ctas(p, kNumSMs * 2);
-        sa_bwd_pre_kernel<C2><<<p.sc[0].ncta + p.sc[1].ncta, kThreads, 0, st>>>(p);
+        split_ctas(p, kNumSMs * 2, 8);
+        sa_bwd_pre_kernel<C2><<<p.sc[0].ncta + p.sc[1].ncta, 256, 0, st>>>(p);
         ISTNET_LAUNCH_CHECK();
         return ISTNET_OK;
     }
-    const size_t smem = Smem<C0, C1, C2, GT>::bytes(p.N, false, true);
-    const int per_sm = (C2 <= 32 && smem * 2 <= 220 * 1024) ? 2 : 1;
-    split_ctas(p, kNumSMs * per_sm);
+    split_ctas(p, kNumSMs * 3, kTileRows * (kBwdThreads / 32));
     const int grid = p.sc[0].ncta + p.sc[1].ncta;
-#define SA_BWD(STAGE)                                                                                                              \
-    do {                                                                                                                           \
-        ISTNET_CUDA_TRY(cudaFuncSetAttribute(sa_bwd_kernel<C0, C1, C2, GT, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        sa_bwd_kernel<C0, C1, C2, GT, STAGE><<<grid, kThreads, smem, st>>>(p);                                                     \
+    constexpr int NW = kBwdThreads / 32;
+    constexpr int WF = 16 + 64 + kTileRows * (C0 + 2 * C1 + C2), CWMAX = C2 * C1;
+    constexpr int SF = (NW * WF > NW * CWMAX ? NW * WF : NW * CWMAX);
+    const size_t smem = sizeof(float) * (C0 * C1 + C1 * C2 + SF + NW * 3 * 32 + ((p.N * 3 + 3) & ~3));
+#define SA_BWD(STAGE)                                                                                                          \
+    do {                                                                                                                       \
+        ISTNET_CUDA_TRY(cudaFuncSetAttribute(sa_bwd_kernel<C0, C1, C2, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        sa_bwd_kernel<C0, C1, C2, STAGE><<<grid, kBwdThreads, smem, st>>>(p);                                                   \
     } while (0)
     if (stage == 0) SA_BWD(0);
     else if (stage == 1) SA_BWD(1);
@@ -779,6 +869,16 @@ static int launch_bwd(SaLevelP &p, int stage, cudaStream_t st) {
     else return ISTNET_ERR_BAD_ARG;
 #undef SA_BWD
     ISTNET_LAUNCH_CHECK();
+    if (stage <= 1) {  // weight gradient of the stage: fixed-order sum of the per-CTA partial rows (channel-parallel launch)
+        const int CW = stage == 0 ? C2 * C1 : C1 * C0;
+        for (int s = 0; s < 2; ++s) {
+            FinP f{};
+            f.kind = ISTNET_FIN_COLSUM;
+            f.sum_f32 = p.sc[s].dw;
+            int e = istnet_fin_finalize_launch(p.sc[s].part_w, p.sc[s].ncta, CW, 1, f, st);
+            if (e) return e;
+        }
+    }
     return ISTNET_OK;
 }
 
@@ -797,7 +897,7 @@ extern "C" int istnet_sa_level_forward(int B, int N, int M, int C0, int C1, int 
             (pass >= 2 && (!p.sc[s].w2 || !p.sc[s].bn1.mean || !p.sc[s].bn2.gamma || !p.sc[s].ysel || !p.sc[s].asel)))
             return ISTNET_ERR_BAD_ARG;
     }
-    if (u && ldu < 2 * C0) return ISTNET_ERR_BAD_ARG;
+    if ((u && ldu < 2 * C0) || !scales_ok(p)) return ISTNET_ERR_BAD_ARG;
     if (C0 == 16 && C1 == 16 && C2 == 32) return launch_fwd<16, 16, 32>(p, pass, query, (cudaStream_t)stream);
     if (C0 == 32 && C1 == 32 && C2 == 64) return launch_fwd<32, 32, 64>(p, pass, query, (cudaStream_t)stream);
     return ISTNET_ERR_UNSUPPORTED;
@@ -828,10 +928,11 @@ extern "C" int istnet_sa_level_backward(int B, int N, int M, int C0, int C1, int
         const SaScale &d = p.sc[s];
         if (!d.idx || !d.w0 || !d.w1 || !d.w2 || !d.bn0.mean || !d.bn1.mean || !d.bn2.mean) return ISTNET_ERR_BAD_ARG;
         if (stage < 0 && (!d.dz || !d.ysel || !d.part || d.fin.kind != ISTNET_FIN_BN_BWD)) return ISTNET_ERR_BAD_ARG;
-        if (stage == 0 && (!d.dz || !d.asel || !d.ws2 || !d.g1 || !d.part || d.fin.kind != ISTNET_FIN_BN_BWD || !d.part_w || !d.tickets_w || !d.dw)) return ISTNET_ERR_BAD_ARG;
-        if (stage == 1 && (!d.ws1 || !d.g1 || !d.g0 || !d.part || d.fin.kind != ISTNET_FIN_BN_BWD || !d.part_w || !d.tickets_w || !d.dw)) return ISTNET_ERR_BAD_ARG;
+        if (stage == 0 && (!d.dz || !d.asel || !d.ws2 || !d.g1 || !d.part || d.fin.kind != ISTNET_FIN_BN_BWD || !d.part_w || !d.dw)) return ISTNET_ERR_BAD_ARG;
+        if (stage == 1 && (!d.ws1 || !d.g1 || !d.g0 || !d.part || d.fin.kind != ISTNET_FIN_BN_BWD || !d.part_w || !d.dw)) return ISTNET_ERR_BAD_ARG;
         if (stage == 2 && (!d.ws0 || !d.g0 || !d.part_w || !d.tickets_w || !d.dw)) return ISTNET_ERR_BAD_ARG;
     }
+    if (!scales_ok(p)) return ISTNET_ERR_BAD_ARG;
     if (stage == 2 && dU) ISTNET_CUDA_TRY(cudaMemsetAsync(dU, 0, sizeof(float) * (size_t)B * N * ldu, (cudaStream_t)stream));
     if (C0 == 16 && C1 == 16 && C2 == 32) return launch_bwd<16, 16, 32>(p, stage, (cudaStream_t)stream);
     if (C0 == 32 && C1 == 32 && C2 == 64) return launch_bwd<32, 32, 64>(p, stage, (cudaStream_t)stream);
@@ -848,14 +949,17 @@ extern "C" int istnet_sa_u(int R, int K, int C0, const float *F, const float *w0
     return ISTNET_OK;
 }
 extern "C" int istnet_sa_u_bwd(int R, int K, int C0, const float *F, const float *dU, const float *w0a, const float *w0b, int ldw0, float *dF,
-                               float *part_w, unsigned *tickets_w, float *dw0a, float *dw0b, int ld_dw, void *stream) {
-    if (R <= 0 || !F || !dU || !w0a || !w0b || !part_w || !tickets_w || !dw0a || !dw0b || ldw0 < 3 + K || ld_dw < 3 + K) return ISTNET_ERR_BAD_ARG;
+                               float *part_w, float *dwf, void *stream) {
+    if (R <= 0 || !F || !dU || !w0a || !w0b || !part_w || !dwf || ldw0 < 3 + K) return ISTNET_ERR_BAD_ARG;
     if (!(K == 64 && C0 == 32)) return ISTNET_ERR_UNSUPPORTED;
     int grid = (R + kWarps * 4 - 1) / (kWarps * 4);
     if (grid > kNumSMs) grid = kNumSMs;
     const size_t smem = (size_t)(kWarps * 4 * 64 + kWarps * 64 * 32) * sizeof(float);
     ISTNET_CUDA_TRY(cudaFuncSetAttribute(sa_u_bwd_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sa_u_bwd_kernel<64, 32><<<grid, kThreads, smem, (cudaStream_t)stream>>>(R, F, dU, w0a, w0b, ldw0, dF, part_w, tickets_w, dw0a, dw0b, ld_dw);
+    sa_u_bwd_kernel<64, 32><<<grid, kThreads, smem, (cudaStream_t)stream>>>(R, F, dU, w0a, w0b, ldw0, dF, part_w);
     ISTNET_LAUNCH_CHECK();
-    return ISTNET_OK;
+    FinP f{};
+    f.kind = ISTNET_FIN_COLSUM;
+    f.sum_f32 = dwf;  // [2*C0][K]: rows 0..C0-1 = scale 0, rest = scale 1
+    return istnet_fin_finalize_launch(part_w, grid, 2 * C0 * K, 1, f, (cudaStream_t)stream);
 }

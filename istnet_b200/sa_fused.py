@@ -52,7 +52,7 @@ def supported(sa, xyz, new_xyz, feats):
         return False
     B, N, _ = xyz.shape
     M = new_xyz.shape[1]
-    return M % 8 == 0 and N * 12 <= 96 * 1024 and B * M * 32 < 2**31
+    return B * M * 32 < 2**31 and B * N < 2**29 and N <= 8192
 
 
 def _bn_of(mlp, l):
@@ -168,7 +168,7 @@ class _SALevelFn(torch.autograd.Function):
                     keep.extend((part, fin))
                     a.part, a.fin = part.data_ptr(), ctypes.pointer(fin)
                 if lw is not None:
-                    n = 3 * C0 if lw == 0 else dW[s][lw].numel()
+                    n = 3 * 32 if lw == 0 else dW[s][lw].numel()  # layer 0: [3 coordinates][32 lanes] partial rows
                     pw = torch.empty(_C.FIN_ROWS * n, **f32)
                     keep.append(pw)
                     a.part_w, a.tickets_w = pw.data_ptr(), _C.tickets(dev).value
@@ -181,8 +181,11 @@ class _SALevelFn(torch.autograd.Function):
         if C > 0:
             d_feats = torch.empty(B, N, C, **f32) if ctx.need_dfeats else None
             pw = torch.empty(_C.FIN_ROWS * 2 * C0 * C, **f32)
+            dwf = torch.empty(2 * C0, C, **f32)
             _C.call("sa_u_bwd", c_int(B * N), c_int(C), c_int(C0), ptr(feats), ptr(dU), ptr(sa.mlps[0][0].conv.weight), ptr(sa.mlps[1][0].conv.weight),
-                    c_int(3 + C), K._p(d_feats), ptr(pw), _C.tickets(dev), ptr(dW[0][0]), ptr(dW[1][0]), c_int(3 + C))
+                    c_int(3 + C), K._p(d_feats), ptr(pw), ptr(dwf))
+            for s in range(2):  # layer-0 weight gradient = [dWx (3 columns, written by stage 2) | dWf]
+                dW[s][0].view(C0, 3 + C)[:, 3:].copy_(dwf[s * C0 : (s + 1) * C0])
         grads = []
         for s in range(2):
             for l in range(3):
