@@ -250,7 +250,9 @@ def main():
     eager_step(resident)  # counts the kernel launches of a step (the graph replays exactly these)
     launches_per_step = _C.LAUNCHES - l_probe
     graphed = None
-    nccl_in_graph = os.environ.get("ISTNET_GRAPH_NCCL", "1") != "0"
+    # ISTNET_GRAPH_NCCL=1 captures the per-bucket NCCL all-reduce (communication stream) and Adam inside the step's graph; the
+    # default keeps NCCL out of the capture: the graph ends with the bucket packing, all-reduce + Adam follow each replay
+    nccl_in_graph = os.environ.get("ISTNET_GRAPH_NCCL", "0") == "1"
     if not args.eager:
         from istnet_b200.graph import GraphedTrainStep
 

@@ -240,6 +240,18 @@ int istnet_marker(unsigned long long *stamps, int slot, void *stream);
 /* istnet_prep_weight for transpose = 0 (planes_fwd) and transpose = 1 (planes_bwd) in one launch */
 int istnet_prep_weight_pair(const float *w, int Cout, int Cin, int kh, int kw, int im2col, void *planes_fwd, long long stride_fwd,
                             int nsplit_fwd, int cs_fwd, void *planes_bwd, long long stride_bwd, int nsplit_bwd, int cs_bwd, void *stream);
+/* istnet_prep_weight_pair for MANY weights in one launch: `table` is a DEVICE array of n istnet_prep_entry; entry i is handled by the
+ * CTAs [block0_i, block0_i + ceil(co*ci*kh*kw / ISTNET_PREP_CHUNK)), block0 ascending from 0; planes_bwd may be null (forward operand
+ * only).  The weights of a model change once per optimizer step, so all of them are re-laid in one launch at the start of a step
+ * instead of one launch in front of every convolution. */
+#define ISTNET_PREP_CHUNK 2048
+typedef struct istnet_prep_entry {
+    const float *w;
+    void *planes_fwd, *planes_bwd;
+    long long stride_fwd, stride_bwd;
+    int Cout, Cin, kh, kw, im2col, nsplit_fwd, cs_fwd, nsplit_bwd, cs_bwd, block0;
+} istnet_prep_entry;
+int istnet_prep_weight_batch(const void *table, int n, int total_blocks, void *stream);
 /* out[c] = sum_g part[g*C + c]: column sums from the per-CTA partials of a statistics epilogue (first of its two quantities) */
 int istnet_colsum_finalize(const float *part, int G, int C, double *ws, float *out_f32, void *stream);
 /* ws[c] = sum_p x[p][c] (double; bias gradients) */
@@ -348,6 +360,26 @@ int istnet_sa_level_backward(int B, int N, int M, int C0, int C1, int C2, const 
 int istnet_sa_u(int R, int K, int C0, const float *F, const float *w0a, const float *w0b, int ldw0, float *u, void *stream);
 int istnet_sa_u_bwd(int R, int K, int C0, const float *F, const float *dU, const float *w0a, const float *w0b, int ldw0, float *dF,
                     float *part_w, float *dwf, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * 5c. Pose-head tail (csrc/heads.cu): AdaptiveAvgPool1d(1) over the points, the rotation / translation / size heads
+ *     [Linear 512-512, ReLU, Linear 512-256, ReLU, Linear 256-k] (ist_net.py:228-248,296-316) and Ortho6d2Mat
+ *     (utils/rotation_utils.py:4-28), forward and backward, batch rows B <= 64.
+ * ---------------------------------------------------------------------------------------------------- */
+/* pooled[b][c] = mean_n feat[(b*N + n)*C + c]  and its adjoint d_feat = d_pooled / N broadcast over the points (C % 4 == 0) */
+int istnet_rows_mean(int B, int N, int C, const float *feat, float *pooled, void *stream);
+int istnet_rows_mean_bwd(int B, int N, int C, const float *dpooled, float *dfeat, void *stream);
+/* y_h[b][o] = act(sum_k w_h[o][k] x_h[b][k] + bias_h[o]) for up to 3 heads in one launch (nn.Linear + nn.ReLU); O[h] outputs each */
+int istnet_heads_linear(int nheads, int B, int K, const float *const *x, const float *const *w, const float *const *bias, float *const *y,
+                        const int *O, int relu, void *stream);
+/* backward: g = dy * [y > 0] (relu) or dy;  dw_h = g^T x, db_h = sum_b g, dx_h = g w_h (dx[h] may be null) */
+int istnet_heads_linear_bwd(int nheads, int B, int K, const float *const *x, const float *const *w, const float *const *y,
+                            const float *const *dy, float *const *dx, float *const *dw, float *const *db, const int *O, int relu,
+                            void *stream);
+int istnet_sum3(long long n, const float *a, const float *b, const float *c, float *out, void *stream);
+/* R[b] = [x y z] columns with y = n(r6[b][3:6]), z = n(r6[b][0:3] x y), x = y x z, n(v) = v / max(|v|, 1e-8); and the gradient */
+int istnet_ortho6d(int B, const float *r6, float *R, void *stream);
+int istnet_ortho6d_bwd(int B, const float *r6, const float *dR, float *dr6, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * 6. Optimizer step of the training loop (utils/solver.py:41-46,98-99: torch.optim.Adam + CyclicLR)

@@ -498,11 +498,11 @@ __global__ void __launch_bounds__(kEwThreads) split_rows4_kernel(unsigned P, int
 //   transpose = 0 (forward operand):        rows = co, cols = ci, tap = r*kw + s
 //   transpose = 1 (data-gradient operand):  rows = ci, cols = co, tap = flipped (kh-1-r, kw-1-s)
 //   im2col   = 1 (strided convs as 1x1 GEMM over patches): one tap, K index = (r*kw + s)*ci_total + ci
-__device__ __forceinline__ void prep_weight_body(int co_n, int ci_n, int kh, int kw, const float *__restrict__ w, int transpose, int im2col,
-                                                 __nv_bfloat16 *pl, long long pl_stride, int nsplit, int cs) {
+__device__ __forceinline__ void prep_weight_range(int co_n, int ci_n, int kh, int kw, const float *__restrict__ w, int transpose, int im2col,
+                                                  __nv_bfloat16 *pl, long long pl_stride, int nsplit, int cs, long long first, long long step) {
     const long long total = (long long)co_n * ci_n * kh * kw;
     const int taps = kh * kw;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    for (long long i = first; i < total; i += step) {
         // iterate in OUTPUT order so that stores are coalesced
         long long o;
         float v;
@@ -533,6 +533,37 @@ __device__ __forceinline__ void prep_weight_body(int co_n, int ci_n, int kh, int
             o = ((long long)tap * ci_n + ci) * cs + co;
         }
         store_planes1(pl + o, pl_stride, nsplit, v);
+    }
+}
+__device__ __forceinline__ void prep_weight_body(int co_n, int ci_n, int kh, int kw, const float *__restrict__ w, int transpose, int im2col,
+                                                 __nv_bfloat16 *pl, long long pl_stride, int nsplit, int cs) {
+    prep_weight_range(co_n, ci_n, kh, kw, w, transpose, im2col, pl, pl_stride, nsplit, cs, blockIdx.x * (long long)blockDim.x + threadIdx.x,
+                      (long long)gridDim.x * blockDim.x);
+}
+// Every registered weight of the model in ONE launch (istnet_prep_weight_batch): the table lists, per weight, the FP32 source, its
+// shape, the forward and (optional) data-gradient operand-plane destinations and the first CTA that works on it; a CTA finds its
+// entry by binary search and handles kPrepChunk consecutive elements of it in both layouts.
+struct PrepEntry {
+    const float *w;
+    __nv_bfloat16 *pf, *pt;
+    long long stride_f, stride_t;
+    int co, ci, kh, kw, im2col, ns_f, cs_f, ns_t, cs_t, block0;
+};
+constexpr int kPrepChunk = kEwThreads * 8;
+__global__ void __launch_bounds__(kEwThreads) prep_weight_batch_kernel(const PrepEntry *__restrict__ table, int n) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {  // last entry with block0 <= blockIdx.x
+        const int mid = (lo + hi + 1) >> 1;
+        if (table[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const PrepEntry e = table[lo];
+    const long long base = (long long)((int)blockIdx.x - e.block0) * kPrepChunk;
+    const long long total = (long long)e.co * e.ci * e.kh * e.kw;
+    const long long end = base + kPrepChunk < total ? base + kPrepChunk : total;
+    // prep_weight_range iterates i = first, first + step, ... < total: bound it to this CTA's chunk by handing it the chunk end
+    for (long long i = base + threadIdx.x; i < end; i += kEwThreads) {
+        prep_weight_range(e.co, e.ci, e.kh, e.kw, e.w, 0, e.im2col, e.pf, e.stride_f, e.ns_f, e.cs_f, i, total);
+        if (e.pt) prep_weight_range(e.co, e.ci, e.kh, e.kw, e.w, 1, e.im2col, e.pt, e.stride_t, e.ns_t, e.cs_t, i, total);
     }
 }
 __global__ void __launch_bounds__(kEwThreads) prep_weight_kernel(int co_n, int ci_n, int kh, int kw, const float *__restrict__ w, int transpose,
@@ -1517,3 +1548,14 @@ extern "C" int istnet_ticket_debug(unsigned long long *out8) {
     return (int)cudaMemcpyFromSymbol(out8, g_ticket_dbg, sizeof(unsigned long long) * 8);
 }
 #endif
+
+// table: device array of n entries laid out as `struct PrepEntry` (see istnet_prep_entry in include/istnet_b200.h); total_blocks =
+// sum over the entries of ceil(co*ci*kh*kw / ISTNET_PREP_CHUNK)
+extern "C" int istnet_prep_weight_batch(const void *table, int n, int total_blocks, void *stream) {
+    if (!table || n <= 0 || total_blocks <= 0) return ISTNET_ERR_BAD_ARG;
+    static_assert(sizeof(PrepEntry) == sizeof(istnet_prep_entry), "PrepEntry must match the C ABI struct");
+    static_assert(kPrepChunk == ISTNET_PREP_CHUNK, "chunk size is part of the ABI (callers compute block0)");
+    prep_weight_batch_kernel<<<total_blocks, kEwThreads, 0, ST>>>((const PrepEntry *)table, n);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}

@@ -139,12 +139,108 @@ def _with_global(x_rows, b, n):
     return [x_rows, f.mean(1, keepdim=True).expand_as(f).reshape(b * n, -1)]
 
 
+FUSED_HEADS = os.environ.get("ISTNET_FUSED_HEADS", "1") != "0"
+
+
+def _ptr_array(tensors):
+    import ctypes
+
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() if t is not None else None for t in tensors])
+
+
+class _PoseTailFn(torch.autograd.Function):
+    """AdaptiveAvgPool1d(1) -> three [Linear, ReLU, Linear, ReLU, Linear] heads -> Ortho6d2Mat on the kernels of csrc/heads.cu:
+    5 launches forward, 6 backward for all three heads (ist_net.py:228-264,296-332; ~25 / ~70 library launches in the reference)."""
+
+    @staticmethod
+    def forward(ctx, feat_rows, b, n, *params):
+        import ctypes
+
+        from . import _C
+        from ._C import c_int, ptr
+
+        dev = feat_rows.device
+        C = feat_rows.shape[1]
+        pooled = torch.empty(b, C, dtype=torch.float32, device=dev)
+        _C.call("rows_mean", c_int(b), c_int(n), c_int(C), ptr(feat_rows), ptr(pooled))
+        W = [[params[6 * h + 2 * l] for l in range(3)] for h in range(3)]
+        Bs = [[params[6 * h + 2 * l + 1] for l in range(3)] for h in range(3)]
+        xs, ys = [pooled] * 3, []
+        for l in range(3):
+            O = [W[h][l].shape[0] for h in range(3)]
+            y = [torch.empty(b, O[h], dtype=torch.float32, device=dev) for h in range(3)]
+            _C.call("heads_linear", c_int(3), c_int(b), c_int(W[0][l].shape[1]), _ptr_array(xs), _ptr_array([W[h][l] for h in range(3)]),
+                    _ptr_array([Bs[h][l] for h in range(3)]), _ptr_array(y), (ctypes.c_int * 3)(*O), c_int(1 if l < 2 else 0))
+            ys.append(y)
+            xs = y
+        R = torch.empty(b, 3, 3, dtype=torch.float32, device=dev)
+        _C.call("ortho6d", c_int(b), ptr(ys[2][0]), ptr(R))
+        ctx.saved = (pooled, ys, W, Bs)
+        ctx.dims = (b, n, C)
+        ctx.params = params
+        return R, ys[2][1], ys[2][2]
+
+    @staticmethod
+    def backward(ctx, dR, dt, ds):
+        import ctypes
+
+        from . import _C
+        from ._C import c_int, c_ll, ptr
+
+        pooled, ys, W, Bs = ctx.saved
+        b, n, C = ctx.dims
+        dev = pooled.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        dR = torch.zeros(b, 3, 3, **f32) if dR is None else dR.contiguous()
+        dt = torch.zeros(b, 3, **f32) if dt is None else dt.contiguous()
+        ds = torch.zeros(b, 3, **f32) if ds is None else ds.contiguous()
+        dr6 = torch.empty(b, 6, **f32)
+        _C.call("ortho6d_bwd", c_int(b), ptr(ys[2][0]), ptr(dR), ptr(dr6))
+        dy = [dr6, dt, ds]
+        gW = [[None] * 3 for _ in range(3)]
+        gB = [[None] * 3 for _ in range(3)]
+        for l in (2, 1, 0):
+            x = ys[l - 1] if l > 0 else [pooled] * 3
+            K_ = W[0][l].shape[1]
+            O = [W[h][l].shape[0] for h in range(3)]
+            dx = [torch.empty(b, K_, **f32) for _ in range(3)]
+            for h in range(3):
+                gW[h][l], gB[h][l] = torch.empty_like(W[h][l]), torch.empty_like(Bs[h][l])
+            _C.call("heads_linear_bwd", c_int(3), c_int(b), c_int(K_), _ptr_array(x), _ptr_array([W[h][l] for h in range(3)]),
+                    _ptr_array(ys[l]), _ptr_array(dy), _ptr_array(dx), _ptr_array([gW[h][l] for h in range(3)]),
+                    _ptr_array([gB[h][l] for h in range(3)]), (ctypes.c_int * 3)(*O), c_int(1 if l < 2 else 0))
+            dy = dx
+        dpooled = torch.empty(b, C, **f32)
+        _C.call("sum3", c_ll(b * C), ptr(dy[0]), ptr(dy[1]), ptr(dy[2]), ptr(dpooled))
+        dfeat = torch.empty(b * n, C, **f32)
+        _C.call("rows_mean_bwd", c_int(b), c_int(n), c_int(C), ptr(dpooled), ptr(dfeat))
+        grads = []
+        for h in range(3):
+            for l in range(3):
+                grads += [gW[h][l], gB[h][l]]
+        ctx.saved = None
+        return (dfeat, None, None) + tuple(g if p.requires_grad else None for g, p in zip(grads, ctx.params))
+
+
 class _PoseHeads(nn.Module):
     """pose_mlp1 -> global mean concat -> pose_mlp2 -> avg pool -> rotation / translation / size heads."""
+
+    def _head_params(self):
+        ps = []
+        for head in (self.rotation_estimator, self.translation_estimator, self.size_estimator):
+            for i in (0, 2, 4):
+                ps += [head[i].weight, head[i].bias]
+        return ps
 
     def _tail(self, feat_rows, b, n):
         feat = _mlp(self.pose_mlp1, feat_rows)
         feat = _mlp(self.pose_mlp2, _with_global(feat, b, n))
+        if FUSED_HEADS and feat.is_cuda and b <= 64 and feat.shape[1] % 4 == 0:
+            feat = feat.contiguous()
+            params = self._head_params()
+            if torch.is_grad_enabled() and (feat.requires_grad or any(p.requires_grad for p in params)):
+                return _PoseTailFn.apply(feat, b, n, *params)
+            return _PoseTailFn.forward(RE._NoCtx(), feat, b, n, *params)
         feat = feat.view(b, n, -1).mean(1)  # AdaptiveAvgPool1d(1)
         r6 = self.rotation_estimator(feat)
         r = ortho6d_to_mat(r6[:, :3].contiguous(), r6[:, 3:].contiguous()).view(-1, 3, 3)
@@ -257,6 +353,7 @@ class IST_Net(nn.Module):
     def forward(self, inputs):
         end_points = {}
         check_fp32_matmul()
+        RE.K.begin_step(self, inputs["pts"].device)  # all weights of the model re-laid as operand planes in one launch (nhwc.WeightBank)
         rgb, pts, choose = inputs["rgb"], inputs["pts"], inputs["choose"]
         cls = inputs["category_label"].reshape(-1)
         c = torch.mean(pts, 1, keepdim=True)
@@ -323,6 +420,7 @@ class PoseNetGT(nn.Module):
 
     def forward(self, inputs):
         check_fp32_matmul()
+        RE.K.begin_step(self, inputs["pts"].device)
         rgb, pts, choose, pts_w_gt = inputs["rgb"], inputs["pts"], inputs["choose"], inputs["qo"]
         c = torch.mean(pts, 1, keepdim=True)
         pts = pts - c

@@ -7,6 +7,7 @@ reference modules (cuDNN conv fwd/dgrad/wgrad, BN fwd/bwd, ReLU/PReLU, Dropout2d
 """
 import ctypes
 import os
+import weakref
 
 import torch
 
@@ -82,6 +83,9 @@ def prep_weight(w, transpose=False, nsplit=None, im2col=False):
         shape = (1, taps * ci, pad8(co)) if transpose else (1, co, pad8(taps * ci))
     else:
         shape = (taps, ci, pad8(co)) if transpose else (taps, co, pad8(ci))
+    if WEIGHT_BANK and not transpose and isinstance(w, torch.nn.Parameter) and w.is_cuda and weight_bank(w.device) is not None:
+        st = (1, taps * ci, pad8(co)) if im2col else (taps, ci, pad8(co))
+        return weight_bank(w.device).get(w, nsplit or NSPLIT, im2col, False, (co, ci, kh, kw), (shape, st))[0]
     pl = torch.empty(nsplit or NSPLIT, *shape, dtype=torch.bfloat16, device=w.device)
     _C.call("prep_weight", ptr(w), c_int(co), c_int(ci), c_int(kh), c_int(kw), c_int(1 if transpose else 0), c_int(1 if im2col else 0),
             *_pl_args(pl), c_int(shape[-1]))
@@ -99,11 +103,139 @@ def prep_weight_pair(w, im2col=False, nsplit=None):
     taps = kh * kw
     sf = (1, co, pad8(taps * ci)) if im2col else (taps, co, pad8(ci))
     st = (1, taps * ci, pad8(co)) if im2col else (taps, ci, pad8(co))
+    if WEIGHT_BANK and isinstance(w, torch.nn.Parameter) and w.is_cuda and weight_bank(w.device) is not None:
+        return weight_bank(w.device).get(w, nsplit or NSPLIT, im2col, True, (co, ci, kh, kw), (sf, st))
     pf = torch.empty(nsplit or NSPLIT, *sf, dtype=torch.bfloat16, device=w.device)
     pt = torch.empty(min(nsplit or NSPLIT, NSPLIT_BWD), *st, dtype=torch.bfloat16, device=w.device)
     _C.call("prep_weight_pair", ptr(w), c_int(co), c_int(ci), c_int(kh), c_int(kw), c_int(1 if im2col else 0), *_pl_args(pf), c_int(sf[-1]),
             *_pl_args(pt), c_int(st[-1]))
     return pf, pt
+
+
+# ---- all weights of a model re-laid in ONE launch per step
+# A convolution weight changes once per optimizer step, yet round 1 re-laid it right in front of every GEMM (~130 launches of 3-9 us
+# on the dependent chain of each stream).  The bank remembers every nn.Parameter that went through prep_weight_pair / prep_weight
+# (persistent destination planes, one table entry each); `begin_step()` — called at the start of IST_Net / PoseNetGT.forward —
+# refreshes ALL of them with one launch of istnet_prep_weight_batch, after which the per-layer calls are table look-ups.
+# Temporaries (weight slices, the head's correction matrix) are not nn.Parameters and keep the immediate path.
+class _PrepEntry(ctypes.Structure):
+    _fields_ = [("w", c_void_p), ("pf", c_void_p), ("pt", c_void_p), ("stride_f", ctypes.c_longlong), ("stride_t", ctypes.c_longlong),
+                ("co", ctypes.c_int), ("ci", ctypes.c_int), ("kh", ctypes.c_int), ("kw", ctypes.c_int), ("im2col", ctypes.c_int),
+                ("ns_f", ctypes.c_int), ("cs_f", ctypes.c_int), ("ns_t", ctypes.c_int), ("cs_t", ctypes.c_int), ("block0", ctypes.c_int)]
+
+
+PREP_CHUNK = 2048  # ISTNET_PREP_CHUNK
+WEIGHT_BANK = os.environ.get("ISTNET_WEIGHT_BANK", "1") != "0"
+
+
+class WeightBank:
+    def __init__(self):
+        self.entries = {}   # (id(param), nsplit, im2col) -> dict(w=weakref, pf, pt, dims, im2col, fresh, ver)
+        self.table = None   # device copy of the entry table
+        self.ptrs = None    # data pointers the table was built with
+        self.blocks = self.n = 0
+        self.step_id = 0    # bumped by begin_step / invalidate; entries refreshed in the current step carry the same id
+        self.dirty = True
+        self._tables = []
+
+    def _live(self):
+        dead = [k for k, e in self.entries.items() if e["w"]() is None]
+        for k in dead:
+            del self.entries[k]
+            self.dirty = True
+        return [(e, e["w"]()) for e in self.entries.values()]
+
+    def _build(self, dev, live):
+        arr = (_PrepEntry * len(live))()
+        b0 = 0
+        for a, (e, w) in zip(arr, live):
+            co, ci, kh, kw = e["dims"]
+            a.w, a.pf, a.pt = w.data_ptr(), e["pf"].data_ptr(), (e["pt"].data_ptr() if e["pt"] is not None else None)
+            a.stride_f, a.stride_t = e["pf"].stride(0), (e["pt"].stride(0) if e["pt"] is not None else 0)
+            a.co, a.ci, a.kh, a.kw, a.im2col = co, ci, kh, kw, int(e["im2col"])
+            a.ns_f, a.cs_f = e["pf"].shape[0], e["pf"].shape[-1]
+            a.ns_t, a.cs_t = (e["pt"].shape[0], e["pt"].shape[-1]) if e["pt"] is not None else (0, 0)
+            a.block0 = b0
+            b0 += (co * ci * kh * kw + PREP_CHUNK - 1) // PREP_CHUNK
+        self.table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        self._tables.append(self.table)  # a CUDA graph captured earlier keeps launching with ITS table: never freed while the bank lives
+        self.blocks, self.n = b0, len(live)
+        self.ptrs = tuple(w.data_ptr() for _, w in live)
+        self.dirty = False
+
+    def invalidate(self):
+        """The weights changed outside autograd's version counting (FlatAdam's kernel): nothing refreshed so far is valid."""
+        self.step_id += 1
+
+    def begin_step(self, dev):
+        """Re-lays every registered weight (one launch).  No-op until a first step has registered the model's weights."""
+        self.step_id += 1
+        if not WEIGHT_BANK or not self.entries:
+            return
+        live = self._live()
+        if not live:
+            return
+        settled = (not self.dirty) and self.ptrs == tuple(w.data_ptr() for _, w in live)
+        if not settled:
+            if torch.cuda.is_current_stream_capturing():
+                return  # table not settled (capture without warm-up): this step uses the immediate path
+            self._build(dev, live)  # new entries, or the optimizer re-pointed the parameters into flat buffers
+        _C.call("prep_weight_batch", ptr(self.table), c_int(self.n), c_int(self.blocks))
+        for e, w in live:
+            e["fresh"], e["ver"] = self.step_id, w._version
+
+    def get(self, w, nsplit, im2col, pair, dims, shapes):
+        """Planes of parameter `w` for this step: from the bank if begin_step refreshed them (and the parameter has not been
+        modified since), else immediate prep + registration."""
+        key = (id(w), nsplit, bool(im2col))
+        e = self.entries.get(key)
+        if e is not None and e["w"]() is w and (e["pt"] is not None or not pair):
+            if e.get("fresh") == self.step_id and e.get("ver") == w._version and not self.dirty:
+                return e["pf"], e["pt"]
+            pf, pt = e["pf"], e["pt"]
+        else:
+            sf, st = shapes
+            pf = torch.empty(nsplit, *sf, dtype=torch.bfloat16, device=w.device)
+            pt = torch.empty(min(nsplit, NSPLIT_BWD), *st, dtype=torch.bfloat16, device=w.device) if pair else None
+            if not torch.cuda.is_current_stream_capturing():  # persistent buffers must not come from a graph's private pool
+                self.entries[key] = {"w": weakref.ref(w), "pf": pf, "pt": pt, "dims": dims, "im2col": im2col}
+                self.dirty = True
+        co, ci, kh, kw = dims
+        if pt is not None:
+            _C.call("prep_weight_pair", ptr(w), c_int(co), c_int(ci), c_int(kh), c_int(kw), c_int(1 if im2col else 0), *_pl_args(pf), c_int(pf.shape[-1]),
+                    *_pl_args(pt), c_int(pt.shape[-1]))
+        else:
+            _C.call("prep_weight", ptr(w), c_int(co), c_int(ci), c_int(kh), c_int(kw), c_int(0), c_int(1 if im2col else 0), *_pl_args(pf), c_int(pf.shape[-1]))
+        return pf, pt
+
+
+_CURRENT_BANK = {}  # device index -> bank of the model whose forward ran last on that device
+
+
+def weight_bank(dev):
+    return _CURRENT_BANK.get(dev.index if dev.index is not None else torch.cuda.current_device())
+
+
+def begin_step(model, dev):
+    """Call once at the start of a model forward (IST_Net / PoseNetGT): refreshes the operand planes of all registered weights of
+    THIS model with one launch.  The bank lives on the model object, so its buffers and table die with the model (and a CUDA
+    graph captured for the model only ever references memory the model owns)."""
+    if dev.type != "cuda" or not WEIGHT_BANK:
+        return
+    bank = model.__dict__.get("_istnet_weight_bank")
+    if bank is None:
+        bank = WeightBank()
+        object.__setattr__(model, "_istnet_weight_bank", bank)
+    _CURRENT_BANK[dev.index if dev.index is not None else torch.cuda.current_device()] = bank
+    bank.begin_step(dev)
+
+
+def invalidate_weights(dev):
+    """An optimizer that writes parameters through raw pointers (parallel.FlatAdam) calls this after its step."""
+    if dev.type == "cuda":
+        b = weight_bank(dev)
+        if b is not None:
+            b.invalidate()
 
 
 def pick_box(H, W):

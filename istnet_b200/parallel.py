@@ -296,6 +296,9 @@ class FlatAdam(torch.optim.Optimizer):
             _C.call("adam_flat", ptr(f["p"]), ptr(f["g"]), ptr(f["m"]), ptr(f["v"]), c_ll(f["p"].numel()), ptr(self.lr_dev), c_float(b1),
                     c_float(b2), c_float(g0["eps"]), c_float(g0["weight_decay"]), c_float(scale), ptr(self.step_dev))
         _C.call("adam_tick", ptr(self.step_dev))
+        from . import nhwc
+
+        nhwc.invalidate_weights(self.step_dev.device)  # parameters changed behind autograd's version counters
 
 
 def broadcast_module(module, src=0, process_group=None):

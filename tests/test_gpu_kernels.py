@@ -424,3 +424,32 @@ def test_interp_rows_backward_vs_float64():
     ref.backward(cot.double())
     assert rel_err(out, ref) < 1e-6
     assert rel_err(feats.grad, f64.grad) < 1e-5
+
+
+def test_pose_tail_pool_heads_ortho6d_vs_float64():
+    """csrc/heads.cu: AdaptiveAvgPool1d(1) + 3 x [Linear, ReLU, Linear, ReLU, Linear] + Ortho6d2Mat (ist_net.py:228-264,
+    utils/rotation_utils.py:4-28), forward and backward, against float64 autograd of the torch modules: 1e-5."""
+    import copy
+
+    from istnet_b200 import model as M
+
+    torch.manual_seed(7)
+    est = M.LightEstimator().cuda()
+    B, N = 5, 96
+    g = torch.Generator(device="cuda").manual_seed(31)
+    feat = torch.randn(B * N, 512, device="cuda", generator=g).requires_grad_(True)
+    r, t, s = M._PoseTailFn.apply(feat, B, N, *est._head_params())
+    cot = [torch.randn(v.shape, device="cuda", generator=g) for v in (r, t, s)]
+    torch.autograd.backward([r, t, s], cot)
+    e64 = copy.deepcopy(est).double()
+    f64 = feat.detach().double().requires_grad_(True)
+    pooled = f64.view(B, N, -1).mean(1)
+    r6 = e64.rotation_estimator(pooled)
+    r_ref = M.ortho6d_to_mat(r6[:, :3].contiguous(), r6[:, 3:].contiguous())
+    t_ref, s_ref = e64.translation_estimator(pooled), e64.size_estimator(pooled)
+    torch.autograd.backward([r_ref, t_ref, s_ref], [c.double() for c in cot])
+    for a, b in ((r, r_ref), (t, t_ref), (s, s_ref), (feat.grad, f64.grad)):
+        assert rel_err(a, b) < 1e-5, rel_err(a, b)
+    for name in ("rotation_estimator", "translation_estimator", "size_estimator"):
+        for (n, p), (_, p64) in zip(getattr(est, name).named_parameters(), getattr(e64, name).named_parameters()):
+            assert rel_err(p.grad, p64.grad) < 1e-5, (name, n, rel_err(p.grad, p64.grad))
