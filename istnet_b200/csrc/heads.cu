@@ -112,9 +112,9 @@ struct HeadBwdPtrs {
     float *db[3];           // [O]
     int O[3];
 };
-// role 0 (blockIdx.z == 0): dW[o][k] = sum_b g[b][o] x[b][k], db[o] = sum_b g[b][o]   with g = dy * [y > 0]
+// role 0 (blocks < nblk_w): dW[o][k] = sum_b g[b][o] x[b][k], db[o] = sum_b g[b][o]   with g = dy * [y > 0]
 //        grid.x covers O*K/kThreads elements (thread = one (o, k), k fastest: coalesced x reads and dW writes)
-// role 1 (blockIdx.z == 1): dx[b][k] = sum_o g[b][o] w[o][k]    thread = one (b, k)
+// role 1 (blocks >= nblk_w): dx[b][k] = sum_o g[b][o] w[o][k]     CTA = one batch row x 32 input features, 8 warps split the outputs
 __global__ void __launch_bounds__(kThreads) heads_linear_bwd_kernel(HeadBwdPtrs p, int B, int K, int relu, int nblk_w) {
     const int h = blockIdx.y;
     const int O = p.O[h];
@@ -133,17 +133,29 @@ __global__ void __launch_bounds__(kThreads) heads_linear_bwd_kernel(HeadBwdPtrs 
         p.dw[h][i] = acc;
         if (k == 0 && p.db[h]) p.db[h][o] = accb;
     } else {
+        // one CTA per (batch row, 32 input features): 8 warps split the O outputs, partial sums combined in a fixed order
+        __shared__ float red[kWarps][32];
         if (!p.dx[h]) return;
-        const long long i = (long long)((int)blockIdx.x - nblk_w) * kThreads + threadIdx.x;
-        if (i >= (long long)B * K) return;
-        const int b = (int)(i / K), k = (int)(i - (long long)b * K);
+        const int kchunks = (K + 31) / 32;
+        const int blk = (int)blockIdx.x - nblk_w;
+        const int b = blk / kchunks, k = (blk - b * kchunks) * 32 + (threadIdx.x & 31);
+        const int sl = threadIdx.x >> 5;
         float acc = 0.f;
-        for (int o = 0; o < O; ++o) {
-            float g = dy[(size_t)b * O + o];
-            if (relu && !(y[(size_t)b * O + o] > 0.f)) g = 0.f;
-            acc = __fmaf_rn(g, __ldg(p.w[h] + (size_t)o * K + k), acc);
+        if (k < K) {
+            for (int o = sl; o < O; o += kWarps) {
+                float g = dy[(size_t)b * O + o];
+                if (relu && !(y[(size_t)b * O + o] > 0.f)) g = 0.f;
+                acc = __fmaf_rn(g, __ldg(p.w[h] + (size_t)o * K + k), acc);
+            }
         }
-        p.dx[h][i] = acc;
+        red[sl][threadIdx.x & 31] = acc;
+        __syncthreads();
+        if (sl == 0 && k < K) {
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < kWarps; ++q) t += red[q][threadIdx.x & 31];
+            p.dx[h][(size_t)b * K + k] = t;
+        }
     }
 }
 // dx_total[i] = a[i] + b[i] + c[i]  (the three heads share the pooled input)
@@ -259,7 +271,7 @@ extern "C" int istnet_heads_linear_bwd(int nheads, int B, int K, const float *co
         any_dx = any_dx || p.dx[h];
     }
     const int nblk_w = (int)(((long long)omax * K + kThreads - 1) / kThreads);
-    const int nblk_x = any_dx ? (int)(((long long)B * K + kThreads - 1) / kThreads) : 0;
+    const int nblk_x = any_dx ? B * ((K + 31) / 32) : 0;
     dim3 grid(nblk_w + nblk_x, nheads, 1);
     heads_linear_bwd_kernel<<<grid, kThreads, 0, ST>>>(p, B, K, relu, nblk_w);
     ISTNET_LAUNCH_CHECK();

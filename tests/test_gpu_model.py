@@ -227,3 +227,28 @@ def test_cuda_graph_step_equals_eager_step():
             # is chaotic (see test_train_step_matches_reference_golden); gross errors (a missed dependency in the captured
             # multi-stream graph would give O(1)) are what this guards against
             assert errs[len(errs) // 2] < 2e-3 and errs[-1] < 0.1, (errs[len(errs) // 2], errs[-1])
+
+
+def test_inference_engine_buckets_match_direct_eval_forward():
+    """Eval-mode inference path (utils/solver.py:217-241): graph-per-bucket engine with padded instance counts and on-device pose
+    assembly vs the plain eval forward + the reference's assembly arithmetic."""
+    from conftest import perturb_batchnorm
+    from istnet_b200.infer import InferenceEngine
+
+    torch.manual_seed(1)
+    m = M.IST_Net(6, False)
+    perturb_batchnorm(m, seed=43)
+    m = m.cuda().eval()
+    eng = InferenceEngine(m, npts=256, img=64)
+    for b, seed in ((3, 71), (1, 72), (4, 73), (3, 74)):
+        d = make_batch(b, 256, 64, seed=seed)
+        inp = {"rgb": d["rgb"].cuda(), "pts": d["pts"].cuda(), "choose": d["choose"].cuda(), "category_label": d["category_label"].reshape(-1).cuda()}
+        rts, scales = eng(inp)
+        with torch.no_grad():
+            ep = m(inp)
+        s = torch.norm(ep["pred_size"], dim=1, keepdim=True)
+        want = torch.eye(4, device="cuda").unsqueeze(0).repeat(b, 1, 1)
+        want[:, :3, 3] = ep["pred_translation"]
+        want[:, :3, :3] = ep["pred_rotation"] * s.unsqueeze(2)
+        assert rel_err(rts, want) < 1e-6 and rel_err(scales, ep["pred_size"] / s) < 1e-6
+    assert sorted(eng._graphs) == [1, 4]
