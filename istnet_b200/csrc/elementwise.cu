@@ -632,6 +632,42 @@ __global__ void __launch_bounds__(kEwThreads) upsample2x_split_kernel(int B, int
         if (out_f32) *reinterpret_cast<float4 *>(out_f32 + op * C + c) = o;
     }
 }
+// C % 8 == 0 (every PSPUpsample width): 8 channels per thread — half the index arithmetic per element and one 16-byte store per
+// plane (the 4-channel kernel ran at 58 % issue utilisation and 2.8 TB/s, profiles/r2_ncu_families_all.txt).  Same arithmetic order.
+__global__ void __launch_bounds__(kEwThreads) upsample2x_split8_kernel(int B, int H, int W, int C, float sh, float sw, const float *__restrict__ x,
+                                                                        __nv_bfloat16 *pl, long long pl_stride, int nsplit, int cs, float *out_f32) {
+    const unsigned lanes = C >> 3, Ho = 2 * H, Wo = 2 * W;
+    const unsigned total = (unsigned)B * Ho * Wo * lanes;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = (int)(i % lanes) * 8;
+        unsigned r = i / lanes;
+        const int wo = (int)(r % Wo); r /= Wo;
+        const int ho = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        int h0, h1, w0, w1;
+        float hl0, hl1, wl0, wl1;
+        up_src_s(ho, H, sh, h0, h1, hl0, hl1);
+        up_src_s(wo, W, sw, w0, w1, wl0, wl1);
+        const float *base = x + (size_t)b * H * W * C + c;
+        const float *p00 = base + ((size_t)h0 * W + w0) * C, *p01 = base + ((size_t)h0 * W + w1) * C;
+        const float *p10 = base + ((size_t)h1 * W + w0) * C, *p11 = base + ((size_t)h1 * W + w1) * C;
+        float o[8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float4 a = ld4(p00 + 4 * q), bq = ld4(p01 + 4 * q), cq = ld4(p10 + 4 * q), d = ld4(p11 + 4 * q);
+            o[4 * q + 0] = hl0 * (wl0 * a.x + wl1 * bq.x) + hl1 * (wl0 * cq.x + wl1 * d.x);
+            o[4 * q + 1] = hl0 * (wl0 * a.y + wl1 * bq.y) + hl1 * (wl0 * cq.y + wl1 * d.y);
+            o[4 * q + 2] = hl0 * (wl0 * a.z + wl1 * bq.z) + hl1 * (wl0 * cq.z + wl1 * d.z);
+            o[4 * q + 3] = hl0 * (wl0 * a.w + wl1 * bq.w) + hl1 * (wl0 * cq.w + wl1 * d.w);
+        }
+        const size_t op = ((size_t)b * Ho + ho) * Wo + wo;
+        if (pl) store_planes8(pl + op * cs + c, pl_stride, nsplit, o);
+        if (out_f32) {
+            *reinterpret_cast<float4 *>(out_f32 + op * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4 *>(out_f32 + op * C + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+    }
+}
 // gather form of the adjoint: dx[b,h,w,:] = sum over the output pixels that read (h,w).  The per-axis weights of the 7
 // candidate outputs are computed once per element (7 + 7 evaluations instead of 49 x 2), the products in the same order.
 __global__ void __launch_bounds__(kEwThreads) upsample2x_bwd_kernel(int B, int H, int W, int C, float sh, float sw, const float *__restrict__ dout,
@@ -723,6 +759,58 @@ __global__ void __launch_bounds__(kEwThreads) im2col_split_kernel(int B, int H, 
                 store_planes1(orow + k, pl_stride, nsplit, v);
             }
         }
+    }
+}
+// Same map with a thread per 8 consecutive patch columns (cs % 8 == 0): the output [rows][cs] is contiguous, so thread i owns the i-th
+// 16 bytes of every plane (coalesced 16-byte stores; the per-column kernel above issues one 2-byte store per plane and element and
+// leaves 109 of 256 threads idle on the 7x7x3 stem: 401 us at 0.65 TB/s, profiles/r2_ncu_families_all.txt).  The (tap row, tap
+// column, channel) decomposition of every column comes from a shared-memory table built once per CTA; channels-last inputs with
+// C % 8 == 0 read their 8 columns as two float4.  Padding columns K..cs-1 are written as zeros.
+__global__ void __launch_bounds__(kEwThreads) im2col_split8_kernel(int B, int H, int W, int C, int kh, int kw, int stride, int pad, int Ho, int Wo,
+                                                                    const float *__restrict__ x, int nchw, __nv_bfloat16 *pl, long long pl_stride,
+                                                                    int nsplit, int cs) {
+    extern __shared__ int im2col_tab[];  // [cs]: r << 22 | s << 14 | c, or -1 for padding columns
+    const int K = kh * kw * C;
+    for (int k = threadIdx.x; k < cs; k += blockDim.x) {
+        int e = -1;
+        if (k < K) {
+            const int tap = k / C;
+            e = ((tap / kw) << 22) | ((tap % kw) << 14) | (k - tap * C);
+        }
+        im2col_tab[k] = e;
+    }
+    __syncthreads();
+    const unsigned chunks = (unsigned)cs >> 3;
+    const unsigned total = (unsigned)B * Ho * Wo * chunks;
+    const bool vec = !nchw && (C & 7) == 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned row = i / chunks;
+        const int k0 = (int)(i - row * chunks) * 8;
+        const int wo = (int)(row % (unsigned)Wo);
+        const unsigned t = row / (unsigned)Wo;
+        const int ho = (int)(t % (unsigned)Ho), b = (int)(t / (unsigned)Ho);
+        const int hb = ho * stride - pad, wb = wo * stride - pad;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        if (vec) {
+            const int e = im2col_tab[k0];
+            const int h = hb + (e >> 22), w = wb + ((e >> 14) & 0xff);
+            if (e >= 0 && h >= 0 && h < H && w >= 0 && w < W) {
+                const float *src = x + (((size_t)b * H + h) * W + w) * C + (e & 0x3fff);
+                const float4 lo = ld4(src), hi = ld4(src + 4);
+                v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int e = im2col_tab[k0 + j];
+                const int h = hb + (e >> 22), w = wb + ((e >> 14) & 0xff), c = e & 0x3fff;
+                if (e >= 0 && h >= 0 && h < H && w >= 0 && w < W)
+                    v[j] = nchw ? __ldg(x + (((size_t)b * C + c) * H + h) * W + w) : __ldg(x + (((size_t)b * H + h) * W + w) * C + c);
+            }
+        }
+        store_planes8(pl + (size_t)row * cs + k0, pl_stride, nsplit, v);
     }
 }
 // dx[b,h,w,c] (+)= sum over (r,s) with (h+pad-r) % stride == 0 ... of dcol[b,ho,wo,(r*kw+s)*C+c]
@@ -1470,8 +1558,12 @@ extern "C" int istnet_upsample2x_split(const float *x, int B, int H, int W, int 
                                        float *out_f32, void *stream) {
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
     if ((long long)B * 4 * H * W * (C / 4) > 0x7fffffffLL) return ISTNET_ERR_UNSUPPORTED;
-    upsample2x_split_kernel<<<ew_grid((long long)B * 4 * H * W * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, up_scale(H, 2 * H), up_scale(W, 2 * W), x,
-                                                                                               (__nv_bfloat16 *)planes, plane_stride, nsplit, cs, out_f32);
+    if ((C & 7) == 0 && (cs & 7) == 0 && (plane_stride & 7) == 0 && (reinterpret_cast<uintptr_t>(planes) & 15) == 0)
+        upsample2x_split8_kernel<<<ew_grid((long long)B * 4 * H * W * (C / 8)), kEwThreads, 0, ST>>>(B, H, W, C, up_scale(H, 2 * H), up_scale(W, 2 * W), x,
+                                                                                                    (__nv_bfloat16 *)planes, plane_stride, nsplit, cs, out_f32);
+    else
+        upsample2x_split_kernel<<<ew_grid((long long)B * 4 * H * W * (C / 4)), kEwThreads, 0, ST>>>(B, H, W, C, up_scale(H, 2 * H), up_scale(W, 2 * W), x,
+                                                                                                   (__nv_bfloat16 *)planes, plane_stride, nsplit, cs, out_f32);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }
@@ -1488,8 +1580,14 @@ extern "C" int istnet_im2col_split(const float *x, int nchw, int B, int H, int W
     const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
     if (B <= 0 || Ho <= 0 || Wo <= 0 || cs < kh * kw * C || nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
     if ((long long)B * Ho * Wo > 0x7fffffffLL) return ISTNET_ERR_UNSUPPORTED;
-    im2col_split_kernel<<<ew_grid((long long)B * Ho * Wo * kEwThreads), kEwThreads, 0, ST>>>(B, H, W, C, kh, kw, stride, pad, Ho, Wo, x, nchw,
-                                                                                             (__nv_bfloat16 *)planes, plane_stride, nsplit, cs);
+    const long long chunks = (long long)B * Ho * Wo * (cs / 8);
+    if ((cs & 7) == 0 && (plane_stride & 7) == 0 && (reinterpret_cast<uintptr_t>(planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+        cs * 4 <= 48 * 1024 && kh < 256 && kw < 256 && C < (1 << 14) && chunks <= 0x7fffffffLL)
+        im2col_split8_kernel<<<ew_grid(chunks), kEwThreads, (size_t)cs * sizeof(int), ST>>>(B, H, W, C, kh, kw, stride, pad, Ho, Wo, x, nchw,
+                                                                                          (__nv_bfloat16 *)planes, plane_stride, nsplit, cs);
+    else
+        im2col_split_kernel<<<ew_grid((long long)B * Ho * Wo * kEwThreads), kEwThreads, 0, ST>>>(B, H, W, C, kh, kw, stride, pad, Ho, Wo, x, nchw,
+                                                                                                 (__nv_bfloat16 *)planes, plane_stride, nsplit, cs);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }

@@ -23,27 +23,40 @@ struct HeadPtrs {            // up to 3 heads per launch
 };
 
 // ------------------------------------------------------------------ pooling over the points
-// pooled[b][c] = (1/N) sum_n feat[(b*N + n)*C + c]   (nn.AdaptiveAvgPool1d(1));  grid = (C/128 or so, B)
+// pooled[b][c] = (1/N) sum_n feat[(b*N + n)*C + c]   (nn.AdaptiveAvgPool1d(1));  grid = (ceil(C/32), B): a CTA owns 32 channels of one
+// instance (8 lanes x float4 = one 128-byte line per row), its 32 row groups stride the N rows with 4 independent loads in flight per
+// thread; fixed-order combine in shared memory (deterministic).  [B=32, N=1024, C=512] -> 512 CTAs (the first version used 128 CTAs
+// with one dependent load stream per thread: 31 us at 2.2 TB/s, profiles/r2_ncu_families.txt).
 __global__ void __launch_bounds__(kThreads) rows_mean_kernel(int N, int C, const float *__restrict__ feat, float *__restrict__ pooled) {
-    __shared__ float red[kWarps][32 * 4];
+    constexpr int kGroups = kThreads / 8;
+    __shared__ float4 red[kThreads];
     const int b = blockIdx.y;
-    const int c = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;   // 4 channels per lane, 128 per CTA
-    const int w = threadIdx.x >> 5;
+    const int q = threadIdx.x & 7, g = threadIdx.x >> 3;
+    const int c = blockIdx.x * 32 + q * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < C) {
         const float *src = feat + (size_t)b * N * C + c;
-        for (int n = w; n < N; n += kWarps) {
+        int n = g;
+        for (; n + 3 * kGroups < N; n += 4 * kGroups) {
+            const float4 v0 = *reinterpret_cast<const float4 *>(src + (size_t)n * C);
+            const float4 v1 = *reinterpret_cast<const float4 *>(src + (size_t)(n + kGroups) * C);
+            const float4 v2 = *reinterpret_cast<const float4 *>(src + (size_t)(n + 2 * kGroups) * C);
+            const float4 v3 = *reinterpret_cast<const float4 *>(src + (size_t)(n + 3 * kGroups) * C);
+            s.x += (v0.x + v1.x) + (v2.x + v3.x); s.y += (v0.y + v1.y) + (v2.y + v3.y);
+            s.z += (v0.z + v1.z) + (v2.z + v3.z); s.w += (v0.w + v1.w) + (v2.w + v3.w);
+        }
+        for (; n < N; n += kGroups) {
             const float4 v = *reinterpret_cast<const float4 *>(src + (size_t)n * C);
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
     }
-    *reinterpret_cast<float4 *>(&red[w][(threadIdx.x & 31) * 4]) = s;
+    red[threadIdx.x] = s;
     __syncthreads();
-    if (w == 0 && c < C) {
+    if (threadIdx.x < 8 && c < C) {
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int q = 0; q < kWarps; ++q) {
-            const float4 v = *reinterpret_cast<const float4 *>(&red[q][(threadIdx.x & 31) * 4]);
+#pragma unroll 8
+        for (int k = 0; k < kGroups; ++k) {
+            const float4 v = red[k * 8 + q];
             t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
         }
         const float inv = 1.f / (float)N;
@@ -226,7 +239,7 @@ __global__ void ortho6d_bwd_kernel(int B, const float *__restrict__ r6, const fl
 
 extern "C" int istnet_rows_mean(int B, int N, int C, const float *feat, float *pooled, void *stream) {
     if (B <= 0 || N <= 0 || C <= 0 || (C & 3) || !feat || !pooled) return ISTNET_ERR_BAD_ARG;
-    dim3 grid(ceil_div(C, 128), B);
+    dim3 grid(ceil_div(C, 32), B);
     rows_mean_kernel<<<grid, kThreads, 0, ST>>>(N, C, feat, pooled);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;

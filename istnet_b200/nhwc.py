@@ -384,6 +384,7 @@ class _MomTable:
         self.host = torch.full((_MOM_SLOTS,), 0.1, dtype=torch.float32).pin_memory()
         self.mirror = [None] * _MOM_SLOTS  # Python copy of what the device holds (no tensor op on the per-call path)
         self.used = 0
+        self.copied = None  # event after the last host->device copy of the table: `host` is rewritten only once that copy is done
 
 
 def _mom_value(bn):
@@ -434,11 +435,15 @@ def refresh_momentum(bn_modules, dev):
         tab, i = _mom_slot(bn, dev)
         v = _mom_value(bn)
         if tab.mirror[i] != v:
+            if not dirty and tab.copied is not None:
+                tab.copied.synchronize()  # a loop running ahead of the device: the previous table copy must have read `host`
             tab.mirror[i] = v
             tab.host[i] = v
             dirty = True
     if dirty:
         tab.dev.copy_(tab.host, non_blocking=True)
+        tab.copied = tab.copied or torch.cuda.Event()
+        tab.copied.record()
     return dirty
 
 

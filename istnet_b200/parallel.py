@@ -264,17 +264,30 @@ class FlatAdam(torch.optim.Optimizer):
                 off += _pad(p.numel())
             self.flat.append({"p": fp, "g": b["flat"], "m": torch.zeros_like(fp), "v": torch.zeros_like(fp)})
         self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        # pinned ring: a training loop that runs ahead of the device rewrites lr every iteration (CyclicLR) while earlier
+        # asynchronous copies may still be pending; a slot is reused only after the copy that read it has completed
+        self.lr_host = torch.zeros(self._LR_RING, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(self._LR_RING)
+        self._lr_events = [None] * self._LR_RING
+        self._lr_slot = 0
         self._lr_mirror = None
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.sync_lr()
+
+    _LR_RING = 16
 
     def sync_lr(self):
         lr = float(self.param_groups[0]["lr"])
         if lr != self._lr_mirror:
             self._lr_mirror = lr
-            self.lr_host[0] = lr
-            self.lr_dev.copy_(self.lr_host, non_blocking=True)
+            i = self._lr_slot = (self._lr_slot + 1) % self._LR_RING
+            if self._lr_events[i] is not None:
+                self._lr_events[i].synchronize()
+            self.lr_host[i] = lr
+            self.lr_dev.copy_(self.lr_host[i : i + 1], non_blocking=True)
+            if self.lr_dev.is_cuda:
+                ev = self._lr_events[i] or torch.cuda.Event()
+                ev.record()
+                self._lr_events[i] = ev
 
     def zero_grad(self, set_to_none=True):
         # gradients are views of the flat buckets that every step overwrites (graph path) or that the reducer zeroes (eager

@@ -252,3 +252,104 @@ def test_inference_engine_buckets_match_direct_eval_forward():
         want[:, :3, :3] = ep["pred_rotation"] * s.unsqueeze(2)
         assert rel_err(rts, want) < 1e-6 and rel_err(scales, ep["pred_size"] / s) < 1e-6
     assert sorted(eng._graphs) == [1, 4]
+
+
+class _Cfg(dict):
+    """attribute dictionary with .get like gorilla.Config"""
+
+    def __getattr__(self, k):
+        try:
+            v = self[k]
+        except KeyError:
+            raise AttributeError(k)
+        return _Cfg(v) if isinstance(v, dict) else v
+
+
+def test_stall_free_solver_loop_matches_the_reference_loop():
+    """istnet_b200.solver.Solver (captured step + flat Adam, CyclicLR and BNMomentumScheduler as device scalars,
+    deferred loss reads) against the loop of utils/solver.py:75-127 written out with torch.optim.Adam on the eager model: same
+    learning-rate and BatchNorm-momentum sequence, same losses, same parameter updates, warm-up / capture leave no trace."""
+    import copy
+
+    from istnet_b200.solver import Solver, bn_momentum_at, cyclic_lr
+
+    cfg = _Cfg(max_epoch=2, num_mini_batch_per_epoch=6, per_write=2, per_val=10, log_dir="/tmp",
+               optimizer={"lr": 0.01, "weight_decay": 0.0}, bn={"bn_momentum": 0.9, "bn_decay": 0.5, "decay_step": 2, "bnm_clip": 0.01},
+               loss={"gamma1": 1.0, "gamma2": 10.0}, freeze_world_enhancer=False)
+    torch.manual_seed(3)
+    m = M.IST_Net(6, False).cuda().train()
+    m_ref = copy.deepcopy(m)
+    ones = {c: torch.ones(4, c, 1, 1, device="cuda") for c in (1024, 256, 64)}
+    for mm in (m, m_ref):
+        mm.rgb_cam_extractor.model.dropout_noise_fn = lambda b, c, p: ones[c]
+    n_it = 4
+    syn = [make_batch(3, 256, 64, seed=100 + i) for i in range(n_it)]
+    real = [make_batch(1, 256, 64, seed=200 + i) for i in range(n_it)]
+    loss_fn = M.SupervisedLoss(M.LossCfg())
+    p0 = {n: p.detach().clone() for n, p in m.named_parameters()}
+
+    # the reference loop (utils/solver.py:83-99,152-188)
+    opt = torch.optim.Adam(m_ref.parameters(), lr=1e-5, weight_decay=0.0)
+    step_up = cfg.max_epoch * cfg.num_mini_batch_per_epoch // 6
+    ref_losses, ref_lrs = [], []
+    for it in range(n_it):
+        lr = cyclic_lr(it, 1e-5, 1e-3, step_up)
+        for g in opt.param_groups:
+            g["lr"] = lr
+        mom = bn_momentum_at(it, 0.9, 0.5, 2, 0.01)
+        for mod in m_ref.modules():
+            if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+                mod.momentum = mom
+        opt.zero_grad()
+        data = {k: torch.cat([syn[it][k], real[it][k]]).cuda() for k in syn[it]}
+        ep = m_ref({k: data[k] for k in ("rgb", "pts", "choose", "category_label", "qo")})
+        ep.update({k: data[k] for k in LABELS})
+        ls = loss_fn({k: v[:3] for k, v in ep.items()})
+        lr_ = loss_fn({k: v[3:] for k, v in ep.items()})
+        la = (ls * 3 + lr_ * 1) / 4
+        la.backward()
+        opt.step()
+        ref_losses.append((la.item(), ls.item(), lr_.item()))
+        ref_lrs.append(lr)
+    assert ref_lrs[0] == 1e-5 and abs(ref_lrs[2] - 1e-3) < 1e-12 and ref_lrs[1] > ref_lrs[0]
+
+    logged = []
+
+    class _Log:
+        def info(self, s):
+            logged.append(s)
+
+        warning = info
+
+    sol = Solver(m, "Camera+Real", {"syn": loss_fn, "real": loss_fn}, {"syn": syn, "real": real}, _Log(), cfg, log_lag=1)
+    hist = {}
+    orig_update = sol.log_buffer.update
+    sol.log_buffer.update = lambda d, count=1: (orig_update(d), [hist.setdefault(k, []).append(v) for k, v in d.items()])[0]
+    info = sol.train()
+    assert sol.iter == n_it and int(sol.optimizer.step_dev.item()) == n_it
+    assert hist["lr"] == ref_lrs
+    got = list(zip(hist["loss_all"], hist["loss_syn"], hist["loss_real"]))
+    assert len(got) == n_it and any("Train - " in s for s in logged)
+    for a, b in zip(got[0], ref_losses[0]):
+        assert abs(a - b) <= 1e-5 * abs(b), (got[0], ref_losses[0])  # same weights, same kernels: the first step is identical
+    for g_, r_ in zip(got[1:], ref_losses[1:]):
+        for a, b in zip(g_, r_):
+            assert abs(a - b) <= 2e-2 * abs(b), (got, ref_losses)  # later steps see the (chaotic, train-mode B=4) updates
+    assert abs(info["loss_all"] - sum(r[0] for r in ref_losses) / n_it) <= 2e-2 * abs(info["loss_all"])
+    # parameters moved the same way; BatchNorm buffers advanced exactly n_it times with the scheduled momentum
+    errs = []
+    ref_params = dict(m_ref.named_parameters())
+    for n, p in m.named_parameters():
+        d_ref = ref_params[n].detach() - p0[n]
+        if d_ref.abs().max().item() > 0:
+            errs.append(rel_err(p.detach() - p0[n], d_ref))
+    errs.sort()
+    assert errs and errs[len(errs) // 2] < 0.1, (errs[len(errs) // 2], errs[-1])
+    bufs_ref = dict(m_ref.named_buffers())
+    for n, b in m.named_buffers():
+        if n.endswith("num_batches_tracked"):
+            assert int(b.item()) == int(bufs_ref[n].item()) == n_it, n
+        elif n.endswith("running_mean") and bufs_ref[n].abs().max().item() > 1e-3:
+            assert rel_err(b, bufs_ref[n]) < 5e-2, (n, rel_err(b, bufs_ref[n]))
+    assert all(abs(mod.momentum - bn_momentum_at(n_it - 1, 0.9, 0.5, 2, 0.01)) < 1e-12 for mod in m.modules()
+               if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm))

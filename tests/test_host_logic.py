@@ -58,3 +58,49 @@ def test_plane_map_and_layout_helpers():
     u = nhwc.ConvUnit(torch.zeros(4, 4, 1, 1), None, None, nhwc.ACT_RELU, nsplit=2, nsplit_out=2)
     assert (u.ns, u.ns_out) == (2, 2) and nhwc.ConvUnit(torch.zeros(4, 4, 1, 1), None, None, nhwc.ACT_RELU).ns == nhwc.NSPLIT
     assert len(IE._sz4([1, 2, 3, 6])) == 4 and [v.value for v in IE._sz4([6])] == [6, 0, 0, 0]
+
+
+def test_solver_schedules_match_torch_cyclic_lr_and_the_reference_momentum_lambda():
+    """istnet_b200.solver evaluates the reference's schedulers in closed form on the host (the values then travel as device scalars):
+    CyclicLR(base 1e-5, max 1e-3, triangular, step_size_up = max_epoch * num_mini_batch_per_epoch // 6; utils/solver.py:46-47) and
+    the BNMomentumScheduler lambda (utils/solver.py:49)."""
+    import warnings
+
+    import torch
+
+    from istnet_b200.solver import bn_momentum_at, cyclic_lr
+
+    for step_up in (1, 2, 7, 20000):
+        opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=0.01)
+        sched = torch.optim.lr_scheduler.CyclicLR(opt, base_lr=1e-5, max_lr=1e-3, step_size_up=step_up, mode="triangular", cycle_momentum=False)
+        its = list(range(0, 40)) if step_up < 100 else [0, 1, 9999, 19999, 20000, 20001, 39999, 40000, 40001, 119999]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for it in its:
+                sched.step(it)  # the reference passes the iteration explicitly (utils/solver.py:89)
+                assert abs(opt.param_groups[0]["lr"] - cyclic_lr(it, 1e-5, 1e-3, step_up)) <= 1e-12, (step_up, it)
+    lmbd = lambda it: max(0.9 * 0.5 ** (int(it / 4000)), 0.01)
+    for it in (0, 1, 3999, 4000, 8000, 25999, 26000, 28000, 119999):
+        assert bn_momentum_at(it, 0.9, 0.5, 4000, 0.01) == lmbd(it)
+    assert bn_momentum_at(119999, 0.9, 0.5, 4000, 0.01) == 0.01
+
+
+def test_solver_batch_merge_and_log_buffer():
+    import torch
+
+    from istnet_b200.solver import LogBuffer, merge_into
+    from istnet_b200.synth import make_batch
+
+    syn, real = make_batch(3, 32, 16, seed=1), make_batch(2, 32, 16, seed=2)
+    keys = ("rgb", "pts", "choose", "category_label", "qo", "rotation_label", "translation_label", "size_label")
+    dst = {k: torch.empty((5,) + tuple(syn[k].shape[1:]), dtype=syn[k].dtype) for k in keys}
+    assert merge_into(dst, syn, real, keys) == 3
+    for k in keys:
+        assert torch.equal(dst[k], torch.cat([syn[k], real[k]], dim=0)), k  # utils/solver.py:163-174
+    lb = LogBuffer()
+    for v in (1.0, 2.0, 3.0, 4.0):
+        lb.update({"loss_all": v, "lr": 0.1})
+    lb.average(2)
+    assert lb._output["loss_all"] == 3.5 and lb.avg["loss_all"] == 2.5
+    lb.clear()
+    assert not lb.val_history and not lb._output

@@ -20,7 +20,11 @@ COLS = OrderedDict([
     ("issue%", "smsp__issue_active.avg.pct_of_peak_sustained_active"), ("l2hit%", "lts__t_sector_hit_rate.pct"),
     ("warps%", "sm__warps_active.avg.pct_of_peak_sustained_active"), ("regs", "launch__registers_per_thread"), ("grid", "launch__grid_size"),
 ])
-UNIT = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+# fallbacks for reports captured with --section SpeedOfLight / MemoryWorkloadAnalysis instead of --set full
+ALT = {"tensor%": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "issue%": "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
+       "GB/s": "dram__bytes.sum.per_second"}
+UNIT = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3,
+        "byte/s": 1e-9, "Kbyte/s": 1e-6, "Mbyte/s": 1e-3, "Gbyte/s": 1.0, "Tbyte/s": 1e3}
 
 
 def num(v, unit):
@@ -38,6 +42,9 @@ def main():
     hdr, units = rows[0], rows[1]
     ki = hdr.index("Kernel Name")
     idx = {k: hdr.index(m) for k, m in COLS.items() if m in hdr}
+    for k, m in ALT.items():
+        if k not in idx and m in hdr:
+            idx[k] = hdr.index(m)
     recs = []
     for r in rows[2:]:
         name = r[ki].replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
@@ -45,7 +52,10 @@ def main():
         rec = {"name": name}
         for k, i in idx.items():
             rec[k] = num(r[i], units[i])
-        rec["GB/s"] = (rec.get("rd_MB", 0) + rec.get("wr_MB", 0)) / max(rec.get("us", 1e-9), 1e-9) * 1e3 if "us" in rec else float("nan")
+        if "rd_MB" in rec:
+            rec["GB/s"] = (rec.get("rd_MB", 0) + rec.get("wr_MB", 0)) / max(rec.get("us", 1e-9), 1e-9) * 1e3
+        else:  # only the rate was collected: traffic = rate x duration
+            rec["rd_MB"], rec["wr_MB"] = rec.get("GB/s", 0.0) * rec.get("us", 0.0) * 1e-3, 0.0
         rec["hbm_frac"] = rec["GB/s"] / HBM
         recs.append(rec)
     keys = ["us", "rd_MB", "wr_MB", "GB/s", "hbm_frac", "tensor%", "sm%", "issue%", "l2hit%", "warps%", "regs", "grid"]
