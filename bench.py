@@ -173,8 +173,9 @@ def gpu_reference_rate(wl, dev, steps=20, warmup=3, tf32=True, graph=True):
                 with torch.cuda.graph(g):
                     one_step()
                 mode = "cuda-graph"
-            except Exception:
+            except Exception as e:  # e.g. an op of the reference dataflow that synchronises or allocates outside the capture
                 g = None
+                mode = "eager (capture failed: " + " ".join(str(e).split())[:160] + ")"
                 torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -381,7 +382,9 @@ def main():
     from istnet_b200 import model as model_mod
 
     nhwc.PROFILE = []
-    model_mod.USE_SIDE_STREAMS, nhwc.WGRAD_SIDE_STREAM = False, False  # time each kernel alone on its launching stream
+    from istnet_b200 import pointnet2 as pn2_mod
+
+    model_mod.USE_SIDE_STREAMS, nhwc.WGRAD_SIDE_STREAM, pn2_mod.SA_FORK = False, False, False  # time each kernel alone on its launching stream
     reducer.zero_grad()
     ep_ = model({k: resident[k] for k in MODEL_IN})
     ep_.update({k: resident[k] for k in LABELS})

@@ -7,6 +7,8 @@ model/pointnet2/pytorch_utils.py:25-206 `SharedMLP`): e.g. `SA_modules.0.mlps.0.
 BN layers are real `nn.BatchNorm2d` instances so the reference BNMomentumScheduler (utils/scheduler.py:277-303)
 finds them; momentum / eps / training are read at call time.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -15,6 +17,8 @@ from . import ext
 from . import functional as PF
 from . import rows_engine as RE
 from . import sa_fused as SF
+
+SA_FORK = os.environ.get("ISTNET_SA_FORK", "1") != "0"  # the two scales of an unfused SA level on two streams
 
 
 class _NormLayer(nn.Sequential):
@@ -93,10 +97,24 @@ class PointnetSAModuleMSG(nn.Module):
             if RE.K.bn_uses_batch_stats(bn0, self.training) or not needs_grad:
                 # both scales, ball query + grouping + SharedMLP + max in one launch per pass (csrc/sa_fused.cu)
                 return new_xyz, SF.sa_level(self, xyz, new_xyz, feats_rows)
-        outs = []
-        for grouper, mlp in zip(self.groupers, self.mlps):
+        def scale(s):
+            grouper, mlp = self.groupers[s], self.mlps[s]
             idx = PF.ball_query(grouper.radius, grouper.nsample, xyz, new_xyz)
-            outs.append(RE.sa_scale(RE.units_from_shared_mlp(mlp), self.training, xyz, new_xyz, idx, feats_rows))
+            return RE.sa_scale(RE.units_from_shared_mlp(mlp), self.training, xyz, new_xyz, idx, feats_rows)
+
+        # the scales of a level are independent chains of small launches (levels 3-4: 64..256 centroids per instance): the last scale
+        # runs on a side stream of the current one, forward and (autograd replays a node on its forward stream) backward
+        side = RE.K.side_stream_for(xyz.device, 1) if (SA_FORK and xyz.is_cuda and len(self.groupers) > 1) else None
+        if side is None:
+            return new_xyz, torch.cat([scale(s) for s in range(len(self.groupers))], dim=2)
+        main = torch.cuda.current_stream(xyz.device)
+        side.wait_stream(main)
+        last = len(self.groupers) - 1
+        with torch.cuda.stream(side):
+            o_last = scale(last)
+        outs = [scale(s) for s in range(last)] + [o_last]
+        main.wait_stream(side)
+        o_last.record_stream(main)
         return new_xyz, torch.cat(outs, dim=2)
 
     def forward(self, xyz, features=None, new_xyz=None):

@@ -232,7 +232,9 @@ def ortho6d_to_mat(x_raw, y_raw):
 
     def nrm(v):
         mag = torch.sqrt(v.pow(2).sum(dim=1, keepdim=True))
-        return v / torch.max(mag, torch.tensor([1e-8], dtype=v.dtype, device=v.device))
+        # the reference builds this constant on the host each call (rotation_utils.py:6: FloatTensor([1e-8]).cuda(), a synchronous
+        # copy that cannot be captured in a CUDA graph); new_full is the same value created on the tensor's device
+        return v / torch.max(mag, mag.new_full((1,), 1e-8))
 
     def cross(u, v):
         return torch.stack(

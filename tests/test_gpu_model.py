@@ -344,7 +344,16 @@ def test_stall_free_solver_loop_matches_the_reference_loop():
         if d_ref.abs().max().item() > 0:
             errs.append(rel_err(p.detach() - p0[n], d_ref))
     errs.sort()
-    assert errs and errs[len(errs) // 2] < 0.1, (errs[len(errs) // 2], errs[-1])
+    # Adam's update is sign-like (m / sqrt(v): +-lr per element on the first step), so on tensors whose gradients carry the chaotic
+    # train-mode noise of this B=4 step (see test_cuda_graph_step_equals_eager_step) a single flipped near-zero element already
+    # gives a max-norm error of 2; the tensors with deterministic gradients (pose tails ...) must agree to FP32 rounding, which
+    # they only do if every step saw the right learning rate, step count and moments.  Adam's arithmetic itself:
+    # test_gpu_kernels.py::test_adam_flat_kernel_matches_torch_adam.
+    exact = sum(1 for e in errs if e < 1e-3)
+    print(f"solver vs reference loop: {len(errs)} tensors, update error quantiles min / 25% / median / max = "
+          f"{errs[0]:.1e} / {errs[len(errs) // 4]:.1e} / {errs[len(errs) // 2]:.1e} / {errs[-1]:.1e}; {exact} tensors < 1e-3")
+    assert exact >= 12 and errs[len(errs) // 2] < 1.0, (exact, errs[len(errs) // 2], errs[-1])
+    assert abs(sol.optimizer.lr_dev.item() - ref_lrs[-1]) <= 1e-9  # the device scalar holds the last scheduled learning rate
     bufs_ref = dict(m_ref.named_buffers())
     for n, b in m.named_buffers():
         if n.endswith("num_batches_tracked"):

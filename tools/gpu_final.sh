@@ -10,7 +10,7 @@ echo "== smoke"; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -5 | te
 echo "== bench"; timeout 900 python bench.py 2>&1 | tail -5 | tee $OUT/${TAG}_bench.log | cut -c1-600
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -2 | tee $OUT/${TAG}_bench_ref.log | cut -c1-400
 echo "== timeline"; timeout 300 python tools/timeline.py > $OUT/${TAG}_timeline.txt 2>&1; tail -2 $OUT/${TAG}_timeline.txt
-echo "== timeline serial"; ISTNET_STREAMS=0 ISTNET_WGRAD_STREAM=0 timeout 300 python tools/timeline.py > $OUT/${TAG}_timeline_serial.txt 2>&1; tail -2 $OUT/${TAG}_timeline_serial.txt
+echo "== timeline serial"; ISTNET_STREAMS=0 ISTNET_WGRAD_STREAM=0 ISTNET_SA_FORK=0 timeout 300 python tools/timeline.py > $OUT/${TAG}_timeline_serial.txt 2>&1; tail -2 $OUT/${TAG}_timeline_serial.txt
 bash tools/gpu_ab.sh ${TAG}
 echo "== inference latency"; timeout 300 python tools/bench_infer.py 2>&1 | tail -14 | tee $OUT/${TAG}_infer.txt
 echo "== launches (eager step)"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --eager --no-cpu-baseline > $OUT/${TAG}_ncu.log 2>&1
