@@ -390,9 +390,11 @@ int istnet_ortho6d_bwd(int B, const float *r6, const float *dR, float *dr6, void
  *   p -= lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps),  t = *step_dev + 1.
  * lr_dev and step_dev are DEVICE scalars (CyclicLR rewrites the learning rate every iteration, solver.py:88-89), so the step can
  * live inside a captured CUDA graph; grad_scale = 1/world_size turns the all-reduced gradient SUM into the mean.
- * istnet_adam_tick increments *step_dev once per optimizer step (after the last bucket). */
-int istnet_adam_flat(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, const float *lr_dev, float beta1,
-                     float beta2, float eps, float weight_decay, float grad_scale, const long long *step_dev, void *stream);
+ * istnet_adam_tick increments *step_dev once per optimizer step (after the last bucket).
+ * beta1 / beta2 are doubles: torch evaluates 1-beta and the bias corrections in double before rounding to FP32 (1 - 0.999 = 1e-3 exactly,
+ * whereas 1.f - 0.999f is off by 4.7e-5 relative). */
+int istnet_adam_flat(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, const float *lr_dev, double beta1,
+                     double beta2, float eps, float weight_decay, float grad_scale, const long long *step_dev, void *stream);
 int istnet_adam_tick(long long *step_dev, void *stream);
 
 #ifdef __cplusplus

@@ -14,15 +14,16 @@ namespace {
 constexpr int kThreads = 256;
 
 __global__ void __launch_bounds__(kThreads) adam_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
-                                                             float *__restrict__ v, long long n4, const float *__restrict__ lr_ptr, float beta1,
-                                                             float beta2, float eps, float wd, float gscale, const long long *__restrict__ step_ptr) {
+                                                             float *__restrict__ v, long long n4, const float *__restrict__ lr_ptr, double beta1d,
+                                                             double beta2d, float eps, float wd, float gscale, const long long *__restrict__ step_ptr) {
     // step_ptr holds the number of steps ALREADY taken (incremented by adam_tick_kernel after all buckets of this step)
     const double t = (double)(*step_ptr + 1);
     const float lr = *lr_ptr;
-    const float bc1 = (float)(1.0 - pow((double)beta1, t));
-    const float bc2s = (float)sqrt(1.0 - pow((double)beta2, t));
+    const float bc1 = (float)(1.0 - pow(beta1d, t));
+    const float bc2s = (float)sqrt(1.0 - pow(beta2d, t));
     const float step_size = lr / bc1;
-    const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+    // torch: exp_avg.lerp_(grad, 1 - beta1); exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2) with the scalars formed in double
+    const float beta2 = (float)beta2d, omb1 = (float)(1.0 - beta1d), omb2 = (float)(1.0 - beta2d);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 pv = reinterpret_cast<float4 *>(p)[i];
         const float4 gv = reinterpret_cast<const float4 *>(g)[i];
@@ -47,7 +48,7 @@ __global__ void adam_tick_kernel(long long *step_ptr) { *step_ptr += 1; }
 // One bucket.  n must be a multiple of 4 and the four buffers 16-byte aligned (flat buckets are padded).  `step` counts completed
 // steps and is NOT modified here: call istnet_adam_tick once after the last bucket of a step.
 extern "C" int istnet_adam_flat(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, const float *lr_dev,
-                                float beta1, float beta2, float eps, float weight_decay, float grad_scale, const long long *step_dev,
+                                double beta1, double beta2, float eps, float weight_decay, float grad_scale, const long long *step_dev,
                                 void *stream) {
     if (n <= 0) return ISTNET_OK;
     if ((n & 3) || !param || !grad || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev) return ISTNET_ERR_BAD_ARG;

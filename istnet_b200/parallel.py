@@ -298,6 +298,8 @@ class FlatAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         from . import _C
+        from ctypes import c_double
+
         from ._C import c_float, c_ll, ptr
 
         g0 = self.param_groups[0]
@@ -306,8 +308,8 @@ class FlatAdam(torch.optim.Optimizer):
         b1, b2 = g0["betas"]
         scale = self.reducer.bucket_scale
         for f in self.flat:
-            _C.call("adam_flat", ptr(f["p"]), ptr(f["g"]), ptr(f["m"]), ptr(f["v"]), c_ll(f["p"].numel()), ptr(self.lr_dev), c_float(b1),
-                    c_float(b2), c_float(g0["eps"]), c_float(g0["weight_decay"]), c_float(scale), ptr(self.step_dev))
+            _C.call("adam_flat", ptr(f["p"]), ptr(f["g"]), ptr(f["m"]), ptr(f["v"]), c_ll(f["p"].numel()), ptr(self.lr_dev), c_double(b1),
+                    c_double(b2), c_float(g0["eps"]), c_float(g0["weight_decay"]), c_float(scale), ptr(self.step_dev))
         _C.call("adam_tick", ptr(self.step_dev))
         from . import nhwc
 

@@ -458,6 +458,8 @@ def test_pose_tail_pool_heads_ortho6d_vs_float64():
 def test_adam_flat_kernel_matches_torch_adam():
     """csrc/optim.cu against torch.optim.Adam (utils/solver.py:41-44) on identical gradients: 5 steps with a learning rate that
     changes every step through the device scalar (CyclicLR), weight decay, and the folded 1/world gradient scale."""
+    import ctypes
+
     from istnet_b200 import _C
     from istnet_b200._C import c_float, c_ll, ptr
 
@@ -477,11 +479,11 @@ def test_adam_flat_kernel_matches_torch_adam():
             ref.grad = grad * scale
             opt.step()
             lr_dev.fill_(lr)
-            _C.call("adam_flat", ptr(p), ptr(grad), ptr(m), ptr(v), c_ll(n), ptr(lr_dev), c_float(0.9), c_float(0.999), c_float(1e-8),
+            _C.call("adam_flat", ptr(p), ptr(grad), ptr(m), ptr(v), c_ll(n), ptr(lr_dev), ctypes.c_double(0.9), ctypes.c_double(0.999), c_float(1e-8),
                     c_float(wd), c_float(scale), ptr(step_dev))
             _C.call("adam_tick", ptr(step_dev))
             assert int(step_dev.item()) == it + 1
             # same formula, FP32 both sides; torch evaluates the bias corrections in double on the host, the kernel in double on the device
-            assert (p - ref.detach()).abs().max().item() <= 2e-6 * lr / 1e-5 * 1e-2 + 1e-7, (it, (p - ref.detach()).abs().max().item())
+            assert (p - ref.detach()).abs().max().item() <= 1e-4 * lr + 5e-7, (it, (p - ref.detach()).abs().max().item())
             st = opt.state[ref]
             assert rel_err(m, st["exp_avg"]) < 1e-6 and rel_err(v, st["exp_avg_sq"]) < 1e-6
