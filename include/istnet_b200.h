@@ -397,6 +397,21 @@ int istnet_adam_flat(float *param, const float *grad, float *exp_avg, float *exp
                      double beta2, float eps, float weight_decay, float grad_scale, const long long *step_dev, void *stream);
 int istnet_adam_tick(long long *step_dev, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * 7. Per-instance input preparation (reference provider/dataset.py:186-233, :369-409)
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* For B instances cut out of F decoded frames resident on the device: rgb_frames [F][H][W][3] uint8 (RGB order), depth [F][H][W]
+ * float32 (hole-filled, sensor units), boxes [B][5] = {frame, rmin, rmax, cmin, cmax} (square windows of get_bbox,
+ * utils/data_utils.py:43-71), choose [B][N] indices into the flattened crop (dataset.py:192-200).  Produces what the reference's
+ * Dataset returns per instance: rgb_out [B][3][S][S] = Normalize(ToTensor(cv2.resize(crop, (S,S), INTER_LINEAR))) bit-exact with
+ * OpenCV's 8-bit bilinear path and torchvision; pts_out [B][N][3] = back-projection (z = depth / norm_scale in FP32, x, y in float64,
+ * one rounding; + optional float64 jitter noise [B][N][3]); choose_out [B][N] int64 positions on the SxS map.
+ * mean3 / std3 are HOST pointers to three floats.  rgb_out may be null (points only); N may be 0 (image only). */
+int istnet_prepare_instances(const unsigned char *rgb_frames, const float *depth, int F, int H, int W, const int *boxes, const int *choose,
+                             int B, int N, int S, double fx, double fy, double cx, double cy, float norm_scale, const float *mean3,
+                             const float *std3, const double *noise, float *rgb_out, float *pts_out, long long *choose_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,8 @@
 // values — no shuffles, no atomics — and there is no block-wide barrier before the final flush: the 12-16 warps of an SM drift
 // apart and hide each other's gather / shared-memory latencies (the first version synchronised the CTA per 128-256-row tile and
 // was latency-bound: profiles/r2_sa_fused_v1_launches.txt).  The forward pass scans the cloud ONCE per centroid for both radii.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ticket.cuh"
 
@@ -820,10 +822,19 @@ static void split_ctas(SaLevelP &p, int total, int rows_per_unit) {
     p.sc[1].cta0 = g0; p.sc[1].ncta = g1;
 }
 
+// CTAs per SM of the persistent grids (tuning knobs, read once): ISTNET_SA_FWD_CTAS (default 2), ISTNET_SA_BWD_CTAS (default 3)
+static int env_ctas(const char *name, int dflt) {
+    const char *e = getenv(name);
+    const int v = e ? atoi(e) : dflt;
+    return v < 1 ? 1 : (v > 4 ? 4 : v);
+}
+static int fwd_ctas_per_sm() { static const int v = env_ctas("ISTNET_SA_FWD_CTAS", 2); return v; }
+static int bwd_ctas_per_sm() { static const int v = env_ctas("ISTNET_SA_BWD_CTAS", 3); return v; }
+
 template <int C0, int C1, int C2>
 static int launch_fwd(SaLevelP &p, int pass, int query, cudaStream_t st) {
     // warp-autonomous forward: one grid for both scales, every CTA's partial row belongs to both reductions
-    int grid = kNumSMs * 2;
+    int grid = kNumSMs * fwd_ctas_per_sm();
     const int units = (p.B * p.M + 7) / 8;  // at least one centroid per warp
     if (grid > units) grid = units;
     if (grid > kMaxPartialRows) grid = kMaxPartialRows;
@@ -852,7 +863,7 @@ static int launch_bwd(SaLevelP &p, int stage, cudaStream_t st) {
         ISTNET_LAUNCH_CHECK();
         return ISTNET_OK;
     }
-    split_ctas(p, kNumSMs * 3, kTileRows * (kBwdThreads / 32));
+    split_ctas(p, kNumSMs * bwd_ctas_per_sm(), kTileRows * (kBwdThreads / 32));
     const int grid = p.sc[0].ncta + p.sc[1].ncta;
     constexpr int NW = kBwdThreads / 32;
     constexpr int WF = 16 + 64 + kTileRows * (C0 + 2 * C1 + C2), CWMAX = C2 * C1;

@@ -125,9 +125,11 @@ def test_posenet_gt_full_resolution_train_step_vs_float64():
 
 def test_cfg4_dense_cloud_train_step_vs_float64():
     """BASELINE.json configs[4] shape: 4096-point crops, train mode."""
-    # measured (profiles/r2_gpu_tests.txt): CUDA path 9.7e-3 / 2.1e-2 / 1.3e-1 against the FP32 reference's 2.1e-3 / 1.2e-2 / 1.3e-1
-    # (median / 90 % / max): same tail, a 4.6x larger median at this B = 2 shape — the two-plane (3e-6 per product) backward
-    # contractions (DESIGN.md section 2) feed a larger seed perturbation into the same chaotic amplification
+    # measured (profiles/r2_gpu_tests.txt): at this B = 2 shape the ratio of the two medians varies from draw to draw — seeds 54..57
+    # give 4.6x, 1.0x, 0.87x, 2.8x (CUDA path 9.7e-3 / 3.4e-3 / 2.2e-3 / 4.5e-3 against the FP32 reference's 2.1e-3 / 3.4e-3 / 2.5e-3 /
+    # 1.6e-3), with identical 90 % and max quantiles.  It is not the operand-plane arithmetic: three planes in every forward and
+    # backward contraction give the same 9.8e-3 at seed 54.  Two FP32 evaluations whose roundings differ flip different ReLU / max
+    # selections, and with two instances per BatchNorm batch a handful of flips moves the median; the bound is 6x for this shape.
     _check("ist_net", 2, 4096, 192, seed=54, median_factor=6.0)
 
 
