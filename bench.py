@@ -285,6 +285,14 @@ def main():
     l_probe = _C.LAUNCHES
     eager_step(resident)  # counts the kernel launches of a step (the graph replays exactly these)
     launches_per_step = _C.LAUNCHES - l_probe
+    trace_stages = os.environ.get("ISTNET_TRACE_STAGES") == "1"
+
+    def stage(msg):  # debugging aid for multi-GPU bring-up: where does a rank stop?
+        if trace_stages:
+            torch.cuda.synchronize()
+            print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+    stage("eager steps done")
     graphed = None
     # ISTNET_GRAPH_NCCL=1 captures the per-bucket NCCL all-reduce (communication stream) and Adam inside the step's graph; the
     # default keeps NCCL out of the capture: the graph ends with the bucket packing, all-reduce + Adam follow each replay
@@ -363,8 +371,10 @@ def main():
             ms = t.item()
         return ms
 
-    for _ in range(warmup):
+    stage("step built (graph captured)" if graphed is not None else "eager mode")
+    for i_ in range(warmup):
         step(resident)
+        stage(f"warm-up step {i_} done")
     barrier()
     l0 = _C.LAUNCHES
     with ClockSampler(local) as clk:
