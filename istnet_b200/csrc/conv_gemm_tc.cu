@@ -382,7 +382,12 @@ static int pick_block_k(int cout, int nsplit) {
 }
 static int pick_bn(int cout, int nsplit, int block_k) {
     const int cap = (nsplit >= 3 && block_k == 64) ? 128 : 256;  // keep >= 2 pipeline stages in 227 KB of shared memory
-    if (cout >= cap) return cap;
+    if (cout > cap) {  // equal-width column tiles: Cout = 384 -> 2 x 192 instead of 256 + a half-empty 256 (25 % of the MMAs on zero padding)
+        const int n = (cout + cap - 1) / cap;
+        const int bn = ((cout + n - 1) / n + 31) / 32 * 32;
+        return bn < cap ? bn : cap;
+    }
+    if (cout == cap) return cap;
     int bn = (cout + 15) / 16 * 16;
     return bn < 16 ? 16 : bn;
 }

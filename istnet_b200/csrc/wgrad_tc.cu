@@ -8,6 +8,10 @@
 // consecutive 64-channel slabs sit 8 KB apart (the descriptor's leading-byte-offset).  The tap shift and the
 // zero padding are the TMA coordinates / out-of-bounds fill, exactly as in the forward kernel.
 // bf16-plane arithmetic as in conv_gemm_tc.cu: all plane products dY_i * X_j with i + j < nsplit, smallest first.
+// Narrow layers (Cout <= 64: up_2 / up_3, ResNet layer1, the fine PointNet++ levels) would leave half of the 128 accumulator rows
+// multiplying zero padding.  For them the shift moves from X to dY — sum_p dY[p] X[p + t] = sum_q dY[q - t] X[q], with the same
+// zero fill outside the image — so that ONE unshifted X tile serves two taps whose (differently shifted) dY tiles fill rows
+// 0..63 and 64..127: 5 instead of 9 CTA columns for a 3x3 filter, every MMA fully used (up_3: 679 -> see profiles/).
 // K (pixels) is split across CTAs; each CTA writes its FP32 partial tile and a second tiny kernel reduces the
 // partials in a fixed order into the PyTorch weight layout [Cout][Cin][kh][kw] — deterministic, unlike the
 // atomics of the reference's custom grads (SURVEY.md §7 hard part 5).
@@ -29,6 +33,7 @@ struct WgradParams {
     int Cout, Cin, BN;        // BN multiple of 64
     int n_ci_tiles;
     int ksplit, stages, nsplit;
+    int pair;                 // Cout <= 64 and more than one tap: the CTA's 128 accumulator rows hold TWO filter taps (rows 64.. = the second)
     float *partial;           // [ksplit][taps][Cout][Cin]
     uint32_t tmem_cols;
 };
@@ -51,7 +56,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // the filter tap is the fastest grid index: the kh*kw CTAs that read the same dY / (shifted) X pixel tiles are
     // co-scheduled and share them through L2
-    const int tap = blockIdx.x;
+    const int taps = p.kh * p.kw;
+    const int tap = p.pair ? 2 * blockIdx.x : blockIdx.x;  // pair mode: taps `tap` and `tap + 1` (the latter may not exist)
     const int co0 = (blockIdx.y / p.n_ci_tiles) * kTileM;
     const int ci0 = (blockIdx.y % p.n_ci_tiles) * p.BN;
     const int split = blockIdx.z;
@@ -90,10 +96,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
                 tc::mbar_arrive_expect_tx(&full_bar[st], stage_bytes);
                 uint8_t *sb = sa + p.nsplit * a_bytes;
                 for (int pl = 0; pl < p.nsplit; ++pl) {
-                    for (int c = 0; c < 2; ++c)
-                        tc::tma_load_5d(sa + pl * a_bytes + c * kSlabBytes, &tm_dy, &full_bar[st], co0 + c * 64, w0, h0, b0, pl);
-                    for (int c = 0; c < n_slabs_b; ++c)
-                        tc::tma_load_5d(sb + pl * b_bytes + c * kSlabBytes, &tm_x, &full_bar[st], ci0 + c * 64, w0 + s - pad_w, h0 + r - pad_h, b0, pl);
+                    if (p.pair) {
+                        for (int c = 0; c < 2; ++c) {  // slab c = dY shifted by minus tap (tap + c); a tap past the filter reads channels >= Cout: zero fill
+                            const int tc_ = tap + c, rc = tc_ / p.kw, sc = tc_ % p.kw;
+                            const bool live = tc_ < taps;
+                            tc::tma_load_5d(sa + pl * a_bytes + c * kSlabBytes, &tm_dy, &full_bar[st], live ? 0 : p.Cout + 64,
+                                            live ? w0 - (sc - pad_w) : w0, live ? h0 - (rc - pad_h) : h0, b0, pl);
+                        }
+                        for (int c = 0; c < n_slabs_b; ++c)
+                            tc::tma_load_5d(sb + pl * b_bytes + c * kSlabBytes, &tm_x, &full_bar[st], ci0 + c * 64, w0, h0, b0, pl);
+                    } else {
+                        for (int c = 0; c < 2; ++c)
+                            tc::tma_load_5d(sa + pl * a_bytes + c * kSlabBytes, &tm_dy, &full_bar[st], co0 + c * 64, w0, h0, b0, pl);
+                        for (int c = 0; c < n_slabs_b; ++c)
+                            tc::tma_load_5d(sb + pl * b_bytes + c * kSlabBytes, &tm_x, &full_bar[st], ci0 + c * 64, w0 + s - pad_w, h0 + r - pad_h, b0, pl);
+                    }
                 }
             }
         }
@@ -127,8 +144,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
         }
     } else {
         const int q = warp & 3;
-        const int co = co0 + q * 32 + lane;
-        float *dst = p.partial + (((size_t)split * (p.kh * p.kw) + tap) * p.Cout + co) * p.Cin;
+        const int m = q * 32 + lane;                                   // accumulator row
+        const int my_tap = p.pair ? tap + (m >> 6) : tap;              // pair mode: rows 64.. belong to the second tap
+        const int co = p.pair ? (my_tap < taps ? (m & 63) : p.Cout) : co0 + m;  // co >= Cout: nothing to store
+        float *dst = p.partial + (((size_t)split * taps + min(my_tap, taps - 1)) * p.Cout + min(co, p.Cout - 1)) * p.Cin;
         if (num_k > 0) {
             tc::mbar_wait(tmem_full_bar, 0);
             tc::tc_fence_after();
@@ -225,13 +244,18 @@ static int wgrad_budget_kb(int bn, int taps) {
     static const int f = wg_env_int("ISTNET_WG_SMEM_KB", 0);
     return f > 0 ? f : ((bn <= 128 && taps > 1) ? 60 : 225);
 }
+static bool wgrad_pair(int cout, int taps) {
+    static const int off = wg_env_int("ISTNET_WG_NOPAIR", 0);
+    return !off && cout <= 64 && taps > 1;
+}
 static int wgrad_stage_bytes(int bn, int nsplit, int pix) { return nsplit * (2 + bn / 64) * pix * 64 * 2; }
 
 extern "C" int istnet_wgrad_ksplit(int B, int H, int W, int Cout, int Cin, int kh, int kw, int nsplit) {
     // fill the chip with an integral number of co-resident CTA "waves", at least 4 pixel tiles per CTA
     const int pix = wgrad_pick_pix();
     const int bn = wgrad_pick_bn(Cin, nsplit);
-    const int base = ceil_div(Cout, kTileM) * ceil_div(Cin, bn) * kh * kw;
+    const int tap_cols = wgrad_pair(Cout, kh * kw) ? (kh * kw + 1) / 2 : kh * kw;
+    const int base = ceil_div(Cout, kTileM) * ceil_div(Cin, bn) * tap_cols;
     const long long pix_tiles = ((long long)B * H * W + pix - 1) / pix;
     const int stage_bytes = wgrad_stage_bytes(bn, nsplit, pix);
     int stages = (wgrad_budget_kb(bn, kh * kw) * 1024 - 1280) / stage_bytes;
@@ -273,6 +297,7 @@ extern "C" int istnet_conv_wgrad(const void *dy_planes, long long dy_plane_strid
     p.BN = wgrad_pick_bn(Cin, nsplit);
     p.n_ci_tiles = ceil_div(Cin, p.BN);
     p.ksplit = ksplit;
+    p.pair = wgrad_pair(Cout, kh * kw) ? 1 : 0;
     p.partial = partial_ws;
     p.tmem_cols = 32;
     while ((int)p.tmem_cols < p.BN) p.tmem_cols *= 2;
@@ -301,7 +326,7 @@ extern "C" int istnet_conv_wgrad(const void *dy_planes, long long dy_plane_strid
         if (e) return e;
     }
     ISTNET_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    dim3 grid(kh * kw, ceil_div(Cout, kTileM) * p.n_ci_tiles, ksplit);
+    dim3 grid(p.pair ? (kh * kw + 1) / 2 : kh * kw, ceil_div(Cout, kTileM) * p.n_ci_tiles, ksplit);
     wgrad_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(t_dy, t_x, p);
     ISTNET_LAUNCH_CHECK();
     const long long total = (long long)kh * kw * Cout * Cin;

@@ -26,7 +26,7 @@ def tc():
 
 CONV_CASES = [(2, 8, 8, 64, 64, 1), (2, 8, 8, 64, 64, 3), (2, 24, 24, 128, 256, 3), (3, 24, 24, 512, 512, 3), (1, 1, 1000, 320, 384, 1),
               (1, 1, 4096, 67, 32, 1), (1, 1, 300, 3, 16, 1), (2, 48, 48, 1024, 256, 3), (2, 16, 16, 128, 18, 1), (1, 1, 512, 2560, 1024, 1),
-              (1, 8, 8, 512, 512, 3)]
+              (1, 8, 8, 512, 512, 3), (1, 1, 640, 256, 384, 1), (2, 8, 8, 96, 320, 3), (1, 1, 256, 64, 600, 1)]
 
 
 @pytest.mark.parametrize("B,H,W,cin,cout,k", CONV_CASES)
@@ -45,7 +45,10 @@ def test_conv_gemm_matches_float64_conv2d(tc, B, H, W, cin, cout, k):
 
 
 @pytest.mark.parametrize("B,H,W,cin,cout,k", [(2, 8, 8, 64, 64, 1), (2, 8, 8, 64, 128, 3), (4, 24, 24, 128, 256, 3), (2, 24, 24, 512, 512, 3),
-                                               (1, 1, 4096, 320, 384, 1), (1, 1, 1000, 67, 32, 1), (3, 16, 16, 128, 18, 1), (1, 1, 512, 3, 16, 1)])
+                                               (1, 1, 4096, 320, 384, 1), (1, 1, 1000, 67, 32, 1), (3, 16, 16, 128, 18, 1), (1, 1, 512, 3, 16, 1),
+                                               # Cout <= 64 with several taps: two taps per accumulator tile (shifted dY), odd sizes, 25 taps
+                                               (2, 12, 20, 64, 64, 3), (3, 9, 7, 256, 64, 3), (2, 16, 16, 32, 16, 3), (1, 10, 10, 64, 48, 3),
+                                               (1, 12, 12, 16, 32, 5), (2, 48, 48, 64, 64, 3)])
 def test_wgrad_matches_float64_autograd(tc, B, H, W, cin, cout, k):
     """tcgen05 weight gradient (MN-major operands, split-K, deterministic reduce) — 2e-5."""
     g = torch.Generator(device="cuda").manual_seed(cin * 7 + cout)
