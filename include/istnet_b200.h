@@ -131,12 +131,14 @@ typedef struct istnet_fin {
  * layer's dy operand planes and, through stat_part, its bias gradient (autograd's threshold_backward + sum in the reference).
  * stat_y (nullable, FP32 [B,H,W,stat_y_cs], needs stat_part): the second statistic becomes sum(out * stat_y) instead of sum(out^2) —
  * with mask_hi this is the reduction of the BatchNorm backward of a conv+BN+ReLU layer below (finish with
- * istnet_bn_bwd_finalize_gy + istnet_bn_bwd_apply). */
+ * istnet_bn_bwd_finalize_gy + istnet_bn_bwd_apply).
+ * bias_group > 0: bias is a table [ceil(P / bias_group)][Cout] and output pixel p receives row p / bias_group — the per-instance form of
+ * the estimators' global feature (ist_net.py:172-173,257-258,325-326: conv([f | mean(f).expand]) = W_a f + (W_b mean(f) + b)). */
 int istnet_conv_gemm(const void *act_planes, long long act_plane_stride, int B, int H, int W, int Cin, int act_cs,
                      const void *wgt_planes, long long wgt_plane_stride, int Cout, int wgt_cs, int kh, int kw, int nsplit,
                      const float *bias, int relu, float *out_f32, int out_cs, void *out_planes, long long out_plane_stride,
                      int nsplit_out, int split_cs, int box_w, int box_h, float *stat_part, int *grid_out, const void *mask_hi, int mask_cs,
-                     const float *stat_y, int stat_y_cs, const istnet_fin *fin, void *stream);
+                     const float *stat_y, int stat_y_cs, const istnet_fin *fin, int bias_group, void *stream);
 
 /* Weight gradient of the layer above (cuDNN wgrad in the reference):
  *   grad_w[co][ci][r][s] = sum_{b,h,w} dy[b,h,w,co] * x[b,h+r-kh/2,w+s-kw/2,ci]       (PyTorch weight layout, FP32)
@@ -376,6 +378,10 @@ int istnet_heads_linear(int nheads, int B, int K, const float *const *x, const f
 int istnet_heads_linear_bwd(int nheads, int B, int K, const float *const *x, const float *const *w, const float *const *y,
                             const float *const *dy, float *const *dx, float *const *dw, float *const *db, const int *O, int relu,
                             void *stream);
+/* out[g][c] = sum over rows r with r / group == g of (sum of the nsplit bf16 planes)[r][c]: per-instance column sums of a gradient held
+ * as operand planes [nsplit][P][cs] (gradient of the per-instance bias of istnet_conv_gemm's bias_group form).  C, cs % 8 == 0. */
+int istnet_rows_group_sum_planes(const void *planes, long long plane_stride, int nsplit, long long P, int C, int cs, int group, float *out,
+                                 void *stream);
 int istnet_sum3(long long n, const float *a, const float *b, const float *c, float *out, void *stream);
 /* R[b] = [x y z] columns with y = n(r6[b][3:6]), z = n(r6[b][0:3] x y), x = y x z, n(v) = v / max(|v|, 1e-8); and the gradient */
 int istnet_ortho6d(int B, const float *r6, float *R, void *stream);

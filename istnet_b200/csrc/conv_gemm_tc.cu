@@ -38,7 +38,8 @@ struct ConvGemmParams {
     int n_tiles_n;            // ceil(Cout / BN)
     int acc_stride;           // TMEM columns between the two accumulators (BN rounded up to 32)
     int stages;
-    const float *bias;        // [Cout] or null
+    const float *bias;        // [Cout] or null; with bias_group > 0: [ceil(P / bias_group)][Cout], row = output pixel / bias_group
+    int bias_group;
     int relu;
     float *out_f32;           // [B,H,W,out_cs] or null
     int out_cs;
@@ -203,16 +204,19 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
                 if (p.bias != nullptr) {
-                    if (valid == 32 && bias_vec) {  // n is a multiple of 32: 16-byte aligned, uniform (broadcast) loads
+                    // per-group bias (the estimators' global feature, ist_net.py:172-173: W [f | mean(f)] = W_a f + W_b mean(f), the second
+                    // term is constant over the 1024 rows of an instance): row pix / bias_group of a [groups][Cout] table
+                    const float *bias = p.bias + ((p.bias_group > 0 && row_ok) ? (pix / (size_t)p.bias_group) * (size_t)p.Cout : 0);
+                    if (valid == 32 && bias_vec && (p.bias_group == 0 || (p.Cout & 3) == 0)) {  // 16-byte aligned loads
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
-                            const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias + n + i));
+                            const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + n + i));
                             f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
                         }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
-                            if (i < valid) f[i] += __ldg(p.bias + n + i);
+                            if (i < valid) f[i] += __ldg(bias + n + i);
                     }
                 }
                 if (p.relu) {
@@ -396,8 +400,8 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
                                 const void *wgt_planes, long long wgt_plane_stride, int Cout, int wgt_cs, int kh, int kw, int nsplit,
                                 const float *bias, int relu, float *out_f32, int out_cs, void *out_planes, long long out_plane_stride,
                                 int nsplit_out, int split_cs, int box_w, int box_h, float *stat_part, int *grid_out, const void *mask_hi,
-                                int mask_cs, const float *stat_y, int stat_y_cs, const istnet_fin *fin, void *stream) {
-    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return ISTNET_ERR_BAD_ARG;
+                                int mask_cs, const float *stat_y, int stat_y_cs, const istnet_fin *fin, int bias_group, void *stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || bias_group < 0 || (bias_group > 0 && !bias)) return ISTNET_ERR_BAD_ARG;
     if (nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
     if ((act_cs & 7) || (wgt_cs & 7) || act_cs < Cin || wgt_cs < Cin) return ISTNET_ERR_BAD_ARG;
     if (box_w <= 0 || box_h <= 0 || (kTileM % (box_w * box_h)) != 0 || box_w > 256 || box_h > 256) return ISTNET_ERR_BAD_ARG;
@@ -414,7 +418,7 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     p.cin_blocks = ceil_div(Cin, kBlockK);
     p.Cout = Cout; p.BN = pick_bn(Cout, nsplit, kBlockK);
     p.nsplit = nsplit;
-    p.bias = bias; p.relu = relu;
+    p.bias = bias; p.relu = relu; p.bias_group = bias_group;
     p.stat_part = stat_part;
     p.mask_hi = (const __nv_bfloat16 *)mask_hi; p.mask_cs = mask_cs;
     p.stat_y = stat_y; p.stat_y_cs = stat_y_cs;

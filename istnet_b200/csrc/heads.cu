@@ -63,6 +63,45 @@ __global__ void __launch_bounds__(kThreads) rows_mean_kernel(int N, int C, const
         *reinterpret_cast<float4 *>(pooled + (size_t)b * C + c) = make_float4(t.x * inv, t.y * inv, t.z * inv, t.w * inv);
     }
 }
+// out[g][c] = sum over the rows r of group g (r / group == g) of sum_planes pl[plane][r][c]: per-instance column sums of a gradient that
+// exists only as bf16 operand planes (the dy operand of the estimators' first layer; its sum over an instance's rows is the gradient
+// of the per-instance bias W_b mean(f) + b).  grid = (ceil(C/64), groups): 8 lanes x 8 channels (one 16-byte load per plane), 32 row
+// groups, fixed-order combine.
+__global__ void __launch_bounds__(kThreads) rows_group_sum_planes_kernel(const __nv_bfloat16 *__restrict__ pl, long long pl_stride, int nsplit, long long P,
+                                                                         int C, int cs, int group, float *__restrict__ out) {
+    constexpr int kGroups = kThreads / 8;
+    __shared__ float red[kThreads][8];
+    const int g = blockIdx.y;
+    const int q = threadIdx.x & 7, rg = threadIdx.x >> 3;
+    const int c = blockIdx.x * 64 + q * 8;
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
+    if (c < C) {
+        const long long r0 = (long long)g * group;
+        const long long r1 = min(P, r0 + group);
+        for (long long r = r0 + rg; r < r1; r += kGroups) {
+            for (int p = 0; p < nsplit; ++p) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(pl + (size_t)p * pl_stride + (size_t)r * cs + c);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    s[2 * i] += __uint_as_float(w[i] << 16);
+                    s[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = s[i];
+    __syncthreads();
+    if (threadIdx.x < 64 && blockIdx.x * 64 + (int)threadIdx.x < C) {
+        const int qq = threadIdx.x >> 3, i = threadIdx.x & 7;
+        float t = 0.f;
+        for (int k = 0; k < kGroups; ++k) t += red[k * 8 + qq][i];
+        out[(size_t)g * C + blockIdx.x * 64 + threadIdx.x] = t;
+    }
+}
 // d_feat[(b*N + n)*C + c] = d_pooled[b][c] / N
 __global__ void __launch_bounds__(kThreads) rows_mean_bwd_kernel(int B, int N, int C, const float *__restrict__ dpooled, float *__restrict__ dfeat) {
     const int lanes = C >> 2;
@@ -241,6 +280,17 @@ extern "C" int istnet_rows_mean(int B, int N, int C, const float *feat, float *p
     if (B <= 0 || N <= 0 || C <= 0 || (C & 3) || !feat || !pooled) return ISTNET_ERR_BAD_ARG;
     dim3 grid(ceil_div(C, 32), B);
     rows_mean_kernel<<<grid, kThreads, 0, ST>>>(N, C, feat, pooled);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
+extern "C" int istnet_rows_group_sum_planes(const void *planes, long long plane_stride, int nsplit, long long P, int C, int cs, int group,
+                                            float *out, void *stream) {
+    if (!planes || !out || P <= 0 || C <= 0 || group <= 0 || nsplit < 1 || nsplit > kMaxPlanes) return ISTNET_ERR_BAD_ARG;
+    if ((C & 7) || (cs & 7) || (plane_stride & 7) || (reinterpret_cast<uintptr_t>(planes) & 15)) return ISTNET_ERR_UNSUPPORTED;
+    const long long groups = (P + group - 1) / group;
+    if (groups > 65535) return ISTNET_ERR_UNSUPPORTED;
+    dim3 grid(ceil_div(C, 64), (unsigned)groups);
+    rows_group_sum_planes_kernel<<<grid, kThreads, 0, ST>>>((const __nv_bfloat16 *)planes, plane_stride, nsplit, P, C, cs, group, out);
     ISTNET_LAUNCH_CHECK();
     return ISTNET_OK;
 }

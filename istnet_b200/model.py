@@ -139,6 +139,20 @@ def _with_global(x_rows, b, n):
     return [x_rows, f.mean(1, keepdim=True).expand_as(f).reshape(b * n, -1)]
 
 
+# The estimators' global feature as a per-instance bias (nhwc.ConvUnit.glob): W [f | mean(f)] = W_a f + (W_b mean(f) + b) — halves the K of
+# the first layer of deform_mlp2 / pose_mlp2 (forward, data gradient, weight gradient) and removes the expanded [rows, 256] tensor
+GLOBAL_BIAS = os.environ.get("ISTNET_GLOBAL_BIAS", "1") != "0"
+
+
+def _mlp_global(seq, x_rows, b, n):
+    """seq(torch.cat([f, mean_over_points(f).expand], channels)) of ist_net.py:172-173,257-258,325-326 on rows."""
+    if GLOBAL_BIAS and x_rows.is_cuda and b <= 64 and x_rows.shape[1] % 8 == 0:
+        units = RE.units_from_conv1d_seq(seq, nsplit=min(HEADS_NSPLIT, RE.K.NSPLIT))
+        units[0].glob = n
+        return RE.run_chain(units, x_rows, False)
+    return _mlp(seq, _with_global(x_rows, b, n))
+
+
 FUSED_HEADS = os.environ.get("ISTNET_FUSED_HEADS", "1") != "0"
 
 
@@ -234,7 +248,7 @@ class _PoseHeads(nn.Module):
 
     def _tail(self, feat_rows, b, n):
         feat = _mlp(self.pose_mlp1, feat_rows)
-        feat = _mlp(self.pose_mlp2, _with_global(feat, b, n))
+        feat = _mlp_global(self.pose_mlp2, feat, b, n)
         if FUSED_HEADS and feat.is_cuda and b <= 64 and feat.shape[1] % 4 == 0:
             feat = feat.contiguous()
             params = self._head_params()
@@ -296,7 +310,7 @@ class FeatureDeformer(nn.Module):
         b, n, _ = pts.shape
         e = _mlp(self.pts_mlp1, _rows(pts))
         x = _mlp(self.deform_mlp1, [e, _rows(pts_local), _rows(rgb_local)])
-        x = _mlp(self.deform_mlp2, _with_global(x, b, n))
+        x = _mlp_global(self.deform_mlp2, x, b, n)
         q = _mlp(self.pred_nocs, x).view(b, n, self.nclass, 3)
         # ist_net.py:178-181: view(-1,3,N) + index_select(cls + nclass*b) == pick the class's 3 channels per instance
         q = torch.gather(q, 2, cls.view(b, 1, 1, 1).expand(b, n, 1, 3)).squeeze(2)

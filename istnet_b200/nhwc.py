@@ -23,6 +23,11 @@ NSPLIT = int(os.environ.get("ISTNET_NSPLIT", "3"))
 NSPLIT_BWD = min(NSPLIT, int(os.environ.get("ISTNET_NSPLIT_BWD", "2")))
 
 
+def _ptrs(tensors):
+    """C array of device pointers (NULL for None) for the `const float *const *` arguments of csrc/heads.cu."""
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() if t is not None else None for t in tensors])
+
+
 def _p(t):
     return ptr(t) if t is not None else NULL
 
@@ -314,7 +319,8 @@ def _timed_only(name, flops, nsplit, launch, desc=""):
     PROFILE.append((name, e0, e1, PROFILE_REPS, flops, nsplit, desc))
 
 
-def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl=None, stat_part=None, mask_hi=None, stat_y=None, fin=None):
+def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl=None, stat_part=None, mask_hi=None, stat_y=None, fin=None,
+              bias_group=0):
     """x: Act with operand planes; writes out_f32 [B,H,W,cout] and/or out_pl.  With stat_part (float buffer of
     >= 2*FIN_ROWS*cout) the epilogue also leaves per-CTA BN-statistics partials there; with `fin` (a _C.Fin) the kernel's last
     CTA finishes that reduction itself (BatchNorm statistics / bias gradient), no finalize launch.  Returns the CTA count G."""
@@ -329,11 +335,11 @@ def conv_gemm(x, w_pl, cout, kh, kw, bias=None, relu=False, out_f32=None, out_pl
         _p(stat_y), c_int(stat_y.shape[-1] if stat_y is not None else 0),
     )
     fin_ref = ctypes.byref(fin) if fin is not None else NULL
-    _C.call("conv_gemm", *args, fin_ref)
+    _C.call("conv_gemm", *args, fin_ref, c_int(bias_group))
     if PROFILE is not None:  # timed repeats must not update running statistics again: same kernel, statistics into scratch outputs
         rep = _scratch_fin(fin) if fin is not None else None
         rep_ref = ctypes.byref(rep) if rep is not None else NULL
-        _timed_only("conv_gemm_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, ns, lambda: _C.call("conv_gemm", *args, rep_ref),
+        _timed_only("conv_gemm_tc_kernel", 2.0 * x.P * cout * x.C * kh * kw, ns, lambda: _C.call("conv_gemm", *args, rep_ref, c_int(bias_group)),
                     f"P={x.P} {x.H}x{x.W} cin={x.C} cout={cout} k={kh}")
     return grid.value
 
@@ -552,6 +558,9 @@ class ConvUnit:
         self.k, self.stride = k, stride
         self.pad = k // 2 if pad is None else pad
         self.cout = conv_w.shape[0]
+        # rows per instance when this 1x1 unit's input is [f | mean_over_the_instance(f).expand] (the estimators' global feature,
+        # ist_net.py:172-173,257-258,325-326) and only f is passed in: conv([f | m]) = W_a f + (W_b m + b), the bracket is a per-instance bias
+        self.glob = None
 
     # ---- forward
     def forward(self, x, training, record, noise=None, res=None, res_bn=None, want_f32=False, want_pair=True, x_f32_nchw=None, defer_act=False):
@@ -566,7 +575,10 @@ class ConvUnit:
             kk = 1
         else:
             xin, kk = x, self.k
-            wp, wd = prep_weight_pair(self.w, nsplit=self.ns) if record else (prep_weight(self.w, nsplit=self.ns), None)
+            if self.glob:
+                wp = wd = None  # made from the W_a half of the weight in _glob_forward
+            else:
+                wp, wd = prep_weight_pair(self.w, nsplit=self.ns) if record else (prep_weight(self.w, nsplit=self.ns), None)
         B, H, W = xin.B, xin.H, xin.W
         P, C = B * H * W, self.cout
         if self.bn is None and self.act == ACT_RELU and noise is None and res is None and not defer_act:
@@ -577,8 +589,12 @@ class ConvUnit:
                 out.f32 = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
             if want_pair or record:
                 out.pl = empty_planes(B, H, W, C, dev, nsplit=self.ns_out)
-            conv_gemm(xin, wp, C, kk, kk, bias=self.b, relu=True, out_f32=out.f32, out_pl=out.pl)
             rec = {"bn": None}
+            if self.glob:
+                wp, wd = self._glob_forward(xin, P, C, record, rec)
+                conv_gemm(xin, wp, C, 1, 1, bias=rec["glob"][5], bias_group=self.glob, relu=True, out_f32=out.f32, out_pl=out.pl)
+            else:
+                conv_gemm(xin, wp, C, kk, kk, bias=self.b, relu=True, out_f32=out.f32, out_pl=out.pl)
             if record:
                 rec.update({"xin": xin, "y": None, "noise": None, "kk": kk, "P": P, "HW": H * W, "in_shape": (x.B, x.H, x.W, x.C),
                             "z_hi": out.hi, "wd": wd})
@@ -618,6 +634,55 @@ class ConvUnit:
             if self.bn is None and self.act != ACT_PRELU:
                 rec["y"] = None  # not needed by the backward of a BN-free ReLU/identity unit
         return out, rec
+
+    def _glob_forward(self, xin, P, C, record, rec):
+        """Global-feature unit: per-instance mean of the input rows, bias table W_b mean + b, operand planes of W_a."""
+        n, ca, dev = self.glob, xin.C, self.w.device
+        if not (self.bn is None and self.act == ACT_RELU and self.k == 1 and self.stride == 1 and xin.f32 is not None and P % n == 0
+                and self.w.numel() == C * 2 * ca):
+            raise RuntimeError("istnet_b200: global-feature unit needs a Conv1d(2*c -> cout)+ReLU on [rows, c] FP32 input rows")
+        nb = P // n
+        w2 = self.w.reshape(C, 2 * ca)
+        wa, wb = w2[:, :ca].contiguous(), w2[:, ca:].contiguous()
+        m = torch.empty(nb, ca, dtype=torch.float32, device=dev)
+        _C.call("rows_mean", c_int(nb), c_int(n), c_int(ca), ptr(xin.f32), ptr(m))
+        table = torch.empty(nb, C, dtype=torch.float32, device=dev)
+        _C.call("heads_linear", c_int(1), c_int(nb), c_int(ca), _ptrs([m]), _ptrs([wb]), _ptrs([self.b]), _ptrs([table]), (ctypes.c_int * 1)(C), c_int(0))
+        wp, wd = prep_weight_pair(wa, nsplit=self.ns) if record else (prep_weight(wa, nsplit=self.ns), None)
+        rec["glob"] = (m, wb, n, nb, ca, table)
+        return wp, wd
+
+    def _glob_data_grads(self, rec, dy, need_dx, grads):
+        """Backward of the global-feature unit: S[b] = sum of dy over the rows of instance b is the gradient of the bias table, so
+        dW_b = S^T mean, d mean = S W_b, and d f = dy W_a + (d mean)[b] / n — the last term again as a per-instance bias, of the
+        data-gradient GEMM."""
+        xin, C = rec["xin"], self.cout
+        m, wb, n, nb, ca, _ = rec["glob"]
+        dev = dy.device
+        main = torch.cuda.current_stream()
+        side = _side_stream(dev) if (need_dx and WGRAD_SIDE_STREAM) else None
+        if side is not None:
+            side.wait_stream(main)
+        S = torch.empty(nb, C, dtype=torch.float32, device=dev)
+        _C.call("rows_group_sum_planes", ptr(dy), c_ll(dy.stride(0)), c_int(dy.shape[0]), c_ll(rec["P"]), c_int(C), c_int(dy.shape[-1]), c_int(n), ptr(S))
+        dm = torch.empty(nb, ca, dtype=torch.float32, device=dev)
+        dwb = torch.empty(C, ca, dtype=torch.float32, device=dev)
+        _C.call("heads_linear_bwd", c_int(1), c_int(nb), c_int(ca), _ptrs([m]), _ptrs([wb]), NULL, _ptrs([S]), _ptrs([dm]), _ptrs([dwb]), NULL,
+                (ctypes.c_int * 1)(C), c_int(0))
+        with torch.cuda.stream(side if side is not None else main):
+            gwa = conv_wgrad(dy, C, xin, 1, 1)
+        if side is not None:
+            dy.record_stream(side)
+            xin.pl.record_stream(side)
+            gwa.record_stream(main)
+            main.wait_stream(side)  # the two halves of the weight gradient are concatenated on the main stream
+        grads[id(self.w)] = torch.cat([gwa.view(C, ca), dwb], 1).reshape(self.w.shape)
+        if not need_dx:
+            return None
+        wd = rec.get("wd")
+        dx = torch.empty(xin.B, xin.H, xin.W, ca, dtype=torch.float32, device=dev)
+        conv_gemm(Act(xin.B, xin.H, xin.W, C, None, dy), wd, ca, 1, 1, out_f32=dx, bias=dm.mul_(1.0 / n), bias_group=n)
+        return dx
 
     # ---- backward
     def backward(self, rec, dz, dz2=None, need_dx=True, g_out=False, grads=None):
@@ -675,6 +740,9 @@ class ConvUnit:
         """Weight gradient (side stream) and data gradient of the convolution.  below = (unit, rec) of the bias+ReLU layer that
         produced this unit's input: the data-gradient GEMM then applies that layer's ReLU mask in its epilogue and returns
         ITS dy operand planes (and fills its bias gradient) instead of the FP32 dx."""
+        if rec.get("glob") is not None:
+            assert below is None
+            return self._glob_data_grads(rec, dy, need_dx, grads)
         xin, kk, C = rec["xin"], rec["kk"], self.cout
         # weight gradient and data gradient are independent: wgrad goes to a side stream and overlaps the dgrad GEMM
         main = torch.cuda.current_stream()

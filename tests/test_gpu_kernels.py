@@ -490,3 +490,41 @@ def test_adam_flat_kernel_matches_torch_adam():
             assert (p - ref.detach()).abs().max().item() <= 1e-4 * lr + 5e-7, (it, (p - ref.detach()).abs().max().item())
             st = opt.state[ref]
             assert rel_err(m, st["exp_avg"]) < 1e-6 and rel_err(v, st["exp_avg_sq"]) < 1e-6
+
+
+def test_global_feature_as_per_instance_bias_equals_the_concatenated_form():
+    """ist_net.py:172-173,257-258,325-326: conv([f | mean(f).expand]) evaluated as W_a f + (W_b mean(f) + b) with the bracket as a
+    per-instance bias of the GEMM epilogue (conv_gemm bias_group), forward and backward, against float64 autograd of the concatenated
+    form and against this repo's own concatenated path."""
+    from istnet_b200 import model as M
+
+    torch.manual_seed(9)
+    b, n, c = 3, 256, 64
+    seq = M._pt_mlp(2 * c, 96, 40).cuda()
+    x = torch.randn(b * n, c, device="cuda")
+    dout = torch.randn(b * n, 40, device="cuda")
+
+    def run(fn):
+        xi = x.clone().requires_grad_(True)
+        for p in seq.parameters():
+            p.grad = None
+        out = fn(xi)
+        out.backward(dout)
+        return out.detach(), xi.grad.detach(), [p.grad.detach().clone() for p in seq.parameters()]
+
+    assert M.GLOBAL_BIAS
+    o1, dx1, g1 = run(lambda xi: M._mlp_global(seq, xi, b, n))
+    o2, dx2, g2 = run(lambda xi: M._mlp(seq, M._with_global(xi, b, n)))
+    seq64 = M._pt_mlp(2 * c, 96, 40).cuda().double()
+    seq64.load_state_dict({k: v.double() for k, v in seq.state_dict().items()})
+    x64 = x.double().requires_grad_(True)
+    f = x64.view(b, n, c)
+    cat = torch.cat([f, f.mean(1, keepdim=True).expand_as(f)], 2).transpose(1, 2)      # [b, 2c, n]
+    o64 = seq64(cat).transpose(1, 2).reshape(b * n, -1)
+    o64.backward(dout.double())
+    g64 = [p.grad for p in seq64.parameters()]
+    tol = 2e-5 if M.HEADS_NSPLIT >= 3 else 1e-4
+    for name, mine, other, ref in (("out", o1, o2, o64), ("dx", dx1, dx2, x64.grad)):
+        assert rel_err(mine, ref) < tol and rel_err(other, ref) < tol, (name, rel_err(mine, ref), rel_err(other, ref))
+    for i, (a, c_, r) in enumerate(zip(g1, g2, g64)):
+        assert rel_err(a, r.reshape(a.shape)) < tol and rel_err(c_, r.reshape(c_.shape)) < tol, (i, rel_err(a, r.reshape(a.shape)))
