@@ -362,3 +362,51 @@ def test_stall_free_solver_loop_matches_the_reference_loop():
             assert rel_err(b, bufs_ref[n]) < 5e-2, (n, rel_err(b, bufs_ref[n]))
     assert all(abs(mod.momentum - bn_momentum_at(n_it - 1, 0.9, 0.5, 2, 0.01)) < 1e-12 for mod in m.modules()
                if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm))
+
+
+def test_solver_optimizer_state_round_trip_resumes_identically():
+    """Checkpoint / resume of the stall-free loop (utils/solver.py:64-68 + train.py:87-96): parameters + BatchNorm buffers through
+    state_dict, Adam's flat moments and step count through optimizer_state() / load_optimizer_state(), iteration counter through
+    start_iter (it drives CyclicLR and the BatchNorm momentum schedule).  Two more iterations after the resume equal the same two
+    iterations of the uninterrupted run."""
+    import copy
+
+    from istnet_b200.solver import Solver
+
+    cfg = _Cfg(max_epoch=2, num_mini_batch_per_epoch=6, per_write=100, per_val=10, log_dir="/tmp",
+               optimizer={"lr": 0.01, "weight_decay": 0.0}, bn={"bn_momentum": 0.9, "bn_decay": 0.5, "decay_step": 2, "bnm_clip": 0.01},
+               loss={"gamma1": 1.0, "gamma2": 10.0}, freeze_world_enhancer=False)
+    torch.manual_seed(4)
+    m = M.IST_Net(6, False).cuda().train()
+    ones = {c: torch.ones(4, c, 1, 1, device="cuda") for c in (1024, 256, 64)}
+    m.rgb_cam_extractor.model.dropout_noise_fn = lambda b, c, p: ones[c]
+    syn = [make_batch(3, 256, 64, seed=300 + i) for i in range(4)]
+    real = [make_batch(1, 256, 64, seed=400 + i) for i in range(4)]
+    loss_fn = M.SupervisedLoss(M.LossCfg())
+    sol = Solver(m, "Camera+Real", {"syn": loss_fn, "real": loss_fn}, {"syn": syn[:2], "real": real[:2]}, None, cfg)
+    sol.train()
+    ckpt_model = copy.deepcopy(m.state_dict())
+    ckpt_opt = sol.optimizer_state()
+    assert ckpt_opt["step"] == 2 and sol.iter == 2
+    sol.dataloaders = {"syn": syn[2:], "real": real[2:]}
+    info_a = sol.train()
+    want = {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+    torch.manual_seed(5)  # different initial weights: everything must come from the checkpoint
+    m2 = M.IST_Net(6, False).cuda().train()
+    m2.rgb_cam_extractor.model.dropout_noise_fn = lambda b, c, p: ones[c]
+    m2.load_state_dict(ckpt_model)
+    sol2 = Solver(m2, "Camera+Real", {"syn": loss_fn, "real": loss_fn}, {"syn": syn[2:], "real": real[2:]}, None, cfg, start_iter=2)
+    sol2.load_optimizer_state(ckpt_opt)
+    info_b = sol2.train()
+    assert sol2.iter == 4 and int(sol2.optimizer.step_dev.item()) == 4
+    assert abs(info_a["lr"] - info_b["lr"]) < 1e-15
+    assert abs(info_a["loss_all"] - info_b["loss_all"]) <= 2e-2 * abs(info_a["loss_all"])
+    errs = sorted(rel_err(v, want[k]) for k, v in m2.state_dict().items() if v.is_floating_point() and want[k].abs().max().item() > 0)
+    exact = sum(1 for e in errs if e < 1e-4)
+    # same caveat as test_stall_free_solver_loop_matches_the_reference_loop: float atomics make two runs of this chaotic B=4 step differ,
+    # and Adam's sign-like update magnifies it on near-zero gradient elements; most tensors must nevertheless coincide
+    assert exact >= len(errs) // 2 and errs[len(errs) // 2] < 1e-2, (exact, len(errs), errs[len(errs) // 2], errs[-1])
+    for k, v in m2.state_dict().items():
+        if k.endswith("num_batches_tracked"):
+            assert int(v.item()) == int(want[k].item()) == 4, k
