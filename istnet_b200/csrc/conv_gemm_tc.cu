@@ -54,6 +54,7 @@ struct ConvGemmParams {
     int stat_y_cs;
     uint32_t tmem_cols;
     FinP fin;                 // optional: the last CTA finishes the statistics reduction (ticket.cuh)
+    int cluster;              // 1, or 2: CTA pairs work on two row tiles of the same column tile and share the weight tile (TMA multicast)
 };
 
 __global__ void __launch_bounds__(kThreadsWide, 1)
@@ -74,7 +75,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = p.kh * p.kw * p.cin_blocks;
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
-    const int n_tiles = m_tiles * p.n_tiles_n;
+    // Work items.  cluster == 2: the CTA pair (cluster) takes two consecutive row tiles of ONE column tile per item; each CTA loads
+    // half of the weight tile and multicasts it into both CTAs' rings, so the weight operand crosses L2 -> SM once per pair.  A stage
+    // may be overwritten only when BOTH consumers have retired it: the MMA commit arrives on the empty barrier of both CTAs (count 2).
+    const int cl = p.cluster;
+    const uint32_t crank = cl > 1 ? tc::cluster_ctarank() : 0u;
+    const int m_groups = (m_tiles + cl - 1) / cl;
+    const int n_work = m_groups * p.n_tiles_n;
+    const int w_first = (int)blockIdx.x / cl, w_step = (int)gridDim.x / cl;
     // PERSISTENT: this CTA processes tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The shared-memory ring keeps running
     // across tiles and the accumulator is double-buffered in tensor memory, so the epilogue of tile i overlaps the TMA /
     // MMA main loop of tile i+1 and the per-CTA set-up (TMEM allocation, barrier init, descriptor prefetch) is paid once.
@@ -83,7 +91,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         tc::prefetch_tmap(&tm_a); tc::prefetch_tmap(&tm_b);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], (uint32_t)cl); }
         for (int s = 0; s < 2; ++s) { tc::mbar_init(&tmem_full_bar[s], 1); tc::mbar_init(&tmem_empty_bar[s], (blockDim.x >> 5) - 2); }
         tc::fence_barrier_init();
     }
@@ -92,6 +100,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         for (int i = threadIdx.x; i < 8 * p.Cout; i += blockDim.x) s_stat[i] = 0.f;
     tc::tc_fence_before();
     __syncthreads();
+    if (cl > 1) tc::cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
@@ -100,9 +109,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         if (lane == 0) {
             const int pad_h = p.kh / 2, pad_w = p.kw / 2;
             int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                int mt = tile % m_tiles;
-                const int n0 = (tile / m_tiles) * p.BN;
+            for (int wi = w_first; wi < n_work; wi += w_step) {
+                int mt = (wi % m_groups) * cl + (int)crank;  // may lie past the last row tile (odd count): every box is then out of bounds = zeros
+                const int n0 = (wi / m_groups) * p.BN;
                 const int tw = mt % p.tiles_w; mt /= p.tiles_w;
                 const int th = mt % p.tiles_h; mt /= p.tiles_h;
                 const int w0 = tw * p.box_w, h0 = th * p.box_h, b0 = mt * p.box_b;
@@ -120,7 +129,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                         uint8_t *sb = sa + p.nsplit * kATileBytes;
                         for (int pl = 0; pl < p.nsplit; ++pl) {
                             tc::tma_load_5d(sa + pl * kATileBytes, &tm_a, &full_bar[st], kb * kBlockK, w0 + s - pad_w, h0 + r - pad_h, b0, pl);
-                            tc::tma_load_4d(sb + pl * b_tile_bytes, &tm_b, &full_bar[st], kb * kBlockK, n0, tap, pl);
+                            if (cl > 1)  // this CTA's half of the weight rows, delivered to both CTAs
+                                tc::tma_load_4d_multicast(sb + pl * b_tile_bytes + crank * (b_tile_bytes / 2), &tm_b, &full_bar[st], kb * kBlockK,
+                                                          n0 + (int)crank * (p.BN / 2), tap, pl, (uint16_t)0x3);
+                            else
+                                tc::tma_load_4d(sb + pl * b_tile_bytes, &tm_b, &full_bar[st], kb * kBlockK, n0, tap, pl);
                         }
                     }
                 }
@@ -133,7 +146,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             const uint32_t ltype = kBlockK == 64 ? 2u : 4u;   // SWIZZLE_128B | SWIZZLE_64B
             const uint32_t sbo = 8u * kBlockK * 2u;           // 8 rows of one swizzle atom
             int it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            for (int wi = w_first; wi < n_work; wi += w_step, ++lt) {
                 const int buf = lt & 1;
                 const uint32_t use = (uint32_t)(lt >> 1);
                 tc::mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);  // epilogue has drained this accumulator
@@ -159,7 +172,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                             }
                         }
                     }
-                    tc::umma_commit(&empty_bar[st]);  // frees the smem stage once these MMAs retire
+                    if (cl > 1) tc::umma_commit_multicast(&empty_bar[st], (uint16_t)0x3);  // both producers wait for both consumers
+                    else tc::umma_commit(&empty_bar[st]);  // frees the smem stage once these MMAs retire
                 }
                 tc::umma_commit(&tmem_full_bar[buf]);
             }
@@ -181,9 +195,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                              ((reinterpret_cast<uintptr_t>(p.out_pl) & 15) == 0);
         const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
         int lt = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
-            int mt = tile % m_tiles;
-            const int n0 = (tile / m_tiles) * p.BN;
+        for (int wi = w_first; wi < n_work; wi += w_step, ++lt) {
+            int mt = (wi % m_groups) * cl + (int)crank;
+            const int n0 = (wi / m_groups) * p.BN;
             const int tw = mt % p.tiles_w; mt /= p.tiles_w;
             const int th = mt % p.tiles_h; mt /= p.tiles_h;
             const int b = mt * p.box_b + pb, h = th * p.box_h + ph_, w = tw * p.box_w + pw;
@@ -337,6 +351,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         if (p.fin.kind == 2) ticket_finish<1>(p.fin, p.stat_part, (int)gridDim.x, p.Cout);
         else ticket_finish<2>(p.fin, p.stat_part, (int)gridDim.x, p.Cout);
     }
+    if (cl > 1) tc::cluster_sync_all();  // no CTA leaves while its peer may still arrive on its barriers
     if (warp == 2) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, p.tmem_cols);
@@ -444,6 +459,10 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     int budget_kb = (p.BN <= 128 && n_tiles >= 2 * kNumSMs) ? 110 : 225;
     static const int budget_override = env_int("ISTNET_CG_SMEM_KB", 0);
     if (budget_override > 0) budget_kb = budget_override;
+    // Optional CTA pairs (ISTNET_CG_CLUSTER=2): wide tiles with one CTA per SM, at least two row tiles
+    static const int cluster_env = env_int("ISTNET_CG_CLUSTER", 1);
+    const long long m_tiles_h = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
+    p.cluster = (cluster_env == 2 && budget_kb == 225 && p.BN >= 128 && (p.BN % 16) == 0 && m_tiles_h >= 2) ? 2 : 1;
     const int stat_bytes = stat_part ? 8 * Cout * (int)sizeof(float) : 0;
     int max_stages = (budget_kb * 1024 - 1024 - 256 - stat_bytes) / stage_bytes;
     if (max_stages < 1) max_stages = 1;
@@ -456,21 +475,6 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256 + stat_bytes;
     if (smem > 227 * 1024) return ISTNET_ERR_UNSUPPORTED;
 
-    CUtensorMap ta, tb;
-    {
-        uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B, (uint64_t)nsplit};
-        uint64_t str[4] = {(uint64_t)act_cs * 2, (uint64_t)W * act_cs * 2, (uint64_t)H * W * act_cs * 2, (uint64_t)act_plane_stride * 2};
-        uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)box_w, (uint32_t)box_h, (uint32_t)p.box_b, 1u};
-        int e = istnet_make_tmap_bf16(&ta, act_planes, 5, dims, str, box, kBlockK * 2);
-        if (e) return e;
-    }
-    {
-        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw), (uint64_t)nsplit};
-        uint64_t str[3] = {(uint64_t)wgt_cs * 2, (uint64_t)Cout * wgt_cs * 2, (uint64_t)wgt_plane_stride * 2};
-        uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.BN, 1u, 1u};
-        int e = istnet_make_tmap_bf16(&tb, wgt_planes, 4, dims, str, box, kBlockK * 2);
-        if (e) return e;
-    }
     // dynamic + static shared memory share the 227 KB per-CTA limit (the ticket tail of the statistics epilogue keeps a few
     // bytes of static shared memory)
     static int static_smem = -1;
@@ -486,13 +490,56 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     if (ctas_per_sm > 512 / (int)p.tmem_cols) ctas_per_sm = 512 / (int)p.tmem_cols;  // tensor memory: 512 columns per SM
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     if (ctas_per_sm > 2) ctas_per_sm = 2;  // grid <= 2 * 148 = 296: the size callers give the statistics scratch (stat_part)
+    if (ctas_per_sm != 1) p.cluster = 1;  // CTA pairs only for the one-CTA-per-SM configuration; decided before the weight map's box is fixed
+    CUtensorMap ta, tb;
+    {
+        uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B, (uint64_t)nsplit};
+        uint64_t str[4] = {(uint64_t)act_cs * 2, (uint64_t)W * act_cs * 2, (uint64_t)H * W * act_cs * 2, (uint64_t)act_plane_stride * 2};
+        uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)box_w, (uint32_t)box_h, (uint32_t)p.box_b, 1u};
+        int e = istnet_make_tmap_bf16(&ta, act_planes, 5, dims, str, box, kBlockK * 2);
+        if (e) return e;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw), (uint64_t)nsplit};
+        uint64_t str[3] = {(uint64_t)wgt_cs * 2, (uint64_t)Cout * wgt_cs * 2, (uint64_t)wgt_plane_stride * 2};
+        uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(p.BN / p.cluster), 1u, 1u};  // cluster: every CTA fetches its half of the rows
+        int e = istnet_make_tmap_bf16(&tb, wgt_planes, 4, dims, str, box, kBlockK * 2);
+        if (e) return e;
+    }
     long long grid_x = (long long)kNumSMs * ctas_per_sm;
     if (grid_x > n_tiles) grid_x = n_tiles;
     if (grid_out) *grid_out = (int)grid_x;
     int threads = ctas_per_sm >= 2 ? kThreads : kThreadsWide;
     static const int threads_override = env_int("ISTNET_CG_THREADS", 0);
     if (threads_override > 0) threads = threads_override;
-    conv_gemm_tc_kernel<<<(unsigned)grid_x, threads, smem, (cudaStream_t)stream>>>(ta, tb, p);
+    if (p.cluster == 2) {
+        cudaLaunchConfig_t cfg{};
+        cfg.blockDim = dim3((unsigned)threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        static int max_clusters = -1;  // co-resident CTA pairs at the full shared-memory footprint (GPC granularity)
+        if (max_clusters < 0) {
+            cfg.gridDim = dim3((unsigned)kNumSMs / 2 * 2);
+            cudaLaunchConfig_t q = cfg;
+            q.dynamicSmemBytes = 227 * 1024 - static_smem;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_tc_kernel, &q) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = kNumSMs / 2 - 2; }
+            max_clusters = n;
+        }
+        const long long n_work = ((m_tiles_h + 1) / 2) * ceil_div(Cout, p.BN);
+        long long pairs = max_clusters < kNumSMs / 2 ? max_clusters : kNumSMs / 2;
+        if (pairs > n_work) pairs = n_work;
+        grid_x = 2 * pairs;
+        if (grid_out) *grid_out = (int)grid_x;
+        cfg.gridDim = dim3((unsigned)grid_x);
+        ISTNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel, ta, tb, p));
+    } else {
+        conv_gemm_tc_kernel<<<(unsigned)grid_x, threads, smem, (cudaStream_t)stream>>>(ta, tb, p);
+    }
     ISTNET_LAUNCH_CHECK();
     if (fin_p.kind != 0 && !fin_in_kernel(Cout))
         return istnet_fin_finalize_launch(stat_part, (int)grid_x, Cout, fin_p.kind == ISTNET_FIN_COLSUM ? 1 : 2, fin_p, (cudaStream_t)stream);
