@@ -57,6 +57,9 @@ struct ConvGemmParams {
     int cluster;              // 1, or 2: CTA pairs work on two row tiles of the same column tile and share the weight tile (TMA multicast)
 };
 
+// CL = CTAs per cluster (compile-time: the single-CTA instantiation is exactly the round-1 kernel; a run-time switch on the hot
+// single-thread producer / MMA-issue loops cost the 3x3 convolutions 12 %, profiles/r2_tensor_core_kernel_table.txt vs _cluster2)
+template <int CL>
 __global__ void __launch_bounds__(kThreadsWide, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const ConvGemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -78,7 +81,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     // Work items.  cluster == 2: the CTA pair (cluster) takes two consecutive row tiles of ONE column tile per item; each CTA loads
     // half of the weight tile and multicasts it into both CTAs' rings, so the weight operand crosses L2 -> SM once per pair.  A stage
     // may be overwritten only when BOTH consumers have retired it: the MMA commit arrives on the empty barrier of both CTAs (count 2).
-    const int cl = p.cluster;
+    constexpr int cl = CL;
     const uint32_t crank = cl > 1 ? tc::cluster_ctarank() : 0u;
     const int m_groups = (m_tiles + cl - 1) / cl;
     const int n_work = m_groups * p.n_tiles_n;
@@ -480,11 +483,13 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
     static int static_smem = -1;
     if (static_smem < 0) {
         cudaFuncAttributes fa;
-        ISTNET_CUDA_TRY(cudaFuncGetAttributes(&fa, conv_gemm_tc_kernel));
+        ISTNET_CUDA_TRY(cudaFuncGetAttributes(&fa, conv_gemm_tc_kernel<1>));
         static_smem = (int)fa.sharedSizeBytes;
     }
     if (smem + (size_t)static_smem > 227 * 1024) return ISTNET_ERR_UNSUPPORTED;
-    ISTNET_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - static_smem));
+    ISTNET_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - static_smem));
+    if (p.cluster == 2)
+        ISTNET_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - static_smem));
     int ctas_per_sm = (int)((227 * 1024) / (smem + static_smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     if (ctas_per_sm > 512 / (int)p.tmem_cols) ctas_per_sm = 512 / (int)p.tmem_cols;  // tensor memory: 512 columns per SM
@@ -527,7 +532,7 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
             cudaLaunchConfig_t q = cfg;
             q.dynamicSmemBytes = 227 * 1024 - static_smem;
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_tc_kernel, &q) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = kNumSMs / 2 - 2; }
+            if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_tc_kernel<2>, &q) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = kNumSMs / 2 - 2; }
             max_clusters = n;
         }
         const long long n_work = ((m_tiles_h + 1) / 2) * ceil_div(Cout, p.BN);
@@ -536,9 +541,9 @@ extern "C" int istnet_conv_gemm(const void *act_planes, long long act_plane_stri
         grid_x = 2 * pairs;
         if (grid_out) *grid_out = (int)grid_x;
         cfg.gridDim = dim3((unsigned)grid_x);
-        ISTNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel, ta, tb, p));
+        ISTNET_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<2>, ta, tb, p));
     } else {
-        conv_gemm_tc_kernel<<<(unsigned)grid_x, threads, smem, (cudaStream_t)stream>>>(ta, tb, p);
+        conv_gemm_tc_kernel<1><<<(unsigned)grid_x, threads, smem, (cudaStream_t)stream>>>(ta, tb, p);
     }
     ISTNET_LAUNCH_CHECK();
     if (fin_p.kind != 0 && !fin_in_kernel(Cout))
