@@ -81,3 +81,29 @@ class InferenceEngine:
                 st[k][b:size].copy_(st[k][0:1].expand_as(st[k][b:size]))
         g.replay()
         return out[0][:b], out[1][:b]
+
+
+def estimate_poses(engine, rgb_frame, depth, valid_mask, det_boxes, class_ids, intrinsics, generator=None, norm_scale=1000.0):
+    """One image of `test_func` (utils/solver.py:217-241) from DEVICE-resident frame data, without a host round trip: the per-instance
+    preparation of the reference's test Dataset (provider/dataset.py:369-409; istnet_b200.dataprep: crop + 8-bit bilinear resize +
+    normalise, valid-pixel sampling, back-projection, `choose` re-mapping) feeds the bucketed eval graph.
+    rgb_frame [H,W,3] uint8 (RGB), depth [H,W] float32 (hole-filled), valid_mask [K,H,W] bool per detection (mask & depth > 0),
+    det_boxes [K,4] host ints (y1,x1,y2,x2), class_ids [K] 0-indexed.  Instances with <= 16 valid pixels are dropped like the
+    reference does (dataset.py:381).  Returns (pred_RTs [k,4,4], pred_scales [k,3], kept indices)."""
+    from . import dataprep
+
+    H, W = depth.shape
+    keep = [j for j in range(len(det_boxes)) if int(valid_mask[j].sum()) > 16]
+    if not keep:
+        z = torch.zeros(0, device=depth.device)
+        return z.view(0, 4, 4), z.view(0, 3), keep
+    boxes_h = [(0,) + dataprep.get_bbox(det_boxes[j], H, W) for j in keep]
+    choose = torch.empty(len(keep), engine.npts, dtype=torch.int32, device=depth.device)
+    for i, j in enumerate(keep):  # each detection samples inside its own mask (dataset.py:375-386)
+        c, ok = dataprep.sample_choose(valid_mask[j : j + 1], [boxes_h[i]], engine.npts, generator=generator)
+        choose[i] = c[0]
+    boxes = torch.tensor(boxes_h, dtype=torch.int32, device=depth.device)
+    inp = dataprep.prepare_instances(rgb_frame.unsqueeze(0), depth.unsqueeze(0), boxes, choose, intrinsics, img_size=engine.img, norm_scale=norm_scale)
+    inp["category_label"] = torch.as_tensor([int(class_ids[j]) for j in keep], dtype=torch.int64, device=depth.device)
+    rts, scales = engine(inp)
+    return rts, scales, keep

@@ -72,3 +72,40 @@ def test_prepared_batch_feeds_the_model_and_cpu_tensors_are_refused():
     assert ep["pred_rotation"].shape == (2, 3, 3) and torch.isfinite(ep["pred_translation"]).all()
     with pytest.raises(RuntimeError, match="CPU not supported"):
         D.prepare_instances(torch.from_numpy(frames), torch.from_numpy(depth).cuda(), boxes, choose, (1.0, 1.0, 0.0, 0.0))
+
+
+def test_frames_to_poses_pipeline_equals_the_manual_steps():
+    """infer.estimate_poses (device data preparation -> bucketed eval graph -> pose assembly) against the same steps done by hand."""
+    from conftest import perturb_batchnorm
+    from istnet_b200 import model as M
+    from istnet_b200.infer import InferenceEngine, estimate_poses
+
+    rng = np.random.default_rng(21)
+    rgb = torch.from_numpy(rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)).cuda()
+    depth = torch.from_numpy(rng.uniform(500, 1500, (480, 640)).astype(np.float32)).cuda()
+    dets = [(100, 200, 220, 330), (250, 300, 330, 420), (10, 10, 14, 13)]
+    masks = torch.zeros(3, 480, 640, dtype=torch.bool, device="cuda")
+    masks[0, 110:210, 210:320] = True
+    masks[1, 255:325, 305:415] = True
+    masks[2, 10:13, 10:13] = True  # 9 valid pixels: dropped (<= 16)
+    torch.manual_seed(2)
+    m = M.IST_Net(6, False)
+    perturb_batchnorm(m, seed=44)
+    m = m.cuda().eval()
+    eng = InferenceEngine(m, npts=256, img=64)
+    intr = (591.0125, 590.16775, 322.525, 244.11084)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    rts, scales, keep = estimate_poses(eng, rgb, depth, masks, dets, [2, 5, 0], intr, generator=g)
+    assert keep == [0, 1] and rts.shape == (2, 4, 4) and scales.shape == (2, 3)
+    # by hand, with the same random draws
+    g = torch.Generator(device="cuda").manual_seed(9)
+    boxes_h = [(0,) + D.get_bbox(dets[j]) for j in keep]
+    choose = torch.stack([D.sample_choose(masks[j : j + 1], [boxes_h[i]], 256, generator=g)[0][0] for i, j in enumerate(keep)])
+    inp = D.prepare_instances(rgb.unsqueeze(0), depth.unsqueeze(0), torch.tensor(boxes_h, dtype=torch.int32).cuda(), choose, intr, img_size=64)
+    inp["category_label"] = torch.tensor([2, 5], device="cuda")
+    with torch.no_grad():
+        ep = m(inp)
+    s = torch.norm(ep["pred_size"], dim=1, keepdim=True)
+    assert torch.allclose(rts[:, :3, :3], ep["pred_rotation"] * s.unsqueeze(2), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(rts[:, :3, 3], ep["pred_translation"], rtol=1e-5, atol=1e-6) and torch.allclose(scales, ep["pred_size"] / s, rtol=1e-5, atol=1e-6)
+    assert torch.isfinite(rts).all()
