@@ -4,7 +4,7 @@ Functional, plain-PyTorch (FP32) restatement of the reference's per-instance hot
 reference-layout `state_dict`.  It exists because the reference tree cannot travel to the GPU
 box: it is (1) the float oracle for the `-m gpu` parity tests, (2) the `cpu_baseline` / `--impl reference`
 arm of bench.py (kind "port").  It is pinned against the UNMODIFIED reference modules imported through
-oracle/ref_harness.py (tests/test_oracle_vs_reference.py, runs where /root/reference exists) and against
+oracle/ref_harness.py (tests/test_oracle_model.py, runs where /root/reference exists) and against
 the golden vectors in tests/golden/ that were produced by the reference itself.
 
 Each function cites the reference lines it follows.  `ops` is a module exposing the nine `_ext` operators

@@ -10,7 +10,7 @@
  * the compiler adds no contraction of its own; every fused multiply-add is an explicit fmaf().
  *
  * Pinned against: (1) the reference's own CUDA extension compiled from /root/reference into
- * oracle/_ref/ and run on the B200 (tests/test_gpu_pointops.py::test_reference_ext_*),
+ * oracle/_ref/ and run on the B200 (tests/test_gpu_pointops.py::test_reference_extension_agrees),
  * (2) the golden vectors under tests/golden/ produced with the reference Python modules.
  */
 #include <math.h>
