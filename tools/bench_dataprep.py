@@ -35,19 +35,24 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 200
 out_bytes = B * (3 * S * S * 4 + N * 12 + N * 8)
 print(f"GPU: {ms * 1000:.1f} us per batch of {B} instances = {B / ms * 1000:.0f} instances/s ({out_bytes / ms / 1e6:.1f} GB/s of outputs)")
-try:
+try:  # the host libraries the reference's Dataset calls, on one core (cv2.resize + torchvision transform + the numpy expressions)
     import cv2
+    import torchvision.transforms as T
 
-    from oracle import dataprep_ref as R  # noqa: E402  (CPU comparison leg only)
-
+    tr = T.Compose([T.ToTensor(), T.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
     ch = choose.cpu().numpy().astype(np.int64)
+    fx, fy, cx, cy = intr
     t0 = time.time()
     for i, b in enumerate(boxes_h):
-        crop = frames[b[0]][b[1]:b[2], b[3]:b[4]]
-        R.normalize_u8(cv2.resize(crop, (S, S), interpolation=cv2.INTER_LINEAR))
-        R.back_project(depth[b[0]], ch[i], b[1:], intr, 1000.0)
-        R.remap_choose(ch[i], b[1:], S)
+        f, rmin, rmax, cmin, cmax = b
+        tr(cv2.resize(frames[f][rmin:rmax, cmin:cmax], (S, S), interpolation=cv2.INTER_LINEAR))
+        cw = cmax - cmin
+        r, c = rmin + ch[i] // cw, cmin + ch[i] % cw
+        z = depth[f][r, c] / 1000.0
+        np.stack([(c - cx) * z / fx, (r - cy) * z / fy, z], 1).astype(np.float32)
+        ratio = S / (rmax - rmin)
+        (np.floor((ch[i] // (rmax - rmin)) * ratio) * S + np.floor((ch[i] % (rmax - rmin)) * ratio)).astype(np.int64)
     dt = time.time() - t0
-    print(f"CPU (cv2.resize + numpy, one core, crop / resize / normalise / back-project only): {B / dt:.0f} instances/s")
+    print(f"CPU (cv2.resize + torchvision + numpy, one core, crop / resize / normalise / back-project only): {B / dt:.0f} instances/s")
 except ImportError:
     pass
