@@ -416,7 +416,15 @@ int istnet_adam_tick(long long *step_dev, void *stream);
  * mean3 / std3 are HOST pointers to three floats.  rgb_out may be null (points only); N may be 0 (image only). */
 int istnet_prepare_instances(const unsigned char *rgb_frames, const float *depth, int F, int H, int W, const int *boxes, const int *choose,
                              int B, int N, int S, double fx, double fy, double cx, double cy, float norm_scale, const float *mean3,
-                             const float *std3, const double *noise, float *rgb_out, float *pts_out, long long *choose_out, void *stream);
+                             const float *std3, const double *noise, const double *label_params, float *rgb_out, float *pts_out,
+                             float *qo_out, long long *choose_out, void *stream);
+/* label_params (nullable, DEVICE, [B][13] doubles = translation[3], |size| + 1e-8, rotation[9] row-major) with qo_out [B][N][3]: the NOCS
+ * coordinates of the training labels, qo = (pts - t) / (|size| + 1e-8) @ R evaluated on the float64 points (provider/dataset.py:249).
+ *
+ * istnet_augment_points: provider/data_augmentation.py:45-130 (bounding-box deformation + rigid perturbation, the two augmentations the
+ * default configuration enables) applied in place to pts / qo [B][N][3]; params DEVICE [B][32] floats = R[9], t[3], stretch e[3],
+ * nocs_scale_aug, do_bb, d[3], Rm[9], do_rt (flags as 0 / 1).  The 3x3 / 3-vector label updates are the caller's (host) job. */
+int istnet_augment_points(int B, int N, const float *params, float *pts, float *qo, void *stream);
 
 #ifdef __cplusplus
 }

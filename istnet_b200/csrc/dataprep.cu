@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(kThreads) crop_resize_normalize_kernel(const u
 __global__ void __launch_bounds__(kThreads) back_project_kernel(const float *__restrict__ depth, int H, int W, const int *__restrict__ boxes,
                                                                 const int *__restrict__ choose, int N, int S, double fx, double fy, double cx,
                                                                 double cy, float norm_scale, const double *__restrict__ noise,
-                                                                float *__restrict__ pts, long long *__restrict__ choose_out) {
+                                                                const double *__restrict__ lab, float *__restrict__ pts, float *__restrict__ qo,
+                                                                long long *__restrict__ choose_out) {
     const int b = blockIdx.y;
     const int *bx = boxes + b * 5;
     const int frame = bx[0], rmin = bx[1], rmax = bx[2], cmin = bx[3], cmax = bx[4];
@@ -80,23 +81,79 @@ __global__ void __launch_bounds__(kThreads) back_project_kernel(const float *__r
         const double zd = (double)z;
         double x = __ddiv_rn(__dmul_rn((double)c - cx, zd), fx), y = __ddiv_rn(__dmul_rn((double)r - cy, zd), fy), zz = zd;
         float px = (float)x, py = (float)y, pz = (float)zz;
+        double dx_ = (double)px, dy_ = (double)py, dz_ = (double)pz;  // the float32 point as float64 (dataset.py:209-210)
         if (noise) {  // pts (float32) + float64 jitter, rounded once
             const double *nz = noise + ((size_t)b * N + n) * 3;
-            px = (float)((double)px + nz[0]); py = (float)((double)py + nz[1]); pz = (float)((double)pz + nz[2]);
+            dx_ = __dadd_rn(dx_, nz[0]); dy_ = __dadd_rn(dy_, nz[1]); dz_ = __dadd_rn(dz_, nz[2]);
+            px = (float)dx_; py = (float)dy_; pz = (float)dz_;
         }
         float *o = pts + ((size_t)b * N + n) * 3;
         o[0] = px; o[1] = py; o[2] = pz;
+        if (lab && qo) {  // dataset.py:249: qo = (pts - t) / (|size| + 1e-8) @ R on the float64 points; lab[b] = t[3], den, R[9] (row-major)
+            const double *L = lab + (size_t)b * 13;
+            const double ux = __ddiv_rn(__dsub_rn(dx_, L[0]), L[3]), uy = __ddiv_rn(__dsub_rn(dy_, L[1]), L[3]), uz = __ddiv_rn(__dsub_rn(dz_, L[2]), L[3]);
+            float *q = qo + ((size_t)b * N + n) * 3;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                q[j] = (float)__dadd_rn(__dadd_rn(__dmul_rn(ux, L[4 + j]), __dmul_rn(uy, L[7 + j])), __dmul_rn(uz, L[10 + j]));
+        }
         // dataset.py:221-226: row / column of the crop pixel use the crop HEIGHT for both (square windows)
         const int col = k % crop, row = k / crop;
         choose_out[(size_t)b * N + n] = (long long)(floor((double)row * ratio) * (double)S + floor((double)col * ratio));
     }
 }
+// provider/data_augmentation.py:45-130 applied to the points and NOCS coordinates of every instance (the 3x3 / 3-vector label updates
+// are done by the caller): par[b] = R[9], t[3], e[3], k, do_bb, d[3], Rm[9], do_rt  (30 floats, stride 32).
+//   bounding-box deformation: p <- R ((R^T (p - t)) * e) + t,  q <- (q * e) / k          (e = per-axis stretch, k = nocs_scale_aug)
+//   rigid perturbation:       p <- Rm (p + d)
+// FP32 like the torch CPU code, multiplies and adds separately rounded.
+__global__ void __launch_bounds__(kThreads) augment_points_kernel(int N, const float *__restrict__ par, float *__restrict__ pts, float *__restrict__ qo) {
+    const int b = blockIdx.y;
+    const float *P = par + (size_t)b * 32;
+    const bool do_bb = P[16] != 0.f, do_rt = P[29] != 0.f;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        float *p = pts + ((size_t)b * N + n) * 3;
+        float x = p[0], y = p[1], z = p[2];
+        if (do_bb) {
+            const float ax = __fsub_rn(x, P[9]), ay = __fsub_rn(y, P[10]), az = __fsub_rn(z, P[11]);
+            float r[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j)  // (p - t) @ R
+                r[j] = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, P[j]), __fmul_rn(ay, P[3 + j])), __fmul_rn(az, P[6 + j])), P[12 + j]);
+            x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r[0], P[0]), __fmul_rn(r[1], P[1])), __fmul_rn(r[2], P[2])), P[9]);   // rep @ R^T + t
+            y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r[0], P[3]), __fmul_rn(r[1], P[4])), __fmul_rn(r[2], P[5])), P[10]);
+            z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r[0], P[6]), __fmul_rn(r[1], P[7])), __fmul_rn(r[2], P[8])), P[11]);
+            if (qo) {
+                float *q = qo + ((size_t)b * N + n) * 3;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) q[j] = __fdiv_rn(__fmul_rn(q[j], P[12 + j]), P[15]);
+            }
+        }
+        if (do_rt) {
+            const float ax = __fadd_rn(x, P[17]), ay = __fadd_rn(y, P[18]), az = __fadd_rn(z, P[19]);
+            x = __fadd_rn(__fadd_rn(__fmul_rn(ax, P[20]), __fmul_rn(ay, P[21])), __fmul_rn(az, P[22]));  // (p + d) @ Rm^T
+            y = __fadd_rn(__fadd_rn(__fmul_rn(ax, P[23]), __fmul_rn(ay, P[24])), __fmul_rn(az, P[25]));
+            z = __fadd_rn(__fadd_rn(__fmul_rn(ax, P[26]), __fmul_rn(ay, P[27])), __fmul_rn(az, P[28]));
+        }
+        p[0] = x; p[1] = y; p[2] = z;
+    }
+}
 }  // namespace
+
+extern "C" int istnet_augment_points(int B, int N, const float *params, float *pts, float *qo, void *stream) {
+    if (B <= 0 || N <= 0 || !params || !pts) return ISTNET_ERR_BAD_ARG;
+    if (B > 65535) return ISTNET_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)((N + kThreads - 1) / kThreads), (unsigned)B);
+    augment_points_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(N, params, pts, qo);
+    ISTNET_LAUNCH_CHECK();
+    return ISTNET_OK;
+}
 
 extern "C" int istnet_prepare_instances(const unsigned char *rgb_frames, const float *depth, int F, int H, int W, const int *boxes,
                                         const int *choose, int B, int N, int S, double fx, double fy, double cx, double cy,
-                                        float norm_scale, const float *mean3, const float *std3, const double *noise, float *rgb_out,
-                                        float *pts_out, long long *choose_out, void *stream) {
+                                        float norm_scale, const float *mean3, const float *std3, const double *noise,
+                                        const double *label_params, float *rgb_out, float *pts_out, float *qo_out, long long *choose_out,
+                                        void *stream) {
     if (F <= 0 || H <= 0 || W <= 0 || B <= 0 || S <= 0 || N < 0 || !boxes || !mean3 || !std3) return ISTNET_ERR_BAD_ARG;
     if ((rgb_out && !rgb_frames) || (N > 0 && (!depth || !choose || !pts_out || !choose_out))) return ISTNET_ERR_BAD_ARG;
     if (B > 65535) return ISTNET_ERR_UNSUPPORTED;
@@ -109,7 +166,8 @@ extern "C" int istnet_prepare_instances(const unsigned char *rgb_frames, const f
     }
     if (N > 0) {
         dim3 grid((unsigned)((N + kThreads - 1) / kThreads), (unsigned)B);
-        back_project_kernel<<<grid, kThreads, 0, st>>>(depth, H, W, boxes, choose, N, S, fx, fy, cx, cy, norm_scale, noise, pts_out, choose_out);
+        back_project_kernel<<<grid, kThreads, 0, st>>>(depth, H, W, boxes, choose, N, S, fx, fy, cx, cy, norm_scale, noise, label_params, pts_out, qo_out,
+                                                       choose_out);
         ISTNET_LAUNCH_CHECK();
     }
     return ISTNET_OK;

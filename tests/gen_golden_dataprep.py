@@ -66,6 +66,51 @@ def main():
     np.savez_compressed(out, frames=frames, depth=depth, boxes=boxes, choose_in=np.stack(chin), noise=np.stack(noises), intrinsics=np.array(INTR),
                         rgb=np.stack(rgbs), pts=np.stack(ptss), pts_jitter=np.stack(ptsn), choose=np.stack(chos), S=S, norm_scale=NORM)
     print(out, os.path.getsize(out), "bytes; windows:", [tuple(int(v) for v in b) for b in boxes])
+    # ---- training labels (dataset.py:236-250) and the two default augmentations (provider/data_augmentation.py:45-130), produced by the
+    # reference's own functions
+    import importlib.util as ilu
+    import math
+    aug_path = "/root/reference/provider/data_augmentation.py"
+    if os.path.isfile(aug_path):
+        spec = ilu.spec_from_file_location("ref_aug", aug_path)
+        A = ilu.module_from_spec(spec); spec.loader.exec_module(A)
+        B = len(boxes)
+        rot_in, tr_in, size_in = np.zeros((B, 3, 3), np.float32), np.zeros((B, 3), np.float32), np.zeros((B, 3), np.float32)
+        symmetric = np.array([1, 0, 1, 0, 0, 1], dtype=bool)
+        sym0 = np.array([1, 0, 1, 0, 0, 0])            # sym_info[0] of get_sym_info (mug with handle: 0)
+        do_bb, do_rt = np.array([1, 1, 0, 0, 1, 1], bool), np.array([1, 0, 1, 0, 1, 1], bool)
+        aug_bb = rng.uniform(0.8, 1.2, (B, 3)).astype(np.float32)
+        aug_t = (rng.uniform(-50, 50, (B, 3)) / 1000.0).astype(np.float32)
+        aug_R = np.stack([A.get_rotation(*rng.uniform(-15, 15, 3)) for _ in range(B)])
+        qo_l, rot_l, out = [], [], {k: [] for k in ("pts", "qo", "R", "t", "s")}
+        for b in range(B):
+            rotation = np.linalg.qr(rng.normal(size=(3, 3)))[0].astype(np.float32)
+            translation = np.array([0.02, -0.03, 0.75], np.float32) + rng.normal(0, 0.02, 3).astype(np.float32)
+            size = rng.uniform(0.1, 0.35, 3).astype(np.float32)
+            rot_in[b], tr_in[b], size_in[b] = rotation, translation, size
+            pts = ptss[b].astype(np.float32) + noises[b]                     # float32 points + float64 jitter (dataset.py:209-210)
+            if symmetric[b]:                                                # dataset.py:241-248
+                theta_x = rotation[0, 0] + rotation[2, 2]
+                theta_y = rotation[0, 2] - rotation[2, 0]
+                r_norm = math.sqrt(theta_x**2 + theta_y**2)
+                s_map = np.array([[theta_x/r_norm, 0.0, -theta_y/r_norm], [0.0, 1.0, 0.0], [theta_y/r_norm, 0.0, theta_x/r_norm]])
+                rotation = rotation @ s_map
+            qo = (pts - translation[np.newaxis, :]) / (np.linalg.norm(size)+1e-8) @ rotation
+            qo_l.append(torch.FloatTensor(qo).numpy()); rot_l.append(torch.FloatTensor(rotation).numpy())
+            PC, RR, TT, SS, NN = torch.FloatTensor(pts), torch.FloatTensor(rotation), torch.FloatTensor(translation), torch.FloatTensor(size), torch.FloatTensor(qo)
+            sym_info = np.array([sym0[b], 1, 0, 1])
+            if do_bb[b]:
+                PC, SS, NN, _ = A.defor_3D_bb(PC, RR, TT, SS, NN, torch.zeros(8, 3), sym=sym_info, aug_bb=torch.as_tensor(aug_bb[b]))
+            if do_rt[b]:
+                PC, RR, TT = A.defor_3D_rt(PC, RR, TT, torch.as_tensor(aug_t[b]), torch.as_tensor(aug_R[b]))
+                TT = TT.view(-1)
+            for k, v in zip(("pts", "qo", "R", "t", "s"), (PC, NN, RR, TT, SS)):
+                out[k].append(v.numpy().copy())
+        out2 = os.path.join(HERE, "golden", "dataprep_aug.npz")
+        np.savez_compressed(out2, rotation=rot_in, translation=tr_in, size=size_in, symmetric=symmetric, sym0=sym0, do_bb=do_bb, do_rt=do_rt,
+                            aug_bb=aug_bb, aug_t=aug_t, aug_R=aug_R, qo=np.stack(qo_l), rotation_label=np.stack(rot_l),
+                            **{"out_" + k: np.stack(v) for k, v in out.items()})
+        print(out2, os.path.getsize(out2), "bytes")
     # get_bbox restatement against the reference's own function on random detection boxes
     ref_utils = "/root/reference/utils"
     if os.path.isdir(ref_utils):

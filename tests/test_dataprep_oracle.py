@@ -63,3 +63,32 @@ def test_get_bbox_and_choose_sampler_host_logic():
     assert set(ch[0].tolist()) <= valid and len(ch[0]) == 32        # 16 valid pixels < 32: drawn with replacement
     ch2, _ = sample_choose(mask, [(0, 0, 40, 0, 40)], 8, generator=g)
     assert len(set(ch2[0].tolist())) == 8 and set(ch2[0].tolist()) <= valid  # more valid pixels than samples: without replacement
+
+
+AUG = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataprep_aug.npz")
+
+
+def test_label_and_augmentation_restatements_match_the_reference_goldens():
+    """NOCS labels (dataset.py:236-250) and the two default augmentations (data_augmentation.py:45-130): the goldens come from the
+    reference's own expressions / functions (tests/gen_golden_dataprep.py); oracle and the product's host-side label logic against them."""
+    import torch
+
+    from istnet_b200.dataprep import augment_label_params, canonical_labels
+
+    g, a = np.load(GOLD), np.load(AUG)
+    B = len(a["do_bb"])
+    rot64, par = canonical_labels(a["rotation"], a["translation"], a["size"], a["symmetric"])
+    for b in range(B):
+        pts64 = g["pts"][b].astype(np.float32) + g["noise"][b]
+        qo, rot = R.nocs_labels(pts64, a["rotation"][b], a["translation"][b], a["size"][b], bool(a["symmetric"][b]))
+        assert np.array_equal(qo, a["qo"][b]), b
+        assert np.array_equal(np.asarray(rot, dtype=np.float32), a["rotation_label"][b]), b
+        assert np.array_equal(rot64[b].astype(np.float32), a["rotation_label"][b]) and np.array_equal(par[b, 4:], np.asarray(rot, np.float64).reshape(9))
+        out = R.augment_points(g["pts_jitter"][b], a["rotation_label"][b], a["translation"][b], a["size"][b], a["qo"][b], int(a["sym0"][b]),
+                               bool(a["do_bb"][b]), a["aug_bb"][b], bool(a["do_rt"][b]), a["aug_t"][b], a["aug_R"][b])
+        for got, key in zip(out, ("out_pts", "out_R", "out_t", "out_s", "out_qo")):
+            assert np.allclose(got, a[key][b], rtol=2e-6, atol=2e-7), (b, key, np.abs(got - a[key][b]).max())
+    _, Rl, tl, sl = augment_label_params(a["rotation_label"], a["translation"], a["size"], a["sym0"], a["do_bb"], a["aug_bb"], a["do_rt"],
+                                         a["aug_t"], a["aug_R"])
+    assert torch.allclose(Rl, torch.from_numpy(a["out_R"]), rtol=2e-6, atol=2e-7)
+    assert torch.allclose(tl, torch.from_numpy(a["out_t"]), rtol=2e-6, atol=2e-7) and torch.allclose(sl, torch.from_numpy(a["out_s"]), rtol=2e-6, atol=2e-7)

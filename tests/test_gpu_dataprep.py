@@ -109,3 +109,29 @@ def test_frames_to_poses_pipeline_equals_the_manual_steps():
     assert torch.allclose(rts[:, :3, :3], ep["pred_rotation"] * s.unsqueeze(2), rtol=1e-5, atol=1e-6)
     assert torch.allclose(rts[:, :3, 3], ep["pred_translation"], rtol=1e-5, atol=1e-6) and torch.allclose(scales, ep["pred_size"] / s, rtol=1e-5, atol=1e-6)
     assert torch.isfinite(rts).all()
+
+
+def test_training_labels_and_augmentation_match_the_reference_goldens():
+    """qo from the float64 (jittered) points in the back-projection kernel, then the bounding-box / rigid augmentations in place
+    (csrc/dataprep.cu) against goldens produced by the reference's own functions (tests/golden/dataprep_aug.npz)."""
+    g, a = np.load(GOLD), np.load(os.path.join(os.path.dirname(GOLD), "dataprep_aug.npz"))
+    S, norm = int(g["S"]), float(g["norm_scale"])
+    rot64, par = D.canonical_labels(a["rotation"], a["translation"], a["size"], a["symmetric"])
+    out = D.prepare_instances(torch.from_numpy(g["frames"]).cuda(), torch.from_numpy(g["depth"]).cuda(), torch.from_numpy(g["boxes"]).cuda(),
+                              torch.from_numpy(g["choose_in"]).cuda(), tuple(g["intrinsics"]), img_size=S, norm_scale=norm,
+                              noise=torch.from_numpy(g["noise"]), label_params=par)
+    assert np.array_equal(out["pts"].cpu().numpy(), g["pts_jitter"])
+    qo = out["qo"].cpu().numpy()
+    # float64 contraction of three products: BLAS and the kernel may round the last bit of the double differently; after the FP32 store
+    # that is at most one ulp on a handful of elements
+    assert np.allclose(qo, a["qo"], rtol=2e-7, atol=1e-9) and (qo != a["qo"]).mean() < 0.01, (np.abs(qo - a["qo"]).max(), (qo != a["qo"]).mean())
+    pts_d, qo_d = out["pts"].clone(), torch.from_numpy(a["qo"]).cuda()
+    Rl, tl, sl = D.augment_instances(pts_d, qo_d, a["rotation_label"], a["translation"], a["size"], a["sym0"], a["do_bb"], a["aug_bb"], a["do_rt"],
+                                     a["aug_t"], a["aug_R"])
+    assert np.allclose(pts_d.cpu().numpy(), a["out_pts"], rtol=2e-6, atol=2e-7), np.abs(pts_d.cpu().numpy() - a["out_pts"]).max()
+    assert np.allclose(qo_d.cpu().numpy(), a["out_qo"], rtol=2e-6, atol=2e-7), np.abs(qo_d.cpu().numpy() - a["out_qo"]).max()
+    assert np.allclose(Rl.numpy(), a["out_R"], rtol=2e-6, atol=2e-7) and np.allclose(tl.numpy(), a["out_t"], rtol=2e-6, atol=2e-7)
+    assert np.allclose(sl.numpy(), a["out_s"], rtol=2e-6, atol=2e-7)
+    # instances without augmentation are untouched bit for bit
+    idle = [b for b in range(len(a["do_bb"])) if not a["do_bb"][b] and not a["do_rt"][b]]
+    assert idle and all(np.array_equal(pts_d[b].cpu().numpy(), g["pts_jitter"][b]) for b in idle)
